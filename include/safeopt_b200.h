@@ -1,0 +1,199 @@
+/*
+ * safeopt_b200 -- C ABI of the B200-native SafeOpt hot path.
+ *
+ * The reference (befelix/SafeOpt) has no FFI: its seam is Python duck typing on a GPy
+ * model.  Each entry point below names the reference call it
+ * stands in for (paths relative to /root/reference).  All functions return an int
+ * status (SO_OK == 0, negative = error); no C++ exception crosses this boundary.
+ *
+ * Ownership: the caller owns every buffer passed in (device buffers are typically
+ * torch tensors' data_ptr()); the library owns only the opaque handle and the fit
+ * state / workspaces hanging off it.  Hot calls (so_posterior_*, so_sets_*,
+ * so_expander_*, so_swarm_*) never allocate and are asynchronous on `stream`
+ * (a cudaStream_t passed as void*; NULL = legacy default stream).
+ * A handle is bound to one device and is not thread-safe.
+ *
+ * Pointer naming: `_h` = host memory, `_d` = device memory on the handle's device.
+ */
+#ifndef SAFEOPT_B200_H
+#define SAFEOPT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SO_ABI_VERSION 1
+
+/* status codes */
+#define SO_OK                  0
+#define SO_ERR_BAD_ARG        -1
+#define SO_ERR_UNSUPPORTED    -2   /* kernel family / shape the device path does not implement */
+#define SO_ERR_NOT_PD         -3   /* Cholesky of K + (noise+1e-8) I failed */
+#define SO_ERR_CUDA           -4
+#define SO_ERR_NOT_FITTED     -5
+#define SO_ERR_CAPACITY       -6
+#define SO_ERR_NO_DEVICE      -7
+
+/* stationary kernel families (GPy class names RBF / Matern32 / Matern52) */
+#define SO_KERNEL_RBF          0
+#define SO_KERNEL_MATERN32     1
+#define SO_KERNEL_MATERN52     2
+
+/* how so_posterior_* combines its safe bit into S (gp_opt.py:481 is an AND over GPs) */
+#define SO_SAFE_NONE           0   /* do not touch S */
+#define SO_SAFE_WRITE          1   /* S[row]  = (l > fmin) */
+#define SO_SAFE_AND            2   /* S[row] &= (l > fmin) */
+
+/* swarm fitness kinds (gp_opt.py:901-1013 `swarm_type`) */
+#define SO_SWARM_GREEDY        0
+#define SO_SWARM_MAXIMIZERS    1
+#define SO_SWARM_EXPANDERS     2
+#define SO_SWARM_SAFE_SET      3
+
+typedef struct so_handle so_handle;
+
+/* Record produced by so_sets_reduce_safe: everything gp_opt.py:504-512, :634-636 and
+ * :705-712 need from one streaming pass.  Rows are GLOBAL row indices (row0 + local). */
+typedef struct so_safe_record {
+    int64_t n_safe;        /* count_nonzero(S)                                  */
+    double  max_l0;        /* max(Q[S,0])  (-inf if none)                       */
+    int64_t argmax_l0;     /* first row attaining it (-1 if none)               */
+    double  max_u0;        /* max(Q[S,1])                                       */
+    int64_t argmax_u0;     /* first row attaining it (ucb query, gp_opt.py:635) */
+    int64_t reserved[3];
+} so_safe_record;
+
+/* Record produced by so_sets_maximizers (gp_opt.py:511-513 and the M part of :642-644). */
+typedef struct so_max_record {
+    int64_t n_max;         /* count_nonzero(M)                                            */
+    double  max_width0;    /* max(u0[M]-l0[M])   (unscaled; host divides by scaling[0])   */
+    double  best_value;    /* max over M of max_i((u_i-l_i)/scaling_i)                    */
+    int64_t best_row;      /* first row attaining best_value (-1 if none)                 */
+    int64_t reserved[4];
+} so_max_record;
+
+/* ------------------------------------------------------------------ lifetime */
+int         so_abi_version(void);
+const char* so_status_string(int status);
+/* Create a context on CUDA device `device` able to hold `max_gps` fitted GPs. */
+int         so_create(int device, int max_gps, so_handle** out);
+int         so_destroy(so_handle* h);
+/* Human-readable detail of the last failing call on this handle ("" if none). */
+const char* so_last_error(const so_handle* h);
+int         so_num_sms(const so_handle* h);
+
+/* ------------------------------------------------------------------ K1: fit
+ * Stands in for GPy `set_XY` -> ExactGaussianInference.inference, reached from
+ * safeopt/gp_opt.py:227, :267, :275 (and the constructor).  Builds
+ * Ky = K(X,X) + (noise_var + 1e-8) I, its lower Cholesky L, L^-1 (packed for the
+ * tensor-core contraction) and alpha = Ky^-1 Y, all in fp64 on the device.
+ *   X_h (N x d row-major), Y_h (N), lengthscale_h (d entries; a non-ARD kernel passes
+ *   its single lengthscale replicated d times).
+ * Synchronises `stream` before returning so that SO_ERR_NOT_PD can be reported. */
+int so_fit(so_handle* h, int gp, const double* X_h, const double* Y_h, int N, int d,
+           int kernel_kind, const double* lengthscale_h, double variance, double noise_var,
+           void* stream);
+/* Test/diagnostic read-back (synchronous): any of the outputs may be NULL.
+ *   L_h, Linv_h: N x N row-major; alpha_h: N. */
+int so_fit_export(so_handle* h, int gp, double* L_h, double* Linv_h, double* alpha_h);
+
+/* ------------------------------------------------------------------ grid description
+ * Stands in for safeopt/utilities.py:21-54 (`linearly_spaced_combinations`) when the
+ * optimiser's parameter_set is bit-identical to such a grid: rows are then generated
+ * from the row index on the device instead of being read from HBM.
+ *   axis_values_h: concatenated per-axis linspace values (sum(n_h) doubles, exactly the
+ *   doubles NumPy produced); n_h: points per axis; d axes.
+ * Row order is the reference's: axis 1 slowest, then axis 0, then axes 2..d-1 fastest
+ * (d == 1: the axis itself).  Must be called again after every so_fit of that gp
+ * (it rebuilds the per-axis kernel factor tables); synchronous on `stream` order. */
+int so_grid_define(so_handle* h, int d, const int32_t* n_h, const double* axis_values_h, void* stream);
+int so_grid_prepare(so_handle* h, int gp, void* stream);
+
+/* ------------------------------------------------------------------ K2: posterior + bounds + safe bit
+ * Stands in for `gp.predict_noiseless(self.inputs)` (safeopt/gp_opt.py:469) fused with
+ * :471-476 (Q columns 2*gp, 2*gp+1) and this GP's factor of :481.
+ * Local rows [0, M) of this rank; `row0` is the global index of local row 0 (grid path
+ * only needs it to decode indices; both paths report global rows elsewhere).
+ *   mean_d, var_d : (M) fp64, may be NULL
+ *   Q_d           : (M x q_stride) fp64 row-major, writes columns q_col, q_col+1; may be NULL
+ *   S_d           : (M) uint8, combined per safe_mode with (l > fmin); may be NULL
+ * so_posterior_rows reads explicit candidates Xstar_d (M x d row-major fp64).
+ * so_posterior_grid generates them from the grid defined by so_grid_define.
+ * so_posterior_rows_simple is a one-thread-per-row DFMA cross-check of the same maths
+ * (tests only; not a fallback -- nothing in the product calls it). */
+int so_posterior_rows(so_handle* h, int gp, const double* Xstar_d, int64_t M, double beta, double fmin,
+                      double* mean_d, double* var_d, double* Q_d, int q_stride, int q_col,
+                      uint8_t* S_d, int safe_mode, void* stream);
+int so_posterior_grid(so_handle* h, int gp, int64_t row0, int64_t M, double beta, double fmin,
+                      double* mean_d, double* var_d, double* Q_d, int q_stride, int q_col,
+                      uint8_t* S_d, int safe_mode, void* stream);
+int so_posterior_rows_simple(so_handle* h, int gp, const double* Xstar_d, int64_t M,
+                             double* mean_d, double* var_d, void* stream);
+/* Materialise grid rows [row0, row0+M) as an (M x d) row-major array (tests, query point). */
+int so_grid_rows(so_handle* h, int64_t row0, int64_t M, double* X_d, void* stream);
+
+/* ------------------------------------------------------------------ K3: set logic (streaming passes over Q)
+ * so_sets_reduce_safe : any(S), max l0[S], argmax (gp_opt.py:504, :512, :635, :708-712)
+ * so_sets_maximizers  : M = S & (u0 >= max_l0); max width over M; best scaled width over M
+ *                       (gp_opt.py:511-513, :642-644)
+ * so_sets_candidates  : s = S & ~M & (max_i((u_i-l_i)/scaling_i) > max_var)
+ *                           & any_i(u_i-l_i > thr_i)            (gp_opt.py:531-536)
+ *                       writes the mask (may be NULL) and appends (key,row) of every
+ *                       candidate, key = max_i(u_i-l_i) unscaled (gp_opt.py:551), to a
+ *                       compact list of capacity `cap`; *n_cand_d counts ALL candidates.
+ * scaling_h / thr_h are G host doubles (thr_i = threshold_i * beta).  Records and
+ * counters live in device memory and must be zero/initialised by so_sets_* itself. */
+int so_sets_reduce_safe(so_handle* h, const double* Q_d, int n_gps, int64_t M, int64_t row0,
+                        const uint8_t* S_d, so_safe_record* rec_d, void* stream);
+int so_sets_maximizers(so_handle* h, const double* Q_d, int n_gps, int64_t M, int64_t row0,
+                       const uint8_t* S_d, double max_l0, const double* scaling_h,
+                       uint8_t* Mmask_d, so_max_record* rec_d, void* stream);
+int so_sets_candidates(so_handle* h, const double* Q_d, int n_gps, int64_t M, int64_t row0,
+                       const uint8_t* S_d, const uint8_t* Mmask_d, double max_var,
+                       const double* scaling_h, const double* thr_h,
+                       uint8_t* cand_mask_d, double* cand_key_d, int64_t* cand_row_d,
+                       int64_t cap, int64_t* n_cand_d, void* stream);
+
+/* ------------------------------------------------------------------ K4: batched expander test
+ * Stands in for the refit/predict/refit loop of safeopt/gp_opt.py:579-606 for B
+ * candidates at once, through the rank-1 identity:
+ *   c(x) = k(x,x_c) - k_x^T Ky^-1 k_c ,  s = var(x_c) + noise + 1e-8
+ *   mean2 = mean(x) + c(x) (u_c - mean(x_c)) / s ,  var2 = max(var(x) - c(x)^2 / s, 1e-15)
+ *   flag[b] = any over rows with S==0 of (mean2 - beta sqrt(var2) >= fmin)
+ * for GP `gp`.  Candidate b is described by its coordinates xc_d (B x d), its posterior
+ * mean/var and the fake observation value u_c (all device arrays of length B).
+ * Rows come from Xstar_d (M x d) or, if Xstar_d == NULL, from the defined grid.
+ * flags_d (B, uint8) is OR-ed into (caller zeroes it), so ranks/launches can accumulate. */
+int so_expander_check(so_handle* h, int gp, const double* Xstar_d, int64_t row0, int64_t M,
+                      const uint8_t* S_d, const double* mean_d, const double* var_d,
+                      const double* xc_d, const double* mean_c_d, const double* var_c_d,
+                      const double* u_c_d, int B, double beta, double fmin,
+                      uint8_t* flags_d, void* stream);
+
+/* ------------------------------------------------------------------ K5/K6: swarm
+ * so_swarm_fitness stands in for SafeOptSwarm._compute_particle_fitness
+ * (safeopt/gp_opt.py:901-1013) given per-GP posterior planes mean_d/var_d laid out
+ * (G x P) (filled by so_posterior_rows with M = P).  Writes values_d (P) and safe_d (P).
+ * so_swarm_step stands in for one iteration of SwarmOptimization.run_swarm
+ * (safeopt/swarm.py:98-130: velocity/position update and clipping) with host-supplied
+ * uniform randoms r_d (2P x d, the reference draws them from np.random). */
+int so_swarm_fitness(so_handle* h, int kind, int n_gps, int64_t P, const double* mean_d,
+                     const double* var_d, double beta, const double* fmin_h,
+                     const double* scaling_h, double best_lower_bound,
+                     double* values_d, uint8_t* safe_d, void* stream);
+int so_swarm_step(so_handle* h, int64_t P, int d, double* pos_d, double* vel_d,
+                  const double* best_pos_d, const double* global_best_d, const double* r_d,
+                  double inertia, const double* velocity_scale_h, const double* bounds_h,
+                  void* stream);
+/* personal/global best update of safeopt/swarm.py:132-146; writes argmax of best_values
+ * (first index) to *best_idx_d. */
+int so_swarm_update_best(so_handle* h, int64_t P, int d, const double* pos_d, const double* values_d,
+                         const uint8_t* safe_d, double* best_pos_d, double* best_values_d,
+                         int64_t* best_idx_d, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAFEOPT_B200_H */

@@ -1,0 +1,124 @@
+// Internal definitions shared by the sm_100a translation units behind include/safeopt_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/safeopt_b200.h"
+
+#define SO_MAX_DIM 16            // max input dimension (parameters + contexts)
+#define SO_JITTER 1e-8           // GPy adds this to the noise variance
+#define SO_VAR_FLOOR 1e-15       // GPy clips predictive variances here
+#define SO_WS_MAX_BLOCKS 1184     // 8 x 148: upper bound on the grid of the reduction passes
+
+// Fitted state of one GP, all in device memory (fp64).
+struct GPState {
+    bool fitted = false;
+    int N = 0, d = 0, kind = 0;
+    int NB = 0;                  // number of 8-row blocks, Npad = 8*NB
+    int capN = 0;                // allocated for this many padded rows
+    double variance = 0, noise = 0;
+    double inv_ls[SO_MAX_DIM];   // 1 / lengthscale_j
+    double* X = nullptr;         // N x d raw training inputs
+    double* Xs = nullptr;        // Npad x d, scaled by 1/lengthscale (padding rows = 0)
+    double* Y = nullptr;         // N
+    double* K = nullptr;         // Npad x Npad work / L (lower, row-major, ld = Npad)
+    double* Linv = nullptr;      // Npad x Npad lower, row-major
+    double* alpha = nullptr;     // Npad (padding = 0)
+    double2* Afrag = nullptr;    // L^-1 packed in DMMA A-fragment order (+1 block of slack)
+    // grid tables (grid fast path): per axis j, E_j[i][n], i < n_j, n < Npad
+    double* E = nullptr;
+    size_t capE = 0;
+    bool grid_ready = false;
+};
+
+struct GridSpec {
+    bool defined = false;
+    int d = 0;
+    int n[SO_MAX_DIM];
+    int64_t stride[SO_MAX_DIM];  // row = sum_j idx_j * stride_j  (reference row order)
+    int off[SO_MAX_DIM];         // offset of axis j in `axis` / table rows
+    int total = 0;               // sum n_j
+    double* axis = nullptr;      // device copy of the axis values
+    int cap = 0;
+    int64_t rows = 0;
+};
+
+struct so_handle {
+    int device = 0;
+    int max_gps = 0;
+    int num_sms = 0;
+    int smem_optin = 0;
+    std::vector<GPState> gps;
+    GridSpec grid;
+    int* d_status = nullptr;     // device int written by fit kernels
+    int* h_status = nullptr;     // pinned host mirror
+    void* ws_partials = nullptr; // per-block partial records of the reduction passes (sets.cu)
+    unsigned int* ws_counter = nullptr;  // last-block-done ticket, self-resetting
+    double* ws_z = nullptr;      // expander batch workspace (expander.cu)
+    size_t ws_z_cap = 0;
+    std::string err;
+};
+
+inline int so_fail(so_handle* h, int code, const std::string& msg) {
+    if (h) h->err = msg;
+    return code;
+}
+
+#define SO_CUDA(h, expr)                                                                        \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess)                                                                  \
+            return so_fail((h), SO_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
+#define SO_CHECK_LAUNCH(h, what)                                                                \
+    do {                                                                                        \
+        cudaError_t _e = cudaGetLastError();                                                    \
+        if (_e != cudaSuccess)                                                                  \
+            return so_fail((h), SO_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// ---- device helpers -------------------------------------------------------------------
+// fp64 tensor-core tile: D(8x8) += A(8x4) * B(4x8).  Lane l holds A[l/4][l%4], B[l%4][l/4],
+// C[l/4][2*(l%4) + {0,1}].  SASS: DMMA.8x8x4 (measured 37.1 TFLOP/s on B200, profiles/r01_fp64_rates_b200.jsonl).
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// Stationary kernel value from the squared scaled distance (GPy K_of_r).
+template <int KIND>
+__device__ __forceinline__ double kernel_of_r2(double r2, double variance) {
+    if (KIND == SO_KERNEL_RBF) {
+        return variance * exp(-0.5 * r2);
+    } else if (KIND == SO_KERNEL_MATERN32) {
+        const double s3 = 1.7320508075688772;
+        double r = sqrt(r2);
+        return variance * (1.0 + s3 * r) * exp(-s3 * r);
+    } else {
+        const double s5 = 2.23606797749979;
+        double r = sqrt(r2);
+        return variance * (1.0 + s5 * r + (5.0 / 3.0) * r2) * exp(-s5 * r);
+    }
+}
+
+// Number of DMMA A-fragment blocks in the packed lower triangle of an NB x NB block matrix.
+__host__ __device__ inline size_t tri_blocks(int NB) { return (size_t)NB * (NB + 1) / 2; }
+
+// Ordered-integer encoding so that atomicMax on int64 orders doubles (incl. -inf).
+__device__ __forceinline__ long long order_encode(double x) {
+    long long b = __double_as_longlong(x);
+    return b >= 0 ? b : (b ^ 0x7fffffffffffffffLL);
+}
+__device__ __forceinline__ double order_decode(long long k) {
+    long long b = k >= 0 ? k : (k ^ 0x7fffffffffffffffLL);
+    return __longlong_as_double(b);
+}

@@ -1,0 +1,461 @@
+// K2 -- fused GP posterior over candidate rows: kernel-row build, the dense triangular
+// contraction V = L^-1 k on the fp64 tensor pipe (DMMA.8x8x4), predictive mean/variance,
+// confidence bounds and the safe bit.  Stands in for `gp.predict_noiseless(self.inputs)`
+// (safeopt/gp_opt.py:469) + :471-476 + this GP's factor of :481.  Nothing of size N x M ever
+// reaches HBM (the reference materialises three such temporaries).
+//
+// Persistent kernel, one 256-thread CTA per SM, looping over tiles of T candidate rows:
+//   gen : k(x*, X) for the tile, written to shared memory directly in DMMA B-fragment order;
+//         the mean k.alpha is accumulated on the way (deterministic shuffle reduction).
+//   mma : warp (g, cg) owns block rows {g, 2RG-1-g, 2RG+g, 4RG-1-g} (+4RG per pass) of L^-1 --
+//         a pairing that balances the triangular work -- and BT column tiles; A fragments stream
+//         from L2 (each is used by exactly one warp per tile, so staging them in shared memory
+//         would add traffic without reuse), B fragments come from shared memory (LDS.128).
+//   epi : column sums of squares -> var = max(k** - |V|^2, 1e-15), l/u = mean -/+ beta*sqrt(var)
+//         with separate multiply and add roundings (NumPy does not contract), S bit.
+// Algorithmic work per row and GP: N^2/2 FMA (contraction) + N kernel evaluations; algorithmic HBM
+// bytes: d*8 in (0 on the grid path) + 32 out (mean, var, l, u) + 1 (S).  See DESIGN.md section 3.
+#include "posterior_core.cuh"
+
+namespace {
+
+__device__ __forceinline__ int pick4(int r0, int r1, int r2, int r3, int i) {
+    return i == 0 ? r0 : (i == 1 ? r1 : (i == 2 ? r2 : r3));
+}
+
+template <int BT>
+__device__ __forceinline__ void mma_phase(const PostParams& p, const double2* __restrict__ sK, double* __restrict__ sSS,
+                                          int warp, int lane) {
+    const int RG = p.RG, NB = p.NB, TB = p.TB, T = p.T;
+    const int g = warp % RG, cg = warp / RG;
+    const double2* sB = sK + (size_t)(cg * BT) * 32 + lane;
+    const double2* Afrag = p.Afrag + lane;
+    double ss[BT][2];
+#pragma unroll
+    for (int c = 0; c < BT; ++c) { ss[c][0] = 0.0; ss[c][1] = 0.0; }
+
+    for (int pass = 0; pass < p.npass; ++pass) {
+        const int base = 4 * RG * pass;
+        const int r0 = base + g, r1 = base + 2 * RG - 1 - g, r2 = base + 2 * RG + g, r3 = base + 4 * RG - 1 - g;
+        // rows are ascending; the ones beyond NB (inactive) form a suffix.  Slots are ordered by
+        // K extent, inactive slots (extent -1) first, so that "slots FIRST..3 active" holds per segment.
+        const int na = (r0 < NB) + (r1 < NB) + (r2 < NB) + (r3 < NB);
+        int ext[4];
+        size_t abase[4];
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            const int src = s - (4 - na);
+            const int r = src >= 0 ? pick4(r0, r1, r2, r3, src) : -1;
+            ext[s] = r;
+            abase[s] = r >= 0 ? (size_t)r * (r + 1) / 2 * 32 : 0;
+        }
+        double acc[4][BT][2];
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+#pragma unroll
+            for (int c = 0; c < BT; ++c) { acc[s][c][0] = 0.0; acc[s][c][1] = 0.0; }
+        double2 a[4];
+#pragma unroll
+        for (int s = 0; s < 4; ++s) a[s] = __ldg(Afrag + abase[s]);
+        mma_segment<BT, 0>(acc, a, Afrag, abase, sB, TB, 0, ext[0]);
+        mma_segment<BT, 1>(acc, a, Afrag, abase, sB, TB, ext[0] + 1, ext[1]);
+        mma_segment<BT, 2>(acc, a, Afrag, abase, sB, TB, ext[1] + 1, ext[2]);
+        mma_segment<BT, 3>(acc, a, Afrag, abase, sB, TB, ext[2] + 1, ext[3]);
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+#pragma unroll
+            for (int c = 0; c < BT; ++c) {
+                ss[c][0] = fma(acc[s][c][0], acc[s][c][0], ss[c][0]);
+                ss[c][1] = fma(acc[s][c][1], acc[s][c][1], ss[c][1]);
+            }
+    }
+    // sum over the 8 rows of a block (lane bits 2..4), fixed tree => deterministic
+#pragma unroll
+    for (int c = 0; c < BT; ++c) {
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+            ss[c][0] += __shfl_xor_sync(0xffffffffu, ss[c][0], o);
+            ss[c][1] += __shfl_xor_sync(0xffffffffu, ss[c][1], o);
+        }
+    }
+    if (lane < 4) {
+#pragma unroll
+        for (int c = 0; c < BT; ++c) {
+            double2* dst = reinterpret_cast<double2*>(sSS + (size_t)g * T + (cg * BT + c) * 8 + 2 * lane);
+            *dst = make_double2(ss[c][0], ss[c][1]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- epilogue
+__device__ __forceinline__ void epilogue(const PostParams& p, const double* __restrict__ sMean, const double* __restrict__ sSS,
+                                         int64_t tile_local0) {
+    const int T = p.T, RG = p.RG;
+    for (int t = threadIdx.x; t < T; t += kThreads) {
+        const int64_t row = tile_local0 + t;
+        if (row >= p.M) continue;
+        double sumsq = 0.0;
+        for (int g = 0; g < RG; ++g) sumsq += sSS[(size_t)g * T + t];
+        const double mu = sMean[t];
+        double v = p.variance - sumsq;
+        v = v > SO_VAR_FLOOR ? v : SO_VAR_FLOOR;
+        const double sd = sqrt(v);
+        const double bs = __dmul_rn(p.beta, sd);
+        const double lo = __dsub_rn(mu, bs), up = __dadd_rn(mu, bs);
+        if (p.mean) p.mean[row] = mu;
+        if (p.var) p.var[row] = v;
+        if (p.Q) {
+            double* qp = p.Q + (size_t)row * p.q_stride + p.q_col;
+            if ((p.q_stride & 1) == 0 && (p.q_col & 1) == 0) {
+                *reinterpret_cast<double2*>(qp) = make_double2(lo, up);
+            } else {
+                qp[0] = lo;
+                qp[1] = up;
+            }
+        }
+        if (p.safe_mode != SO_SAFE_NONE && p.S) {
+            const uint8_t safe = lo > p.fmin ? 1 : 0;
+            p.S[row] = p.safe_mode == SO_SAFE_WRITE ? safe : (uint8_t)(p.S[row] & safe);
+        }
+    }
+}
+
+template <int BT, int KIND, bool GRID>
+__global__ void __launch_bounds__(kThreads, 1) k_posterior(const __grid_constant__ PostParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const SmemLayout L = smem_layout(p.NB, p.T, p.d, p.RG, GRID);
+    double2* sK = reinterpret_cast<double2*>(smem_raw);
+    double* sAlpha = reinterpret_cast<double*>(smem_raw + L.alpha_off);
+    double* sXs = reinterpret_cast<double*>(smem_raw + L.xs_off);
+    double* sXt = reinterpret_cast<double*>(smem_raw + L.xt_off);
+    double* sMean = reinterpret_cast<double*>(smem_raw + L.mean_off);
+    double* sSS = reinterpret_cast<double*>(smem_raw + L.ss_off);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int Npad = 8 * p.NB, T = p.T;
+
+    for (int i = threadIdx.x; i < Npad; i += kThreads) sAlpha[i] = p.alpha[i];
+    if (!GRID) {
+        for (int i = threadIdx.x; i < Npad * p.d; i += kThreads) sXs[i] = p.Xs[i];
+        if ((int64_t)blockIdx.x < p.ntiles) load_tile_rows(p, sXt, (int64_t)blockIdx.x * T);
+    }
+    __syncthreads();
+
+    int par = 0;
+    for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, par ^= 1) {
+        const int64_t tile_local0 = tile * T;
+        double* sMeanT = sMean + par * T;
+        double* sSST = sSS + (size_t)par * p.RG * T;
+        if (GRID) gen_grid(p, sK, sAlpha, sMeanT, p.row0 + tile_local0, warp, lane);
+        else gen_rows<KIND>(p, sK, sAlpha, sXs, sXt + (size_t)par * T * p.d, sMeanT, warp, lane);
+        __syncthreads();
+        if (!GRID) {
+            const int64_t next = tile + gridDim.x;
+            if (next < p.ntiles) load_tile_rows(p, sXt + (size_t)(par ^ 1) * T * p.d, next * T);
+        }
+        mma_phase<BT>(p, sK, sSST, warp, lane);
+        __syncthreads();
+        epilogue(p, sMeanT, sSST, tile_local0);
+    }
+}
+
+// ---------------------------------------------------------------- cross-check kernel (tests only)
+__global__ void __launch_bounds__(256) k_posterior_simple(const double* __restrict__ Linv, const double* __restrict__ alpha,
+                                                          const double* __restrict__ Xs, const double* __restrict__ Xstar,
+                                                          int N, int Npad, int d, int kind, double variance,
+                                                          const double* __restrict__ inv_ls_d, int64_t M,
+                                                          double* __restrict__ mean, double* __restrict__ var) {
+    extern __shared__ double sk[];
+    __shared__ double red[2][8];
+    const int64_t row = blockIdx.x;
+    if (row >= M) return;
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        double r2 = 0.0;
+        for (int j = 0; j < d; ++j) {
+            double t = Xstar[(size_t)row * d + j] * inv_ls_d[j] - Xs[(size_t)n * d + j];
+            r2 = fma(t, t, r2);
+        }
+        double k;
+        switch (kind) {
+            case SO_KERNEL_RBF: k = kernel_of_r2<SO_KERNEL_RBF>(r2, variance); break;
+            case SO_KERNEL_MATERN32: k = kernel_of_r2<SO_KERNEL_MATERN32>(r2, variance); break;
+            default: k = kernel_of_r2<SO_KERNEL_MATERN52>(r2, variance); break;
+        }
+        sk[n] = k;
+    }
+    __syncthreads();
+    double ss = 0.0, mu = 0.0;
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        double v = 0.0;
+        for (int m = 0; m <= n; ++m) v = fma(Linv[(size_t)n * Npad + m], sk[m], v);
+        ss = fma(v, v, ss);
+        mu = fma(sk[n], alpha[n], mu);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        mu += __shfl_xor_sync(0xffffffffu, mu, o);
+    }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = ss; red[1][threadIdx.x >> 5] = mu; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0, m = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { s += red[0][w]; m += red[1][w]; }
+        double v = variance - s;
+        var[row] = v > SO_VAR_FLOOR ? v : SO_VAR_FLOOR;
+        mean[row] = m;
+    }
+}
+
+// ---------------------------------------------------------------- grid tables / rows
+__global__ void k_grid_tables(const double* __restrict__ axis, const double* __restrict__ Xs, double* __restrict__ E,
+                              int total, int N, int Npad, int d, const int* __restrict__ axis_of, double variance,
+                              const double* __restrict__ inv_ls_d) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    if (n >= Npad || i >= total) return;
+    const int j = axis_of[i];
+    double v = 0.0;
+    if (n < N) {
+        const double t = axis[i] * inv_ls_d[j] - Xs[(size_t)n * d + j];
+        v = exp(-0.5 * (t * t));
+        if (j == 0) v *= variance;
+    }
+    E[(size_t)i * Npad + n] = v;
+}
+
+struct GridDecode {
+    int d;
+    int n[kGridMaxDim];
+    int off[kGridMaxDim];
+    int64_t stride[kGridMaxDim];
+};
+
+__global__ void k_grid_rows(GridDecode gd, const double* __restrict__ axis, int64_t row0, int64_t M, double* __restrict__ X) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= M) return;
+    const int64_t row = row0 + r;
+    for (int j = 0; j < gd.d; ++j) {
+        const int idx = (int)((row / gd.stride[j]) % gd.n[j]);
+        X[(size_t)r * gd.d + j] = axis[gd.off[j] + idx];
+    }
+}
+
+// ---------------------------------------------------------------- host
+struct LaunchPlan { int BT, RG, CG, T, TB, npass; size_t smem; };
+
+int plan_launch(so_handle* h, const GPState& g, int64_t M, bool grid, LaunchPlan& lp) {
+    const int NB = g.NB;
+    if (NB >= 32) { lp.RG = 8; lp.CG = 1; }
+    else if (NB >= 16) { lp.RG = 4; lp.CG = 2; }
+    else if (NB >= 8) { lp.RG = 2; lp.CG = 4; }
+    else { lp.RG = 1; lp.CG = 8; }
+    const size_t limit = (size_t)h->smem_optin;
+    int BT = 8;
+    while (BT >= 2 && smem_layout(NB, 8 * BT * lp.CG, g.d, lp.RG, grid).total > limit) BT >>= 1;
+    if (BT < 2) return so_fail(h, SO_ERR_CAPACITY, "posterior: N too large for the shared-memory tile (N <= ~1600)");
+    // few tiles -> smaller tiles so that more SMs get work
+    while (BT > 2 && (M + 8 * BT * lp.CG - 1) / (8 * BT * lp.CG) < 2 * (int64_t)h->num_sms) BT >>= 1;
+    lp.BT = BT;
+    lp.T = 8 * BT * lp.CG;
+    lp.TB = BT * lp.CG;
+    lp.npass = (NB + 4 * lp.RG - 1) / (4 * lp.RG);
+    lp.smem = smem_layout(NB, lp.T, g.d, lp.RG, grid).total;
+    return SO_OK;
+}
+
+template <int BT, int KIND, bool GRID>
+int launch_one(so_handle* h, const PostParams& p, const LaunchPlan& lp, cudaStream_t stream) {
+    static int configured_for = -1;
+    if (configured_for != h->device) {
+        SO_CUDA(h, cudaFuncSetAttribute(k_posterior<BT, KIND, GRID>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
+        configured_for = h->device;
+    }
+    const int grid = (int)(p.ntiles < (int64_t)h->num_sms ? p.ntiles : (int64_t)h->num_sms);
+    k_posterior<BT, KIND, GRID><<<grid, kThreads, lp.smem, stream>>>(p);
+    SO_CHECK_LAUNCH(h, "k_posterior");
+    return SO_OK;
+}
+
+template <int KIND, bool GRID>
+int launch_bt(so_handle* h, const PostParams& p, const LaunchPlan& lp, cudaStream_t stream) {
+    switch (lp.BT) {
+        case 8: return launch_one<8, KIND, GRID>(h, p, lp, stream);
+        case 4: return launch_one<4, KIND, GRID>(h, p, lp, stream);
+        default: return launch_one<2, KIND, GRID>(h, p, lp, stream);
+    }
+}
+
+int run_posterior(so_handle* h, int gp, const double* Xstar_d, bool grid, int64_t row0, int64_t M, double beta, double fmin,
+                  double* mean_d, double* var_d, double* Q_d, int q_stride, int q_col, uint8_t* S_d, int safe_mode,
+                  void* stream_) {
+    if (!h) return SO_ERR_BAD_ARG;
+    if (gp < 0 || gp >= h->max_gps) return so_fail(h, SO_ERR_BAD_ARG, "posterior: gp index out of range");
+    GPState& g = h->gps[gp];
+    if (!g.fitted) return so_fail(h, SO_ERR_NOT_FITTED, "posterior: GP not fitted");
+    if (M < 0) return so_fail(h, SO_ERR_BAD_ARG, "posterior: M < 0");
+    if (M == 0) return SO_OK;
+    if (Q_d && (q_stride < 2 || q_col < 0 || q_col + 2 > q_stride))
+        return so_fail(h, SO_ERR_BAD_ARG, "posterior: Q column out of range");
+    if (safe_mode < SO_SAFE_NONE || safe_mode > SO_SAFE_AND) return so_fail(h, SO_ERR_BAD_ARG, "posterior: bad safe_mode");
+    if (grid) {
+        if (!h->grid.defined) return so_fail(h, SO_ERR_BAD_ARG, "posterior_grid: no grid defined");
+        if (!g.grid_ready) return so_fail(h, SO_ERR_NOT_FITTED, "posterior_grid: so_grid_prepare not called after so_fit");
+        if (g.kind != SO_KERNEL_RBF) return so_fail(h, SO_ERR_UNSUPPORTED, "posterior_grid: separable tables need an RBF kernel");
+        if (row0 < 0 || row0 + M > h->grid.rows) return so_fail(h, SO_ERR_BAD_ARG, "posterior_grid: rows outside the grid");
+    } else if (!Xstar_d) {
+        return so_fail(h, SO_ERR_BAD_ARG, "posterior_rows: null candidate pointer");
+    }
+    DeviceGuard guard(h->device);
+    LaunchPlan lp;
+    int rc = plan_launch(h, g, M, grid, lp);
+    if (rc) return rc;
+    PostParams p;
+    p.N = g.N; p.NB = g.NB; p.d = g.d; p.RG = lp.RG; p.CG = lp.CG; p.T = lp.T; p.TB = lp.TB; p.npass = lp.npass;
+    p.kind = g.kind;
+    p.Afrag = g.Afrag; p.alpha = g.alpha; p.Xs = g.Xs;
+    for (int j = 0; j < SO_MAX_DIM; ++j) p.inv_ls[j] = g.inv_ls[j];
+    p.variance = g.variance;
+    p.Xstar = Xstar_d; p.M = M; p.row0 = row0; p.ntiles = (M + lp.T - 1) / lp.T;
+    p.gd = 0; p.E = g.E;
+    if (grid) {
+        p.gd = h->grid.d;
+        for (int j = 0; j < kGridMaxDim; ++j) {
+            p.gn[j] = j < p.gd ? h->grid.n[j] : 1;
+            p.goff[j] = j < p.gd ? h->grid.off[j] : 0;
+            p.gstride[j] = j < p.gd ? h->grid.stride[j] : 1;
+        }
+    }
+    p.beta = beta; p.fmin = fmin;
+    p.mean = mean_d; p.var = var_d; p.Q = Q_d; p.q_stride = q_stride; p.q_col = q_col; p.S = S_d; p.safe_mode = safe_mode;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (grid) return launch_bt<SO_KERNEL_RBF, true>(h, p, lp, stream);
+    switch (g.kind) {
+        case SO_KERNEL_RBF: return launch_bt<SO_KERNEL_RBF, false>(h, p, lp, stream);
+        case SO_KERNEL_MATERN32: return launch_bt<SO_KERNEL_MATERN32, false>(h, p, lp, stream);
+        default: return launch_bt<SO_KERNEL_MATERN52, false>(h, p, lp, stream);
+    }
+}
+
+}  // namespace
+
+extern "C" int so_posterior_rows(so_handle* h, int gp, const double* Xstar_d, int64_t M, double beta, double fmin,
+                                 double* mean_d, double* var_d, double* Q_d, int q_stride, int q_col, uint8_t* S_d,
+                                 int safe_mode, void* stream) {
+    return run_posterior(h, gp, Xstar_d, false, 0, M, beta, fmin, mean_d, var_d, Q_d, q_stride, q_col, S_d, safe_mode, stream);
+}
+
+extern "C" int so_posterior_grid(so_handle* h, int gp, int64_t row0, int64_t M, double beta, double fmin, double* mean_d,
+                                 double* var_d, double* Q_d, int q_stride, int q_col, uint8_t* S_d, int safe_mode,
+                                 void* stream) {
+    return run_posterior(h, gp, nullptr, true, row0, M, beta, fmin, mean_d, var_d, Q_d, q_stride, q_col, S_d, safe_mode, stream);
+}
+
+extern "C" int so_posterior_rows_simple(so_handle* h, int gp, const double* Xstar_d, int64_t M, double* mean_d,
+                                        double* var_d, void* stream_) {
+    if (!h || gp < 0 || gp >= h->max_gps || !Xstar_d || !mean_d || !var_d || M < 0) return SO_ERR_BAD_ARG;
+    GPState& g = h->gps[gp];
+    if (!g.fitted) return so_fail(h, SO_ERR_NOT_FITTED, "posterior_rows_simple: GP not fitted");
+    if (M == 0) return SO_OK;
+    DeviceGuard guard(h->device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    double* inv_ls_d = nullptr;
+    SO_CUDA(h, cudaMalloc(&inv_ls_d, sizeof(double) * SO_MAX_DIM));
+    SO_CUDA(h, cudaMemcpyAsync(inv_ls_d, g.inv_ls, sizeof(double) * SO_MAX_DIM, cudaMemcpyHostToDevice, stream));
+    k_posterior_simple<<<(unsigned)M, 256, sizeof(double) * g.N, stream>>>(g.Linv, g.alpha, g.Xs, Xstar_d, g.N, 8 * g.NB, g.d,
+                                                                          g.kind, g.variance, inv_ls_d, M, mean_d, var_d);
+    SO_CHECK_LAUNCH(h, "k_posterior_simple");
+    SO_CUDA(h, cudaStreamSynchronize(stream));
+    cudaFree(inv_ls_d);
+    return SO_OK;
+}
+
+extern "C" int so_grid_define(so_handle* h, int d, const int32_t* n_h, const double* axis_values_h, void* stream_) {
+    if (!h || !n_h || !axis_values_h) return SO_ERR_BAD_ARG;
+    if (d < 1 || d > kGridMaxDim) return so_fail(h, SO_ERR_UNSUPPORTED, "so_grid_define: the grid fast path supports 1 <= d <= 6");
+    DeviceGuard guard(h->device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    GridSpec& gs = h->grid;
+    int total = 0;
+    int64_t rows = 1;
+    for (int j = 0; j < d; ++j) {
+        if (n_h[j] < 1) return so_fail(h, SO_ERR_BAD_ARG, "so_grid_define: axis with no points");
+        gs.n[j] = n_h[j];
+        gs.off[j] = total;
+        total += n_h[j];
+        rows *= n_h[j];
+    }
+    // reference row order (safeopt/utilities.py:50-54, meshgrid 'xy'): axis 1 slowest, then axis 0,
+    // then axes 2..d-1 (fastest)
+    if (d == 1) {
+        gs.stride[0] = 1;
+    } else {
+        int64_t s = 1;
+        for (int j = d - 1; j >= 2; --j) { gs.stride[j] = s; s *= n_h[j]; }
+        gs.stride[0] = s; s *= n_h[0];
+        gs.stride[1] = s;
+    }
+    if (total > gs.cap) {
+        SO_CUDA(h, cudaStreamSynchronize(stream));
+        if (gs.axis) cudaFree(gs.axis);
+        gs.axis = nullptr;
+        SO_CUDA(h, cudaMalloc(&gs.axis, sizeof(double) * total + sizeof(int) * total));
+        gs.cap = total;
+    }
+    SO_CUDA(h, cudaMemcpyAsync(gs.axis, axis_values_h, sizeof(double) * total, cudaMemcpyHostToDevice, stream));
+    std::vector<int> axis_of(total);
+    for (int j = 0; j < d; ++j)
+        for (int i = 0; i < n_h[j]; ++i) axis_of[gs.off[j] + i] = j;
+    SO_CUDA(h, cudaMemcpyAsync(reinterpret_cast<int*>(gs.axis + gs.cap), axis_of.data(), sizeof(int) * total, cudaMemcpyHostToDevice, stream));
+    SO_CUDA(h, cudaStreamSynchronize(stream));
+    gs.d = d; gs.total = total; gs.rows = rows; gs.defined = true;
+    for (auto& g : h->gps) g.grid_ready = false;
+    return SO_OK;
+}
+
+extern "C" int so_grid_prepare(so_handle* h, int gp, void* stream_) {
+    if (!h || gp < 0 || gp >= h->max_gps) return SO_ERR_BAD_ARG;
+    GPState& g = h->gps[gp];
+    GridSpec& gs = h->grid;
+    if (!gs.defined) return so_fail(h, SO_ERR_BAD_ARG, "so_grid_prepare: no grid defined");
+    if (!g.fitted) return so_fail(h, SO_ERR_NOT_FITTED, "so_grid_prepare: GP not fitted");
+    if (g.kind != SO_KERNEL_RBF) return so_fail(h, SO_ERR_UNSUPPORTED, "so_grid_prepare: separable tables need an RBF kernel");
+    if (g.d != gs.d) return so_fail(h, SO_ERR_BAD_ARG, "so_grid_prepare: grid dimension differs from the GP input dimension");
+    DeviceGuard guard(h->device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int Npad = 8 * g.NB;
+    const size_t need = (size_t)gs.total * g.capN + SO_MAX_DIM;
+    if (need > g.capE) {
+        SO_CUDA(h, cudaStreamSynchronize(stream));
+        if (g.E) cudaFree(g.E);
+        g.E = nullptr;
+        SO_CUDA(h, cudaMalloc(&g.E, sizeof(double) * need));
+        g.capE = need;
+    }
+    double* inv_ls_d = g.E + (size_t)gs.total * g.capN;
+    SO_CUDA(h, cudaMemcpyAsync(inv_ls_d, g.inv_ls, sizeof(double) * SO_MAX_DIM, cudaMemcpyHostToDevice, stream));
+    dim3 grd((Npad + 127) / 128, gs.total);
+    k_grid_tables<<<grd, 128, 0, stream>>>(gs.axis, g.Xs, g.E, gs.total, g.N, Npad, g.d,
+                                           reinterpret_cast<const int*>(gs.axis + gs.cap), g.variance, inv_ls_d);
+    SO_CHECK_LAUNCH(h, "k_grid_tables");
+    g.grid_ready = true;
+    return SO_OK;
+}
+
+extern "C" int so_grid_rows(so_handle* h, int64_t row0, int64_t M, double* X_d, void* stream_) {
+    if (!h || !X_d || M < 0) return SO_ERR_BAD_ARG;
+    GridSpec& gs = h->grid;
+    if (!gs.defined) return so_fail(h, SO_ERR_BAD_ARG, "so_grid_rows: no grid defined");
+    if (row0 < 0 || row0 + M > gs.rows) return so_fail(h, SO_ERR_BAD_ARG, "so_grid_rows: rows outside the grid");
+    if (M == 0) return SO_OK;
+    DeviceGuard guard(h->device);
+    GridDecode gd;
+    gd.d = gs.d;
+    for (int j = 0; j < kGridMaxDim; ++j) {
+        gd.n[j] = j < gs.d ? gs.n[j] : 1;
+        gd.off[j] = j < gs.d ? gs.off[j] : 0;
+        gd.stride[j] = j < gs.d ? gs.stride[j] : 1;
+    }
+    k_grid_rows<<<(unsigned)((M + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(gd, gs.axis, row0, M, X_d);
+    SO_CHECK_LAUNCH(h, "k_grid_rows");
+    return SO_OK;
+}

@@ -1,0 +1,223 @@
+"""Device engine: one C-ABI handle plus the torch tensors that own every device buffer.
+
+PyTorch is plumbing here (allocation, streams, host<->device copies, torch.distributed); every
+arithmetic step of the hot path is a call into ``csrc/libsafeopt_b200.so``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import DeviceError, NativeLibraryError
+
+SAFE_REC_DTYPE = np.dtype([("n_safe", "<i8"), ("max_l0", "<f8"), ("argmax_l0", "<i8"), ("max_u0", "<f8"),
+                           ("argmax_u0", "<i8"), ("reserved", "<i8", (3,))])
+MAX_REC_DTYPE = np.dtype([("n_max", "<i8"), ("max_width0", "<f8"), ("best_value", "<f8"), ("best_row", "<i8"),
+                          ("reserved", "<i8", (4,))])
+assert SAFE_REC_DTYPE.itemsize == 64 and MAX_REC_DTYPE.itemsize == 64
+
+
+def _np_f64(a) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+
+
+def _ptr(t) -> C.c_void_p:
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _hptr(a: Optional[np.ndarray]) -> C.c_void_p:
+    return C.c_void_p(0 if a is None else a.ctypes.data)
+
+
+class DeviceEngine:
+    """Owns a ``so_handle`` on one CUDA device."""
+
+    def __init__(self, device=None, max_gps: int = 8):
+        try:
+            import torch
+        except ImportError as exc:  # pragma: no cover
+            raise NativeLibraryError("PyTorch is required for device memory management") from exc
+        self.torch = torch
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise NativeLibraryError("no CUDA device visible: safeopt_b200 has no CPU execution path")
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise NativeLibraryError("safeopt_b200 runs on CUDA devices only (got %s)" % device)
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.device = device
+        self.max_gps = int(max_gps)
+        handle = C.c_void_p()
+        rc = self.lib.so_create(device.index, self.max_gps, C.byref(handle))
+        if rc != 0:
+            raise DeviceError(rc, "so_create", "")
+        self.handle = handle
+        self.num_sms = self.lib.so_num_sms(handle)
+        self.launches = 0          # kernels launched through this engine (bench bookkeeping)
+        self._grid_axes = None
+
+    # ------------------------------------------------------------------ helpers
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.so_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):  # pragma: no cover - interpreter shutdown order
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self) -> C.c_void_p:
+        return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _check(self, rc: int, where: str):
+        if rc != 0:
+            detail = self.lib.so_last_error(self.handle).decode(errors="replace")
+            raise DeviceError(rc, where, detail)
+
+    def empty(self, shape, dtype="f64"):
+        t = self.torch
+        dt = {"f64": t.float64, "u8": t.uint8, "i64": t.int64, "f32": t.float32}[dtype]
+        return t.empty(shape, dtype=dt, device=self.device)
+
+    def zeros(self, shape, dtype="f64"):
+        t = self.torch
+        dt = {"f64": t.float64, "u8": t.uint8, "i64": t.int64, "f32": t.float32}[dtype]
+        return t.zeros(shape, dtype=dt, device=self.device)
+
+    def to_device(self, arr: np.ndarray, pinned: bool = False):
+        t = self.torch.from_numpy(np.ascontiguousarray(arr))
+        if pinned:
+            t = t.pin_memory()
+        return t.to(self.device, non_blocking=pinned)
+
+    def synchronize(self):
+        self.torch.cuda.current_stream(self.device).synchronize()
+
+    # ------------------------------------------------------------------ K1
+    def fit(self, gp: int, X, Y, kind: int, lengthscale, variance: float, noise_var: float):
+        X = _np_f64(X)
+        Y = _np_f64(Y).reshape(-1)
+        N, d = X.shape
+        ls = _np_f64(lengthscale).reshape(-1)
+        if ls.size == 1:
+            ls = np.full(d, float(ls[0]))
+        if ls.size != d:
+            raise ValueError("lengthscale must have 1 or %d entries" % d)
+        rc = self.lib.so_fit(self.handle, gp, _hptr(X), _hptr(Y), N, d, kind, _hptr(ls), float(variance),
+                             float(noise_var), self._stream())
+        self._check(rc, "so_fit")
+        self.launches += 6
+
+    def fit_export(self, gp: int, N: int):
+        L = np.empty((N, N))
+        Linv = np.empty((N, N))
+        alpha = np.empty(N)
+        self._check(self.lib.so_fit_export(self.handle, gp, _hptr(L), _hptr(Linv), _hptr(alpha)), "so_fit_export")
+        return L, Linv, alpha
+
+    # ------------------------------------------------------------------ grid
+    def define_grid(self, axes: Sequence[np.ndarray]):
+        n = np.asarray([len(a) for a in axes], dtype=np.int32)
+        vals = _np_f64(np.concatenate([np.asarray(a, dtype=np.float64) for a in axes]))
+        self._check(self.lib.so_grid_define(self.handle, len(axes), _hptr(n), _hptr(vals), self._stream()), "so_grid_define")
+        self._grid_axes = [np.asarray(a, dtype=np.float64) for a in axes]
+
+    def prepare_grid(self, gp: int):
+        self._check(self.lib.so_grid_prepare(self.handle, gp, self._stream()), "so_grid_prepare")
+        self.launches += 1
+
+    def grid_rows(self, row0: int, M: int):
+        d = len(self._grid_axes)
+        out = self.empty((M, d))
+        self._check(self.lib.so_grid_rows(self.handle, row0, M, _ptr(out), self._stream()), "so_grid_rows")
+        self.launches += 1
+        return out
+
+    # ------------------------------------------------------------------ K2
+    def posterior_rows(self, gp, Xstar, beta, fmin, mean=None, var=None, Q=None, q_col=0, S=None, safe_mode=_lib.SAFE_NONE):
+        M = Xstar.shape[0]
+        q_stride = 0 if Q is None else Q.shape[1]
+        rc = self.lib.so_posterior_rows(self.handle, gp, _ptr(Xstar), M, float(beta), float(fmin), _ptr(mean), _ptr(var),
+                                        _ptr(Q), q_stride, q_col, _ptr(S), safe_mode, self._stream())
+        self._check(rc, "so_posterior_rows")
+        self.launches += 1 if M else 0
+
+    def posterior_grid(self, gp, row0, M, beta, fmin, mean=None, var=None, Q=None, q_col=0, S=None, safe_mode=_lib.SAFE_NONE):
+        q_stride = 0 if Q is None else Q.shape[1]
+        rc = self.lib.so_posterior_grid(self.handle, gp, int(row0), int(M), float(beta), float(fmin), _ptr(mean), _ptr(var),
+                                        _ptr(Q), q_stride, q_col, _ptr(S), safe_mode, self._stream())
+        self._check(rc, "so_posterior_grid")
+        self.launches += 1 if M else 0
+
+    def posterior_rows_simple(self, gp, Xstar):
+        M = Xstar.shape[0]
+        mean, var = self.empty((M,)), self.empty((M,))
+        self._check(self.lib.so_posterior_rows_simple(self.handle, gp, _ptr(Xstar), M, _ptr(mean), _ptr(var), self._stream()),
+                    "so_posterior_rows_simple")
+        return mean, var
+
+    # ------------------------------------------------------------------ K3
+    def reduce_safe(self, Q, n_gps, row0, S, rec):
+        self._check(self.lib.so_sets_reduce_safe(self.handle, _ptr(Q), n_gps, Q.shape[0], int(row0), _ptr(S), _ptr(rec),
+                                                 self._stream()), "so_sets_reduce_safe")
+        self.launches += 1
+
+    def maximizers(self, Q, n_gps, row0, S, max_l0, scaling, Mmask, rec):
+        sc = _np_f64(scaling)
+        self._check(self.lib.so_sets_maximizers(self.handle, _ptr(Q), n_gps, Q.shape[0], int(row0), _ptr(S), float(max_l0),
+                                                _hptr(sc), _ptr(Mmask), _ptr(rec), self._stream()), "so_sets_maximizers")
+        self.launches += 1
+
+    def candidates(self, Q, n_gps, row0, S, Mmask, max_var, scaling, thr, cand_mask, cand_key, cand_row, n_cand):
+        sc, th = _np_f64(scaling), _np_f64(thr)
+        cap = 0 if cand_key is None else cand_key.shape[0]
+        self._check(self.lib.so_sets_candidates(self.handle, _ptr(Q), n_gps, Q.shape[0], int(row0), _ptr(S), _ptr(Mmask),
+                                                float(max_var), _hptr(sc), _hptr(th), _ptr(cand_mask), _ptr(cand_key),
+                                                _ptr(cand_row), cap, _ptr(n_cand), self._stream()), "so_sets_candidates")
+        self.launches += 1
+
+    # ------------------------------------------------------------------ K4
+    def expander_check(self, gp, Xstar, row0, M, S, mean, var, xc, mean_c, var_c, u_c, beta, fmin, flags):
+        B = xc.shape[0]
+        rc = self.lib.so_expander_check(self.handle, gp, _ptr(Xstar), int(row0), int(M), _ptr(S), _ptr(mean), _ptr(var),
+                                        _ptr(xc), _ptr(mean_c), _ptr(var_c), _ptr(u_c), B, float(beta), float(fmin),
+                                        _ptr(flags), self._stream())
+        self._check(rc, "so_expander_check")
+        self.launches += 2 if M else 0
+
+    # ------------------------------------------------------------------ K5/K6
+    def swarm_fitness(self, kind, n_gps, P, mean, var, beta, fmin, scaling, best_lower_bound, values, safe):
+        fm, sc = _np_f64(fmin), _np_f64(scaling)
+        rc = self.lib.so_swarm_fitness(self.handle, kind, n_gps, int(P), _ptr(mean), _ptr(var), float(beta), _hptr(fm),
+                                       _hptr(sc), float(best_lower_bound), _ptr(values), _ptr(safe), self._stream())
+        self._check(rc, "so_swarm_fitness")
+        self.launches += 1
+
+    def swarm_step(self, pos, vel, best_pos, global_best, r, inertia, velocity_scale, bounds):
+        P, d = pos.shape
+        vs = _np_f64(velocity_scale)
+        bd = None if bounds is None else _np_f64(bounds)
+        rc = self.lib.so_swarm_step(self.handle, P, d, _ptr(pos), _ptr(vel), _ptr(best_pos), _ptr(global_best), _ptr(r),
+                                    float(inertia), _hptr(vs), _hptr(bd), self._stream())
+        self._check(rc, "so_swarm_step")
+        self.launches += 1
+
+    def swarm_update_best(self, pos, values, safe, best_pos, best_values, best_idx):
+        P, d = pos.shape
+        rc = self.lib.so_swarm_update_best(self.handle, P, d, _ptr(pos), _ptr(values), _ptr(safe), _ptr(best_pos),
+                                           _ptr(best_values), _ptr(best_idx), self._stream())
+        self._check(rc, "so_swarm_update_best")
+        self.launches += 1
+
+    # ------------------------------------------------------------------ records
+    def read_record(self, rec, dtype):
+        return rec.cpu().numpy().view(dtype)[0]

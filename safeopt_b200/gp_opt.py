@@ -1,0 +1,760 @@
+"""SafeOpt / SafeOptSwarm with the reference's class surface, executed on B200 GPUs.
+
+Drop-in for the hot path of /root/reference/safeopt/gp_opt.py: same constructor signatures,
+methods, attributes and exceptions; the arithmetic below ``update_confidence_intervals`` /
+``compute_sets`` / ``get_new_query_point`` / ``_compute_particle_fitness`` runs in the
+hand-written sm_100a kernels behind include/safeopt_b200.h.  Host Python only orchestrates:
+it reads hyper-parameters off the GPy-style models, launches stream-ordered kernels, exchanges
+64-byte records between ranks and maps row indices back to parameters.
+
+Multi-GPU: when ``torch.distributed`` is initialised every rank constructs the same optimiser;
+rows are sharded in contiguous blocks (distributed.shard_bounds), the fit is recomputed per rank.
+"""
+from __future__ import annotations
+
+import logging
+from collections.abc import Sequence
+from functools import partial
+from typing import List, Optional
+
+import numpy as np
+
+from . import _lib
+from .distributed import Comm, combine_max_first, shard_bounds
+from .engine import MAX_REC_DTYPE, SAFE_REC_DTYPE, DeviceEngine
+from .gpmodel import extract_hyper, fingerprint
+from .swarm import SwarmOptimization
+from .utilities import detect_grid, grid_rows_from_index, linearly_spaced_combinations
+
+__all__ = ["SafeOpt", "SafeOptSwarm", "GaussianProcessOptimization"]
+
+
+class GaussianProcessOptimization(object):
+    """Common bookkeeping of the optimisers (reference: gp_opt.py:30-278).
+
+    Parameters
+    ----------
+    gp : GPy-style Gaussian process, or a list of them (first = objective, rest = constraints).
+    fmin : float or list of floats -- safety thresholds (``-np.inf`` / ``None`` = unconstrained).
+    beta : float or callable(t) -- confidence-interval scaling.
+    num_contexts : int -- trailing input columns that are contexts.
+    threshold : float or list -- expanders narrower than this (unscaled) are ignored.
+    scaling : list of floats or "auto" (sqrt of each kernel's prior variance).
+    """
+
+    def __init__(self, gp, fmin, beta=2, num_contexts=0, threshold=0, scaling="auto"):
+        super(GaussianProcessOptimization, self).__init__()
+        self.gps = gp if isinstance(gp, list) else [gp]
+        self.gp = self.gps[0]
+
+        self.fmin = fmin
+        if not isinstance(self.fmin, list):
+            self.fmin = [self.fmin] * len(self.gps)
+        self.fmin = np.atleast_1d(np.asarray(self.fmin, dtype=float).squeeze())
+
+        self.beta = beta if callable(beta) else (lambda t: beta)
+
+        if isinstance(scaling, str) and scaling == "auto":
+            origin = np.zeros((1, self.gps[0].input_dim))
+            self.scaling = np.sqrt(np.asarray([g.kern.Kdiag(origin)[0] for g in self.gps], dtype=float))
+        else:
+            self.scaling = np.asarray(scaling, dtype=float)
+            if self.scaling.shape[0] != len(self.gps):
+                raise ValueError("The number of scaling values should be equal to the number of GPs")
+
+        self.threshold = threshold
+        self._parameter_set = None
+        self.bounds = None
+        self.num_samples = 0
+        self.num_contexts = num_contexts
+
+        self._x = None
+        self._y = None
+        self._get_initial_xy()
+
+    # ---- data access (gp_opt.py:101-130)
+    @property
+    def x(self):
+        return self._x
+
+    @property
+    def y(self):
+        return self._y
+
+    @property
+    def data(self):
+        """The measurements held by the GP models, ``(x, y)``."""
+        return self._x, self._y
+
+    @property
+    def t(self):
+        """Time step = number of measurements."""
+        return self._x.shape[0]
+
+    def _get_initial_xy(self):
+        self._x = self.gp.X
+        cols = [self.gp.Y]
+        for other in self.gps[1:]:
+            if not np.allclose(self._x, other.X):
+                raise NotImplementedError("The GPs have different measurements.")
+            cols.append(other.Y)
+        self._y = np.concatenate(cols, axis=1)
+
+    def plot(self, *args, **kwargs):
+        """Plotting is outside the accelerated path (matplotlib-only code in the reference)."""
+        raise NotImplementedError("plotting is out of scope for safeopt_b200; use the reference's plot helpers "
+                                  "with opt.Q / opt.S / opt.M / opt.G")
+
+    # ---- data management (gp_opt.py:187-278)
+    def _add_context(self, x, context):
+        context = np.atleast_2d(context)
+        nc = context.shape[1]
+        out = np.empty((x.shape[0], x.shape[1] + nc), dtype=float)
+        out[:, :x.shape[1]] = x
+        out[:, x.shape[1]:] = context
+        return out
+
+    def _add_data_point(self, gp, x, y, context=None):
+        """Append one observation to a single GP (does not touch ``self.x`` / ``self.y``)."""
+        if context is not None:
+            x = self._add_context(x, context)
+        gp.set_XY(np.vstack([gp.X, x]), np.vstack([gp.Y, y]))
+
+    def add_new_data_point(self, x, y, context=None):
+        """Add an observation ``y`` (one column per GP, NaN = not measured) at parameters ``x``."""
+        x = np.atleast_2d(x)
+        y = np.atleast_2d(y)
+        if self.num_contexts:
+            x = self._add_context(x, context)
+        for i, gp in enumerate(self.gps):
+            ok = ~np.isnan(y[:, i])
+            if np.any(ok):
+                self._add_data_point(gp, x[ok, :], y[ok, [i]])
+        self._x = np.concatenate((self._x, x), axis=0)
+        self._y = np.concatenate((self._y, y), axis=0)
+
+    def _remove_last_data_point(self, gp):
+        gp.set_XY(gp.X[:-1, :], gp.Y[:-1, :])
+
+    def remove_last_data_point(self):
+        """Undo the last ``add_new_data_point``."""
+        last_y = self._y[-1]
+        for gp, yi in zip(self.gps, last_y):
+            if not np.isnan(yi):
+                gp.set_XY(gp.X[:-1, :], gp.Y[:-1, :])
+        self._x = self._x[:-1, :]
+        self._y = self._y[:-1, :]
+
+
+class _DeviceFits:
+    """Keeps the device-side fit of each GP in step with the user's model objects."""
+
+    def __init__(self, engine: DeviceEngine, gps):
+        self.engine = engine
+        self.gps = gps
+        self._fp = [None] * len(gps)
+        self.hypers = [None] * len(gps)
+        self.refits = 0
+
+    def refresh(self, after_fit=None):
+        for i, gp in enumerate(self.gps):
+            hyper = extract_hyper(gp)
+            fp = fingerprint(gp, hyper)
+            if fp != self._fp[i]:
+                Y = np.asarray(gp.Y, dtype=float)
+                self.engine.fit(i, gp.X, Y[:, 0], hyper.kind, hyper.lengthscale, hyper.variance, hyper.noise_var)
+                self._fp[i] = fp
+                self.hypers[i] = hyper
+                self.refits += 1
+                if after_fit is not None:
+                    after_fit(i, hyper)
+
+    def invalidate(self):
+        self._fp = [None] * len(self.gps)
+
+
+class SafeOpt(GaussianProcessOptimization):
+    """Safe Bayesian optimisation over a finite parameter set (reference: gp_opt.py:281-712).
+
+    Parameters are the reference's (``gp, parameter_set, fmin, lipschitz=None, beta=2,
+    num_contexts=0, threshold=0, scaling='auto'``) plus ``device`` (CUDA device, default current).
+
+    Examples
+    --------
+    >>> from safeopt_b200 import SafeOpt, linearly_spaced_combinations, GPRegression
+    >>> import numpy as np
+    >>> gp = GPRegression(np.array([[0.]]), np.array([[1.]]), noise_var=0.01 ** 2)
+    >>> parameter_set = linearly_spaced_combinations([[-1., 1.]], num_samples=100)
+    >>> opt = SafeOpt(gp, parameter_set, fmin=[0.])
+    >>> next_parameters = opt.optimize()                                   # doctest: +SKIP
+    >>> opt.add_new_data_point(next_parameters, np.array([[1.]]))          # doctest: +SKIP
+    """
+
+    def __init__(self, gp, parameter_set, fmin, lipschitz=None, beta=2, num_contexts=0, threshold=0,
+                 scaling="auto", device=None):
+        super(SafeOpt, self).__init__(gp, fmin=fmin, beta=beta, num_contexts=num_contexts, threshold=threshold,
+                                      scaling=scaling)
+        parameter_set = np.asarray(parameter_set, dtype=float)
+        if self.num_contexts > 0:
+            zeros = np.zeros((parameter_set.shape[0], self.num_contexts), dtype=parameter_set.dtype)
+            self.inputs = np.hstack((parameter_set, zeros))
+            self.parameter_set = self.inputs[:, :-self.num_contexts]
+        else:
+            self.inputs = self.parameter_set = parameter_set
+
+        self.liptschitz = lipschitz          # (sic) attribute name of the reference, gp_opt.py:366
+        if self.liptschitz is not None:
+            if not isinstance(self.liptschitz, list):
+                self.liptschitz = [self.liptschitz] * len(self.gps)
+            self.liptschitz = np.atleast_1d(np.asarray(self.liptschitz, dtype=float).squeeze())
+        self._use_lipschitz = lipschitz is not None
+
+        # ---- device state
+        self._comm = Comm()
+        self._engine = DeviceEngine(device, max_gps=len(self.gps))
+        self._fits = _DeviceFits(self._engine, self.gps)
+        n_rows = self.inputs.shape[0]
+        self._row0, self._row1 = shard_bounds(n_rows, self._comm.world, self._comm.rank)
+        m_local = self._row1 - self._row0
+        self._grid_axes = None
+        self._rows_d = None
+        if self.num_contexts == 0:
+            self._grid_axes = detect_grid(self.inputs)
+        if self._grid_axes is not None:
+            self._engine.define_grid(self._grid_axes)
+        else:
+            self._rows_d = self._engine.to_device(np.ascontiguousarray(self.inputs[self._row0:self._row1]))
+        eng = self._engine
+        G = len(self.gps)
+        self._Q_d = eng.empty((m_local, 2 * G))
+        self._S_d = eng.zeros((m_local,), "u8")
+        self._M_d = eng.zeros((m_local,), "u8")
+        self._mean_d = eng.empty((G, m_local))
+        self._var_d = eng.empty((G, m_local))
+        self._rec_safe_d = eng.zeros((64,), "u8")
+        self._rec_max_d = eng.zeros((64,), "u8")
+        self._n_cand_d = eng.zeros((1,), "i64")
+        self._cand_key_d = None
+        self._cand_row_d = None
+        self._G_rows: List[int] = []          # global rows currently in the expander set
+        self._host_cache = {}
+        self._safe_info = None                # combined record of the last compute_safe_set
+        self._max_info = None
+        self._ci_beta = None
+        self.last_trace = {}
+
+    # ------------------------------------------------------------------ reference properties
+    @property
+    def use_lipschitz(self):
+        """Whether expanders are judged with the Lipschitz constant instead of the GP (gp_opt.py:391-407)."""
+        return self._use_lipschitz
+
+    @use_lipschitz.setter
+    def use_lipschitz(self, value):
+        if value and self.liptschitz is None:
+            raise ValueError("Lipschitz constant not defined")
+        self._use_lipschitz = value
+
+    @property
+    def parameter_set(self):
+        """Discrete parameter samples for Bayesian optimisation."""
+        return self._parameter_set
+
+    @parameter_set.setter
+    def parameter_set(self, parameter_set):
+        self._parameter_set = parameter_set
+        self.bounds = list(zip(np.min(self._parameter_set, axis=0), np.max(self._parameter_set, axis=0)))
+        self.num_samples = [len(np.unique(self._parameter_set[:, i])) for i in range(self._parameter_set.shape[1])]
+
+    @property
+    def context_fixed_inputs(self):
+        """Fixed inputs for the current context (gp_opt.py:424-431)."""
+        n = self.gp.input_dim - 1
+        nc = self.num_contexts
+        if nc > 0:
+            contexts = self.inputs[0, -self.num_contexts:]
+            return list(zip(range(n, n - nc, -1), contexts))
+
+    @property
+    def context(self):
+        """Current context variables."""
+        if self.num_contexts:
+            return self.inputs[0, -self.num_contexts:]
+
+    @context.setter
+    def context(self, context):
+        if self.num_contexts:
+            if context is None:
+                raise ValueError("Need to provide value for context.")
+            self.inputs[:, -self.num_contexts:] = context
+            ctx = np.atleast_1d(np.asarray(context, dtype=float)).ravel()
+            self._rows_d[:, -self.num_contexts:] = self._engine.to_device(ctx)
+
+    # ------------------------------------------------------------------ host views of device state
+    def _gather_rows(self, local: np.ndarray) -> np.ndarray:
+        if not self._comm.active:
+            return local
+        n_rows = self.inputs.shape[0]
+        per = -(-n_rows // self._comm.world)
+        pad = np.zeros((per,) + local.shape[1:], dtype=local.dtype)
+        pad[:local.shape[0]] = local
+        allr = self._comm.all_gather(pad)
+        return allr.reshape((-1,) + local.shape[1:])[:n_rows]
+
+    def _host(self, key, tensor, as_bool=False):
+        if key not in self._host_cache:
+            arr = tensor.cpu().numpy()
+            arr = self._gather_rows(arr)
+            self._host_cache[key] = arr.astype(bool) if as_bool else arr
+        return self._host_cache[key]
+
+    @property
+    def Q(self):
+        """Confidence intervals, ``(M, 2G)`` float64: columns ``l0, u0, l1, u1, ...`` (copied from the device on access)."""
+        return self._host("Q", self._Q_d)
+
+    @property
+    def S(self):
+        """Safe set mask ``(M,)`` bool."""
+        return self._host("S", self._S_d, as_bool=True)
+
+    @property
+    def M(self):
+        """Maximiser mask ``(M,)`` bool."""
+        return self._host("M", self._M_d, as_bool=True)
+
+    @property
+    def G(self):
+        """Expander mask ``(M,)`` bool."""
+        g = np.zeros(self.inputs.shape[0], dtype=bool)
+        if self._G_rows:
+            g[np.asarray(self._G_rows, dtype=np.int64)] = True
+        return g
+
+    def _invalidate_host(self, *keys):
+        for k in (keys or list(self._host_cache)):
+            self._host_cache.pop(k, None)
+
+    def _row_coordinates(self, rows) -> np.ndarray:
+        rows = np.atleast_1d(np.asarray(rows, dtype=np.int64))
+        if self._grid_axes is not None:
+            return grid_rows_from_index(self._grid_axes, rows)
+        return np.asarray(self.inputs[rows], dtype=float)
+
+    # ------------------------------------------------------------------ hot path
+    def _after_fit(self, i, hyper):
+        if self._grid_axes is not None and hyper.kind == _lib.KERNEL_RBF:
+            self._engine.prepare_grid(i)
+
+    def _use_grid_kernel(self, i) -> bool:
+        return self._grid_axes is not None and self._fits.hypers[i].kind == _lib.KERNEL_RBF
+
+    def _ensure_rows_on_device(self):
+        """Explicit rows are needed when some GP cannot use the separable grid tables."""
+        if self._rows_d is None:
+            self._rows_d = self._engine.grid_rows(self._row0, self._row1 - self._row0)
+        return self._rows_d
+
+    def update_confidence_intervals(self, context=None):
+        """Recompute ``Q`` from the GP posteriors on every candidate (reference: gp_opt.py:453-476).
+
+        One fused kernel per GP: kernel rows, the L^-1 contraction on the fp64 tensor pipe,
+        mean/variance, ``l/u`` and that GP's safe bit (the AND over GPs of gp_opt.py:481)."""
+        beta = self.beta(self.t)
+        self.context = context
+        self._fits.refresh(self._after_fit)
+        eng = self._engine
+        m_local = self._row1 - self._row0
+        for i in range(len(self.gps)):
+            mode = _lib.SAFE_WRITE if i == 0 else _lib.SAFE_AND
+            if self._use_grid_kernel(i):
+                eng.posterior_grid(i, self._row0, m_local, beta, self.fmin[i], mean=self._mean_d[i], var=self._var_d[i],
+                                   Q=self._Q_d, q_col=2 * i, S=self._S_d, safe_mode=mode)
+            else:
+                eng.posterior_rows(i, self._ensure_rows_on_device(), beta, self.fmin[i], mean=self._mean_d[i],
+                                   var=self._var_d[i], Q=self._Q_d, q_col=2 * i, S=self._S_d, safe_mode=mode)
+        self._ci_beta = beta
+        self._ci_fmin = self.fmin.copy()
+        self._safe_info = None
+        self._invalidate_host()
+
+    def compute_safe_set(self):
+        """Safe set from the current bounds (reference: gp_opt.py:478-481).
+
+        The S bytes were written by ``update_confidence_intervals``; this pass reduces them to the
+        record the later steps need (count, best safe lower/upper bound and where)."""
+        if self._ci_beta is None:
+            raise RuntimeError("call update_confidence_intervals() first")
+        if not np.array_equal(self._ci_fmin, self.fmin):
+            # thresholds changed since the bounds were computed: redo the (fused) pass
+            self.update_confidence_intervals(context=self.context)
+        eng = self._engine
+        eng.reduce_safe(self._Q_d, len(self.gps), self._row0, self._S_d, self._rec_safe_d)
+        rec = eng.read_record(self._rec_safe_d, SAFE_REC_DTYPE)
+        allr = self._comm.all_gather(np.array([rec["n_safe"], rec["argmax_l0"], rec["argmax_u0"]], dtype=np.int64))
+        allv = self._comm.all_gather(np.array([rec["max_l0"], rec["max_u0"]], dtype=np.float64))
+        max_l0, arg_l0 = combine_max_first(allv[:, 0], allr[:, 1])
+        max_u0, arg_u0 = combine_max_first(allv[:, 1], allr[:, 2])
+        self._safe_info = dict(n_safe=int(allr[:, 0].sum()), max_l0=max_l0, argmax_l0=arg_l0, max_u0=max_u0,
+                               argmax_u0=arg_u0)
+        self._invalidate_host("S")
+
+    def compute_sets(self, full_sets=False):
+        """Safe set, maximisers ``M`` and expanders ``G`` (reference: gp_opt.py:483-615)."""
+        beta = self.beta(self.t)
+        self.compute_safe_set()
+        eng = self._engine
+        G = len(self.gps)
+        self._G_rows = []
+        self._max_info = None
+        self.last_trace = {}
+        self._invalidate_host("M")
+        if self._safe_info["n_safe"] == 0:
+            self._M_d.zero_()
+            return
+
+        eng.maximizers(self._Q_d, G, self._row0, self._S_d, self._safe_info["max_l0"], self.scaling, self._M_d,
+                       self._rec_max_d)
+        rec = eng.read_record(self._rec_max_d, MAX_REC_DTYPE)
+        allv = self._comm.all_gather(np.array([rec["max_width0"], rec["best_value"]], dtype=np.float64))
+        allr = self._comm.all_gather(np.array([rec["n_max"], rec["best_row"]], dtype=np.int64))
+        max_var = float(np.max(allv[:, 0])) / self.scaling[0]
+        best_value, best_row = combine_max_first(allv[:, 1], allr[:, 1])
+        self._max_info = dict(n_max=int(allr[:, 0].sum()), max_var=max_var, best_value=best_value, best_row=best_row)
+
+        m_local = self._row1 - self._row0
+        if self._cand_key_d is None:
+            self._cand_key_d = eng.empty((max(m_local, 1),))
+            self._cand_row_d = eng.empty((max(m_local, 1),), "i64")
+        thr = np.broadcast_to(np.asarray(self.threshold, dtype=float), (G,)) * beta
+        if full_sets:
+            # every safe point is a candidate, natural order (gp_opt.py:527-528, :555)
+            rows_local = eng.torch.nonzero(self._S_d, as_tuple=False).reshape(-1) + self._row0
+            keys_local = None
+        else:
+            eng.candidates(self._Q_d, G, self._row0, self._S_d, self._M_d, max_var, self.scaling, thr, None,
+                           self._cand_key_d, self._cand_row_d, self._n_cand_d)
+            n_local = int(self._n_cand_d.cpu().item())
+            rows_local = self._cand_row_d[:n_local]
+            keys_local = self._cand_key_d[:n_local]
+        n_total = int(self._comm.all_gather(np.array([rows_local.shape[0]], dtype=np.int64)).sum())
+        self.last_trace = dict(max_l=self._safe_info["max_l0"], max_var=max_var, n_candidates=n_total)
+        if n_total == 0:
+            return
+        self._expander_search(beta, rows_local, keys_local, full_sets)
+
+    # ---- expander search ------------------------------------------------------------------
+    def _ordered_candidates(self, rows_local, keys_local):
+        """Global visiting order: widest (unscaled) interval first, ties by row (gp_opt.py:551-552)."""
+        t = self._engine.torch
+        if keys_local is None:
+            rows = rows_local.cpu().numpy()
+            allr = self._gather_var(rows)
+            return np.sort(allr)
+        # deterministic local order first (the append order of the candidate kernel is not)
+        order = t.argsort(rows_local)
+        rows_local, keys_local = rows_local[order], keys_local[order]
+        order = t.argsort(keys_local, descending=True, stable=True)
+        rows = rows_local[order].cpu().numpy()
+        keys = keys_local[order].cpu().numpy()
+        if not self._comm.active:
+            return rows
+        allr, allk = self._gather_var(rows), self._gather_var(keys)
+        order = np.lexsort((allr, -allk))
+        return allr[order]
+
+    def _gather_var(self, arr: np.ndarray) -> np.ndarray:
+        if not self._comm.active:
+            return arr
+        counts = self._comm.all_gather(np.array([arr.shape[0]], dtype=np.int64)).ravel()
+        cap = int(counts.max())
+        pad = np.zeros(cap, dtype=arr.dtype)
+        pad[:arr.shape[0]] = arr
+        allp = self._comm.all_gather(pad)
+        return np.concatenate([allp[r, :counts[r]] for r in range(self._comm.world)])
+
+    def _rows_values(self, rows: np.ndarray):
+        """(Q rows, mean, var) of arbitrary global rows, fetched from whichever rank owns them."""
+        t = self._engine.torch
+        G = len(self.gps)
+        rows = np.asarray(rows, dtype=np.int64)
+        own = (rows >= self._row0) & (rows < self._row1)
+        q = np.zeros((rows.size, 2 * G))
+        mean = np.zeros((G, rows.size))
+        var = np.zeros((G, rows.size))
+        if own.any():
+            idx = t.from_numpy(rows[own] - self._row0).to(self._engine.device)
+            q[own] = self._Q_d.index_select(0, idx).cpu().numpy()
+            mean[:, own] = self._mean_d.index_select(1, idx).cpu().numpy()
+            var[:, own] = self._var_d.index_select(1, idx).cpu().numpy()
+        if self._comm.active:
+            q = self._comm.all_gather(q).sum(axis=0)
+            mean = self._comm.all_gather(mean).sum(axis=0)
+            var = self._comm.all_gather(var).sum(axis=0)
+        return q, mean, var
+
+    def _expander_search(self, beta, rows_local, keys_local, full_sets):
+        eng = self._engine
+        order = self._ordered_candidates(rows_local, keys_local)
+        constrained = [i for i in range(len(self.gps)) if self.fmin[i] != -np.inf]
+        m_local = self._row1 - self._row0
+        B = _lib.EXPANDER_MAX_BATCH
+        visited = 0
+        found: List[int] = []
+        if self.use_lipschitz:
+            raise NotImplementedError("the Lipschitz expander branch (gp_opt.py:558-576) is not built yet "
+                                      "(SURVEY.md section 8f-3); set lipschitz=None")
+        for start in range(0, order.size, B):
+            rows = order[start:start + B]
+            nb = rows.size
+            q, mean, var = self._rows_values(rows)
+            xc = self._row_coordinates(rows)
+            if self.num_contexts:
+                xc = np.asarray(self.inputs[rows], dtype=float)
+            ok = np.ones(nb, dtype=bool) if constrained else np.zeros(nb, dtype=bool)
+            xc_d = eng.to_device(xc)
+            for i in constrained:
+                flags = eng.zeros((B,), "u8")
+                rows_arg = None if self._use_grid_kernel(i) else self._ensure_rows_on_device()
+                eng.expander_check(i, rows_arg, self._row0, m_local, self._S_d, self._mean_d[i], self._var_d[i], xc_d,
+                                   eng.to_device(mean[i]), eng.to_device(var[i]), eng.to_device(q[:, 2 * i + 1]),
+                                   beta, self.fmin[i], flags)
+                f = self._comm.any_flags(flags.cpu().numpy())[:nb].astype(bool)
+                ok &= f
+                if not ok.any() and not full_sets:
+                    break
+            if full_sets:
+                visited += nb
+                found.extend(int(r) for r in rows[ok])
+            elif ok.any():
+                first = int(np.flatnonzero(ok)[0])
+                visited += first + 1
+                found.append(int(rows[first]))      # the search stops at the first expander (gp_opt.py:611-612)
+                break
+            else:
+                visited += nb
+        self._G_rows = found
+        self.last_trace.update(visited=visited, order=order)
+
+    # ------------------------------------------------------------------ query
+    def get_new_query_point(self, ucb=False):
+        """Next parameters to evaluate (reference: gp_opt.py:617-649)."""
+        if self._safe_info is None:
+            self.compute_safe_set()
+        if self._safe_info["n_safe"] == 0:
+            raise EnvironmentError("There are no safe points to evaluate.")
+        if ucb:
+            row = self._safe_info["argmax_u0"]
+        else:
+            if self._max_info is None:
+                raise RuntimeError("call compute_sets() before get_new_query_point()")
+            value, row = self._max_info["best_value"], self._max_info["best_row"]
+            if self._G_rows:
+                q, _, _ = self._rows_values(np.asarray(self._G_rows, dtype=np.int64))
+                gval = np.max((q[:, 1::2] - q[:, ::2]) / self.scaling, axis=1)
+                vals = np.concatenate(([value], gval))
+                rows = np.concatenate(([row], self._G_rows)).astype(np.int64)
+                value, row = combine_max_first(vals, rows)
+        self.last_query_row = int(row)
+        x = self._row_coordinates([row])[0] if not self.num_contexts else np.asarray(self.inputs[row], dtype=float)
+        return x[:-self.num_contexts] if self.num_contexts else x
+
+    def optimize(self, context=None, ucb=False):
+        """One SafeOpt iteration: bounds, sets, query point (reference: gp_opt.py:651-675)."""
+        self.update_confidence_intervals(context=context)
+        if ucb:
+            self.compute_safe_set()
+        else:
+            self.compute_sets()
+        return self.get_new_query_point(ucb=ucb)
+
+    def get_maximum(self, context=None):
+        """Best safe lower bound and where it is, or ``None`` (reference: gp_opt.py:677-712)."""
+        self.update_confidence_intervals(context=context)
+        self.compute_safe_set()
+        if self._safe_info["n_safe"] == 0:
+            return None
+        row = self._safe_info["argmax_l0"]
+        x = self._row_coordinates([row])[0] if not self.num_contexts else np.asarray(self.inputs[row], dtype=float)
+        return x[:-self.num_contexts or None], np.float64(self._safe_info["max_l0"])
+
+
+class SafeOptSwarm(GaussianProcessOptimization):
+    """SafeOpt for higher dimensions with particle swarms (reference: gp_opt.py:715-1192).
+
+    Parameters are the reference's (``gp, fmin, bounds, beta=2, scaling='auto', threshold=0,
+    swarm_size=20``) plus ``device``.  No Lipschitz constant, no contexts (as in the reference).
+    The particle posterior + fitness runs on the GPU; particle initialisation and the sequential
+    safe-set insertion stay in host NumPy exactly as in the reference.
+    """
+
+    def __init__(self, gp, fmin, bounds, beta=2, scaling="auto", threshold=0, swarm_size=20, device=None):
+        super(SafeOptSwarm, self).__init__(gp, fmin=fmin, beta=beta, num_contexts=0, threshold=threshold,
+                                           scaling=scaling)
+        self.S = np.asarray(self.gps[0].X)
+        self.swarm_size = swarm_size
+        self.max_iters = 100
+        self.bounds = bounds if isinstance(bounds, list) else [bounds] * self.S.shape[1]
+        self.best_lower_bound = -np.inf
+        self.greedy_point = self.S[0, :]
+
+        self._engine = DeviceEngine(device, max_gps=len(self.gps))
+        self._fits = _DeviceFits(self._engine, self.gps)
+        self.optimal_velocities = self.optimize_particle_velocity()
+        swarm_types = ["greedy", "maximizers", "expanders"]
+        self.swarms = {kind: SwarmOptimization(swarm_size, self.optimal_velocities,
+                                               partial(self._compute_particle_fitness, kind), bounds=self.bounds)
+                       for kind in swarm_types}
+
+    def optimize_particle_velocity(self):
+        """Per-dimension velocities at which the prior correlation drops to ~0.95 (gp_opt.py:818-872).
+
+        O(G*d*30) scalar kernel evaluations, host side like the reference."""
+        d = self.gp.input_dim
+        origin = np.zeros((1, d), dtype=float)
+        vel = np.empty((len(self.gps), d), dtype=float)
+        for i, gp in enumerate(self.gps):
+            for j in range(d):
+                probe = np.zeros((1, d), dtype=float)
+                hi, lo = 1000.0, 0.0
+                while True:
+                    mid = (hi + lo) / 2
+                    probe[0, j] = mid
+                    corr = np.asarray(gp.kern.K(origin, probe)).squeeze() / self.scaling[i] ** 2
+                    enough = corr > 0.94
+                    slow = corr < 0.95
+                    if slow:
+                        hi = mid
+                    elif enough:
+                        lo = mid
+                    if (slow and enough) or hi - lo < 1e-5:
+                        break
+                vel[i, j] = mid
+        out = np.min(vel, axis=0)
+        out /= np.sqrt(d)
+        return out
+
+    def _compute_penalty(self, slack):
+        """Constraint-violation penalty (gp_opt.py:874-899); host helper kept for API parity."""
+        slack = np.atleast_1d(np.asarray(slack, dtype=float))
+        pen = np.clip(slack, None, 0)
+        pen[(slack < 0) & (slack > -0.001)] *= 2
+        pen[(slack <= -0.001) & (slack > -0.1)] *= 5
+        pen[(slack <= -0.1) & (slack > -1)] *= 10
+        big = slack < -1
+        pen[big] = -300 * pen[big] ** 2
+        return pen
+
+    def _fitness_device(self, swarm_type, particles_d):
+        """Fitness of device-resident particles; returns device tensors (values, safe)."""
+        eng = self._engine
+        self._fits.refresh()
+        beta = self.beta(self.t)
+        P = particles_d.shape[0]
+        G = len(self.gps)
+        mean, var = eng.empty((G, P)), eng.empty((G, P))
+        n_needed = 1 if swarm_type == "greedy" else G
+        for i in range(n_needed):
+            eng.posterior_rows(i, particles_d, beta, -np.inf, mean=mean[i], var=var[i])
+        values, safe = eng.empty((P,)), eng.empty((P,), "u8")
+        eng.swarm_fitness(_lib.SWARM_KINDS[swarm_type], G if n_needed == G else 1, P, mean, var, beta,
+                          self.fmin[:n_needed] if n_needed == G else self.fmin[:1], self.scaling[:max(n_needed, 1)],
+                          self.best_lower_bound, values, safe)
+        return values, safe
+
+    def _compute_particle_fitness(self, swarm_type, particles):
+        """Fitness value and safety flag of every particle (reference: gp_opt.py:901-1013).
+
+        ``swarm_type`` is 'greedy', 'maximizers', 'expanders' or 'safe_set'."""
+        if swarm_type not in _lib.SWARM_KINDS:
+            raise AssertionError("Invalid swarm type")
+        particles = np.ascontiguousarray(np.atleast_2d(np.asarray(particles, dtype=float)))
+        values, safe = self._fitness_device(swarm_type, self._engine.to_device(particles))
+        return values.cpu().numpy(), safe.cpu().numpy().astype(bool)
+
+    def get_new_query_point(self, swarm_type):
+        """Run one swarm and return (point, value / std-devs) (reference: gp_opt.py:1015-1134)."""
+        beta = self.beta(self.t)
+        safe_size, input_dim = self.S.shape
+
+        _, safe = self._compute_particle_fitness("safe_set", self.S)
+        num_safe = safe.sum()
+        if num_safe == 0:
+            raise RuntimeError("The safe set is empty.")
+        if num_safe >= self.swarm_size and num_safe != len(safe):
+            logging.warning("Warning: {} unsafe points removed. Model might be violated"
+                            .format(np.count_nonzero(~safe)))
+            self.S = self.S[safe]
+            safe_size = self.S.shape[0]
+
+        if swarm_type == "greedy":
+            random_id = np.random.randint(safe_size, size=self.swarm_size - 3)
+            best_sampled_point = np.argmax(self.gp.Y)
+            particles = np.vstack((self.S[random_id, :], self.greedy_point, self.gp.X[-1, :],
+                                   self.gp.X[best_sampled_point]))
+        else:
+            random_id = np.random.randint(safe_size, size=self.swarm_size)
+            particles = self.S[random_id, :]
+
+        swarm = self.swarms[swarm_type]
+        swarm.init_swarm(particles)
+        swarm.run_swarm(self.max_iters)
+
+        if swarm_type != "greedy":
+            num_added = 0
+            covariance = self.gp.kern.K(swarm.best_positions, np.vstack((self.S, swarm.best_positions)))
+            covariance /= self.scaling[0] ** 2
+            initial_safe = len(self.S)
+            n, m = np.shape(covariance)
+            mask = np.zeros(m, dtype=bool)
+            mask[:initial_safe] = True
+            for j in range(n):
+                if np.all(covariance[j, mask] <= 0.95):
+                    self.S = np.vstack((self.S, swarm.best_positions[[j], :]))
+                    num_added += 1
+                    mask[initial_safe + j] = True
+            logging.debug("At the end of swarm {}, {} points were appended to the safeset".format(swarm_type, num_added))
+        else:
+            mean, var = self._posterior_host(0, self.greedy_point[None, :])
+            lower_bound = mean.squeeze() - beta * np.sqrt(var.squeeze())
+            if lower_bound < np.max(swarm.best_values):
+                self.greedy_point = swarm.global_best.copy()
+
+        if swarm_type == "greedy":
+            return swarm.global_best.copy(), np.max(swarm.best_values)
+
+        var = np.empty(len(self.gps), dtype=float)
+        for i in range(len(self.gps)):
+            var[i] = self._posterior_host(i, swarm.global_best[None, :])[1].squeeze()
+        return swarm.global_best, np.sqrt(var)
+
+    def _posterior_host(self, i, X):
+        """Posterior of GP ``i`` at a few host points through the device path."""
+        eng = self._engine
+        self._fits.refresh()
+        Xd = eng.to_device(np.ascontiguousarray(np.asarray(X, dtype=float)))
+        mean, var = eng.empty((Xd.shape[0],)), eng.empty((Xd.shape[0],))
+        eng.posterior_rows(i, Xd, 0.0, -np.inf, mean=mean, var=var)
+        return mean.cpu().numpy(), var.cpu().numpy()
+
+    def optimize(self, ucb=False):
+        """One SafeOptSwarm iteration (reference: gp_opt.py:1136-1177)."""
+        self.greedy, self.best_lower_bound = self.get_new_query_point("greedy")
+        x_maxi, std_maxi = self.get_new_query_point("maximizers")
+        if ucb:
+            logging.info("Using ucb criterion.")
+            return x_maxi
+        x_exp, std_exp = self.get_new_query_point("expanders")
+        std_exp[(std_exp < self.threshold) | (self.fmin == -np.inf)] = 0
+        std_exp /= self.scaling
+        std_exp = np.max(std_exp)
+        std_maxi = std_maxi[0] / self.scaling[0]
+        logging.info("The best maximizer has std. dev. %f" % std_maxi)
+        logging.info("The best expander has std. dev. %f" % std_exp)
+        logging.info("The greedy estimate of lower bound has value %f" % self.best_lower_bound)
+        return x_maxi if std_maxi > std_exp else x_exp
+
+    def get_maximum(self):
+        """Best observed point (reference: gp_opt.py:1179-1192)."""
+        best = np.argmax(self.gp.Y)
+        return self.gp.X[best, :], self.gp.Y[best]
