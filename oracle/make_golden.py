@@ -1,0 +1,155 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference package (imported from
+/root/reference through oracle.compat) over oracle.gpy_lite.  TEST INFRASTRUCTURE ONLY.
+
+Run in the build container (the reference tree does not exist on the GPU box):
+
+    OPENBLAS_NUM_THREADS=1 python -m oracle.make_golden
+
+Every fixture stores its inputs (training data, hyper-parameters, grid description, thresholds)
+next to the reference's outputs (Q, masks, query row/point, maximum), so the GPU tests can rebuild
+the problem without the reference.  Masks are stored as packed bits.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import warnings
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+OUT = os.path.join(ROOT, "tests", "golden")
+
+KINDS = {"rbf": 0, "mat32": 1, "mat52": 2}
+
+
+def kernel_of(GPy, kind, d, variance, ls):
+    cls = {"rbf": GPy.kern.RBF, "mat32": GPy.kern.Matern32, "mat52": GPy.kern.Matern52}[kind]
+    return cls(d, variance=variance, lengthscale=np.asarray(ls, dtype=float), ARD=True)
+
+
+def row_of(grid, x):
+    hit = np.flatnonzero(np.all(grid == x[None, :], axis=1))
+    return int(hit[0])
+
+
+def grid_case(ref, GPy, name, X, Y, kind, variance, ls, noise, bounds, n, fmin, beta, threshold, full_sets=False, explicit_jitter=False):
+    d = X.shape[1]
+    G = Y.shape[1]
+    gps = [GPy.models.GPRegression(X, Y[:, [i]], kernel=kernel_of(GPy, kind, d, variance, ls), noise_var=noise) for i in range(G)]
+    grid = ref.linearly_spaced_combinations(bounds, n)
+    opt = ref.SafeOpt(gps if G > 1 else gps[0], grid, fmin=list(fmin) if G > 1 else fmin[0], beta=beta, threshold=threshold)
+    if full_sets:
+        opt.update_confidence_intervals()
+        opt.compute_sets(full_sets=True)
+        x_next = opt.get_new_query_point()
+    else:
+        x_next = opt.optimize()
+    S, M, Gm = opt.S.copy(), opt.M.copy(), opt.G.copy()
+    Q = opt.Q.copy()
+    row = row_of(grid, np.atleast_1d(x_next))
+    mx = opt.get_maximum()
+    x_ucb = opt.optimize(ucb=True)
+    # smallest distances of any bound to a decision threshold (hard part 2)
+    margin_S = float(np.min(np.abs(Q[:, ::2] - np.asarray(fmin)[None, :])))
+    margin_M = float(np.min(np.abs(Q[S, 1] - np.max(Q[S, 0])))) if S.any() else np.inf
+    np.savez_compressed(
+        os.path.join(OUT, name + ".npz"), X=X, Y=Y, kind=KINDS[kind], variance=variance, lengthscale=np.asarray(ls, dtype=float),
+        noise_var=noise, bounds=np.asarray(bounds, dtype=float), num_samples=np.asarray(n if not np.isscalar(n) else [n] * d),
+        fmin=np.asarray(fmin, dtype=float), beta=beta, threshold=threshold, full_sets=full_sets,
+        Q=Q, S=np.packbits(S), M=np.packbits(M), G=np.packbits(Gm), n_rows=grid.shape[0],
+        x_next=np.atleast_1d(x_next), row_next=row, max_x=np.atleast_1d(mx[0]), max_val=float(mx[1]),
+        row_ucb=row_of(grid, np.atleast_1d(x_ucb)), margin_S=margin_S, margin_M=margin_M)
+    print("%-28s M=%-7d N=%-4d G=%d  |S|=%d |M|=%d |G|=%d row=%d  margins S %.1e M %.1e" % (
+        name, grid.shape[0], X.shape[0], G, S.sum(), M.sum(), Gm.sum(), row, margin_S, margin_M))
+
+
+def synth(seed, N, d, G, spread, noise_sd=0.05):
+    rs = np.random.RandomState(seed)
+    X = rs.uniform(-spread, spread, size=(N, d))
+    f = 2.0 * np.exp(-np.sum(X * X, axis=1) / 8.0)
+    Y = np.stack([f + noise_sd * np.random.RandomState(seed + 1 + i).randn(N) for i in range(G)], axis=1)
+    return X, Y
+
+
+def loop_case(ref, GPy, name, iters=20):
+    """A short Bayesian-optimisation run: the sequence of query rows is the fixture."""
+    X, Y = synth(1, 6, 2, 1, 1.0)
+    bounds, n = [(-5.0, 5.0)] * 2, 30
+    gp = GPy.models.GPRegression(X, Y, kernel=kernel_of(GPy, "rbf", 2, 2.0, [1.0, 1.0]), noise_var=0.05 ** 2)
+    grid = ref.linearly_spaced_combinations(bounds, n)
+    opt = ref.SafeOpt(gp, grid, fmin=0.3, beta=2.0, threshold=0.05)
+    rows, ys, ng = [], [], []
+    for _ in range(iters):
+        x = opt.optimize()
+        rows.append(row_of(grid, x))
+        ng.append(int(opt.G.sum()))
+        y = 2.0 * np.exp(-np.sum(x * x) / 8.0)
+        ys.append(y)
+        opt.add_new_data_point(x, np.array([[y]]))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), X=X, Y=Y, bounds=np.asarray(bounds), num_samples=n, fmin=0.3, beta=2.0,
+                        threshold=0.05, variance=2.0, lengthscale=np.ones(2), noise_var=0.05 ** 2, rows=np.asarray(rows),
+                        ys=np.asarray(ys), n_expanders=np.asarray(ng))
+    print("%-28s rows %s  expander iterations %d" % (name, rows[:8], int(np.sum(np.asarray(ng) > 0))))
+
+
+def swarm_case(ref, GPy, name):
+    rs = np.random.RandomState(7)
+    d, N, G, P = 3, 40, 2, 600
+    X = rs.uniform(-0.5, 0.5, size=(N, d))
+    f = 1.0 - 0.3 * np.sum(X * X, axis=1)
+    Y = np.stack([f + 0.05 * np.random.RandomState(8 + i).randn(N) for i in range(G)], axis=1)
+    gps = [GPy.models.GPRegression(X, Y[:, [i]], kernel=kernel_of(GPy, "rbf", d, 2.0, np.ones(d)), noise_var=0.05 ** 2) for i in range(G)]
+    fmin = [0.0, 0.2]
+    opt = ref.SafeOptSwarm(gps, fmin, bounds=[(-1.0, 1.0)] * d, beta=2.0, swarm_size=20)
+    opt.best_lower_bound = 0.7
+    particles = rs.uniform(-1.0, 1.0, size=(P, d))
+    out = {}
+    for kind in ["greedy", "maximizers", "expanders", "safe_set"]:
+        v, s = opt._compute_particle_fitness(kind, particles)
+        out["values_" + kind] = np.asarray(v, dtype=float)
+        out["safe_" + kind] = np.asarray(np.broadcast_to(s, (P,)), dtype=bool)
+    pen_in = np.array([0.5, 0.0, -0.0005, -0.001, -0.05, -0.1, -0.5, -1.0, -1.5, -3.0])
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), X=X, Y=Y, fmin=np.asarray(fmin), particles=particles, beta=2.0,
+                        variance=2.0, lengthscale=np.ones(d), noise_var=0.05 ** 2, best_lower_bound=0.7,
+                        velocities=opt.optimal_velocities, scaling=opt.scaling, penalty_in=pen_in,
+                        penalty_out=opt._compute_penalty(pen_in.copy()), **out)
+    print("%-28s velocities %s" % (name, opt.optimal_velocities))
+
+
+def main():
+    warnings.simplefilter("ignore")
+    os.makedirs(OUT, exist_ok=True)
+    from oracle import compat, gpy_lite as GPy
+    ref = compat.import_reference()
+    sys.path.insert(0, os.path.join(ROOT))
+    from safeopt_b200 import workloads
+
+    # closed-form doctest configuration (gp_opt.py:327-338)
+    grid_case(ref, GPy, "doctest_1d", np.array([[0.0]]), np.array([[1.0]]), "rbf", 1.0, [1.0], 0.01 ** 2, [(-1.0, 1.0)], 100, [0.0], 2.0, 0)
+    # named configurations (reduced grids where the full one would be too large for a fixture)
+    for name, ns in [("C1", None), ("C2", None), ("C3", 80), ("C4", 10)]:
+        w = workloads.config(name, num_samples=ns)
+        grid_case(ref, GPy, "config_%s" % name + ("" if ns is None else "_n%d" % ns), w.X, w.Y, "rbf", w.variance, w.lengthscale, w.noise_var,
+                  w.bounds, w.num_samples, w.fmin, w.beta, w.threshold)
+    # expander-exercising problems
+    X, Y = synth(0, 40, 2, 1, 2.5)
+    grid_case(ref, GPy, "expander_g1", X, Y, "rbf", 2.0, [1.0, 1.0], 0.05 ** 2, [(-5.0, 5.0)] * 2, 40, [0.5], 2.0, 0.05)
+    X, Y = synth(0, 40, 2, 2, 2.5)
+    grid_case(ref, GPy, "expander_g2", X, Y, "rbf", 2.0, [1.0, 1.0], 0.05 ** 2, [(-5.0, 5.0)] * 2, 40, [0.5, 0.5], 2.0, 0.05)
+    X, Y = synth(0, 40, 2, 1, 1.5)
+    grid_case(ref, GPy, "expander_tight", X, Y, "rbf", 2.0, [1.0, 1.0], 0.05 ** 2, [(-5.0, 5.0)] * 2, 40, [1.5], 2.0, 0.05)
+    X, Y = synth(0, 40, 2, 1, 2.5)
+    grid_case(ref, GPy, "full_sets_g1", X, Y, "rbf", 2.0, [1.0, 1.0], 0.05 ** 2, [(-5.0, 5.0)] * 2, 20, [0.5], 2.0, 0.05, full_sets=True)
+    # Matern kernels, ARD lengthscales, ragged axes, unconstrained objective (fmin = -inf for GP 0)
+    X, Y = synth(3, 50, 3, 1, 2.0)
+    grid_case(ref, GPy, "matern32_3d", X, Y, "mat32", 1.5, [0.8, 1.3, 1.0], 0.02, [(-3.0, 3.0), (-2.0, 2.0), (-1.0, 4.0)], [9, 14, 11], [0.2], 3.0, 0.1)
+    X, Y = synth(4, 33, 2, 2, 2.0)
+    grid_case(ref, GPy, "matern52_2d_g2", X, Y, "mat52", 2.0, [1.2, 0.7], 0.05 ** 2, [(-4.0, 4.0)] * 2, [31, 45], [-np.inf, 0.4], 2.0, 0.05)
+    loop_case(ref, GPy, "bo_loop_2d")
+    swarm_case(ref, GPy, "swarm_fitness_3d")
+
+
+if __name__ == "__main__":
+    main()

@@ -86,3 +86,52 @@ def combine_max_first(values: np.ndarray, rows: np.ndarray) -> Tuple[float, int]
         if best_r < 0 or v > best_v or (v == best_v and r < best_r):
             best_v, best_r = float(v), r
     return best_v, best_r
+
+
+def reduce_safe_records(comm: Comm, n_safe, max_l0, argmax_l0, max_u0, argmax_u0) -> dict:
+    """Combine the per-rank results of so_sets_reduce_safe into the global record
+    (gp_opt.py:504, :512, :634-636, :708-712): one all-gather of 40 bytes per rank."""
+    ints = comm.all_gather(np.array([n_safe, argmax_l0, argmax_u0], dtype=np.int64))
+    vals = comm.all_gather(np.array([max_l0, max_u0], dtype=np.float64))
+    best_l, row_l = combine_max_first(vals[:, 0], ints[:, 1])
+    best_u, row_u = combine_max_first(vals[:, 1], ints[:, 2])
+    return dict(n_safe=int(ints[:, 0].sum()), max_l0=best_l, argmax_l0=row_l, max_u0=best_u, argmax_u0=row_u)
+
+
+def reduce_max_records(comm: Comm, n_max, max_width0, best_value, best_row, scaling0) -> dict:
+    """Combine the per-rank results of so_sets_maximizers (gp_opt.py:511-513, :642-644)."""
+    vals = comm.all_gather(np.array([max_width0, best_value], dtype=np.float64))
+    ints = comm.all_gather(np.array([n_max, best_row], dtype=np.int64))
+    value, row = combine_max_first(vals[:, 1], ints[:, 1])
+    return dict(n_max=int(ints[:, 0].sum()), max_var=float(np.max(vals[:, 0])) / scaling0, best_value=value, best_row=row)
+
+
+def gather_ragged(comm: Comm, arr: np.ndarray) -> np.ndarray:
+    """Concatenate per-rank 1-D arrays of different lengths in rank order."""
+    if not comm.active:
+        return arr
+    counts = comm.all_gather(np.array([arr.shape[0]], dtype=np.int64)).ravel()
+    cap = max(int(counts.max()), 1)
+    pad = np.zeros(cap, dtype=arr.dtype)
+    pad[:arr.shape[0]] = arr
+    allp = comm.all_gather(pad)
+    return np.concatenate([allp[r, :counts[r]] for r in range(comm.world)])
+
+
+def gather_row_blocks(comm: Comm, local: np.ndarray, n_rows: int) -> np.ndarray:
+    """Reassemble a row-sharded array (blocks from shard_bounds) on every rank."""
+    if not comm.active:
+        return local
+    per = -(-n_rows // comm.world)
+    pad = np.zeros((per,) + local.shape[1:], dtype=local.dtype)
+    pad[:local.shape[0]] = local
+    allr = comm.all_gather(pad)
+    return allr.reshape((-1,) + local.shape[1:])[:n_rows]
+
+
+def order_candidates(comm: Comm, rows_sorted: np.ndarray, keys_sorted: np.ndarray) -> np.ndarray:
+    """Global visiting order of expander candidates: key descending, ties by ascending row."""
+    if not comm.active:
+        return rows_sorted
+    allr, allk = gather_ragged(comm, rows_sorted), gather_ragged(comm, keys_sorted)
+    return allr[np.lexsort((allr, -allk))]

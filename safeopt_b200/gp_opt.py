@@ -20,7 +20,8 @@ from typing import List, Optional
 import numpy as np
 
 from . import _lib
-from .distributed import Comm, combine_max_first, shard_bounds
+from .distributed import (Comm, combine_max_first, gather_ragged, gather_row_blocks, order_candidates,
+                          reduce_max_records, reduce_safe_records, shard_bounds)
 from .engine import MAX_REC_DTYPE, SAFE_REC_DTYPE, DeviceEngine
 from .gpmodel import extract_hyper, fingerprint
 from .swarm import SwarmOptimization
@@ -292,14 +293,7 @@ class SafeOpt(GaussianProcessOptimization):
 
     # ------------------------------------------------------------------ host views of device state
     def _gather_rows(self, local: np.ndarray) -> np.ndarray:
-        if not self._comm.active:
-            return local
-        n_rows = self.inputs.shape[0]
-        per = -(-n_rows // self._comm.world)
-        pad = np.zeros((per,) + local.shape[1:], dtype=local.dtype)
-        pad[:local.shape[0]] = local
-        allr = self._comm.all_gather(pad)
-        return allr.reshape((-1,) + local.shape[1:])[:n_rows]
+        return gather_row_blocks(self._comm, local, self.inputs.shape[0])
 
     def _host(self, key, tensor, as_bool=False):
         if key not in self._host_cache:
@@ -391,12 +385,8 @@ class SafeOpt(GaussianProcessOptimization):
         eng = self._engine
         eng.reduce_safe(self._Q_d, len(self.gps), self._row0, self._S_d, self._rec_safe_d)
         rec = eng.read_record(self._rec_safe_d, SAFE_REC_DTYPE)
-        allr = self._comm.all_gather(np.array([rec["n_safe"], rec["argmax_l0"], rec["argmax_u0"]], dtype=np.int64))
-        allv = self._comm.all_gather(np.array([rec["max_l0"], rec["max_u0"]], dtype=np.float64))
-        max_l0, arg_l0 = combine_max_first(allv[:, 0], allr[:, 1])
-        max_u0, arg_u0 = combine_max_first(allv[:, 1], allr[:, 2])
-        self._safe_info = dict(n_safe=int(allr[:, 0].sum()), max_l0=max_l0, argmax_l0=arg_l0, max_u0=max_u0,
-                               argmax_u0=arg_u0)
+        self._safe_info = reduce_safe_records(self._comm, rec["n_safe"], rec["max_l0"], rec["argmax_l0"], rec["max_u0"],
+                                              rec["argmax_u0"])
         self._invalidate_host("S")
 
     def compute_sets(self, full_sets=False):
@@ -416,11 +406,9 @@ class SafeOpt(GaussianProcessOptimization):
         eng.maximizers(self._Q_d, G, self._row0, self._S_d, self._safe_info["max_l0"], self.scaling, self._M_d,
                        self._rec_max_d)
         rec = eng.read_record(self._rec_max_d, MAX_REC_DTYPE)
-        allv = self._comm.all_gather(np.array([rec["max_width0"], rec["best_value"]], dtype=np.float64))
-        allr = self._comm.all_gather(np.array([rec["n_max"], rec["best_row"]], dtype=np.int64))
-        max_var = float(np.max(allv[:, 0])) / self.scaling[0]
-        best_value, best_row = combine_max_first(allv[:, 1], allr[:, 1])
-        self._max_info = dict(n_max=int(allr[:, 0].sum()), max_var=max_var, best_value=best_value, best_row=best_row)
+        self._max_info = reduce_max_records(self._comm, rec["n_max"], rec["max_width0"], rec["best_value"], rec["best_row"],
+                                            self.scaling[0])
+        max_var = self._max_info["max_var"]
 
         m_local = self._row1 - self._row0
         if self._cand_key_d is None:
@@ -457,21 +445,10 @@ class SafeOpt(GaussianProcessOptimization):
         order = t.argsort(keys_local, descending=True, stable=True)
         rows = rows_local[order].cpu().numpy()
         keys = keys_local[order].cpu().numpy()
-        if not self._comm.active:
-            return rows
-        allr, allk = self._gather_var(rows), self._gather_var(keys)
-        order = np.lexsort((allr, -allk))
-        return allr[order]
+        return order_candidates(self._comm, rows, keys)
 
     def _gather_var(self, arr: np.ndarray) -> np.ndarray:
-        if not self._comm.active:
-            return arr
-        counts = self._comm.all_gather(np.array([arr.shape[0]], dtype=np.int64)).ravel()
-        cap = int(counts.max())
-        pad = np.zeros(cap, dtype=arr.dtype)
-        pad[:arr.shape[0]] = arr
-        allp = self._comm.all_gather(pad)
-        return np.concatenate([allp[r, :counts[r]] for r in range(self._comm.world)])
+        return gather_ragged(self._comm, arr)
 
     def _rows_values(self, rows: np.ndarray):
         """(Q rows, mean, var) of arbitrary global rows, fetched from whichever rank owns them."""

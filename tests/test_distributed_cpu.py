@@ -1,0 +1,120 @@
+"""world_size-2 ``gloo`` tests (CPU) of the multi-GPU host logic: row sharding, record reduction with
+first-row tie-breaks, ragged gathers and candidate ordering.  Each rank derives the records its GPU
+kernels would produce from its shard of a golden fixture's Q with NumPy, combines them through
+``safeopt_b200.distributed`` and must reproduce the single-process reference result."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _local_safe_record(Q, S, row0):
+    rows = np.flatnonzero(S)
+    if rows.size == 0:
+        return 0, -np.inf, -1, -np.inf, -1
+    l, u = Q[rows, 0], Q[rows, 1]
+    return rows.size, l.max(), row0 + rows[np.argmax(l)], u.max(), row0 + rows[np.argmax(u)]
+
+
+def _local_max_record(Q, S, max_l0, scaling, row0):
+    M = S & (Q[:, 1] >= max_l0)
+    rows = np.flatnonzero(M)
+    if rows.size == 0:
+        return M, (0, -np.inf, -np.inf, -1)
+    w = (Q[rows, 1::2] - Q[rows, ::2])
+    val = np.max(w / scaling, axis=1)
+    return M, (rows.size, (Q[rows, 1] - Q[rows, 0]).max(), val.max(), row0 + rows[np.argmax(val)])
+
+
+def _worker(rank, world, port, fixture, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from conftest import load_golden, unpack_mask
+        from safeopt_b200 import distributed as D
+        g = load_golden(fixture)
+        n_rows = int(g["n_rows"])
+        Q = g["Q"]
+        fmin = g["fmin"]
+        G = Q.shape[1] // 2
+        scaling = np.full(G, np.sqrt(float(g["variance"])))
+        comm = D.Comm()
+        assert comm.world == world and comm.rank == rank and comm.active
+        r0, r1 = D.shard_bounds(n_rows, world, rank)
+        Ql = Q[r0:r1]
+        Sl = np.all(Ql[:, ::2] > fmin, axis=1)
+        safe = D.reduce_safe_records(comm, *_local_safe_record(Ql, Sl, r0))
+        S_ref = unpack_mask(g["S"], n_rows)
+        assert safe["n_safe"] == int(S_ref.sum())
+        rows_ref = np.flatnonzero(S_ref)
+        assert safe["max_l0"] == Q[S_ref, 0].max() and safe["argmax_l0"] == rows_ref[np.argmax(Q[S_ref, 0])]
+        assert safe["argmax_u0"] == rows_ref[np.argmax(Q[S_ref, 1])] == int(g["row_ucb"])
+        Ml, rec = _local_max_record(Ql, Sl, safe["max_l0"], scaling, r0)
+        mx = D.reduce_max_records(comm, *rec, scaling[0])
+        M_ref = unpack_mask(g["M"], n_rows)
+        assert mx["n_max"] == int(M_ref.sum())
+        assert mx["max_var"] == np.max(Q[M_ref, 1] - Q[M_ref, 0]) / scaling[0]
+        # reassemble sharded masks
+        assert np.array_equal(D.gather_row_blocks(comm, Sl.astype(np.uint8), n_rows).astype(bool), S_ref)
+        assert np.array_equal(D.gather_row_blocks(comm, Ml.astype(np.uint8), n_rows).astype(bool), M_ref)
+        assert np.array_equal(D.gather_row_blocks(comm, Ql, n_rows), Q)
+        # candidates: s = S & ~M & wide enough; global order = key desc, row asc
+        beta, thr = float(g["beta"]), float(g["threshold"])
+        w = Ql[:, 1::2] - Ql[:, ::2]
+        s = Sl & ~Ml & (np.max(w / scaling, axis=1) > mx["max_var"]) & np.any(w > thr * beta, axis=1)
+        rows = np.flatnonzero(s) + r0
+        keys = np.max(w[s], axis=1)
+        o = np.lexsort((rows, -keys))
+        order = D.order_candidates(comm, rows[o], keys[o])
+        wf = Q[:, 1::2] - Q[:, ::2]
+        sf = S_ref & ~M_ref & (np.max(wf / scaling, axis=1) > mx["max_var"]) & np.any(wf > thr * beta, axis=1)
+        rf, kf = np.flatnonzero(sf), np.max(wf[sf], axis=1)
+        assert np.array_equal(order, rf[np.lexsort((rf, -kf))])
+        # the no-expander query point: best scaled width over M, first row on ties
+        G_ref = unpack_mask(g["G"], n_rows)
+        if not G_ref.any():
+            assert mx["best_row"] == int(g["row_next"])
+        # flags OR across ranks
+        f = np.zeros(8, dtype=np.uint8)
+        f[rank] = 1
+        assert np.array_equal(comm.any_flags(f)[:world], np.ones(world, dtype=np.uint8))
+        assert np.array_equal(D.gather_ragged(comm, np.arange(rank + 1, dtype=np.int64)), np.concatenate([np.arange(r + 1) for r in range(world)]))
+        open(os.path.join(out_dir, "ok_%d" % rank), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("fixture", ["config_C3_n80", "expander_g2", "doctest_1d"])
+def test_sharded_record_reduction_gloo(fixture, tmp_path):
+    world = 2
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, fixture, str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(os.path.join(str(tmp_path), "ok_%d" % r)) for r in range(world))
+
+
+def test_single_rank_comm_is_identity():
+    from safeopt_b200 import distributed as D
+    comm = D.Comm()
+    assert not comm.active and comm.world == 1
+    a = np.arange(6.0).reshape(2, 3)
+    assert np.array_equal(comm.all_gather(a)[0], a)
+    assert np.array_equal(D.gather_row_blocks(comm, a, 2), a)
+    assert D.reduce_safe_records(comm, 3, 1.5, 7, 2.5, 9) == dict(n_safe=3, max_l0=1.5, argmax_l0=7, max_u0=2.5, argmax_u0=9)

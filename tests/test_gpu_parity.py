@@ -1,0 +1,356 @@
+"""GPU parity tests (run with ``-m gpu`` on a B200): the CUDA path, called through the C ABI, against
+the CPU oracle on the same seeded inputs, against the committed golden fixtures produced by the
+reference itself, and -- at BASELINE.json's full sizes -- through size-independent properties.
+
+Tolerances (fp64; SURVEY.md section 7, hard part 1): |d mean| <= 1e-11 * max|y|, |d var| <= 1e-10 * k(x,x),
+|d l|, |d u| <= 1e-9 * sqrt(k(x,x)); masks and query rows bit-exact (fixture margins are >= 1e-5)."""
+import numpy as np
+import pytest
+
+from conftest import GRID_CASES, device_kernel, golden_problem, load_golden, oracle_kernel, unpack_mask
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+if not torch.cuda.is_available():  # pragma: no cover - the CPU run deselects this module with -m "not gpu"
+    pytest.skip("no CUDA device", allow_module_level=True)
+
+import safeopt_b200 as sb  # noqa: E402
+from safeopt_b200 import _lib, workloads  # noqa: E402
+from safeopt_b200.engine import DeviceEngine  # noqa: E402
+from oracle import gpy_lite, safeopt_port as port  # noqa: E402
+
+
+def _problem(N, d, seed):
+    rs = np.random.RandomState(seed)
+    X = rs.uniform(-1.5, 1.5, (N, d))
+    Y = 2 * np.exp(-np.sum(X * X, 1) / 8) + 0.05 * rs.randn(N)
+    ls = rs.uniform(0.7, 1.5, d)
+    return X, Y, ls, rs
+
+
+# ---------------------------------------------------------------- K1
+@pytest.mark.parametrize("N,d,kind", [(1, 1, 0), (5, 1, 0), (7, 2, 1), (64, 2, 0), (100, 3, 1), (256, 4, 0), (300, 2, 2), (512, 6, 0)])
+def test_fit_matches_lapack(N, d, kind):
+    X, Y, ls, _ = _problem(N, d, N)
+    eng = DeviceEngine(max_gps=1)
+    eng.fit(0, X, Y, kind, ls, 2.0, 0.05 ** 2)
+    L, Linv, alpha = eng.fit_export(0, N)
+    gp = gpy_lite.GPRegression(X, Y[:, None], kernel=oracle_kernel(kind, d, 2.0, ls), noise_var=0.05 ** 2)
+    assert np.abs(L - np.tril(gp.woodbury_chol)).max() < 1e-12
+    assert np.abs(Linv @ L - np.eye(N)).max() < 1e-11
+    assert np.abs(alpha - gp.woodbury_vector[:, 0]).max() < 1e-10 * max(1.0, np.abs(alpha).max())
+    eng.close()
+
+
+def test_fit_reports_not_positive_definite():
+    eng = DeviceEngine(max_gps=1)
+    X = np.zeros((3, 1))            # three identical points, zero noise -> singular even with the 1e-8 jitter in fp64? no: jitter keeps it PD
+    eng.fit(0, X, np.zeros(3), 0, [1.0], 1.0, 0.0)
+    Xbad = np.array([[0.0], [np.nan]])
+    with pytest.raises(sb.DeviceError) as err:
+        eng.fit(0, Xbad, np.zeros(2), 0, [1.0], 1.0, 0.0)
+    assert err.value.status == _lib.SO_ERR_NOT_PD
+    with pytest.raises(sb.DeviceError):
+        eng.posterior_rows(0, eng.to_device(np.zeros((4, 1))), 2.0, 0.0, mean=eng.empty((4,)), var=eng.empty((4,)))
+    with pytest.raises(sb.DeviceError):
+        eng.fit(0, X, np.zeros(3), 7, [1.0], 1.0, 0.0)
+    eng.close()
+
+
+# ---------------------------------------------------------------- K2
+@pytest.mark.parametrize("N,d,kind,M", [(1, 1, 0, 100), (5, 1, 0, 100), (9, 2, 2, 1), (64, 2, 0, 5000), (100, 3, 1, 3000),
+                                        (128, 2, 2, 4097), (256, 4, 0, 20000), (300, 2, 0, 3000), (512, 6, 0, 4000),
+                                        (40, 2, 0, 70000), (700, 3, 1, 900)])
+def test_posterior_matches_oracle(N, d, kind, M):
+    X, Y, ls, rs = _problem(N, d, N + 1)
+    Xs = rs.uniform(-5, 5, (M, d))
+    eng = DeviceEngine(max_gps=1)
+    eng.fit(0, X, Y, kind, ls, 2.0, 0.05 ** 2)
+    Xd = eng.to_device(Xs)
+    mean, var, Q, S = eng.empty((M,)), eng.empty((M,)), eng.empty((M, 2)), eng.zeros((M,), "u8")
+    eng.posterior_rows(0, Xd, 2.0, 0.0, mean=mean, var=var, Q=Q, q_col=0, S=S, safe_mode=_lib.SAFE_WRITE)
+    ms, vs = eng.posterior_rows_simple(0, Xd)
+    gp = gpy_lite.GPRegression(X, Y[:, None], kernel=oracle_kernel(kind, d, 2.0, ls), noise_var=0.05 ** 2)
+    mo, vo = gp.predict_noiseless(Xs)
+    mean, var, ms, vs, Q, S = [t.cpu().numpy() for t in (mean, var, ms, vs, Q, S)]
+    scale_y = max(1.0, np.abs(Y).max())
+    assert np.abs(mean - ms).max() < 1e-12 * scale_y and np.abs(var - vs).max() < 1e-12 * 2.0     # tensor-core vs plain DFMA kernel
+    assert np.abs(mean - mo[:, 0]).max() < 1e-11 * scale_y
+    assert np.abs(var - vo[:, 0]).max() < 1e-10 * 2.0
+    Qo = np.stack([mo[:, 0] - 2 * np.sqrt(vo[:, 0]), mo[:, 0] + 2 * np.sqrt(vo[:, 0])], 1)
+    assert np.abs(Q - Qo).max() < 1e-9 * np.sqrt(2.0) * 2
+    # the device's own Q and S are exactly consistent; against the oracle only outside the tolerance band
+    assert np.array_equal(S.astype(bool), Q[:, 0] > 0.0)
+    clear = np.abs(Qo[:, 0]) > 1e-8
+    assert np.array_equal(S.astype(bool)[clear], (Qo[:, 0] > 0.0)[clear])
+    assert np.array_equal(Q[:, 0], mean - 2.0 * np.sqrt(var)) and np.array_equal(Q[:, 1], mean + 2.0 * np.sqrt(var))
+    eng.close()
+
+
+def test_posterior_safe_modes_and_columns():
+    X, Y, ls, rs = _problem(30, 2, 3)
+    Xs = rs.uniform(-4, 4, (999, 2))
+    eng = DeviceEngine(max_gps=2)
+    eng.fit(0, X, Y, 0, ls, 2.0, 0.01)
+    eng.fit(1, X, Y - 0.5, 1, ls, 1.0, 0.01)
+    Xd = eng.to_device(Xs)
+    Q = eng.zeros((999, 4))
+    S = eng.zeros((999,), "u8")
+    eng.posterior_rows(0, Xd, 2.0, 0.3, Q=Q, q_col=0, S=S, safe_mode=_lib.SAFE_WRITE)
+    S0 = S.clone()
+    eng.posterior_rows(1, Xd, 2.0, 0.1, Q=Q, q_col=2, S=S, safe_mode=_lib.SAFE_AND)
+    Qh = Q.cpu().numpy()
+    assert np.array_equal(S0.cpu().numpy().astype(bool), Qh[:, 0] > 0.3)
+    assert np.array_equal(S.cpu().numpy().astype(bool), (Qh[:, 0] > 0.3) & (Qh[:, 2] > 0.1))
+    eng.posterior_rows(1, Xd, 2.0, 0.1, Q=Q, q_col=2, S=S, safe_mode=_lib.SAFE_NONE)
+    assert np.array_equal(S.cpu().numpy().astype(bool), (Qh[:, 0] > 0.3) & (Qh[:, 2] > 0.1))
+    eng.posterior_rows(0, Xd[:0], 2.0, 0.0, Q=Q[:0], S=S[:0], safe_mode=_lib.SAFE_WRITE)      # empty input is a no-op
+    eng.close()
+
+
+@pytest.mark.parametrize("d,n,N", [(1, 100, 5), (2, 60, 64), (3, [7, 9, 11], 30), (4, 12, 256), (5, 4, 20), (6, 3, 40)])
+def test_grid_path_equals_rows_path(d, n, N):
+    from safeopt_b200.utilities import detect_grid
+    w = workloads.grid_workload("t", d, 10, N)
+    grid = sb.linearly_spaced_combinations(w.bounds, n)
+    axes = detect_grid(grid)
+    eng = DeviceEngine(max_gps=1)
+    eng.fit(0, w.X, w.Y[:, 0], 0, w.lengthscale, w.variance, w.noise_var)
+    eng.define_grid(axes)
+    eng.prepare_grid(0)
+    M = grid.shape[0]
+    assert np.array_equal(eng.grid_rows(0, M).cpu().numpy(), grid)              # device row order == reference row order
+    m1, v1, m2, v2 = eng.empty((M,)), eng.empty((M,)), eng.empty((M,)), eng.empty((M,))
+    eng.posterior_grid(0, 0, M, 2.0, 0.0, mean=m1, var=v1)
+    eng.posterior_rows(0, eng.to_device(grid), 2.0, 0.0, mean=m2, var=v2)
+    assert (m1 - m2).abs().max().item() < 1e-12 and (v1 - v2).abs().max().item() < 1e-12
+    h = M // 3                                                                    # a shard starting mid-grid gives the same rows
+    m3 = eng.empty((M - h,))
+    eng.posterior_grid(0, h, M - h, 2.0, 0.0, mean=m3)
+    assert torch.equal(m3, m1[h:])
+    eng.close()
+
+
+# ---------------------------------------------------------------- golden fixtures produced by the reference
+@pytest.mark.parametrize("explicit", [False, True])
+@pytest.mark.parametrize("name", GRID_CASES)
+def test_safeopt_matches_golden(name, explicit):
+    g = load_golden(name)
+    n_rows = int(g["n_rows"])
+    gps, grid, fmin = golden_problem(g, "gpu")
+    if explicit:
+        grid = np.ascontiguousarray(grid)[:, :]
+        grid = grid + 0.0
+        grid.flat[0] = np.nextafter(grid.flat[0], -np.inf)       # no longer a bitwise product grid -> explicit-rows kernels
+    opt = sb.SafeOpt(gps if len(gps) > 1 else gps[0], grid, fmin if len(fmin) > 1 else fmin[0], beta=float(g["beta"]),
+                     threshold=float(g["threshold"]))
+    assert (opt._grid_axes is None) == explicit
+    if bool(g["full_sets"]):
+        opt.update_confidence_intervals()
+        opt.compute_sets(full_sets=True)
+        x = opt.get_new_query_point()
+    else:
+        x = opt.optimize()
+    tol = 1e-9 * 2 * np.sqrt(float(g["variance"]))
+    assert np.abs(opt.Q - g["Q"]).max() < tol
+    assert min(float(g["margin_S"]), float(g["margin_M"])) > 100 * tol          # masks are decidable at this tolerance
+    assert np.array_equal(opt.S, unpack_mask(g["S"], n_rows))
+    assert np.array_equal(opt.M, unpack_mask(g["M"], n_rows))
+    assert np.array_equal(opt.G, unpack_mask(g["G"], n_rows))
+    assert opt.last_query_row == int(g["row_next"])
+    if not explicit:
+        assert np.array_equal(x, g["x_next"])
+    mx = opt.get_maximum()
+    assert abs(mx[1] - float(g["max_val"])) < tol
+    if not explicit:
+        assert np.array_equal(mx[0], g["max_x"])
+    opt.optimize(ucb=True)
+    assert opt.last_query_row == int(g["row_ucb"])
+
+
+def test_bo_loop_matches_golden():
+    g = load_golden("bo_loop_2d")
+    gp = sb.GPRegression(g["X"], g["Y"], kernel=sb.RBF(2, variance=2.0, lengthscale=np.ones(2), ARD=True), noise_var=float(g["noise_var"]))
+    grid = sb.linearly_spaced_combinations([tuple(b) for b in g["bounds"]], int(g["num_samples"]))
+    opt = sb.SafeOpt(gp, grid, float(g["fmin"]), beta=float(g["beta"]), threshold=float(g["threshold"]))
+    for it, row_ref in enumerate(g["rows"]):
+        x = opt.optimize()
+        assert opt.last_query_row == int(row_ref), "trajectory diverged at iteration %d" % it
+        assert int(opt.G.sum()) == int(g["n_expanders"][it])
+        opt.add_new_data_point(x, np.array([[g["ys"][it]]]))
+    assert opt.t == 6 + len(g["rows"]) and opt._fits.refits == len(g["rows"])
+
+
+def test_no_safe_points_raises_like_reference():
+    gp = sb.GPRegression(np.array([[0.0]]), np.array([[-1.0]]), noise_var=0.01 ** 2)
+    opt = sb.SafeOpt(gp, sb.linearly_spaced_combinations([(-1, 1)], 50), fmin=0.0)
+    with pytest.raises(EnvironmentError):
+        opt.optimize()
+    assert opt.get_maximum() is None
+    assert not opt.S.any() and not opt.M.any() and not opt.G.any()
+
+
+# ---------------------------------------------------------------- swarm
+def test_swarm_fitness_matches_golden():
+    g = load_golden("swarm_fitness_3d")
+    X, Y = g["X"], g["Y"]
+    d = X.shape[1]
+    gps = [sb.GPRegression(X, Y[:, [i]], kernel=sb.RBF(d, variance=2.0, lengthscale=np.ones(d), ARD=True), noise_var=float(g["noise_var"]))
+           for i in range(Y.shape[1])]
+    opt = sb.SafeOptSwarm(gps, list(g["fmin"]), bounds=[(-1.0, 1.0)] * d, beta=float(g["beta"]), swarm_size=20)
+    assert np.allclose(opt.optimal_velocities, g["velocities"], rtol=0, atol=1e-12)
+    assert np.array_equal(opt._compute_penalty(g["penalty_in"].copy()), g["penalty_out"])
+    opt.best_lower_bound = float(g["best_lower_bound"])
+    for kind in ["greedy", "maximizers", "expanders", "safe_set"]:
+        v, s = opt._compute_particle_fitness(kind, g["particles"])
+        ref = g["values_" + kind]
+        assert np.abs(v - ref).max() < 1e-9 * max(1.0, np.abs(ref).max()), kind
+        assert np.array_equal(s, g["safe_" + kind]), kind
+    with pytest.raises(AssertionError):
+        opt._compute_particle_fitness("bogus", g["particles"])
+
+
+def test_swarm_step_kernels_match_port():
+    rs = np.random.RandomState(4)
+    P, d = 777, 3
+    eng = DeviceEngine(max_gps=1)
+    pos, vel = rs.uniform(-1, 1, (P, d)), rs.uniform(0, 0.1, (P, d))
+    bpos, bval = rs.uniform(-1, 1, (P, d)), rs.randn(P)
+    gbest = bpos[np.argmax(bval)].copy()
+    r = rs.rand(2 * P, d)
+    vs = np.array([0.1, 0.2, 0.15])
+    bounds = np.array([(-1.0, 1.0)] * d)
+    values, safe = rs.randn(P), rs.rand(P) > 0.3
+    fit = lambda x: (values, safe)
+    p2, v2, bp2, bv2, gb2 = port.pso_step(pos, vel, bpos, bval, gbest, r[:P], r[P:], 0.73, vs, bounds, fit)
+    pd, vd, bpd, bvd = [eng.to_device(a.copy()) for a in (pos, vel, bpos, bval)]
+    eng.swarm_step(pd, vd, bpd, eng.to_device(gbest), eng.to_device(r), 0.73, vs, bounds)
+    assert np.array_equal(pd.cpu().numpy(), p2) and np.array_equal(vd.cpu().numpy(), v2)
+    idx = eng.zeros((1,), "i64")
+    eng.swarm_update_best(pd, eng.to_device(values), eng.to_device(safe.astype(np.uint8)), bpd, bvd, idx)
+    assert np.array_equal(bvd.cpu().numpy(), bv2) and np.array_equal(bpd.cpu().numpy(), bp2)
+    assert int(idx.item()) == int(np.argmax(bv2))
+    eng.close()
+
+
+def test_safeoptswarm_runs_and_reference_smoke_test():
+    # /root/reference/safeopt/tests/test_swarm.py:13-22
+    gp = sb.GPRegression(np.array([[0.0]]), np.array([[-1.0]]), noise_var=0.01 ** 2)
+    opt = sb.SafeOptSwarm(gp, fmin=[0.0], bounds=[[-1.0, 1.0]])
+    with pytest.raises(RuntimeError):
+        opt.optimize()
+    # docstring example gp_opt.py:755-777
+    gp = sb.GPRegression(np.array([[0.0]]), np.array([[1.0]]), noise_var=0.01 ** 2)
+    opt = sb.SafeOptSwarm(gp, fmin=[0.0], bounds=[[-1.0, 1.0]])
+    np.random.seed(0)
+    x = opt.optimize()
+    assert x.shape == (1,) and -1.0 <= x[0] <= 1.0
+    opt.add_new_data_point(x, np.array([[1.0]]))
+    assert opt.t == 2 and opt.get_maximum()[1] == 1.0
+
+
+def test_device_swarm_large_matches_host_swarm_logic():
+    w = workloads.swarm_workload(n_particles=4096, n_train=64)
+    gps = [sb.GPRegression(w.X, w.Y[:, [i]], kernel=sb.RBF(w.d, variance=w.variance, lengthscale=w.lengthscale, ARD=True), noise_var=w.noise_var)
+           for i in range(w.n_gps)]
+    opt = sb.SafeOptSwarm(gps, [0.0, 0.2], bounds=w.bounds, beta=2.0)
+    opt.best_lower_bound = 0.5
+    fit_dev = lambda p: opt._fitness_device("maximizers", p)
+    fit_host = lambda p: opt._compute_particle_fitness("maximizers", p)
+    np.random.seed(3)
+    hs = sb.SwarmOptimization(w.n_particles, opt.optimal_velocities, fit_host, bounds=w.bounds)
+    hs.init_swarm(w.particles.copy())
+    hs.run_swarm(5)
+    np.random.seed(3)
+    ds = sb.DeviceSwarm(opt._engine, opt.optimal_velocities, fit_dev, bounds=w.bounds, rng="host")
+    ds.init_swarm(w.particles.copy())
+    ds.run_swarm(5)
+    assert np.abs(ds.positions.cpu().numpy() - hs.positions).max() < 1e-9
+    assert np.abs(ds.best_values.cpu().numpy() - hs.best_values).max() < 1e-8
+    assert np.abs(ds.global_best.cpu().numpy() - hs.global_best).max() < 1e-9
+
+
+# ---------------------------------------------------------------- full-size properties (BASELINE config 4 and 2)
+def test_config_c4_full_size_properties():
+    w = workloads.config("C4")
+    grid = sb.linearly_spaced_combinations(w.bounds, w.num_samples)
+    gp = sb.GPRegression(w.X, w.Y, kernel=sb.RBF(w.d, variance=w.variance, lengthscale=w.lengthscale, ARD=True), noise_var=w.noise_var)
+    opt = sb.SafeOpt(gp, grid, 0.0, beta=w.beta, threshold=w.threshold)
+    assert opt._grid_axes is not None and grid.shape[0] == 6_250_000
+    x = opt.optimize()
+    Q, S, M, G = opt.Q, opt.S, opt.M, opt.G
+    # idempotence of the set logic on the device's own Q (bit-exact, size independent)
+    assert np.array_equal(S, Q[:, 0] > 0.0)
+    best_l = Q[S, 0].max()
+    assert np.array_equal(M, S & (Q[:, 1] >= best_l))
+    MG = M | G
+    width = (Q[:, 1] - Q[:, 0]) / opt.scaling[0]
+    assert opt.last_query_row == np.flatnonzero(MG)[np.argmax(width[MG])]
+    assert np.array_equal(x, grid[opt.last_query_row])
+    # random rows against the oracle
+    rows = np.random.RandomState(0).choice(grid.shape[0], 20000, replace=False)
+    go = gpy_lite.GPRegression(w.X, w.Y, kernel=gpy_lite.RBF(w.d, variance=w.variance, lengthscale=w.lengthscale, ARD=True), noise_var=w.noise_var)
+    Qo = port.confidence_intervals([go], grid[rows], w.beta)
+    assert np.abs(Q[rows] - Qo).max() < 1e-9 * 2 * np.sqrt(w.variance)
+    # sharding invariance: the second half computed as its own shard is bit-identical
+    eng = opt._engine
+    h = grid.shape[0] // 2
+    m_half = eng.empty((grid.shape[0] - h,))
+    eng.posterior_grid(0, h, grid.shape[0] - h, w.beta, 0.0, mean=m_half)
+    assert torch.equal(m_half, opt._mean_d[0, h:])
+    # ucb / maximum agree with NumPy on the device's Q
+    mx = opt.get_maximum()
+    assert mx[1] == Q[S, 0].max() and np.array_equal(mx[0], grid[np.flatnonzero(S)[np.argmax(Q[S, 0])]])
+
+
+def test_config_c3_three_gps_properties():
+    w = workloads.config("C3")
+    grid = sb.linearly_spaced_combinations(w.bounds, w.num_samples)
+    gps = [sb.GPRegression(w.X, w.Y[:, [i]], kernel=sb.RBF(w.d, variance=w.variance, lengthscale=w.lengthscale, ARD=True), noise_var=w.noise_var)
+           for i in range(3)]
+    opt = sb.SafeOpt(gps, grid, w.fmin, beta=w.beta, threshold=w.threshold)
+    opt.optimize()
+    Q, S, M = opt.Q, opt.S, opt.M
+    assert Q.shape == (250000, 6)
+    assert np.array_equal(S, np.all(Q[:, ::2] > 0.0, axis=1))
+    assert np.array_equal(M, S & (Q[:, 1] >= Q[S, 0].max()))
+    rows = np.random.RandomState(1).choice(grid.shape[0], 5000, replace=False)
+    gos = [gpy_lite.GPRegression(w.X, w.Y[:, [i]], kernel=gpy_lite.RBF(w.d, variance=w.variance, lengthscale=w.lengthscale, ARD=True),
+                                 noise_var=w.noise_var) for i in range(3)]
+    assert np.abs(Q[rows] - port.confidence_intervals(gos, grid[rows], w.beta)).max() < 1e-9 * 2 * np.sqrt(w.variance)
+
+
+# ---------------------------------------------------------------- multi-GPU (runs when the box has >= 2 GPUs)
+def _nccl_worker(rank, world, port_no, out):
+    import os
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port_no)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        g = load_golden("expander_g2")
+        gps, grid, fmin = golden_problem(g, "gpu")
+        opt = sb.SafeOpt(gps, grid, fmin, beta=float(g["beta"]), threshold=float(g["threshold"]), device=torch.device("cuda", rank))
+        opt.optimize()
+        n_rows = int(g["n_rows"])
+        ok = (opt.last_query_row == int(g["row_next"]) and np.array_equal(opt.S, unpack_mask(g["S"], n_rows))
+              and np.array_equal(opt.M, unpack_mask(g["M"], n_rows)) and np.array_equal(opt.G, unpack_mask(g["G"], n_rows))
+              and np.abs(opt.Q - g["Q"]).max() < 1e-8)
+        open(os.path.join(out, "ok_%d" % rank), "w").write("1" if ok else "0")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_sharded_optimize_matches_golden(tmp_path):
+    import os
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port_no = s.getsockname()[1]
+    s.close()
+    mp.spawn(_nccl_worker, args=(2, port_no, str(tmp_path)), nprocs=2, join=True)
+    assert all(open(os.path.join(str(tmp_path), "ok_%d" % r)).read() == "1" for r in range(2))

@@ -1,0 +1,247 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every declared symbol, grid
+recognition, hyper-parameter extraction, the reference's own API-surface tests (which need no GP
+arithmetic), and loud failure without a GPU."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import safeopt_b200 as sb
+from safeopt_b200 import _lib, gpmodel
+from safeopt_b200.distributed import combine_max_first, shard_bounds
+from safeopt_b200.gp_opt import GaussianProcessOptimization
+from safeopt_b200.utilities import detect_grid, grid_row_strides, grid_rows_from_index
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+# ---------------------------------------------------------------- C ABI
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "safeopt_b200.h")).read()
+    declared = set(re.findall(r"\b(so_[a-z_0-9]+)\s*\(", header))
+    declared -= {"so_handle"}
+    assert len(declared) >= 20
+    lib = _lib.load()
+    for name in sorted(declared):
+        assert hasattr(lib, name), "libsafeopt_b200.so does not export %s" % name
+        assert name in _lib.SIGNATURES, "ctypes binding lacks %s" % name
+    assert set(_lib.SIGNATURES) == declared
+    assert lib.so_abi_version() == _lib.ABI_VERSION
+    assert _lib.status_string(_lib.SO_ERR_NOT_PD) == "covariance matrix not positive definite"
+
+
+def test_record_layouts_match_header():
+    import ctypes
+    from safeopt_b200.engine import MAX_REC_DTYPE, SAFE_REC_DTYPE
+    assert ctypes.sizeof(_lib.SafeRecord) == SAFE_REC_DTYPE.itemsize == 64
+    assert ctypes.sizeof(_lib.MaxRecord) == MAX_REC_DTYPE.itemsize == 64
+    assert [f[0] for f in _lib.SafeRecord._fields_] == list(SAFE_REC_DTYPE.names)
+    assert [f[0] for f in _lib.MaxRecord._fields_] == list(MAX_REC_DTYPE.names)
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU failure mode")
+def test_fails_loudly_without_gpu():
+    gp = sb.GPRegression(np.zeros((1, 1)), np.ones((1, 1)))
+    grid = sb.linearly_spaced_combinations([(-1, 1)], 10)
+    with pytest.raises(sb.NativeLibraryError):
+        sb.SafeOpt(gp, grid, 0.0)
+    with pytest.raises(sb.NativeLibraryError):
+        gp.predict_noiseless(grid)
+    with pytest.raises(sb.NativeLibraryError):
+        sb.SafeOptSwarm(gp, 0.0, bounds=[(-1, 1)])
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure; no module of the product may import it."""
+    pkg = os.path.join(ROOT, "safeopt_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), fn
+
+
+# ---------------------------------------------------------------- grid recognition
+@pytest.mark.parametrize("bounds,n", [([(-1, 1)], 7), ([(-5, 5)] * 2, [4, 5]), ([(-5, 5), (0, 1), (2, 3)], [3, 4, 5]),
+                                      ([(-5, 5)] * 4, [3, 2, 4, 5]), ([(0, 1)] * 5, 3)])
+def test_detect_grid_roundtrip(bounds, n):
+    from oracle import safeopt_port as port
+    grid = sb.linearly_spaced_combinations(bounds, n)
+    assert np.array_equal(grid, port.linearly_spaced_combinations(bounds, n))
+    axes = detect_grid(grid)
+    assert axes is not None
+    ns = n if isinstance(n, list) else [n] * len(bounds)
+    assert [len(a) for a in axes] == ns
+    for a, (lo, hi), k in zip(axes, bounds, ns):
+        assert np.array_equal(a, np.linspace(lo, hi, k))
+    assert np.array_equal(grid_rows_from_index(axes, np.arange(grid.shape[0])), grid)
+    strides = grid_row_strides(ns)
+    if len(ns) >= 2:
+        assert strides[1] == max(strides)
+
+
+def test_detect_grid_rejects_non_grids():
+    grid = sb.linearly_spaced_combinations([(-5, 5)] * 3, 4).copy()
+    bad = grid.copy()
+    bad[5, 1] += 1e-9
+    assert detect_grid(bad) is None
+    assert detect_grid(np.random.RandomState(0).rand(64, 3)) is None
+    assert detect_grid(grid[:-1]) is None
+    assert detect_grid(grid.astype(np.float32)) is None
+    assert detect_grid(sb.linearly_spaced_combinations([(0, 1)] * 7, 2)) is None      # beyond the grid fast path (d <= 6)
+
+
+def test_linearly_spaced_combinations_api():
+    g = sb.linearly_spaced_combinations([(-1, 1), (0, 2)], 3)
+    assert g.shape == (9, 2)
+    g = sb.linearly_spaced_combinations([(-1, 1), (0, 2)], [2, 5])
+    assert g.shape == (10, 2)
+
+
+# ---------------------------------------------------------------- sharding / record combine
+def test_shard_bounds_cover_rows_exactly():
+    for M in [0, 1, 7, 100, 6_250_000]:
+        for world in [1, 2, 3, 8]:
+            spans = [shard_bounds(M, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == M
+            for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
+                assert a1 == b0 and a0 <= a1
+
+
+def test_combine_max_first_is_numpy_argmax():
+    rs = np.random.RandomState(3)
+    for _ in range(50):
+        v = rs.randint(0, 4, size=8).astype(float)
+        rows = rs.permutation(100)[:8]
+        val, row = combine_max_first(v, rows)
+        assert val == v.max() and row == rows[v == v.max()].min()
+    assert combine_max_first([1.0, 5.0], [-1, -1]) == (-np.inf, -1)
+    assert combine_max_first([1.0, -np.inf], [4, -1]) == (1.0, 4)
+
+
+# ---------------------------------------------------------------- hyper-parameter adapter
+def test_extract_hyper_from_product_and_oracle_models():
+    from oracle import gpy_lite
+    X = np.random.RandomState(0).rand(5, 3)
+    Y = np.zeros((5, 1))
+    gp = gpy_lite.GPRegression(X, Y, kernel=gpy_lite.Matern52(3, variance=1.5, lengthscale=[1, 2, 3], ARD=True), noise_var=0.1)
+    h = gpmodel.extract_hyper(gp)
+    assert h.kind == _lib.KERNEL_MATERN52 and np.array_equal(h.lengthscale, [1, 2, 3]) and h.variance == 1.5 and h.noise_var == 0.1
+    gp = gpy_lite.GPRegression(X, Y, kernel=gpy_lite.RBF(3, variance=2.0, lengthscale=0.7), noise_var=0.2)
+    h = gpmodel.extract_hyper(gp)
+    assert h.kind == _lib.KERNEL_RBF and np.allclose(h.lengthscale, 0.7) and h.lengthscale.shape == (3,)
+    # context example shape: k_param (dims 0,1) * k_context (dim 2)
+    prod = gpy_lite.RBF(2, variance=2.0, lengthscale=[1.0, 0.5], ARD=True, active_dims=[0, 1]) * \
+        gpy_lite.RBF(1, variance=3.0, lengthscale=4.0, active_dims=[2])
+    gp = gpy_lite.GPRegression(X, Y, kernel=prod, noise_var=0.2)
+    h = gpmodel.extract_hyper(gp)
+    assert h.kind == _lib.KERNEL_RBF and np.array_equal(h.lengthscale, [1.0, 0.5, 4.0]) and h.variance == 6.0
+    bad = gpy_lite.RBF(2, active_dims=[0, 1]) * gpy_lite.Matern32(1, active_dims=[2])
+    with pytest.raises(gpmodel.UnsupportedModelError):
+        gpmodel.extract_hyper(gpy_lite.GPRegression(X, Y, kernel=bad))
+
+    class Weird:
+        input_dim = 3
+        lengthscale = np.ones(1)
+        variance = np.ones(1)
+    gp.kern = Weird()
+    with pytest.raises(gpmodel.UnsupportedModelError):
+        gpmodel.extract_hyper(gp)
+
+
+def test_host_kernels_match_oracle():
+    from oracle import gpy_lite
+    X = np.random.RandomState(1).randn(6, 2)
+    Z = np.random.RandomState(2).randn(4, 2)
+    for a, b in [(sb.RBF, gpy_lite.RBF), (sb.Matern32, gpy_lite.Matern32), (sb.Matern52, gpy_lite.Matern52)]:
+        ka = a(2, variance=1.7, lengthscale=[0.6, 1.4], ARD=True)
+        kb = b(2, variance=1.7, lengthscale=[0.6, 1.4], ARD=True)
+        assert np.allclose(ka.K(X, Z), kb.K(X, Z), atol=1e-13)
+        assert np.allclose(ka.K(X), kb.K(X), atol=1e-13)
+        assert np.allclose(ka.Kdiag(X), kb.Kdiag(X))
+
+
+# ---------------------------------------------------------------- the reference's own unit tests, on our classes
+class TestGPOptimizationSurface(object):
+    """Mirrors /root/reference/safeopt/tests/test_gps.py (no GP arithmetic involved => runs on CPU)."""
+
+    @pytest.fixture
+    def gps(self):
+        gp1 = sb.GPRegression(np.array([[0]]), np.array([[0]]), kernel=sb.RBF(1, variance=2))
+        gp2 = sb.GPRegression(np.array([[0]]), np.array([[0]]), kernel=sb.Matern32(1, variance=4))
+        return gp1, gp2
+
+    def test_init(self, gps):
+        gp1, _ = gps
+        opt = GaussianProcessOptimization(gp1, fmin=0, beta=2, num_contexts=1, threshold=0, scaling="auto")
+        assert opt.beta(0) == 2
+        opt = GaussianProcessOptimization(gp1, fmin=[0], beta=lambda x: 5, num_contexts=1, threshold=0, scaling="auto")
+        assert opt.beta(10) == 5
+
+    def test_multi_init(self, gps):
+        opt = GaussianProcessOptimization(list(gps), fmin=0, beta=2, num_contexts=1, threshold=0, scaling="auto")
+        np.testing.assert_allclose(opt.scaling, np.array([np.sqrt(2), np.sqrt(4)]))
+
+    def test_scaling(self, gps):
+        pytest.raises(ValueError, GaussianProcessOptimization, list(gps), 2, scaling=[5])
+        opt = GaussianProcessOptimization(list(gps), fmin=[1, 0], beta=2, num_contexts=1, threshold=0, scaling=[1, 2])
+        np.testing.assert_allclose(opt.scaling, np.array([1, 2]))
+
+    def test_data_adding(self, gps):
+        gp1, gp2 = gps
+        gp1.set_XY(np.array([[0.]]), np.array([[1.]]))
+        opt = GaussianProcessOptimization(gp1, 0)
+        opt.add_new_data_point(2, 3)
+        x, y = opt.data
+        np.testing.assert_allclose(x, np.array([[0], [2]]))
+        np.testing.assert_allclose(y, np.array([[1], [3]]))
+        gp1.set_XY(np.array([[0.]]), np.array([[1.]]))
+        gp2.set_XY(np.array([[0.]]), np.array([[11.]]))
+        opt = GaussianProcessOptimization([gp1, gp2], [0, 1])
+        opt.add_new_data_point(2, [2, 3])
+        x, y = opt.data
+        np.testing.assert_allclose(x, np.array([[0], [2]]))
+        np.testing.assert_allclose(y, np.array([[1, 11], [2, 3]]))
+        opt.add_new_data_point(3, [2, np.nan])
+        np.testing.assert_allclose(opt.x, np.array([[0], [2], [3]]))
+        np.testing.assert_allclose(opt.y, np.array([[1, 11], [2, 3], [2, np.nan]]))
+        for i, gp in enumerate(opt.gps):
+            not_nan = ~np.isnan(opt.y[:, i])
+            np.testing.assert_allclose(gp.X, opt.x[not_nan, :])
+            np.testing.assert_allclose(gp.Y[:, 0], opt.y[not_nan, i])
+        opt.remove_last_data_point()
+        np.testing.assert_allclose(opt.x, np.array([[0], [2]]))
+        np.testing.assert_allclose(opt.y, np.array([[1, 11], [2, 3]]))
+        for i, gp in enumerate(opt.gps):
+            not_nan = ~np.isnan(opt.y[:, i])
+            np.testing.assert_allclose(gp.X, opt.x[not_nan, :])
+            np.testing.assert_allclose(gp.Y[:, 0], opt.y[not_nan, i])
+
+    def test_contexts(self):
+        gp1 = sb.GPRegression(np.array([[0, 0]]), np.array([[5]]), kernel=sb.RBF(2, variance=2))
+        gp2 = sb.GPRegression(np.array([[0, 0]]), np.array([[6]]), kernel=sb.Matern32(2, variance=4))
+        opt = GaussianProcessOptimization([gp1, gp2], fmin=[0, 0], num_contexts=1)
+        opt.add_new_data_point(1, [3, 4], context=2)
+        np.testing.assert_allclose(opt.x, np.array([[0, 0], [1, 2]]))
+        np.testing.assert_allclose(opt.y, np.array([[5, 6], [3, 4]]))
+        for i, gp in enumerate(opt.gps):
+            np.testing.assert_allclose(gp.X, opt.x)
+            np.testing.assert_allclose(gp.Y[:, 0], opt.y[:, i])
+
+
+def test_workloads_are_deterministic():
+    from safeopt_b200 import workloads
+    a, b = workloads.config("C4"), workloads.config("C4")
+    assert np.array_equal(a.X, b.X) and np.array_equal(a.Y, b.Y) and a.n_rows == 50 ** 4 and a.n_train == 256
+    c3 = workloads.config("C3")
+    assert c3.Y.shape == (128, 3) and c3.n_rows == 250000
+    sw = workloads.swarm_workload(1000, 64)
+    assert sw.particles.shape == (1000, 6) and sw.Y.shape == (64, 2)
