@@ -39,7 +39,7 @@ UNIT = "evals/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="C4", choices=["C1", "C2", "C3", "C4"])
@@ -76,7 +76,7 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -182,8 +182,7 @@ def run_b200(args, w, rank, world, local_rank):
 
     grid = sb.linearly_spaced_combinations(w.bounds, w.num_samples)
     if args.explicit_rows:
-        grid = np.ascontiguousarray(grid)
-        grid[0, 0] = np.nextafter(grid[0, 0], 0.0)     # breaks the bitwise grid test -> explicit-rows kernels
+        os.environ["SAFEOPT_B200_GRID_FAST_PATH"] = "0"      # explicit-rows kernels (200 MB of candidates in HBM)
     gps = [sb.GPRegression(w.X, w.Y[:, [i]], kernel=sb.RBF(w.d, variance=w.variance, lengthscale=w.lengthscale, ARD=True),
                            noise_var=w.noise_var, device=dev) for i in range(w.n_gps)]
     opt = sb.SafeOpt(gps if w.n_gps > 1 else gps[0], grid, w.fmin if w.n_gps > 1 else w.fmin[0], beta=w.beta,

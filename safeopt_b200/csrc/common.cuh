@@ -29,6 +29,9 @@ struct GPState {
     // grid tables (grid fast path): per axis j, E_j[i][n], i < n_j, n < Npad
     double* E = nullptr;
     size_t capE = 0;
+    // two-level product tables (warp-specialised kernel): fast_rows + slow_rows rows of Npad doubles
+    double* P2 = nullptr;
+    size_t capP2 = 0;
     bool grid_ready = false;
 };
 
@@ -42,6 +45,8 @@ struct GridSpec {
     double* axis = nullptr;      // device copy of the axis values
     int cap = 0;
     int64_t rows = 0;
+    int in_fast[SO_MAX_DIM];     // axis belongs to the fast (low-order) group of the product tables
+    int64_t fast_rows = 1, slow_rows = 1;
 };
 
 struct so_handle {

@@ -15,13 +15,10 @@
 //         with separate multiply and add roundings (NumPy does not contract), S bit.
 // Algorithmic work per row and GP: N^2/2 FMA (contraction) + N kernel evaluations; algorithmic HBM
 // bytes: d*8 in (0 on the grid path) + 32 out (mean, var, l, u) + 1 (S).  See DESIGN.md section 3.
-#include "posterior_core.cuh"
+#include "posterior_ws.cuh"
+#include <cstdlib>
 
 namespace {
-
-__device__ __forceinline__ int pick4(int r0, int r1, int r2, int r3, int i) {
-    return i == 0 ? r0 : (i == 1 ? r1 : (i == 2 ? r2 : r3));
-}
 
 template <int BT>
 __device__ __forceinline__ void mma_phase(const PostParams& p, const double2* __restrict__ sK, double* __restrict__ sSS,
@@ -285,6 +282,65 @@ int launch_bt(so_handle* h, const PostParams& p, const LaunchPlan& lp, cudaStrea
     }
 }
 
+// ---- warp-specialised variant -------------------------------------------------------------------
+struct WsPlan { int BT, RG, CG, T, TB, npass, gpt, Rg; size_t smem; };
+
+int plan_ws(so_handle* h, const GPState& g, int64_t M, bool grid, WsPlan& wp) {
+    const int NB = g.NB;
+    if (NB >= 32) { wp.RG = 8; wp.CG = 1; }
+    else if (NB >= 16) { wp.RG = 4; wp.CG = 2; }
+    else if (NB >= 8) { wp.RG = 2; wp.CG = 4; }
+    else { wp.RG = 1; wp.CG = 8; }
+    wp.npass = (NB + 4 * wp.RG - 1) / (4 * wp.RG);
+    wp.gpt = (NB + kGroupK - 1) / kGroupK;
+    const size_t limit = (size_t)h->smem_optin;
+    const int min_groups = wp.npass > 1 ? wp.gpt : 2;
+    int BT = 8 / wp.CG;
+    auto fit = [&](int bt) {
+        int rg = wp.gpt + 2;
+        while (rg >= min_groups && ws_smem(NB, 8 * bt * wp.CG, g.d, wp.RG, rg, grid).total > limit) --rg;
+        return rg >= min_groups ? rg : 0;
+    };
+    while (BT >= 1 && fit(BT) == 0) BT >>= 1;
+    if (BT < 1) return so_fail(h, SO_ERR_CAPACITY, "posterior: N too large for the shared-memory ring");
+    while (BT > 1 && (M + 8 * BT * wp.CG - 1) / (8 * BT * wp.CG) < 2 * (int64_t)h->num_sms) BT >>= 1;
+    wp.BT = BT;
+    wp.T = 8 * BT * wp.CG;
+    wp.TB = BT * wp.CG;
+    wp.Rg = fit(BT);
+    wp.smem = ws_smem(NB, wp.T, g.d, wp.RG, wp.Rg, grid).total;
+    return SO_OK;
+}
+
+template <int BT, int KIND, bool GRID>
+int launch_ws_one(so_handle* h, const WsParams& wp, const WsPlan& pl, cudaStream_t stream) {
+    static int configured_for = -1;
+    if (configured_for != h->device) {
+        SO_CUDA(h, cudaFuncSetAttribute(k_posterior_ws<BT, KIND, GRID>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
+        configured_for = h->device;
+    }
+    const int grid = (int)(wp.p.ntiles < (int64_t)h->num_sms ? wp.p.ntiles : (int64_t)h->num_sms);
+    k_posterior_ws<BT, KIND, GRID><<<grid, kWsThreads, pl.smem, stream>>>(wp);
+    SO_CHECK_LAUNCH(h, "k_posterior_ws");
+    return SO_OK;
+}
+
+template <int KIND, bool GRID>
+int launch_ws_bt(so_handle* h, const WsParams& wp, const WsPlan& pl, cudaStream_t stream) {
+    switch (pl.BT) {
+        case 8: return launch_ws_one<8, KIND, GRID>(h, wp, pl, stream);
+        case 4: return launch_ws_one<4, KIND, GRID>(h, wp, pl, stream);
+        case 2: return launch_ws_one<2, KIND, GRID>(h, wp, pl, stream);
+        default: return launch_ws_one<1, KIND, GRID>(h, wp, pl, stream);
+    }
+}
+
+// SO_K2_VARIANT=bulk selects the bulk-synchronous kernel (kept for A/B measurements); default = warp-specialised.
+bool use_bulk_variant() {
+    const char* v = std::getenv("SO_K2_VARIANT");
+    return v && std::string(v) == "bulk";
+}
+
 int run_posterior(so_handle* h, int gp, const double* Xstar_d, bool grid, int64_t row0, int64_t M, double beta, double fmin,
                   double* mean_d, double* var_d, double* Q_d, int q_stride, int q_col, uint8_t* S_d, int safe_mode,
                   void* stream_) {
@@ -306,33 +362,46 @@ int run_posterior(so_handle* h, int gp, const double* Xstar_d, bool grid, int64_
         return so_fail(h, SO_ERR_BAD_ARG, "posterior_rows: null candidate pointer");
     }
     DeviceGuard guard(h->device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const bool bulk = use_bulk_variant();
     LaunchPlan lp;
-    int rc = plan_launch(h, g, M, grid, lp);
+    WsPlan pl;
+    int rc = bulk ? plan_launch(h, g, M, grid, lp) : plan_ws(h, g, M, grid, pl);
     if (rc) return rc;
-    PostParams p;
-    p.N = g.N; p.NB = g.NB; p.d = g.d; p.RG = lp.RG; p.CG = lp.CG; p.T = lp.T; p.TB = lp.TB; p.npass = lp.npass;
-    p.kind = g.kind;
+    WsParams wp;
+    PostParams& p = wp.p;
+    p.N = g.N; p.NB = g.NB; p.d = g.d; p.kind = g.kind;
+    if (bulk) { p.RG = lp.RG; p.CG = lp.CG; p.T = lp.T; p.TB = lp.TB; p.npass = lp.npass; }
+    else { p.RG = pl.RG; p.CG = pl.CG; p.T = pl.T; p.TB = pl.TB; p.npass = pl.npass; }
     p.Afrag = g.Afrag; p.alpha = g.alpha; p.Xs = g.Xs;
     for (int j = 0; j < SO_MAX_DIM; ++j) p.inv_ls[j] = g.inv_ls[j];
     p.variance = g.variance;
-    p.Xstar = Xstar_d; p.M = M; p.row0 = row0; p.ntiles = (M + lp.T - 1) / lp.T;
+    p.Xstar = Xstar_d; p.M = M; p.row0 = row0; p.ntiles = (M + p.T - 1) / p.T;
     p.gd = 0; p.E = g.E;
+    for (int j = 0; j < kGridMaxDim; ++j) { p.gn[j] = 1; p.goff[j] = 0; p.gstride[j] = 1; }
     if (grid) {
         p.gd = h->grid.d;
-        for (int j = 0; j < kGridMaxDim; ++j) {
-            p.gn[j] = j < p.gd ? h->grid.n[j] : 1;
-            p.goff[j] = j < p.gd ? h->grid.off[j] : 0;
-            p.gstride[j] = j < p.gd ? h->grid.stride[j] : 1;
-        }
+        for (int j = 0; j < p.gd; ++j) { p.gn[j] = h->grid.n[j]; p.goff[j] = h->grid.off[j]; p.gstride[j] = h->grid.stride[j]; }
     }
     p.beta = beta; p.fmin = fmin;
     p.mean = mean_d; p.var = var_d; p.Q = Q_d; p.q_stride = q_stride; p.q_col = q_col; p.S = S_d; p.safe_mode = safe_mode;
-    cudaStream_t stream = (cudaStream_t)stream_;
-    if (grid) return launch_bt<SO_KERNEL_RBF, true>(h, p, lp, stream);
+    if (bulk) {
+        if (grid) return launch_bt<SO_KERNEL_RBF, true>(h, p, lp, stream);
+        switch (g.kind) {
+            case SO_KERNEL_RBF: return launch_bt<SO_KERNEL_RBF, false>(h, p, lp, stream);
+            case SO_KERNEL_MATERN32: return launch_bt<SO_KERNEL_MATERN32, false>(h, p, lp, stream);
+            default: return launch_bt<SO_KERNEL_MATERN52, false>(h, p, lp, stream);
+        }
+    }
+    wp.gpt = pl.gpt; wp.Rg = pl.Rg;
+    wp.fast_rows = h->grid.fast_rows;
+    wp.Pfast = g.P2;
+    wp.Pslow = g.P2 ? g.P2 + (size_t)h->grid.fast_rows * 8 * g.NB : nullptr;
+    if (grid) return launch_ws_bt<SO_KERNEL_RBF, true>(h, wp, pl, stream);
     switch (g.kind) {
-        case SO_KERNEL_RBF: return launch_bt<SO_KERNEL_RBF, false>(h, p, lp, stream);
-        case SO_KERNEL_MATERN32: return launch_bt<SO_KERNEL_MATERN32, false>(h, p, lp, stream);
-        default: return launch_bt<SO_KERNEL_MATERN52, false>(h, p, lp, stream);
+        case SO_KERNEL_RBF: return launch_ws_bt<SO_KERNEL_RBF, false>(h, wp, pl, stream);
+        case SO_KERNEL_MATERN32: return launch_ws_bt<SO_KERNEL_MATERN32, false>(h, wp, pl, stream);
+        default: return launch_ws_bt<SO_KERNEL_MATERN52, false>(h, wp, pl, stream);
     }
 }
 
@@ -407,6 +476,22 @@ extern "C" int so_grid_define(so_handle* h, int d, const int32_t* n_h, const dou
         for (int i = 0; i < n_h[j]; ++i) axis_of[gs.off[j] + i] = j;
     SO_CUDA(h, cudaMemcpyAsync(reinterpret_cast<int*>(gs.axis + gs.cap), axis_of.data(), sizeof(int) * total, cudaMemcpyHostToDevice, stream));
     SO_CUDA(h, cudaStreamSynchronize(stream));
+    // product-table split: the fast group is the longest low-order suffix of the row order with <= 4096 rows
+    {
+        int order[SO_MAX_DIM];      // slowest ... fastest
+        if (d == 1) order[0] = 0;
+        else { order[0] = 1; order[1] = 0; for (int j = 2; j < d; ++j) order[j] = j; }
+        for (int j = 0; j < d; ++j) gs.in_fast[j] = 0;
+        int64_t fr = 1;
+        for (int k = d - 1; k >= 0; --k) {
+            const int j = order[k];
+            if (k != d - 1 && fr * n_h[j] > 4096) break;
+            fr *= n_h[j];
+            gs.in_fast[j] = 1;
+        }
+        gs.fast_rows = fr;
+        gs.slow_rows = rows / fr;
+    }
     gs.d = d; gs.total = total; gs.rows = rows; gs.defined = true;
     for (auto& g : h->gps) g.grid_ready = false;
     return SO_OK;
@@ -437,6 +522,33 @@ extern "C" int so_grid_prepare(so_handle* h, int gp, void* stream_) {
     k_grid_tables<<<grd, 128, 0, stream>>>(gs.axis, g.Xs, g.E, gs.total, g.N, Npad, g.d,
                                            reinterpret_cast<const int*>(gs.axis + gs.cap), g.variance, inv_ls_d);
     SO_CHECK_LAUNCH(h, "k_grid_tables");
+    {
+        const int64_t trows = gs.fast_rows + gs.slow_rows;
+        const size_t need2 = (size_t)trows * Npad;
+        if (need2 * sizeof(double) > ((size_t)4 << 30))
+            return so_fail(h, SO_ERR_CAPACITY, "so_grid_prepare: product tables would exceed 4 GiB; use explicit rows");
+        if (need2 > g.capP2) {
+            SO_CUDA(h, cudaStreamSynchronize(stream));
+            if (g.P2) cudaFree(g.P2);
+            g.P2 = nullptr;
+            const size_t cap2 = (size_t)trows * g.capN;
+            SO_CUDA(h, cudaMalloc(&g.P2, sizeof(double) * cap2));
+            g.capP2 = cap2;
+        }
+        TableSpec ts;
+        ts.d = gs.d;
+        for (int j = 0; j < kGridMaxDim; ++j) {
+            ts.n[j] = j < gs.d ? gs.n[j] : 1;
+            ts.off[j] = j < gs.d ? gs.off[j] : 0;
+            ts.stride[j] = j < gs.d ? gs.stride[j] : 1;
+            ts.in_fast[j] = j < gs.d ? gs.in_fast[j] : 0;
+        }
+        ts.fast_rows = gs.fast_rows; ts.slow_rows = gs.slow_rows;
+        if (trows > 2147483647) return so_fail(h, SO_ERR_CAPACITY, "so_grid_prepare: too many table rows");
+        k_grid_tables2<<<(unsigned)trows, 128, 0, stream>>>(ts, gs.axis, g.Xs, g.P2, g.P2 + (size_t)gs.fast_rows * Npad, g.N, Npad,
+                                                             g.d, g.variance, inv_ls_d);
+        SO_CHECK_LAUNCH(h, "k_grid_tables2");
+    }
     g.grid_ready = true;
     return SO_OK;
 }

@@ -155,6 +155,10 @@ __device__ __forceinline__ void mma_segment(double (&acc)[4][BT][2], double2 (&a
     }
 }
 
+__device__ __forceinline__ int pick4(int r0, int r1, int r2, int r3, int i) {
+    return i == 0 ? r0 : (i == 1 ? r1 : (i == 2 ? r2 : r3));
+}
+
 __device__ __forceinline__ void load_tile_rows(const PostParams& p, double* __restrict__ sXt, int64_t tile_local0) {
     const int d = p.d, T = p.T;
     for (int e = threadIdx.x; e < T * d; e += kThreads) {

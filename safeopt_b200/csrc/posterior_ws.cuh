@@ -1,0 +1,465 @@
+// K2, warp-specialised form.  One persistent 384-thread CTA per SM:
+//
+//   warps 0-3  (producers, 96 registers)  : build the k(x*, X) tile of the NEXT candidates k-block by
+//                                           k-block, straight into DMMA fragment order, in a shared-memory
+//                                           ring of "groups" (4 k-blocks = 32 training points x T rows);
+//                                           they also accumulate the mean k.alpha.
+//   warps 4-11 (consumers, 208 registers) : the triangular contraction V = L^-1 k on the fp64 tensor
+//                                           pipe (DMMA.8x8x4), column sums of squares, epilogue.
+//
+// Ring slots are handed over with mbarriers (full: 128 producer-lane arrivals, empty: 256 consumer-
+// lane arrivals), so the tensor pipe never waits for kernel-row generation and there is no CTA-wide
+// barrier in steady state (the r01 profile of the bulk-synchronous version showed 23% of the time in
+// the generation phase, profiles/r01_k_posterior_v1_ncu.txt).  Registers are re-split with setmaxnreg.
+//
+// Grid path: k(x*, x_n) = Pslow[row / F][n] * Pfast[row % F][n] with two product tables built once per
+// fit (k_grid_tables2): the F fastest-varying grid rows and the M/F slow combinations.  Two 16-byte
+// loads and two multiplies per pair of kernel values instead of two fp64 exp (~21 FMA slots each on the
+// one FP64 pipe DMMA also uses).
+#pragma once
+#include "posterior_core.cuh"
+
+namespace {
+
+constexpr int kWsThreads = 384;
+constexpr int kProducerWarps = 4;
+constexpr int kConsumerWarps = 8;
+constexpr int kGroupK = 4;            // k-blocks per ring slot
+
+struct WsParams {
+    PostParams p;
+    const double* Pfast;              // fast_rows x Npad
+    const double* Pslow;              // slow_rows x Npad (carries the signal variance)
+    int64_t fast_rows;
+    int gpt;                          // groups per tile = ceil(NB / 4)
+    int Rg;                           // ring depth in groups
+};
+
+struct WsSmem {
+    size_t ring_off, alpha_off, xs_off, xt_off, meanp_off, ss_off, bar_off, total;
+};
+
+__host__ __device__ inline WsSmem ws_smem(int NB, int T, int d, int RG, int Rg, bool grid) {
+    WsSmem L;
+    const size_t Npad = 8 * (size_t)NB;
+    L.ring_off = 0;
+    size_t off = (size_t)Rg * kGroupK * 8 * T * sizeof(double);
+    L.alpha_off = off; off += Npad * sizeof(double);
+    L.xs_off = off; off += grid ? 0 : Npad * d * sizeof(double);
+    L.xt_off = off; off += grid ? 0 : 2 * (size_t)T * d * sizeof(double);
+    L.meanp_off = off; off += 2 * (size_t)kProducerWarps * T * sizeof(double);
+    L.ss_off = off; off += 2 * (size_t)RG * T * sizeof(double);
+    L.bar_off = off; off += (2 * (size_t)Rg + 4) * sizeof(unsigned long long);
+    L.total = off;
+    return L;
+}
+
+// ---- mbarrier / register-split primitives (PTX; SASS: SYNCS.*, USETMAXREG) ----------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+template <int REGS> __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(REGS)); }
+template <int REGS> __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(REGS)); }
+__device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(threads) : "memory"); }
+
+// streaming 16-byte load that does not allocate in L1 (A fragments and fast-table rows are used once per tile per SM)
+__device__ __forceinline__ double2 ldg_stream(const double2* p) {
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+
+// ---------------------------------------------------------------- producer
+template <int KIND, bool GRID>
+__device__ __forceinline__ void ws_producer(const WsParams& wp, double2* sRing, const double* sAlpha, const double* sXs,
+                                            double* sXt, double* sMeanP, unsigned long long* full, unsigned long long* empty,
+                                            unsigned long long* meanfull, unsigned long long* meanempty, int pw, int lane) {
+    const PostParams& p = wp.p;
+    const int NB = p.NB, TB = p.TB, T = p.T, N = p.N, d = p.d, Npad = 8 * p.NB;
+    const int q = lane & 3, tl = lane >> 2;
+    const double2* sA2 = reinterpret_cast<const double2*>(sAlpha);
+    const int64_t last = p.row0 + p.M - 1;
+    const int ptid = pw * 32 + lane;
+    int pslot = 0;                 // ring position of the next group this producer fills
+    unsigned pwrap = 0;
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+        const int par = it & 1;
+        const int64_t tile_local0 = tile * T;
+        unsigned foff[8], soff[8];    // offsets (in double2) of this lane's fast / slow table rows
+        double m[8];
+#pragma unroll
+        for (int ct = 0; ct < 8; ++ct) { m[ct] = 0.0; foff[ct] = 0; soff[ct] = 0; }
+        if (GRID) {
+#pragma unroll
+            for (int ct = 0; ct < 8; ++ct) {
+                if (ct < TB) {
+                    int64_t row = p.row0 + tile_local0 + ct * 8 + tl;
+                    if (row > last) row = last;
+                    const int64_t si = row / wp.fast_rows, fi = row - si * wp.fast_rows;
+                    foff[ct] = (unsigned)(fi * (Npad / 2)) + q;
+                    soff[ct] = (unsigned)(si * (Npad / 2)) + q;
+                }
+            }
+        } else {
+            // stage the tile's candidate rows (scaled by 1/lengthscale); producers only
+            double* xt = sXt + (size_t)par * T * d;
+            for (int e = ptid; e < T * d; e += kProducerWarps * 32) {
+                const int t = e / d, j = e - t * d;
+                int64_t row = tile_local0 + t;
+                if (row >= p.M) row = p.M - 1;
+                xt[e] = p.Xstar[(size_t)row * d + j] * p.inv_ls[j];
+            }
+            named_bar_sync(2, kProducerWarps * 32);
+        }
+        const double* xt = sXt + (size_t)par * T * d;
+        for (int gi = 0; gi < wp.gpt; ++gi) {
+            const int slot = pslot;
+            mbar_wait(&empty[slot], (pwrap & 1u) ^ 1u);
+            if (++pslot == wp.Rg) { pslot = 0; ++pwrap; }
+            const int kb = gi * kGroupK + pw;
+            if (kb < NB) {
+                double2* dst = sRing + ((size_t)slot * kGroupK + pw) * TB * 32 + lane;
+                const double2 a = sA2[4 * kb + q];
+                if (GRID) {
+                    const double2* Pf = reinterpret_cast<const double2*>(wp.Pfast) + 4 * kb;
+                    const double2* Ps = reinterpret_cast<const double2*>(wp.Pslow) + 4 * kb;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        double2 vf[4], vs[4];
+#pragma unroll
+                        for (int c4 = 0; c4 < 4; ++c4) {
+                            const int ct = 4 * h + c4;
+                            if (ct < TB) { vf[c4] = ldg_stream(Pf + foff[ct]); vs[c4] = __ldg(Ps + soff[ct]); }
+                        }
+#pragma unroll
+                        for (int c4 = 0; c4 < 4; ++c4) {
+                            const int ct = 4 * h + c4;
+                            if (ct < TB) {
+                                double2 v;
+                                v.x = vf[c4].x * vs[c4].x;
+                                v.y = vf[c4].y * vs[c4].y;
+                                m[ct] = fma(v.x, a.x, m[ct]);
+                                m[ct] = fma(v.y, a.y, m[ct]);
+                                dst[ct * 32] = v;
+                            }
+                        }
+                    }
+                } else {
+                    const int n0 = 8 * kb + 2 * q;
+                    const double* x0 = sXs + (size_t)n0 * d;
+#pragma unroll
+                    for (int ct = 0; ct < 8; ++ct)
+                        if (ct < TB) {
+                            const double* xr = xt + (size_t)(ct * 8 + tl) * d;
+                            double r0 = 0.0, r1 = 0.0;
+                            for (int j = 0; j < d; ++j) {
+                                const double xv = xr[j];
+                                const double t0 = xv - x0[j], t1 = xv - x0[d + j];
+                                r0 = fma(t0, t0, r0);
+                                r1 = fma(t1, t1, r1);
+                            }
+                            double2 v;
+                            v.x = n0 < N ? kernel_of_r2<KIND>(r0, p.variance) : 0.0;
+                            v.y = n0 + 1 < N ? kernel_of_r2<KIND>(r1, p.variance) : 0.0;
+                            m[ct] = fma(v.x, a.x, m[ct]);
+                            m[ct] = fma(v.y, a.y, m[ct]);
+                            dst[ct * 32] = v;
+                        }
+                }
+            }
+            mbar_arrive(&full[slot]);
+        }
+        // partial means of this producer warp (its k-blocks only); the epilogue adds the four partials in order
+        mbar_wait(&meanempty[par], (((unsigned)(it >> 1)) & 1u) ^ 1u);
+#pragma unroll
+        for (int ct = 0; ct < 8; ++ct)
+            if (ct < TB) {
+                double v = m[ct];
+                v += __shfl_xor_sync(0xffffffffu, v, 1);
+                v += __shfl_xor_sync(0xffffffffu, v, 2);
+                if (q == 0) sMeanP[((size_t)par * kProducerWarps + pw) * T + ct * 8 + tl] = v;
+            }
+        mbar_arrive(&meanfull[par]);
+    }
+}
+
+// ---------------------------------------------------------------- consumer
+// 32-bit shared-memory addresses and 32-bit fragment offsets keep the scalar state of the contraction
+// loop small: the accumulators alone take 128 of the 208 registers.
+__device__ __forceinline__ void mbar_arrive_u32(unsigned bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_u32(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ double2 lds_f64x2(unsigned addr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+
+struct RingCursor {           // position of group 0 of the current tile in the ring
+    int slot0;
+    unsigned wrap0;
+    int Rg;
+    unsigned full0, empty0;   // shared addresses of full[0], empty[0]
+    unsigned ring0;           // shared address of the ring (+ this lane's fragment offset)
+    unsigned group_bytes, kb_bytes;
+    __device__ __forceinline__ void locate(int gi, int& slot, unsigned& parity) const {
+        int s = slot0 + gi;
+        unsigned w = wrap0;
+        while (s >= Rg) { s -= Rg; ++w; }
+        slot = s;
+        parity = w & 1u;
+    }
+};
+
+template <int BT, int FIRST>
+__device__ __forceinline__ void ws_segment(double (&acc)[4][BT][2], double2 (&a)[4], const double2* __restrict__ Afrag,
+                                           const unsigned (&abase)[4], const RingCursor& rc, int kb_lo, int kb_hi,
+                                           bool release, int NB, int& next_release) {
+    int slot = 0;
+    unsigned parity = 0;
+    for (int kb = kb_lo; kb <= kb_hi; ++kb) {
+        const int gi = kb >> 2;
+        if ((kb & 3) == 0 || kb == kb_lo) {
+            rc.locate(gi, slot, parity);
+            mbar_wait_u32(rc.full0 + 8u * slot, parity);
+        }
+        double2 an[4];
+#pragma unroll
+        for (int s = FIRST; s < 4; ++s) an[s] = ldg_stream(Afrag + abase[s] + (unsigned)(kb + 1) * 32u);
+        const unsigned bp = rc.ring0 + (unsigned)slot * rc.group_bytes + (unsigned)(kb & 3) * rc.kb_bytes;
+#pragma unroll
+        for (int c = 0; c < BT; ++c) {
+            const double2 b = lds_f64x2(bp + c * 512u);
+#pragma unroll
+            for (int s = FIRST; s < 4; ++s) {
+                dmma884(acc[s][c][0], acc[s][c][1], a[s].x, b.x);
+                dmma884(acc[s][c][0], acc[s][c][1], a[s].y, b.y);
+            }
+        }
+#pragma unroll
+        for (int s = FIRST; s < 4; ++s) a[s] = an[s];
+        if (release && ((kb & 3) == 3 || kb == NB - 1)) {
+            mbar_arrive_u32(rc.empty0 + 8u * slot);
+            next_release = gi + 1;
+        }
+    }
+}
+
+template <int BT>
+__device__ __forceinline__ void ws_consumer(const WsParams& wp, const double2* sRing, double* sMeanP, double* sSS,
+                                            unsigned long long* full, unsigned long long* empty, unsigned long long* meanfull,
+                                            unsigned long long* meanempty, int cw, int lane) {
+    const PostParams& p = wp.p;
+    const int RG = p.RG, NB = p.NB, T = p.T;
+    const int g = cw % RG, cg = cw / RG;
+    const double2* Afrag = p.Afrag + lane;
+    const int ctid = cw * 32 + lane;
+    RingCursor rc;
+    rc.Rg = wp.Rg;
+    rc.full0 = smem_u32(full);
+    rc.empty0 = smem_u32(empty);
+    rc.ring0 = smem_u32(sRing) + (unsigned)(cg * BT * 32 + lane) * 16u;
+    rc.kb_bytes = (unsigned)p.TB * 512u;
+    rc.group_bytes = rc.kb_bytes * kGroupK;
+    rc.slot0 = 0;
+    rc.wrap0 = 0;
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+        const int par = it & 1;
+        double* sSST = sSS + (size_t)par * RG * T;
+        int next_release = 0;
+        for (int pass = 0; pass < p.npass; ++pass) {
+            const bool release = pass == p.npass - 1;
+            const int base = 4 * RG * pass;
+            const int r0 = base + g, r1 = base + 2 * RG - 1 - g, r2 = base + 2 * RG + g, r3 = base + 4 * RG - 1 - g;
+            // rows are ascending; the ones beyond NB (inactive) form a suffix.  Slots are ordered by K extent,
+            // inactive slots (extent -1) first, so that "slots FIRST..3 active" holds in every segment.
+            const int na = (r0 < NB) + (r1 < NB) + (r2 < NB) + (r3 < NB);
+            int ext[4];
+            unsigned abase[4];
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                const int src = s - (4 - na);
+                const int r = src >= 0 ? pick4(r0, r1, r2, r3, src) : -1;
+                ext[s] = r;
+                abase[s] = r >= 0 ? (unsigned)(r * (r + 1) / 2) * 32u : 0u;
+            }
+            double acc[4][BT][2];
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+#pragma unroll
+                for (int c = 0; c < BT; ++c) { acc[s][c][0] = 0.0; acc[s][c][1] = 0.0; }
+            double2 a[4];
+#pragma unroll
+            for (int s = 0; s < 4; ++s) a[s] = ldg_stream(Afrag + abase[s]);
+            ws_segment<BT, 0>(acc, a, Afrag, abase, rc, 0, ext[0], release, NB, next_release);
+            ws_segment<BT, 1>(acc, a, Afrag, abase, rc, ext[0] + 1, ext[1], release, NB, next_release);
+            ws_segment<BT, 2>(acc, a, Afrag, abase, rc, ext[1] + 1, ext[2], release, NB, next_release);
+            ws_segment<BT, 3>(acc, a, Afrag, abase, rc, ext[2] + 1, ext[3], release, NB, next_release);
+            // column sums of squares of this pass: over the 4 slots, then over the 8 rows of a block
+            // (lane bits 2..4, fixed tree => deterministic); accumulated across passes in this warp's own
+            // shared-memory slots so that no registers stay live across the contraction loop
+#pragma unroll
+            for (int c = 0; c < BT; ++c) {
+                double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    s0 = fma(acc[s][c][0], acc[s][c][0], s0);
+                    s1 = fma(acc[s][c][1], acc[s][c][1], s1);
+                }
+#pragma unroll
+                for (int o = 4; o < 32; o <<= 1) {
+                    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+                    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                }
+                if (lane < 4) {
+                    double2* dst = reinterpret_cast<double2*>(sSST + (size_t)g * T + (cg * BT + c) * 8 + 2 * lane);
+                    if (pass == 0) *dst = make_double2(s0, s1);
+                    else { const double2 prev = *dst; *dst = make_double2(prev.x + s0, prev.y + s1); }
+                }
+            }
+        }
+        // groups this warp never touched in its last pass still have to be handed back
+        for (int gi = next_release; gi < wp.gpt; ++gi) {
+            int slot;
+            unsigned parity;
+            rc.locate(gi, slot, parity);
+            mbar_wait_u32(rc.full0 + 8u * slot, parity);
+            mbar_arrive_u32(rc.empty0 + 8u * slot);
+        }
+        // advance the ring cursor by one tile
+        rc.slot0 += wp.gpt;
+        while (rc.slot0 >= rc.Rg) { rc.slot0 -= rc.Rg; ++rc.wrap0; }
+        named_bar_sync(1, kConsumerWarps * 32);
+        if (ctid < T) {
+            mbar_wait(&meanfull[par], ((unsigned)(it >> 1)) & 1u);
+            const int64_t row = tile * T + ctid;
+            if (row < p.M) {
+                double sumsq = 0.0;
+                for (int gg = 0; gg < RG; ++gg) sumsq += sSST[(size_t)gg * T + ctid];
+                const double* mp = sMeanP + (size_t)par * kProducerWarps * T + ctid;
+                const double mu = ((mp[0] + mp[T]) + mp[2 * T]) + mp[3 * T];
+                double v = p.variance - sumsq;
+                v = v > SO_VAR_FLOOR ? v : SO_VAR_FLOOR;
+                const double sd = sqrt(v);
+                const double bs = __dmul_rn(p.beta, sd);
+                const double lo = __dsub_rn(mu, bs), up = __dadd_rn(mu, bs);
+                if (p.mean) p.mean[row] = mu;
+                if (p.var) p.var[row] = v;
+                if (p.Q) {
+                    double* qp = p.Q + (size_t)row * p.q_stride + p.q_col;
+                    if ((p.q_stride & 1) == 0 && (p.q_col & 1) == 0) *reinterpret_cast<double2*>(qp) = make_double2(lo, up);
+                    else { qp[0] = lo; qp[1] = up; }
+                }
+                if (p.safe_mode != SO_SAFE_NONE && p.S) {
+                    const uint8_t safe = lo > p.fmin ? 1 : 0;
+                    p.S[row] = p.safe_mode == SO_SAFE_WRITE ? safe : (uint8_t)(p.S[row] & safe);
+                }
+            }
+        }
+        mbar_arrive(&meanempty[par]);
+    }
+}
+
+template <int BT, int KIND, bool GRID>
+__global__ void __launch_bounds__(kWsThreads, 1) k_posterior_ws(const __grid_constant__ WsParams wp) {
+    const PostParams& p = wp.p;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const WsSmem L = ws_smem(p.NB, p.T, p.d, p.RG, wp.Rg, GRID);
+    double2* sRing = reinterpret_cast<double2*>(smem_raw + L.ring_off);
+    double* sAlpha = reinterpret_cast<double*>(smem_raw + L.alpha_off);
+    double* sXs = reinterpret_cast<double*>(smem_raw + L.xs_off);
+    double* sXt = reinterpret_cast<double*>(smem_raw + L.xt_off);
+    double* sMeanP = reinterpret_cast<double*>(smem_raw + L.meanp_off);
+    double* sSS = reinterpret_cast<double*>(smem_raw + L.ss_off);
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + L.bar_off);
+    unsigned long long* full = bars;
+    unsigned long long* empty = bars + wp.Rg;
+    unsigned long long* meanfull = bars + 2 * wp.Rg;
+    unsigned long long* meanempty = meanfull + 2;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int Npad = 8 * p.NB;
+
+    for (int i = threadIdx.x; i < Npad; i += kWsThreads) sAlpha[i] = p.alpha[i];
+    if (!GRID)
+        for (int i = threadIdx.x; i < Npad * p.d; i += kWsThreads) sXs[i] = p.Xs[i];
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < wp.Rg; ++s) {
+            mbar_init(&full[s], kProducerWarps * 32);
+            mbar_init(&empty[s], kConsumerWarps * 32);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&meanfull[s], kProducerWarps * 32);
+            mbar_init(&meanempty[s], kConsumerWarps * 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp < kProducerWarps) {
+        reg_dealloc<96>();
+        ws_producer<KIND, GRID>(wp, sRing, sAlpha, sXs, sXt, sMeanP, full, empty, meanfull, meanempty, warp, lane);
+    } else {
+        reg_alloc<208>();
+        ws_consumer<BT>(wp, sRing, sMeanP, sSS, full, empty, meanfull, meanempty, warp - kProducerWarps, lane);
+    }
+}
+
+// Product tables of the grid path.  Row r of the fast table is the product over the fast axes of
+// exp(-0.5 ((x_j - X_nj)/l_j)^2) for grid row r (< fast_rows); row s of the slow table the same over the
+// slow axes for grid row s * fast_rows, times the signal variance.  Padding columns n >= N are zero.
+struct TableSpec {
+    int d;
+    int n[kGridMaxDim];
+    int off[kGridMaxDim];
+    int64_t stride[kGridMaxDim];
+    int in_fast[kGridMaxDim];
+    int64_t fast_rows, slow_rows;
+};
+
+__global__ void k_grid_tables2(TableSpec ts, const double* __restrict__ axis, const double* __restrict__ Xs,
+                               double* __restrict__ Pfast, double* __restrict__ Pslow, int N, int Npad, int d,
+                               double variance, const double* __restrict__ inv_ls_d) {
+    const int64_t r = blockIdx.x;             // one table row per block
+    const bool fast = r < ts.fast_rows;
+    const int64_t tr = fast ? r : r - ts.fast_rows;
+    const int64_t grow = fast ? tr : tr * ts.fast_rows;
+    for (int n = threadIdx.x; n < Npad; n += blockDim.x) {
+        double v = 0.0;
+        if (n < N) {
+            v = fast ? 1.0 : variance;
+            for (int j = 0; j < ts.d; ++j) {
+                if ((ts.in_fast[j] != 0) != fast) continue;
+                const int idx = (int)((grow / ts.stride[j]) % ts.n[j]);
+                const double t = axis[ts.off[j] + idx] * inv_ls_d[j] - Xs[(size_t)n * d + j];
+                v *= exp(-0.5 * (t * t));
+            }
+        }
+        (fast ? Pfast : Pslow)[(size_t)tr * Npad + n] = v;
+    }
+}
+
+}  // namespace

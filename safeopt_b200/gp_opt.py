@@ -13,6 +13,7 @@ rows are sharded in contiguous blocks (distributed.shard_bounds), the fit is rec
 from __future__ import annotations
 
 import logging
+import os
 from collections.abc import Sequence
 from functools import partial
 from typing import List, Optional
@@ -219,7 +220,8 @@ class SafeOpt(GaussianProcessOptimization):
         m_local = self._row1 - self._row0
         self._grid_axes = None
         self._rows_d = None
-        if self.num_contexts == 0:
+        # SAFEOPT_B200_GRID_FAST_PATH=0 forces the explicit-rows kernels (tests / A-B measurements)
+        if self.num_contexts == 0 and os.environ.get("SAFEOPT_B200_GRID_FAST_PATH", "1") != "0":
             self._grid_axes = detect_grid(self.inputs)
         if self._grid_axes is not None:
             self._engine.define_grid(self._grid_axes)

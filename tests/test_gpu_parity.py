@@ -135,14 +135,12 @@ def test_grid_path_equals_rows_path(d, n, N):
 # ---------------------------------------------------------------- golden fixtures produced by the reference
 @pytest.mark.parametrize("explicit", [False, True])
 @pytest.mark.parametrize("name", GRID_CASES)
-def test_safeopt_matches_golden(name, explicit):
+def test_safeopt_matches_golden(name, explicit, monkeypatch):
     g = load_golden(name)
     n_rows = int(g["n_rows"])
     gps, grid, fmin = golden_problem(g, "gpu")
     if explicit:
-        grid = np.ascontiguousarray(grid)[:, :]
-        grid = grid + 0.0
-        grid.flat[0] = np.nextafter(grid.flat[0], -np.inf)       # no longer a bitwise product grid -> explicit-rows kernels
+        monkeypatch.setenv("SAFEOPT_B200_GRID_FAST_PATH", "0")       # explicit-rows kernels on the same parameter set
     opt = sb.SafeOpt(gps if len(gps) > 1 else gps[0], grid, fmin if len(fmin) > 1 else fmin[0], beta=float(g["beta"]),
                      threshold=float(g["threshold"]))
     assert (opt._grid_axes is None) == explicit
@@ -159,12 +157,10 @@ def test_safeopt_matches_golden(name, explicit):
     assert np.array_equal(opt.M, unpack_mask(g["M"], n_rows))
     assert np.array_equal(opt.G, unpack_mask(g["G"], n_rows))
     assert opt.last_query_row == int(g["row_next"])
-    if not explicit:
-        assert np.array_equal(x, g["x_next"])
+    assert np.array_equal(x, g["x_next"])
     mx = opt.get_maximum()
     assert abs(mx[1] - float(g["max_val"])) < tol
-    if not explicit:
-        assert np.array_equal(mx[0], g["max_x"])
+    assert np.array_equal(mx[0], g["max_x"])
     opt.optimize(ucb=True)
     assert opt.last_query_row == int(g["row_ucb"])
 
