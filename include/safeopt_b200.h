@@ -172,6 +172,13 @@ int so_expander_check(so_handle* h, int gp, const double* Xstar_d, int64_t row0,
                       const double* u_c_d, int B, double beta, double fmin,
                       uint8_t* flags_d, void* stream);
 
+/* Lipschitz variant of the expander test (the original SafeOpt rule), safeopt/gp_opt.py:558-576:
+ *   flag[b] |= any over rows with S==0 of (u_c[b] - lipschitz * ||x_c[b] - x||_2 >= fmin)
+ * Rows come from Xstar_d (M x d) or, if Xstar_d == NULL, from the defined grid (d is then ignored). */
+int so_expander_lipschitz(so_handle* h, const double* Xstar_d, int d, int64_t row0, int64_t M,
+                          const uint8_t* S_d, const double* xc_d, const double* u_c_d, int B,
+                          double lipschitz, double fmin, uint8_t* flags_d, void* stream);
+
 /* ------------------------------------------------------------------ K5/K6: swarm
  * so_swarm_fitness stands in for SafeOptSwarm._compute_particle_fitness
  * (safeopt/gp_opt.py:901-1013) given per-GP posterior planes mean_d/var_d laid out

@@ -34,12 +34,13 @@ def row_of(grid, x):
     return int(hit[0])
 
 
-def grid_case(ref, GPy, name, X, Y, kind, variance, ls, noise, bounds, n, fmin, beta, threshold, full_sets=False, explicit_jitter=False):
+def grid_case(ref, GPy, name, X, Y, kind, variance, ls, noise, bounds, n, fmin, beta, threshold, full_sets=False, lipschitz=None):
     d = X.shape[1]
     G = Y.shape[1]
     gps = [GPy.models.GPRegression(X, Y[:, [i]], kernel=kernel_of(GPy, kind, d, variance, ls), noise_var=noise) for i in range(G)]
     grid = ref.linearly_spaced_combinations(bounds, n)
-    opt = ref.SafeOpt(gps if G > 1 else gps[0], grid, fmin=list(fmin) if G > 1 else fmin[0], beta=beta, threshold=threshold)
+    opt = ref.SafeOpt(gps if G > 1 else gps[0], grid, fmin=list(fmin) if G > 1 else fmin[0], beta=beta, threshold=threshold,
+                      lipschitz=lipschitz)
     if full_sets:
         opt.update_confidence_intervals()
         opt.compute_sets(full_sets=True)
@@ -58,6 +59,7 @@ def grid_case(ref, GPy, name, X, Y, kind, variance, ls, noise, bounds, n, fmin, 
         os.path.join(OUT, name + ".npz"), X=X, Y=Y, kind=KINDS[kind], variance=variance, lengthscale=np.asarray(ls, dtype=float),
         noise_var=noise, bounds=np.asarray(bounds, dtype=float), num_samples=np.asarray(n if not np.isscalar(n) else [n] * d),
         fmin=np.asarray(fmin, dtype=float), beta=beta, threshold=threshold, full_sets=full_sets,
+        lipschitz=np.asarray([] if lipschitz is None else np.atleast_1d(lipschitz), dtype=float),
         Q=Q, S=np.packbits(S), M=np.packbits(M), G=np.packbits(Gm), n_rows=grid.shape[0],
         x_next=np.atleast_1d(x_next), row_next=row, max_x=np.atleast_1d(mx[0]), max_val=float(mx[1]),
         row_ucb=row_of(grid, np.atleast_1d(x_ucb)), margin_S=margin_S, margin_M=margin_M)
@@ -118,6 +120,34 @@ def swarm_case(ref, GPy, name):
     print("%-28s velocities %s" % (name, opt.optimal_velocities))
 
 
+def context_case(ref, GPy, name, lipschitz=None, threshold=5.0):
+    """examples/context_example.ipynb shape: 1 parameter + 1 context, product of RBF kernels on disjoint dims.
+    (With the GP-based expander test and candidates present the reference raises IndexError -- gp_opt.py:585-588
+    hands a 1-D x to _add_context; fixtures therefore use the Lipschitz rule or a threshold that leaves no candidates.)"""
+    rs = np.random.RandomState(21)
+    N = 12
+    X = np.hstack([rs.uniform(-1.0, 1.0, (N, 1)), rs.uniform(0.0, 1.0, (N, 1))])
+    f = np.exp(-X[:, 0] ** 2) * (1.0 + 0.5 * X[:, 1])
+    Y = (f + 0.02 * rs.randn(N))[:, None]
+    kern = GPy.kern.RBF(1, variance=2.0, lengthscale=0.7, active_dims=[0]) * GPy.kern.RBF(1, variance=1.5, lengthscale=2.0, active_dims=[1])
+    gp = GPy.models.GPRegression(X, Y, kernel=kern, noise_var=0.02 ** 2)
+    pset = ref.linearly_spaced_combinations([(-2.0, 2.0)], 300)
+    opt = ref.SafeOpt(gp, pset, fmin=0.2, num_contexts=1, beta=2.0, threshold=threshold, lipschitz=lipschitz)
+    out = {}
+    for k, ctx in enumerate([0.25, 0.9]):
+        x = opt.optimize(context=np.array([ctx]))
+        out["ctx%d" % k] = ctx
+        out["Q%d" % k] = opt.Q.copy()
+        out["S%d" % k], out["M%d" % k], out["G%d" % k] = np.packbits(opt.S), np.packbits(opt.M), np.packbits(opt.G)
+        out["x%d" % k] = np.atleast_1d(x)
+        mx = opt.get_maximum(context=np.array([ctx]))
+        out["maxx%d" % k], out["maxv%d" % k] = np.atleast_1d(mx[0]), float(mx[1])
+        print("%-28s ctx=%.2f |S|=%d |M|=%d |G|=%d x=%s" % (name, ctx, opt.S.sum(), opt.M.sum(), opt.G.sum(), x))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), X=X, Y=Y, pset=pset, fmin=0.2, beta=2.0, threshold=threshold,
+                        lipschitz=np.asarray([] if lipschitz is None else [lipschitz], dtype=float),
+                        var0=2.0, ls0=0.7, var1=1.5, ls1=2.0, noise_var=0.02 ** 2, n_rows=pset.shape[0], **out)
+
+
 def main():
     warnings.simplefilter("ignore")
     os.makedirs(OUT, exist_ok=True)
@@ -149,6 +179,14 @@ def main():
     grid_case(ref, GPy, "matern52_2d_g2", X, Y, "mat52", 2.0, [1.2, 0.7], 0.05 ** 2, [(-4.0, 4.0)] * 2, [31, 45], [-np.inf, 0.4], 2.0, 0.05)
     loop_case(ref, GPy, "bo_loop_2d")
     swarm_case(ref, GPy, "swarm_fitness_3d")
+    # Lipschitz expander rule (gp_opt.py:558-576) and contexts (gp_opt.py:424-451)
+    X, Y = synth(0, 40, 2, 1, 2.5)
+    grid_case(ref, GPy, "lipschitz_g1", X, Y, "rbf", 2.0, [1.0, 1.0], 0.05 ** 2, [(-5.0, 5.0)] * 2, 40, [0.5], 2.0, 0.05, lipschitz=2.0)
+    X, Y = synth(0, 40, 2, 2, 2.5)
+    grid_case(ref, GPy, "lipschitz_g2", X, Y, "rbf", 2.0, [1.0, 1.0], 0.05 ** 2, [(-5.0, 5.0)] * 2, 40, [0.5, 0.5], 2.0, 0.05,
+              lipschitz=[5.0, 0.1])
+    context_case(ref, GPy, "context_1p1c")
+    context_case(ref, GPy, "context_1p1c_lipschitz", lipschitz=1.5, threshold=0.05)
 
 
 if __name__ == "__main__":

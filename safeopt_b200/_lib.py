@@ -76,6 +76,7 @@ SIGNATURES = {
     "so_sets_maximizers": (_i, [_P, _P, _i, _i64, _i64, _P, _dbl, _P, _P, _P, _P]),
     "so_sets_candidates": (_i, [_P, _P, _i, _i64, _i64, _P, _P, _dbl, _P, _P, _P, _P, _P, _i64, _P, _P]),
     "so_expander_check": (_i, [_P, _i, _P, _i64, _i64, _P, _P, _P, _P, _P, _P, _P, _i, _dbl, _dbl, _P, _P]),
+    "so_expander_lipschitz": (_i, [_P, _P, _i, _i64, _i64, _P, _P, _P, _i, _dbl, _dbl, _P, _P]),
     "so_swarm_fitness": (_i, [_P, _i, _i, _i64, _P, _P, _dbl, _P, _P, _dbl, _P, _P, _P]),
     "so_swarm_step": (_i, [_P, _i64, _i, _P, _P, _P, _P, _P, _dbl, _P, _P, _P]),
     "so_swarm_update_best": (_i, [_P, _i64, _i, _P, _P, _P, _P, _P, _P, _P]),

@@ -1,10 +1,10 @@
 // K2, warp-specialised form.  One persistent 384-thread CTA per SM:
 //
-//   warps 0-3  (producers, 96 registers)  : build the k(x*, X) tile of the NEXT candidates k-block by
+//   warps 0-3  (producers, 104 registers) : build the k(x*, X) tile of the NEXT candidates k-block by
 //                                           k-block, straight into DMMA fragment order, in a shared-memory
 //                                           ring of "groups" (4 k-blocks = 32 training points x T rows);
 //                                           they also accumulate the mean k.alpha.
-//   warps 4-11 (consumers, 208 registers) : the triangular contraction V = L^-1 k on the fp64 tensor
+//   warps 4-11 (consumers, 200 registers) : the triangular contraction V = L^-1 k on the fp64 tensor
 //                                           pipe (DMMA.8x8x4), column sums of squares, epilogue.
 //
 // Ring slots are handed over with mbarriers (full: 128 producer-lane arrivals, empty: 256 consumer-
@@ -25,6 +25,14 @@ constexpr int kWsThreads = 384;
 constexpr int kProducerWarps = 4;
 constexpr int kConsumerWarps = 8;
 constexpr int kGroupK = 4;            // k-blocks per ring slot
+// setmaxnreg moves registers inside the pool the CTA was LAUNCHED with (384 threads x 168 registers = 64512),
+// not the whole SM file: 128 x producer + 256 x consumer must not exceed it or the last consumer warp
+// spins in USETMAXREG.TRY_ALLOC forever (that was the first version's hang with 96/208).
+constexpr int kLaunchRegs = 168;
+constexpr int kProducerRegs = 104;
+constexpr int kConsumerRegs = 200;
+static_assert(kProducerWarps * 32 * kProducerRegs + kConsumerWarps * 32 * kConsumerRegs <= kWsThreads * kLaunchRegs,
+              "register split exceeds the CTA's launch allocation");
 
 struct WsParams {
     PostParams p;
@@ -199,7 +207,7 @@ __device__ __forceinline__ void ws_producer(const WsParams& wp, double2* sRing, 
 
 // ---------------------------------------------------------------- consumer
 // 32-bit shared-memory addresses and 32-bit fragment offsets keep the scalar state of the contraction
-// loop small: the accumulators alone take 128 of the 208 registers.
+// loop small: the accumulators alone take 128 of the 200 registers.
 __device__ __forceinline__ void mbar_arrive_u32(unsigned bar) {
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(bar) : "memory");
 }
@@ -420,10 +428,10 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_posterior_ws(const __grid_con
     __syncthreads();
 
     if (warp < kProducerWarps) {
-        reg_dealloc<96>();
+        reg_dealloc<kProducerRegs>();
         ws_producer<KIND, GRID>(wp, sRing, sAlpha, sXs, sXt, sMeanP, full, empty, meanfull, meanempty, warp, lane);
     } else {
-        reg_alloc<208>();
+        reg_alloc<kConsumerRegs>();
         ws_consumer<BT>(wp, sRing, sMeanP, sSS, full, empty, meanfull, meanempty, warp - kProducerWarps, lane);
     }
 }

@@ -61,9 +61,28 @@ class Comm:
         import torch
         dev = self._tensor_device()
         t = torch.from_numpy(arr).to(dev)
-        out = [torch.empty_like(t) for _ in range(self.world)]
-        self._dist.all_gather(out, t)
-        return np.stack([o.cpu().numpy() for o in out], axis=0)
+        return self.all_gather_tensor(t).reshape((self.world,) + arr.shape)
+
+    def all_gather_tensor(self, t):
+        """Gather a (device) tensor from every rank with ONE collective and ONE copy to the host;
+        returns a NumPy array of shape (world, *t.shape).  Used for the 64-byte records the set
+        kernels leave in device memory, so a record costs gather + D2H instead of D2H + H2D + gather + D2H."""
+        if not self.active:
+            return t.cpu().numpy()[None, ...]
+        import torch
+        out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+        try:
+            self._dist.all_gather_into_tensor(out, t.contiguous())
+        except (RuntimeError, AttributeError, NotImplementedError):
+            parts = [torch.empty_like(t) for _ in range(self.world)]
+            self._dist.all_gather(parts, t.contiguous())
+            out = torch.stack(parts, dim=0)
+        return out.cpu().numpy()
+
+    def gather_records(self, rec_u8, dtype: np.dtype) -> np.ndarray:
+        """All ranks' copies of a device-resident record (uint8 tensor of dtype.itemsize bytes)."""
+        raw = self.all_gather_tensor(rec_u8)
+        return np.ascontiguousarray(raw).view(dtype).reshape(-1)
 
     def any_flags(self, flags: np.ndarray) -> np.ndarray:
         """Elementwise OR of uint8 flag arrays across ranks."""
@@ -88,22 +107,19 @@ def combine_max_first(values: np.ndarray, rows: np.ndarray) -> Tuple[float, int]
     return best_v, best_r
 
 
-def reduce_safe_records(comm: Comm, n_safe, max_l0, argmax_l0, max_u0, argmax_u0) -> dict:
-    """Combine the per-rank results of so_sets_reduce_safe into the global record
-    (gp_opt.py:504, :512, :634-636, :708-712): one all-gather of 40 bytes per rank."""
-    ints = comm.all_gather(np.array([n_safe, argmax_l0, argmax_u0], dtype=np.int64))
-    vals = comm.all_gather(np.array([max_l0, max_u0], dtype=np.float64))
-    best_l, row_l = combine_max_first(vals[:, 0], ints[:, 1])
-    best_u, row_u = combine_max_first(vals[:, 1], ints[:, 2])
-    return dict(n_safe=int(ints[:, 0].sum()), max_l0=best_l, argmax_l0=row_l, max_u0=best_u, argmax_u0=row_u)
+def reduce_safe_records(recs) -> dict:
+    """Combine the per-rank records of so_sets_reduce_safe (structured array, one entry per rank) into the
+    global one (gp_opt.py:504, :512, :634-636, :708-712); ties go to the lowest global row."""
+    best_l, row_l = combine_max_first(recs["max_l0"], recs["argmax_l0"])
+    best_u, row_u = combine_max_first(recs["max_u0"], recs["argmax_u0"])
+    return dict(n_safe=int(np.sum(recs["n_safe"])), max_l0=best_l, argmax_l0=row_l, max_u0=best_u, argmax_u0=row_u)
 
 
-def reduce_max_records(comm: Comm, n_max, max_width0, best_value, best_row, scaling0) -> dict:
-    """Combine the per-rank results of so_sets_maximizers (gp_opt.py:511-513, :642-644)."""
-    vals = comm.all_gather(np.array([max_width0, best_value], dtype=np.float64))
-    ints = comm.all_gather(np.array([n_max, best_row], dtype=np.int64))
-    value, row = combine_max_first(vals[:, 1], ints[:, 1])
-    return dict(n_max=int(ints[:, 0].sum()), max_var=float(np.max(vals[:, 0])) / scaling0, best_value=value, best_row=row)
+def reduce_max_records(recs, scaling0) -> dict:
+    """Combine the per-rank records of so_sets_maximizers (gp_opt.py:511-513, :642-644)."""
+    value, row = combine_max_first(recs["best_value"], recs["best_row"])
+    return dict(n_max=int(np.sum(recs["n_max"])), max_var=float(np.max(recs["max_width0"])) / scaling0, best_value=value,
+                best_row=row)
 
 
 def gather_ragged(comm: Comm, arr: np.ndarray) -> np.ndarray:

@@ -194,6 +194,12 @@ class DeviceEngine:
         self._check(rc, "so_expander_check")
         self.launches += 2 if M else 0
 
+    def expander_lipschitz(self, Xstar, d, row0, M, S, xc, u_c, lipschitz, fmin, flags):
+        rc = self.lib.so_expander_lipschitz(self.handle, _ptr(Xstar), int(d), int(row0), int(M), _ptr(S), _ptr(xc), _ptr(u_c),
+                                            xc.shape[0], float(lipschitz), float(fmin), _ptr(flags), self._stream())
+        self._check(rc, "so_expander_lipschitz")
+        self.launches += 1 if M else 0
+
     # ------------------------------------------------------------------ K5/K6
     def swarm_fitness(self, kind, n_gps, P, mean, var, beta, fmin, scaling, best_lower_bound, values, safe):
         fm, sc = _np_f64(fmin), _np_f64(scaling)

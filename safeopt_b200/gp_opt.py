@@ -386,9 +386,7 @@ class SafeOpt(GaussianProcessOptimization):
             self.update_confidence_intervals(context=self.context)
         eng = self._engine
         eng.reduce_safe(self._Q_d, len(self.gps), self._row0, self._S_d, self._rec_safe_d)
-        rec = eng.read_record(self._rec_safe_d, SAFE_REC_DTYPE)
-        self._safe_info = reduce_safe_records(self._comm, rec["n_safe"], rec["max_l0"], rec["argmax_l0"], rec["max_u0"],
-                                              rec["argmax_u0"])
+        self._safe_info = reduce_safe_records(self._comm.gather_records(self._rec_safe_d, SAFE_REC_DTYPE))
         self._invalidate_host("S")
 
     def compute_sets(self, full_sets=False):
@@ -407,9 +405,7 @@ class SafeOpt(GaussianProcessOptimization):
 
         eng.maximizers(self._Q_d, G, self._row0, self._S_d, self._safe_info["max_l0"], self.scaling, self._M_d,
                        self._rec_max_d)
-        rec = eng.read_record(self._rec_max_d, MAX_REC_DTYPE)
-        self._max_info = reduce_max_records(self._comm, rec["n_max"], rec["max_width0"], rec["best_value"], rec["best_row"],
-                                            self.scaling[0])
+        self._max_info = reduce_max_records(self._comm.gather_records(self._rec_max_d, MAX_REC_DTYPE), self.scaling[0])
         max_var = self._max_info["max_var"]
 
         m_local = self._row1 - self._row0
@@ -424,10 +420,13 @@ class SafeOpt(GaussianProcessOptimization):
         else:
             eng.candidates(self._Q_d, G, self._row0, self._S_d, self._M_d, max_var, self.scaling, thr, None,
                            self._cand_key_d, self._cand_row_d, self._n_cand_d)
-            n_local = int(self._n_cand_d.cpu().item())
+            counts = self._comm.all_gather_tensor(self._n_cand_d).reshape(-1)
+            n_local = int(counts[self._comm.rank])
             rows_local = self._cand_row_d[:n_local]
             keys_local = self._cand_key_d[:n_local]
-        n_total = int(self._comm.all_gather(np.array([rows_local.shape[0]], dtype=np.int64)).sum())
+        if full_sets:
+            counts = self._comm.all_gather(np.array([rows_local.shape[0]], dtype=np.int64)).reshape(-1)
+        n_total = int(counts.sum())
         self.last_trace = dict(max_l=self._safe_info["max_l0"], max_var=max_var, n_candidates=n_total)
         if n_total == 0:
             return
@@ -480,9 +479,6 @@ class SafeOpt(GaussianProcessOptimization):
         B = _lib.EXPANDER_MAX_BATCH
         visited = 0
         found: List[int] = []
-        if self.use_lipschitz:
-            raise NotImplementedError("the Lipschitz expander branch (gp_opt.py:558-576) is not built yet "
-                                      "(SURVEY.md section 8f-3); set lipschitz=None")
         for start in range(0, order.size, B):
             rows = order[start:start + B]
             nb = rows.size
@@ -494,6 +490,16 @@ class SafeOpt(GaussianProcessOptimization):
             xc_d = eng.to_device(xc)
             for i in constrained:
                 flags = eng.zeros((B,), "u8")
+                if self.use_lipschitz:
+                    # gp_opt.py:558-576: distance rule on the raw inputs, no GP arithmetic
+                    rows_arg = None if self._grid_axes is not None else self._rows_d
+                    eng.expander_lipschitz(rows_arg, xc.shape[1], self._row0, m_local, self._S_d, xc_d,
+                                           eng.to_device(q[:, 2 * i + 1]), self.liptschitz[i], self.fmin[i], flags)
+                    f = self._comm.any_flags(flags.cpu().numpy())[:nb].astype(bool)
+                    ok &= f
+                    if not ok.any() and not full_sets:
+                        break
+                    continue
                 rows_arg = None if self._use_grid_kernel(i) else self._ensure_rows_on_device()
                 eng.expander_check(i, rows_arg, self._row0, m_local, self._S_d, self._mean_d[i], self._var_d[i], xc_d,
                                    eng.to_device(mean[i]), eng.to_device(var[i]), eng.to_device(q[:, 2 * i + 1]),

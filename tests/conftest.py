@@ -24,7 +24,15 @@ def unpack_mask(packed, n):
 
 
 GRID_CASES = ["doctest_1d", "config_C1", "config_C2", "config_C3_n80", "config_C4_n10", "expander_g1", "expander_g2",
-              "expander_tight", "full_sets_g1", "matern32_3d", "matern52_2d_g2"]
+              "expander_tight", "full_sets_g1", "matern32_3d", "matern52_2d_g2", "lipschitz_g1", "lipschitz_g2"]
+
+
+def golden_lipschitz(g):
+    """Lipschitz constants of a grid fixture as the constructor argument (None if the GP rule is used)."""
+    lip = np.atleast_1d(g["lipschitz"]) if "lipschitz" in g.files else np.zeros(0)
+    if lip.size == 0:
+        return None
+    return [float(v) for v in lip] if lip.size > 1 else float(lip[0])
 
 
 def oracle_kernel(kind, d, variance, ls):

@@ -61,14 +61,20 @@ def _worker(rank, world, port, fixture, out_dir):
         r0, r1 = D.shard_bounds(n_rows, world, rank)
         Ql = Q[r0:r1]
         Sl = np.all(Ql[:, ::2] > fmin, axis=1)
-        safe = D.reduce_safe_records(comm, *_local_safe_record(Ql, Sl, r0))
+        from safeopt_b200.engine import MAX_REC_DTYPE, SAFE_REC_DTYPE
+        rec = np.zeros(1, dtype=SAFE_REC_DTYPE)
+        rec["n_safe"], rec["max_l0"], rec["argmax_l0"], rec["max_u0"], rec["argmax_u0"] = _local_safe_record(Ql, Sl, r0)
+        # the record travels as 64 raw bytes, exactly like the device-resident one
+        safe = D.reduce_safe_records(comm.gather_records(torch.from_numpy(rec.view(np.uint8).copy()), SAFE_REC_DTYPE))
         S_ref = unpack_mask(g["S"], n_rows)
         assert safe["n_safe"] == int(S_ref.sum())
         rows_ref = np.flatnonzero(S_ref)
         assert safe["max_l0"] == Q[S_ref, 0].max() and safe["argmax_l0"] == rows_ref[np.argmax(Q[S_ref, 0])]
         assert safe["argmax_u0"] == rows_ref[np.argmax(Q[S_ref, 1])] == int(g["row_ucb"])
         Ml, rec = _local_max_record(Ql, Sl, safe["max_l0"], scaling, r0)
-        mx = D.reduce_max_records(comm, *rec, scaling[0])
+        mrec = np.zeros(1, dtype=MAX_REC_DTYPE)
+        mrec["n_max"], mrec["max_width0"], mrec["best_value"], mrec["best_row"] = rec
+        mx = D.reduce_max_records(comm.gather_records(torch.from_numpy(mrec.view(np.uint8).copy()), MAX_REC_DTYPE), scaling[0])
         M_ref = unpack_mask(g["M"], n_rows)
         assert mx["n_max"] == int(M_ref.sum())
         assert mx["max_var"] == np.max(Q[M_ref, 1] - Q[M_ref, 0]) / scaling[0]
@@ -117,4 +123,8 @@ def test_single_rank_comm_is_identity():
     a = np.arange(6.0).reshape(2, 3)
     assert np.array_equal(comm.all_gather(a)[0], a)
     assert np.array_equal(D.gather_row_blocks(comm, a, 2), a)
-    assert D.reduce_safe_records(comm, 3, 1.5, 7, 2.5, 9) == dict(n_safe=3, max_l0=1.5, argmax_l0=7, max_u0=2.5, argmax_u0=9)
+    from safeopt_b200.engine import SAFE_REC_DTYPE
+    rec = np.zeros(1, dtype=SAFE_REC_DTYPE)
+    rec["n_safe"], rec["max_l0"], rec["argmax_l0"], rec["max_u0"], rec["argmax_u0"] = 3, 1.5, 7, 2.5, 9
+    got = D.reduce_safe_records(comm.gather_records(torch.from_numpy(rec.view(np.uint8).copy()), SAFE_REC_DTYPE))
+    assert got == dict(n_safe=3, max_l0=1.5, argmax_l0=7, max_u0=2.5, argmax_u0=9)

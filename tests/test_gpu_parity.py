@@ -7,7 +7,7 @@ Tolerances (fp64; SURVEY.md section 7, hard part 1): |d mean| <= 1e-11 * max|y|,
 import numpy as np
 import pytest
 
-from conftest import GRID_CASES, device_kernel, golden_problem, load_golden, oracle_kernel, unpack_mask
+from conftest import GRID_CASES, device_kernel, golden_lipschitz, golden_problem, load_golden, oracle_kernel, unpack_mask
 
 pytestmark = pytest.mark.gpu
 
@@ -142,7 +142,7 @@ def test_safeopt_matches_golden(name, explicit, monkeypatch):
     if explicit:
         monkeypatch.setenv("SAFEOPT_B200_GRID_FAST_PATH", "0")       # explicit-rows kernels on the same parameter set
     opt = sb.SafeOpt(gps if len(gps) > 1 else gps[0], grid, fmin if len(fmin) > 1 else fmin[0], beta=float(g["beta"]),
-                     threshold=float(g["threshold"]))
+                     threshold=float(g["threshold"]), lipschitz=golden_lipschitz(g))
     assert (opt._grid_axes is None) == explicit
     if bool(g["full_sets"]):
         opt.update_confidence_intervals()
@@ -163,6 +163,42 @@ def test_safeopt_matches_golden(name, explicit, monkeypatch):
     assert np.array_equal(mx[0], g["max_x"])
     opt.optimize(ucb=True)
     assert opt.last_query_row == int(g["row_ucb"])
+
+
+@pytest.mark.parametrize("name", ["context_1p1c", "context_1p1c_lipschitz"])
+def test_contexts_match_golden(name):
+    """Contexts (gp_opt.py:424-451) with a product of RBF kernels on disjoint dims (examples/context_example.ipynb)."""
+    g = load_golden(name)
+    kern = sb.RBF(1, variance=float(g["var0"]), lengthscale=float(g["ls0"]), active_dims=[0]) * \
+        sb.RBF(1, variance=float(g["var1"]), lengthscale=float(g["ls1"]), active_dims=[1])
+    gp = sb.GPRegression(g["X"], g["Y"], kernel=kern, noise_var=float(g["noise_var"]))
+    lip = g["lipschitz"]
+    opt = sb.SafeOpt(gp, g["pset"], float(g["fmin"]), num_contexts=1, beta=float(g["beta"]), threshold=float(g["threshold"]),
+                     lipschitz=None if lip.size == 0 else float(lip[0]))
+    n_rows = int(g["n_rows"])
+    with pytest.raises(ValueError):
+        opt.optimize()                                   # a context is required (gp_opt.py:448-450)
+    for k in range(2):
+        ctx = np.array([float(g["ctx%d" % k])])
+        x = opt.optimize(context=ctx)
+        assert np.abs(opt.Q - g["Q%d" % k]).max() < 1e-9 * 2 * np.sqrt(3.0)
+        assert np.array_equal(opt.S, unpack_mask(g["S%d" % k], n_rows))
+        assert np.array_equal(opt.M, unpack_mask(g["M%d" % k], n_rows))
+        assert np.array_equal(opt.G, unpack_mask(g["G%d" % k], n_rows))
+        assert np.array_equal(x, g["x%d" % k]) and x.shape == (1,)
+        assert np.array_equal(opt.context, ctx)
+        mx = opt.get_maximum(context=ctx)
+        assert np.array_equal(mx[0], g["maxx%d" % k]) and abs(mx[1] - float(g["maxv%d" % k])) < 1e-9
+    opt.add_new_data_point(x, np.array([[0.5]]), context=ctx)
+    assert opt.x.shape == (13, 2) and opt.x[-1, 1] == ctx[0]
+
+
+def test_use_lipschitz_switch():
+    gp = sb.GPRegression(np.array([[0.0]]), np.array([[1.0]]), noise_var=0.01 ** 2)
+    opt = sb.SafeOpt(gp, sb.linearly_spaced_combinations([(-1, 1)], 50), fmin=0.0)
+    assert opt.use_lipschitz is False
+    with pytest.raises(ValueError):
+        opt.use_lipschitz = True                          # gp_opt.py:403-407
 
 
 def test_bo_loop_matches_golden():

@@ -3,7 +3,7 @@ the reference's own package (build container only) and the committed golden fixt
 import numpy as np
 import pytest
 
-from conftest import GRID_CASES, golden_problem, load_golden, unpack_mask
+from conftest import GRID_CASES, golden_lipschitz, golden_problem, load_golden, unpack_mask
 from oracle import gpy_lite, safeopt_port as port
 
 
@@ -98,7 +98,8 @@ def test_port_reproduces_golden(name):
         pytest.skip("large fixture is covered by the GPU parity test")
     gps, grid, fmin = golden_problem(g, "cpu")
     beta, thr = float(g["beta"]), float(g["threshold"])
-    prob = port.GridProblem.create(gps, grid, fmin if len(fmin) > 1 else fmin[0], beta=beta, threshold=thr)
+    prob = port.GridProblem.create(gps, grid, fmin if len(fmin) > 1 else fmin[0], beta=beta, threshold=thr,
+                                   lipschitz=golden_lipschitz(g))
     if bool(g["full_sets"]):
         prob.Q = port.confidence_intervals(prob.gps, grid, beta)
         prob.S, prob.M, prob.G = port.compute_sets(prob.gps, grid, prob.Q, prob.fmin, beta, prob.scaling, thr, full_sets=True)
