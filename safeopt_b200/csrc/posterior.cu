@@ -312,26 +312,26 @@ int plan_ws(so_handle* h, const GPState& g, int64_t M, bool grid, WsPlan& wp) {
     return SO_OK;
 }
 
-template <int BT, int KIND, bool GRID>
+template <int BT, int KIND, int MODE>
 int launch_ws_one(so_handle* h, const WsParams& wp, const WsPlan& pl, cudaStream_t stream) {
     static int configured_for = -1;
     if (configured_for != h->device) {
-        SO_CUDA(h, cudaFuncSetAttribute(k_posterior_ws<BT, KIND, GRID>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
+        SO_CUDA(h, cudaFuncSetAttribute(k_posterior_ws<BT, KIND, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
         configured_for = h->device;
     }
     const int grid = (int)(wp.p.ntiles < (int64_t)h->num_sms ? wp.p.ntiles : (int64_t)h->num_sms);
-    k_posterior_ws<BT, KIND, GRID><<<grid, kWsThreads, pl.smem, stream>>>(wp);
+    k_posterior_ws<BT, KIND, MODE><<<grid, kWsThreads, pl.smem, stream>>>(wp);
     SO_CHECK_LAUNCH(h, "k_posterior_ws");
     return SO_OK;
 }
 
-template <int KIND, bool GRID>
+template <int KIND, int MODE>
 int launch_ws_bt(so_handle* h, const WsParams& wp, const WsPlan& pl, cudaStream_t stream) {
     switch (pl.BT) {
-        case 8: return launch_ws_one<8, KIND, GRID>(h, wp, pl, stream);
-        case 4: return launch_ws_one<4, KIND, GRID>(h, wp, pl, stream);
-        case 2: return launch_ws_one<2, KIND, GRID>(h, wp, pl, stream);
-        default: return launch_ws_one<1, KIND, GRID>(h, wp, pl, stream);
+        case 8: return launch_ws_one<8, KIND, MODE>(h, wp, pl, stream);
+        case 4: return launch_ws_one<4, KIND, MODE>(h, wp, pl, stream);
+        case 2: return launch_ws_one<2, KIND, MODE>(h, wp, pl, stream);
+        default: return launch_ws_one<1, KIND, MODE>(h, wp, pl, stream);
     }
 }
 
@@ -366,8 +366,11 @@ int run_posterior(so_handle* h, int gp, const double* Xstar_d, bool grid, int64_
     const bool bulk = use_bulk_variant();
     LaunchPlan lp;
     WsPlan pl;
-    int rc = bulk ? plan_launch(h, g, M, grid, lp) : plan_ws(h, g, M, grid, pl);
+    const bool tma = grid && !bulk && g.tma_ready && std::getenv("SO_K2_NO_TMA") == nullptr;
+    // the TMA-mode tables are laid out for one tile size, so the few-tiles heuristic is skipped there
+    int rc = bulk ? plan_launch(h, g, M, grid, lp) : plan_ws(h, g, tma ? (int64_t)1 << 60 : M, grid, pl);
     if (rc) return rc;
+    if (tma && pl.T != g.tma_T) return so_fail(h, SO_ERR_BAD_ARG, "posterior_grid: tile size differs from the prepared tables");
     WsParams wp;
     PostParams& p = wp.p;
     p.N = g.N; p.NB = g.NB; p.d = g.d; p.kind = g.kind;
@@ -397,11 +400,23 @@ int run_posterior(so_handle* h, int gp, const double* Xstar_d, bool grid, int64_
     wp.fast_rows = h->grid.fast_rows;
     wp.Pfast = g.P2;
     wp.Pslow = g.P2 ? g.P2 + (size_t)h->grid.fast_rows * 8 * g.NB : nullptr;
-    if (grid) return launch_ws_bt<SO_KERNEL_RBF, true>(h, wp, pl, stream);
+    wp.PfFrag = g.PfFrag; wp.Aprime = g.Aprime; wp.Wslow = g.Wslow; wp.a_stride = g.a_stride; wp.tpb = g.tma_tpb;
+    wp.first_tile = 0;
+    if (tma) {
+        // tiles are aligned to the slow blocks of the product grid: global tile = (row / F) * tpb + (row % F) / T
+        const int64_t F = h->grid.fast_rows;
+        const int64_t last_row = row0 + M - 1;
+        const int64_t t0 = (row0 / F) * g.tma_tpb + (row0 % F) / pl.T;
+        const int64_t t1 = (last_row / F) * g.tma_tpb + (last_row % F) / pl.T;
+        wp.first_tile = t0;
+        p.ntiles = t1 - t0 + 1;
+        return launch_ws_bt<SO_KERNEL_RBF, kModeTma>(h, wp, pl, stream);
+    }
+    if (grid) return launch_ws_bt<SO_KERNEL_RBF, kModeGrid>(h, wp, pl, stream);
     switch (g.kind) {
-        case SO_KERNEL_RBF: return launch_ws_bt<SO_KERNEL_RBF, false>(h, wp, pl, stream);
-        case SO_KERNEL_MATERN32: return launch_ws_bt<SO_KERNEL_MATERN32, false>(h, wp, pl, stream);
-        default: return launch_ws_bt<SO_KERNEL_MATERN52, false>(h, wp, pl, stream);
+        case SO_KERNEL_RBF: return launch_ws_bt<SO_KERNEL_RBF, kModeRows>(h, wp, pl, stream);
+        case SO_KERNEL_MATERN32: return launch_ws_bt<SO_KERNEL_MATERN32, kModeRows>(h, wp, pl, stream);
+        default: return launch_ws_bt<SO_KERNEL_MATERN52, kModeRows>(h, wp, pl, stream);
     }
 }
 
@@ -548,6 +563,54 @@ extern "C" int so_grid_prepare(so_handle* h, int gp, void* stream_) {
         k_grid_tables2<<<(unsigned)trows, 128, 0, stream>>>(ts, gs.axis, g.Xs, g.P2, g.P2 + (size_t)gs.fast_rows * Npad, g.N, Npad,
                                                              g.d, g.variance, inv_ls_d);
         SO_CHECK_LAUNCH(h, "k_grid_tables2");
+    }
+    // ---- TMA-mode tables (fragment-ordered fast table, scaled operands, Wslow)
+    g.tma_ready = false;
+    {
+        WsPlan pl;
+        if (plan_ws(h, g, (int64_t)1 << 60, true, pl) == SO_OK) {
+            const int T = pl.T, TB = pl.TB, gpt = pl.gpt;
+            const int tpb = (int)((gs.fast_rows + T - 1) / T);
+            const size_t pf_elems = (size_t)tpb * gpt * kGroupK * TB * 32;
+            const size_t a_stride = (tri_blocks(g.NB) + 1) * 32;
+            const size_t ap_elems = (size_t)gs.slow_rows * a_stride + 64;
+            const size_t w_elems = (size_t)gs.slow_rows * Npad;
+            const size_t limit = (size_t)8 << 30;       // 8 GiB of scaled operands at most, else kModeGrid
+            if (ap_elems * sizeof(double2) <= limit && gs.slow_rows <= 65535) {
+                if (pf_elems > g.capPfFrag) {
+                    SO_CUDA(h, cudaStreamSynchronize(stream));
+                    if (g.PfFrag) cudaFree(g.PfFrag);
+                    g.PfFrag = nullptr;
+                    SO_CUDA(h, cudaMalloc(&g.PfFrag, sizeof(double2) * pf_elems * 2));
+                    g.capPfFrag = pf_elems * 2;
+                }
+                if (ap_elems > g.capAprime) {
+                    SO_CUDA(h, cudaStreamSynchronize(stream));
+                    if (g.Aprime) cudaFree(g.Aprime);
+                    g.Aprime = nullptr;
+                    const size_t cap = ap_elems + ap_elems / 4;
+                    SO_CUDA(h, cudaMalloc(&g.Aprime, sizeof(double2) * cap));
+                    g.capAprime = cap;
+                }
+                if (w_elems > g.capWslow) {
+                    SO_CUDA(h, cudaStreamSynchronize(stream));
+                    if (g.Wslow) cudaFree(g.Wslow);
+                    g.Wslow = nullptr;
+                    SO_CUDA(h, cudaMalloc(&g.Wslow, sizeof(double) * w_elems * 2));
+                    g.capWslow = w_elems * 2;
+                }
+                const double* Pfast = g.P2;
+                const double* Pslow = g.P2 + (size_t)gs.fast_rows * Npad;
+                k_pffrag<<<(unsigned)((pf_elems + 255) / 256 < 4096 ? (pf_elems + 255) / 256 : 4096), 256, 0, stream>>>(
+                    Pfast, g.PfFrag, gs.fast_rows, g.N, Npad, T, TB, gpt, tpb);
+                SO_CHECK_LAUNCH(h, "k_pffrag");
+                dim3 grd((unsigned)((a_stride + 255) / 256), (unsigned)gs.slow_rows);
+                k_aprime<<<grd, 256, 0, stream>>>(g.Afrag, Pslow, g.alpha, g.Aprime, g.Wslow, g.NB, a_stride);
+                SO_CHECK_LAUNCH(h, "k_aprime");
+                SO_CUDA(h, cudaMemsetAsync(g.Aprime + (size_t)gs.slow_rows * a_stride, 0, sizeof(double2) * 64, stream));
+                g.a_stride = a_stride; g.tma_T = T; g.tma_tpb = tpb; g.tma_ready = true;
+            }
+        }
     }
     g.grid_ready = true;
     return SO_OK;

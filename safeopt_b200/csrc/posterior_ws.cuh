@@ -34,6 +34,18 @@ constexpr int kConsumerRegs = 200;
 static_assert(kProducerWarps * 32 * kProducerRegs + kConsumerWarps * 32 * kConsumerRegs <= kWsThreads * kLaunchRegs,
               "register split exceeds the CTA's launch allocation");
 
+// Producer modes.
+//   kModeRows : explicit candidate rows; producers evaluate the kernel (distance + exp / Matern profile).
+//   kModeGrid : product grid, producers multiply two table entries per kernel value (fallback when the
+//               scaled-operand tables of kModeTma would be too large).
+//   kModeTma  : product grid, NO fp64 work in tile generation: the slow-axis factor is folded into the A operand
+//               (A'(s) = L^-1 diag(Pslow[s]), one packed matrix per slow index, L2-resident), so the B tile is a
+//               contiguous 16 KB slice per group of the fragment-ordered fast table and one thread moves it with
+//               cp.async.bulk (TMA) straight into the ring; the producer warps only accumulate the mean from the
+//               ring.  Motivation: profiles/r01_k_posterior_ws_grid_ncu.txt -- with DMMA saturating the single
+//               FP64 pipe, producers that multiply were starved (math-throttle) and consumers waited 28% of the time.
+constexpr int kModeRows = 0, kModeGrid = 1, kModeTma = 2;
+
 struct WsParams {
     PostParams p;
     const double* Pfast;              // fast_rows x Npad
@@ -41,6 +53,13 @@ struct WsParams {
     int64_t fast_rows;
     int gpt;                          // groups per tile = ceil(NB / 4)
     int Rg;                           // ring depth in groups
+    // kModeTma
+    const double2* PfFrag;            // [tile-in-block][group][kb][col tile][lane], zero padded
+    const double2* Aprime;            // slow_rows packed scaled operands, a_stride double2 apart
+    const double* Wslow;              // slow_rows x Npad: Pslow[s][n] * alpha[n]
+    size_t a_stride;
+    int tpb;                          // tiles per slow block = ceil(fast_rows / T)
+    int64_t first_tile;               // global tile index of this shard's first tile
 };
 
 struct WsSmem {
@@ -82,6 +101,17 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 template <int REGS> __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(REGS)); }
 template <int REGS> __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(REGS)); }
 __device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(threads) : "memory"); }
+
+// TMA bulk copy global -> shared with byte-count completion on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}\n" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
 
 // streaming 16-byte load that does not allocate in L1 (A fragments and fast-table rows are used once per tile per SM)
 __device__ __forceinline__ double2 ldg_stream(const double2* p) {
@@ -205,6 +235,65 @@ __device__ __forceinline__ void ws_producer(const WsParams& wp, double2* sRing, 
     }
 }
 
+// ---------------------------------------------------------------- producer, kModeTma
+__device__ __forceinline__ void ws_producer_tma(const WsParams& wp, double2* sRing, double* sMeanP, unsigned long long* full,
+                                                unsigned long long* empty, unsigned long long* meanfull,
+                                                unsigned long long* meanempty, int pw, int lane) {
+    const PostParams& p = wp.p;
+    const int NB = p.NB, TB = p.TB, T = p.T, Npad = 8 * p.NB;
+    const int q = lane & 3, tl = lane >> 2;
+    const unsigned group_bytes = (unsigned)(kGroupK * TB * 512);
+    const size_t group_elems = (size_t)kGroupK * TB * 32;
+    int pslot = 0;
+    unsigned pwrap = 0;
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+        const int par = it & 1;
+        const int64_t gt = wp.first_tile + tile;
+        const int64_t si = gt / wp.tpb;
+        const int j = (int)(gt - si * wp.tpb);
+        const double2* w2 = reinterpret_cast<const double2*>(wp.Wslow + (size_t)si * Npad) + q;
+        const double2* src = wp.PfFrag + (size_t)j * wp.gpt * group_elems;
+        double m[8];
+#pragma unroll
+        for (int ct = 0; ct < 8; ++ct) m[ct] = 0.0;
+        for (int gi = 0; gi < wp.gpt; ++gi) {
+            const int slot = pslot;
+            const unsigned par_full = pwrap & 1u;
+            if (pw == 0 && lane == 0) {
+                mbar_wait(&empty[slot], par_full ^ 1u);
+                mbar_expect_tx(&full[slot], group_bytes);
+                tma_bulk_g2s(sRing + (size_t)slot * group_elems, src + (size_t)gi * group_elems, group_bytes, &full[slot]);
+            }
+            if (++pslot == wp.Rg) { pslot = 0; ++pwrap; }
+            const int kb = gi * kGroupK + pw;
+            mbar_wait(&full[slot], par_full);
+            if (kb < NB) {
+                const double2 wv = __ldg(w2 + 4 * kb);
+                const double2* srcs = sRing + ((size_t)slot * kGroupK + pw) * TB * 32 + lane;
+#pragma unroll
+                for (int ct = 0; ct < 8; ++ct)
+                    if (ct < TB) {
+                        const double2 v = srcs[ct * 32];
+                        m[ct] = fma(v.x, wv.x, m[ct]);
+                        m[ct] = fma(v.y, wv.y, m[ct]);
+                    }
+            }
+            mbar_arrive(&empty[slot]);
+        }
+        mbar_wait(&meanempty[par], (((unsigned)(it >> 1)) & 1u) ^ 1u);
+#pragma unroll
+        for (int ct = 0; ct < 8; ++ct)
+            if (ct < TB) {
+                double v = m[ct];
+                v += __shfl_xor_sync(0xffffffffu, v, 1);
+                v += __shfl_xor_sync(0xffffffffu, v, 2);
+                if (q == 0) sMeanP[((size_t)par * kProducerWarps + pw) * T + ct * 8 + tl] = v;
+            }
+        mbar_arrive(&meanfull[par]);
+    }
+}
+
 // ---------------------------------------------------------------- consumer
 // 32-bit shared-memory addresses and 32-bit fragment offsets keep the scalar state of the contraction
 // loop small: the accumulators alone take 128 of the 200 registers.
@@ -276,7 +365,7 @@ __device__ __forceinline__ void ws_segment(double (&acc)[4][BT][2], double2 (&a)
     }
 }
 
-template <int BT>
+template <int BT, bool TMA>
 __device__ __forceinline__ void ws_consumer(const WsParams& wp, const double2* sRing, double* sMeanP, double* sSS,
                                             unsigned long long* full, unsigned long long* empty, unsigned long long* meanfull,
                                             unsigned long long* meanempty, int cw, int lane) {
@@ -299,6 +388,17 @@ __device__ __forceinline__ void ws_consumer(const WsParams& wp, const double2* s
         const int par = it & 1;
         double* sSST = sSS + (size_t)par * RG * T;
         int next_release = 0;
+        int64_t tile_row0 = tile * T;         // local row of column 0 of this tile
+        int valid_cols = T;
+        if (TMA) {
+            const int64_t gt = wp.first_tile + tile;
+            const int64_t si = gt / wp.tpb;
+            const int j = (int)(gt - si * wp.tpb);
+            Afrag = wp.Aprime + (size_t)si * wp.a_stride + lane;
+            tile_row0 = si * wp.fast_rows + (int64_t)j * T - p.row0;
+            const int64_t left = wp.fast_rows - (int64_t)j * T;
+            valid_cols = left < T ? (int)left : T;
+        }
         for (int pass = 0; pass < p.npass; ++pass) {
             const bool release = pass == p.npass - 1;
             const int base = 4 * RG * pass;
@@ -364,8 +464,8 @@ __device__ __forceinline__ void ws_consumer(const WsParams& wp, const double2* s
         named_bar_sync(1, kConsumerWarps * 32);
         if (ctid < T) {
             mbar_wait(&meanfull[par], ((unsigned)(it >> 1)) & 1u);
-            const int64_t row = tile * T + ctid;
-            if (row < p.M) {
+            const int64_t row = tile_row0 + ctid;
+            if (ctid < valid_cols && row >= 0 && row < p.M) {
                 double sumsq = 0.0;
                 for (int gg = 0; gg < RG; ++gg) sumsq += sSST[(size_t)gg * T + ctid];
                 const double* mp = sMeanP + (size_t)par * kProducerWarps * T + ctid;
@@ -392,10 +492,12 @@ __device__ __forceinline__ void ws_consumer(const WsParams& wp, const double2* s
     }
 }
 
-template <int BT, int KIND, bool GRID>
+template <int BT, int KIND, int MODE>
 __global__ void __launch_bounds__(kWsThreads, 1) k_posterior_ws(const __grid_constant__ WsParams wp) {
+    constexpr bool GRID = MODE != kModeRows;
+    constexpr bool TMA = MODE == kModeTma;
     const PostParams& p = wp.p;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const WsSmem L = ws_smem(p.NB, p.T, p.d, p.RG, wp.Rg, GRID);
     double2* sRing = reinterpret_cast<double2*>(smem_raw + L.ring_off);
     double* sAlpha = reinterpret_cast<double*>(smem_raw + L.alpha_off);
@@ -416,8 +518,10 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_posterior_ws(const __grid_con
         for (int i = threadIdx.x; i < Npad * p.d; i += kWsThreads) sXs[i] = p.Xs[i];
     if (threadIdx.x == 0) {
         for (int s = 0; s < wp.Rg; ++s) {
-            mbar_init(&full[s], kProducerWarps * 32);
-            mbar_init(&empty[s], kConsumerWarps * 32);
+            // kModeTma: one expect_tx arrival + the TMA byte count complete `full`; the producer warps also read the
+            // slot (mean) and therefore take part in `empty`
+            mbar_init(&full[s], TMA ? 1 : kProducerWarps * 32);
+            mbar_init(&empty[s], TMA ? (kConsumerWarps + kProducerWarps) * 32 : kConsumerWarps * 32);
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&meanfull[s], kProducerWarps * 32);
@@ -429,10 +533,11 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_posterior_ws(const __grid_con
 
     if (warp < kProducerWarps) {
         reg_dealloc<kProducerRegs>();
-        ws_producer<KIND, GRID>(wp, sRing, sAlpha, sXs, sXt, sMeanP, full, empty, meanfull, meanempty, warp, lane);
+        if (TMA) ws_producer_tma(wp, sRing, sMeanP, full, empty, meanfull, meanempty, warp, lane);
+        else ws_producer<KIND, GRID>(wp, sRing, sAlpha, sXs, sXt, sMeanP, full, empty, meanfull, meanempty, warp, lane);
     } else {
         reg_alloc<kConsumerRegs>();
-        ws_consumer<BT>(wp, sRing, sMeanP, sSS, full, empty, meanfull, meanempty, warp - kProducerWarps, lane);
+        ws_consumer<BT, TMA>(wp, sRing, sMeanP, sSS, full, empty, meanfull, meanempty, warp - kProducerWarps, lane);
     }
 }
 
@@ -468,6 +573,59 @@ __global__ void k_grid_tables2(TableSpec ts, const double* __restrict__ axis, co
         }
         (fast ? Pfast : Pslow)[(size_t)tr * Npad + n] = v;
     }
+}
+
+// kModeTma tables.  PfFrag: the fast table re-ordered so that the 16 KB a ring slot needs for (tile j of a slow block,
+// group g) are contiguous: [j][g][kb in group][col tile][lane] double2, lane l -> rows j*T + 8ct + l/4, training
+// points 8kb + 2(l%4) + {0,1}; zero beyond fast_rows / N.
+__global__ void k_pffrag(const double* __restrict__ Pfast, double2* __restrict__ PfFrag, int64_t fast_rows, int N, int Npad,
+                         int T, int TB, int gpt, int tpb) {
+    const size_t total = (size_t)tpb * gpt * kGroupK * TB * 32;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int lane = (int)(e & 31);
+        size_t r = e >> 5;
+        const int ct = (int)(r % TB); r /= TB;
+        const int kbi = (int)(r % kGroupK); r /= kGroupK;
+        const int g = (int)(r % gpt);
+        const int j = (int)(r / gpt);
+        const int64_t row = (int64_t)j * T + ct * 8 + (lane >> 2);
+        const int n0 = 8 * (g * kGroupK + kbi) + 2 * (lane & 3);
+        double2 v = make_double2(0.0, 0.0);
+        if (row < fast_rows) {
+            if (n0 < N) v.x = Pfast[(size_t)row * Npad + n0];
+            if (n0 + 1 < N) v.y = Pfast[(size_t)row * Npad + n0 + 1];
+        }
+        PfFrag[e] = v;
+    }
+}
+
+// A'(s) = L^-1 diag(Pslow[s]) in the packed fragment order of Afrag, and Wslow[s] = Pslow[s] * alpha.
+__global__ void k_aprime(const double2* __restrict__ Afrag, const double* __restrict__ Pslow, const double* __restrict__ alpha,
+                         double2* __restrict__ Aprime, double* __restrict__ Wslow, int NB, size_t a_stride) {
+    const int64_t si = blockIdx.y;
+    const int Npad = 8 * NB;
+    const double* ps = Pslow + (size_t)si * Npad;
+    const size_t nfrag = tri_blocks(NB) * 32;
+    double2* dst = Aprime + (size_t)si * a_stride;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < a_stride; e += (size_t)gridDim.x * blockDim.x) {
+        double2 v = make_double2(0.0, 0.0);
+        if (e < nfrag) {
+            const size_t blk = e >> 5;
+            const int lane = (int)(e & 31);
+            // block index -> (i, kb) with blk = i(i+1)/2 + kb
+            int i = (int)((sqrt(8.0 * (double)blk + 1.0) - 1.0) * 0.5);
+            while ((size_t)(i + 1) * (i + 2) / 2 <= blk) ++i;
+            while ((size_t)i * (i + 1) / 2 > blk) --i;
+            const int kb = (int)(blk - (size_t)i * (i + 1) / 2);
+            const int c0 = 8 * kb + 2 * (lane & 3);
+            const double2 a = Afrag[e];
+            v.x = a.x * ps[c0];
+            v.y = a.y * ps[c0 + 1];
+        }
+        dst[e] = v;
+    }
+    if (blockIdx.x == 0)
+        for (int n = threadIdx.x; n < Npad; n += blockDim.x) Wslow[(size_t)si * Npad + n] = ps[n] * alpha[n];
 }
 
 }  // namespace
