@@ -283,15 +283,18 @@ int launch_bt(so_handle* h, const PostParams& p, const LaunchPlan& lp, cudaStrea
 }
 
 // ---- warp-specialised variant -------------------------------------------------------------------
-struct WsPlan { int BT, RG, CG, T, TB, npass, gpt, Rg; size_t smem; };
+struct WsPlan { int BT, RG, CG, T, TB, npass, gpt, Rg, CW; size_t smem; };
 
-int plan_ws(so_handle* h, const GPState& g, int64_t M, bool grid, WsPlan& wp) {
+int plan_ws(so_handle* h, const GPState& g, int64_t M, bool grid, WsPlan& wp, bool wide = false) {
     const int NB = g.NB;
-    if (NB >= 32) { wp.RG = 8; wp.CG = 1; }
+    // wide: 16 consumer warps x 2 block rows (TMA mode, NB >= 32); else 8 consumer warps x 4 block rows
+    wp.CW = (wide && NB >= 32) ? 16 : 8;
+    const int rows = wp.CW == 16 ? 2 : 4;
+    if (NB >= 32) { wp.RG = wp.CW; wp.CG = 1; }
     else if (NB >= 16) { wp.RG = 4; wp.CG = 2; }
     else if (NB >= 8) { wp.RG = 2; wp.CG = 4; }
     else { wp.RG = 1; wp.CG = 8; }
-    wp.npass = (NB + 4 * wp.RG - 1) / (4 * wp.RG);
+    wp.npass = (NB + rows * wp.RG - 1) / (rows * wp.RG);
     wp.gpt = (NB + kGroupK - 1) / kGroupK;
     const size_t limit = (size_t)h->smem_optin;
     const int min_groups = wp.npass > 1 ? wp.gpt : 2;
@@ -312,17 +315,23 @@ int plan_ws(so_handle* h, const GPState& g, int64_t M, bool grid, WsPlan& wp) {
     return SO_OK;
 }
 
-template <int BT, int KIND, int MODE>
-int launch_ws_one(so_handle* h, const WsParams& wp, const WsPlan& pl, cudaStream_t stream) {
+template <int BT, int KIND, int MODE, int CW>
+int launch_ws_cw(so_handle* h, const WsParams& wp, const WsPlan& pl, cudaStream_t stream) {
     static int configured_for = -1;
     if (configured_for != h->device) {
-        SO_CUDA(h, cudaFuncSetAttribute(k_posterior_ws<BT, KIND, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
+        SO_CUDA(h, cudaFuncSetAttribute(k_posterior_ws<BT, KIND, MODE, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
         configured_for = h->device;
     }
     const int grid = (int)(wp.p.ntiles < (int64_t)h->num_sms ? wp.p.ntiles : (int64_t)h->num_sms);
-    k_posterior_ws<BT, KIND, MODE><<<grid, kWsThreads, pl.smem, stream>>>(wp);
+    k_posterior_ws<BT, KIND, MODE, CW><<<grid, WsShape<CW>::kThreads, pl.smem, stream>>>(wp);
     SO_CHECK_LAUNCH(h, "k_posterior_ws");
     return SO_OK;
+}
+
+template <int BT, int KIND, int MODE>
+int launch_ws_one(so_handle* h, const WsParams& wp, const WsPlan& pl, cudaStream_t stream) {
+    if (MODE == kModeTma && BT == 8 && pl.CW == 16) return launch_ws_cw<BT, KIND, MODE, (MODE == kModeTma && BT == 8) ? 16 : 8>(h, wp, pl, stream);
+    return launch_ws_cw<BT, KIND, MODE, 8>(h, wp, pl, stream);
 }
 
 template <int KIND, int MODE>
@@ -368,7 +377,7 @@ int run_posterior(so_handle* h, int gp, const double* Xstar_d, bool grid, int64_
     WsPlan pl;
     const bool tma = grid && !bulk && g.tma_ready && std::getenv("SO_K2_NO_TMA") == nullptr;
     // the TMA-mode tables are laid out for one tile size, so the few-tiles heuristic is skipped there
-    int rc = bulk ? plan_launch(h, g, M, grid, lp) : plan_ws(h, g, tma ? (int64_t)1 << 60 : M, grid, pl);
+    int rc = bulk ? plan_launch(h, g, M, grid, lp) : plan_ws(h, g, tma ? (int64_t)1 << 60 : M, grid, pl, tma && std::getenv("SO_K2_NARROW") == nullptr);
     if (rc) return rc;
     if (tma && pl.T != g.tma_T) return so_fail(h, SO_ERR_BAD_ARG, "posterior_grid: tile size differs from the prepared tables");
     WsParams wp;
@@ -568,7 +577,7 @@ extern "C" int so_grid_prepare(so_handle* h, int gp, void* stream_) {
     g.tma_ready = false;
     {
         WsPlan pl;
-        if (plan_ws(h, g, (int64_t)1 << 60, true, pl) == SO_OK) {
+        if (plan_ws(h, g, (int64_t)1 << 60, true, pl, std::getenv("SO_K2_NARROW") == nullptr) == SO_OK) {
             const int T = pl.T, TB = pl.TB, gpt = pl.gpt;
             const int tpb = (int)((gs.fast_rows + T - 1) / T);
             const size_t pf_elems = (size_t)tpb * gpt * kGroupK * TB * 32;

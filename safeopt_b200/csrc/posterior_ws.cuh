@@ -21,18 +21,27 @@
 
 namespace {
 
-constexpr int kWsThreads = 384;
 constexpr int kProducerWarps = 4;
-constexpr int kConsumerWarps = 8;
 constexpr int kGroupK = 4;            // k-blocks per ring slot
-// setmaxnreg moves registers inside the pool the CTA was LAUNCHED with (384 threads x 168 registers = 64512),
-// not the whole SM file: 128 x producer + 256 x consumer must not exceed it or the last consumer warp
-// spins in USETMAXREG.TRY_ALLOC forever (that was the first version's hang with 96/208).
-constexpr int kLaunchRegs = 168;
-constexpr int kProducerRegs = 104;
-constexpr int kConsumerRegs = 200;
-static_assert(kProducerWarps * 32 * kProducerRegs + kConsumerWarps * 32 * kConsumerRegs <= kWsThreads * kLaunchRegs,
-              "register split exceeds the CTA's launch allocation");
+// Two shapes of the consumer side:
+//   CW = 8  consumer warps x 4 block rows x 8 column tiles (128 accumulator registers, 200 regs/thread) -- used when the
+//           producers need registers themselves (explicit rows / multiply mode) or N is small;
+//   CW = 16 consumer warps x 2 block rows x 8 column tiles (64 accumulator registers, 104 regs/thread) -- TMA mode: four
+//           consumer warps per SM sub-partition hide each other's non-DMMA time (A-fragment latency in the one- and
+//           two-row tail segments, loop control, reductions): the r01 profile of the 8-warp shape had every consumer warp
+//           outside the DMMA stream 44% of the time and the pipe 72% busy.
+// setmaxnreg moves registers inside the pool the CTA was LAUNCHED with (threads x launch registers), not the whole SM
+// file: 128 x producer + 32 CW x consumer must not exceed it or the last consumer warp spins in USETMAXREG.TRY_ALLOC
+// forever (that was the first version's hang with 96/208 on a 384 x 168 pool).
+template <int CW> struct WsShape;
+template <> struct WsShape<8> {
+    static constexpr int kThreads = 384, kLaunchRegs = 168, kProducerRegs = 104, kConsumerRegs = 200, kRows = 4;
+};
+template <> struct WsShape<16> {
+    static constexpr int kThreads = 640, kLaunchRegs = 96, kProducerRegs = 56, kConsumerRegs = 104, kRows = 2;
+};
+static_assert(128 * WsShape<8>::kProducerRegs + 256 * WsShape<8>::kConsumerRegs <= WsShape<8>::kThreads * WsShape<8>::kLaunchRegs, "");
+static_assert(128 * WsShape<16>::kProducerRegs + 512 * WsShape<16>::kConsumerRegs <= WsShape<16>::kThreads * WsShape<16>::kLaunchRegs, "");
 
 // Producer modes.
 //   kModeRows : explicit candidate rows; producers evaluate the kernel (distance + exp / Matern profile).
@@ -331,9 +340,9 @@ struct RingCursor {           // position of group 0 of the current tile in the 
     }
 };
 
-template <int BT, int FIRST>
-__device__ __forceinline__ void ws_segment(double (&acc)[4][BT][2], double2 (&a)[4], const double2* __restrict__ Afrag,
-                                           const unsigned (&abase)[4], const RingCursor& rc, int kb_lo, int kb_hi,
+template <int BT, int ROWS, int FIRST>
+__device__ __forceinline__ void ws_segment(double (&acc)[ROWS][BT][2], double2 (&a)[ROWS], const double2* __restrict__ Afrag,
+                                           const unsigned (&abase)[ROWS], const RingCursor& rc, int kb_lo, int kb_hi,
                                            bool release, int NB, int& next_release) {
     int slot = 0;
     unsigned parity = 0;
@@ -343,21 +352,21 @@ __device__ __forceinline__ void ws_segment(double (&acc)[4][BT][2], double2 (&a)
             rc.locate(gi, slot, parity);
             mbar_wait_u32(rc.full0 + 8u * slot, parity);
         }
-        double2 an[4];
+        double2 an[ROWS];
 #pragma unroll
-        for (int s = FIRST; s < 4; ++s) an[s] = ldg_stream(Afrag + abase[s] + (unsigned)(kb + 1) * 32u);
+        for (int s = FIRST; s < ROWS; ++s) an[s] = ldg_stream(Afrag + abase[s] + (unsigned)(kb + 1) * 32u);
         const unsigned bp = rc.ring0 + (unsigned)slot * rc.group_bytes + (unsigned)(kb & 3) * rc.kb_bytes;
 #pragma unroll
         for (int c = 0; c < BT; ++c) {
             const double2 b = lds_f64x2(bp + c * 512u);
 #pragma unroll
-            for (int s = FIRST; s < 4; ++s) {
+            for (int s = FIRST; s < ROWS; ++s) {
                 dmma884(acc[s][c][0], acc[s][c][1], a[s].x, b.x);
                 dmma884(acc[s][c][0], acc[s][c][1], a[s].y, b.y);
             }
         }
 #pragma unroll
-        for (int s = FIRST; s < 4; ++s) a[s] = an[s];
+        for (int s = FIRST; s < ROWS; ++s) a[s] = an[s];
         if (release && ((kb & 3) == 3 || kb == NB - 1)) {
             mbar_arrive_u32(rc.empty0 + 8u * slot);
             next_release = gi + 1;
@@ -365,7 +374,7 @@ __device__ __forceinline__ void ws_segment(double (&acc)[4][BT][2], double2 (&a)
     }
 }
 
-template <int BT, bool TMA>
+template <int BT, int CW, bool TMA>
 __device__ __forceinline__ void ws_consumer(const WsParams& wp, const double2* sRing, double* sMeanP, double* sSS,
                                             unsigned long long* full, unsigned long long* empty, unsigned long long* meanfull,
                                             unsigned long long* meanempty, int cw, int lane) {
@@ -401,32 +410,37 @@ __device__ __forceinline__ void ws_consumer(const WsParams& wp, const double2* s
         }
         for (int pass = 0; pass < p.npass; ++pass) {
             const bool release = pass == p.npass - 1;
-            const int base = 4 * RG * pass;
-            const int r0 = base + g, r1 = base + 2 * RG - 1 - g, r2 = base + 2 * RG + g, r3 = base + 4 * RG - 1 - g;
-            // rows are ascending; the ones beyond NB (inactive) form a suffix.  Slots are ordered by K extent,
-            // inactive slots (extent -1) first, so that "slots FIRST..3 active" holds in every segment.
+            constexpr int ROWS = WsShape<CW>::kRows;
+            const int base = ROWS * RG * pass;
+            // ROWS = 4: block rows {g, 2RG-1-g, 2RG+g, 4RG-1-g}; ROWS = 2: {g, 2RG-1-g} -- pairings that equalise the
+            // triangular work.  Rows are ascending; the ones beyond NB (inactive) form a suffix.  Slots are ordered by K
+            // extent, inactive slots (extent -1) first, so that "slots FIRST..ROWS-1 active" holds in every segment.
+            const int r0 = base + g, r1 = base + 2 * RG - 1 - g;
+            const int r2 = ROWS == 4 ? base + 2 * RG + g : (1 << 28), r3 = ROWS == 4 ? base + 4 * RG - 1 - g : (1 << 28);
             const int na = (r0 < NB) + (r1 < NB) + (r2 < NB) + (r3 < NB);
-            int ext[4];
-            unsigned abase[4];
+            int ext[ROWS];
+            unsigned abase[ROWS];
 #pragma unroll
-            for (int s = 0; s < 4; ++s) {
-                const int src = s - (4 - na);
+            for (int s = 0; s < ROWS; ++s) {
+                const int src = s - (ROWS - na);
                 const int r = src >= 0 ? pick4(r0, r1, r2, r3, src) : -1;
                 ext[s] = r;
                 abase[s] = r >= 0 ? (unsigned)(r * (r + 1) / 2) * 32u : 0u;
             }
-            double acc[4][BT][2];
+            double acc[ROWS][BT][2];
 #pragma unroll
-            for (int s = 0; s < 4; ++s)
+            for (int s = 0; s < ROWS; ++s)
 #pragma unroll
                 for (int c = 0; c < BT; ++c) { acc[s][c][0] = 0.0; acc[s][c][1] = 0.0; }
-            double2 a[4];
+            double2 a[ROWS];
 #pragma unroll
-            for (int s = 0; s < 4; ++s) a[s] = ldg_stream(Afrag + abase[s]);
-            ws_segment<BT, 0>(acc, a, Afrag, abase, rc, 0, ext[0], release, NB, next_release);
-            ws_segment<BT, 1>(acc, a, Afrag, abase, rc, ext[0] + 1, ext[1], release, NB, next_release);
-            ws_segment<BT, 2>(acc, a, Afrag, abase, rc, ext[1] + 1, ext[2], release, NB, next_release);
-            ws_segment<BT, 3>(acc, a, Afrag, abase, rc, ext[2] + 1, ext[3], release, NB, next_release);
+            for (int s = 0; s < ROWS; ++s) a[s] = ldg_stream(Afrag + abase[s]);
+            ws_segment<BT, ROWS, 0>(acc, a, Afrag, abase, rc, 0, ext[0], release, NB, next_release);
+            ws_segment<BT, ROWS, 1>(acc, a, Afrag, abase, rc, ext[0] + 1, ext[1], release, NB, next_release);
+            if (ROWS == 4) {
+                ws_segment<BT, ROWS, (ROWS == 4 ? 2 : 1)>(acc, a, Afrag, abase, rc, ext[1] + 1, ext[ROWS == 4 ? 2 : 1], release, NB, next_release);
+                ws_segment<BT, ROWS, (ROWS == 4 ? 3 : 1)>(acc, a, Afrag, abase, rc, ext[ROWS == 4 ? 2 : 1] + 1, ext[ROWS - 1], release, NB, next_release);
+            }
             // column sums of squares of this pass: over the 4 slots, then over the 8 rows of a block
             // (lane bits 2..4, fixed tree => deterministic); accumulated across passes in this warp's own
             // shared-memory slots so that no registers stay live across the contraction loop
@@ -434,7 +448,7 @@ __device__ __forceinline__ void ws_consumer(const WsParams& wp, const double2* s
             for (int c = 0; c < BT; ++c) {
                 double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-                for (int s = 0; s < 4; ++s) {
+                for (int s = 0; s < WsShape<CW>::kRows; ++s) {
                     s0 = fma(acc[s][c][0], acc[s][c][0], s0);
                     s1 = fma(acc[s][c][1], acc[s][c][1], s1);
                 }
@@ -461,7 +475,7 @@ __device__ __forceinline__ void ws_consumer(const WsParams& wp, const double2* s
         // advance the ring cursor by one tile
         rc.slot0 += wp.gpt;
         while (rc.slot0 >= rc.Rg) { rc.slot0 -= rc.Rg; ++rc.wrap0; }
-        named_bar_sync(1, kConsumerWarps * 32);
+        named_bar_sync(1, CW * 32);
         if (ctid < T) {
             mbar_wait(&meanfull[par], ((unsigned)(it >> 1)) & 1u);
             const int64_t row = tile_row0 + ctid;
@@ -492,8 +506,9 @@ __device__ __forceinline__ void ws_consumer(const WsParams& wp, const double2* s
     }
 }
 
-template <int BT, int KIND, int MODE>
-__global__ void __launch_bounds__(kWsThreads, 1) k_posterior_ws(const __grid_constant__ WsParams wp) {
+template <int BT, int KIND, int MODE, int CW>
+__global__ void __launch_bounds__(WsShape<CW>::kThreads, 1) k_posterior_ws(const __grid_constant__ WsParams wp) {
+    constexpr int kWsThreads = WsShape<CW>::kThreads;
     constexpr bool GRID = MODE != kModeRows;
     constexpr bool TMA = MODE == kModeTma;
     const PostParams& p = wp.p;
@@ -521,23 +536,23 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_posterior_ws(const __grid_con
             // kModeTma: one expect_tx arrival + the TMA byte count complete `full`; the producer warps also read the
             // slot (mean) and therefore take part in `empty`
             mbar_init(&full[s], TMA ? 1 : kProducerWarps * 32);
-            mbar_init(&empty[s], TMA ? (kConsumerWarps + kProducerWarps) * 32 : kConsumerWarps * 32);
+            mbar_init(&empty[s], TMA ? (CW + kProducerWarps) * 32 : CW * 32);
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&meanfull[s], kProducerWarps * 32);
-            mbar_init(&meanempty[s], kConsumerWarps * 32);
+            mbar_init(&meanempty[s], CW * 32);
         }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     __syncthreads();
 
     if (warp < kProducerWarps) {
-        reg_dealloc<kProducerRegs>();
+        reg_dealloc<WsShape<CW>::kProducerRegs>();
         if (TMA) ws_producer_tma(wp, sRing, sMeanP, full, empty, meanfull, meanempty, warp, lane);
         else ws_producer<KIND, GRID>(wp, sRing, sAlpha, sXs, sXt, sMeanP, full, empty, meanfull, meanempty, warp, lane);
     } else {
-        reg_alloc<kConsumerRegs>();
-        ws_consumer<BT, TMA>(wp, sRing, sMeanP, sSS, full, empty, meanfull, meanempty, warp - kProducerWarps, lane);
+        reg_alloc<WsShape<CW>::kConsumerRegs>();
+        ws_consumer<BT, CW, TMA>(wp, sRing, sMeanP, sSS, full, empty, meanfull, meanempty, warp - kProducerWarps, lane);
     }
 }
 
