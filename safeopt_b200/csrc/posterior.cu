@@ -285,7 +285,7 @@ int launch_bt(so_handle* h, const PostParams& p, const LaunchPlan& lp, cudaStrea
 // ---- warp-specialised variant -------------------------------------------------------------------
 struct WsPlan { int BT, RG, CG, T, TB, npass, gpt, Rg, CW; size_t smem; };
 
-int plan_ws(so_handle* h, const GPState& g, int64_t M, bool grid, WsPlan& wp, bool wide = false) {
+int plan_ws(so_handle* h, const GPState& g, int64_t M, bool grid, WsPlan& wp, bool wide = false, bool tma = false) {
     const int NB = g.NB;
     // wide: 16 consumer warps x 2 block rows (TMA mode, NB >= 32); else 8 consumer warps x 4 block rows
     wp.CW = (wide && NB >= 32) ? 16 : 8;
@@ -301,7 +301,7 @@ int plan_ws(so_handle* h, const GPState& g, int64_t M, bool grid, WsPlan& wp, bo
     int BT = 8 / wp.CG;
     auto fit = [&](int bt) {
         int rg = wp.gpt + 2;
-        while (rg >= min_groups && ws_smem(NB, 8 * bt * wp.CG, g.d, wp.RG, rg, grid).total > limit) --rg;
+        while (rg >= min_groups && ws_smem(NB, 8 * bt * wp.CG, g.d, wp.RG, rg, grid, tma).total > limit) --rg;
         return rg >= min_groups ? rg : 0;
     };
     while (BT >= 1 && fit(BT) == 0) BT >>= 1;
@@ -311,7 +311,7 @@ int plan_ws(so_handle* h, const GPState& g, int64_t M, bool grid, WsPlan& wp, bo
     wp.T = 8 * BT * wp.CG;
     wp.TB = BT * wp.CG;
     wp.Rg = fit(BT);
-    wp.smem = ws_smem(NB, wp.T, g.d, wp.RG, wp.Rg, grid).total;
+    wp.smem = ws_smem(NB, wp.T, g.d, wp.RG, wp.Rg, grid, tma).total;
     return SO_OK;
 }
 
@@ -377,7 +377,7 @@ int run_posterior(so_handle* h, int gp, const double* Xstar_d, bool grid, int64_
     WsPlan pl;
     const bool tma = grid && !bulk && g.tma_ready && std::getenv("SO_K2_NO_TMA") == nullptr;
     // the TMA-mode tables are laid out for one tile size, so the few-tiles heuristic is skipped there
-    int rc = bulk ? plan_launch(h, g, M, grid, lp) : plan_ws(h, g, tma ? (int64_t)1 << 60 : M, grid, pl, tma && std::getenv("SO_K2_NARROW") == nullptr);
+    int rc = bulk ? plan_launch(h, g, M, grid, lp) : plan_ws(h, g, tma ? (int64_t)1 << 60 : M, grid, pl, tma && std::getenv("SO_K2_NARROW") == nullptr, tma);
     if (rc) return rc;
     if (tma && pl.T != g.tma_T) return so_fail(h, SO_ERR_BAD_ARG, "posterior_grid: tile size differs from the prepared tables");
     WsParams wp;
@@ -577,7 +577,7 @@ extern "C" int so_grid_prepare(so_handle* h, int gp, void* stream_) {
     g.tma_ready = false;
     {
         WsPlan pl;
-        if (plan_ws(h, g, (int64_t)1 << 60, true, pl, std::getenv("SO_K2_NARROW") == nullptr) == SO_OK) {
+        if (plan_ws(h, g, (int64_t)1 << 60, true, pl, std::getenv("SO_K2_NARROW") == nullptr, true) == SO_OK) {
             const int T = pl.T, TB = pl.TB, gpt = pl.gpt;
             const int tpb = (int)((gs.fast_rows + T - 1) / T);
             const size_t pf_elems = (size_t)tpb * gpt * kGroupK * TB * 32;

@@ -75,7 +75,7 @@ struct WsSmem {
     size_t ring_off, alpha_off, xs_off, xt_off, meanp_off, ss_off, bar_off, total;
 };
 
-__host__ __device__ inline WsSmem ws_smem(int NB, int T, int d, int RG, int Rg, bool grid) {
+__host__ __device__ inline WsSmem ws_smem(int NB, int T, int d, int RG, int Rg, bool grid, bool tma = false) {
     WsSmem L;
     const size_t Npad = 8 * (size_t)NB;
     L.ring_off = 0;
@@ -83,7 +83,8 @@ __host__ __device__ inline WsSmem ws_smem(int NB, int T, int d, int RG, int Rg, 
     L.alpha_off = off; off += Npad * sizeof(double);
     L.xs_off = off; off += grid ? 0 : Npad * d * sizeof(double);
     L.xt_off = off; off += grid ? 0 : 2 * (size_t)T * d * sizeof(double);
-    L.meanp_off = off; off += 2 * (size_t)kProducerWarps * T * sizeof(double);
+    // mean partials: per producer warp (compute modes) or per k-block (TMA mode, written by the consumers)
+    L.meanp_off = off; off += 2 * (size_t)(tma ? NB : kProducerWarps) * T * sizeof(double);
     L.ss_off = off; off += 2 * (size_t)RG * T * sizeof(double);
     L.bar_off = off; off += (2 * (size_t)Rg + 4) * sizeof(unsigned long long);
     L.total = off;
@@ -244,62 +245,70 @@ __device__ __forceinline__ void ws_producer(const WsParams& wp, double2* sRing, 
     }
 }
 
-// ---------------------------------------------------------------- producer, kModeTma
-__device__ __forceinline__ void ws_producer_tma(const WsParams& wp, double2* sRing, double* sMeanP, unsigned long long* full,
-                                                unsigned long long* empty, unsigned long long* meanfull,
-                                                unsigned long long* meanempty, int pw, int lane) {
+// ---------------------------------------------------------------- producer group, kModeTma
+// warp 0 (one lane): walks the tiles ahead of the consumers and moves each 16 KB group of the fragment-ordered fast table
+// into the ring with one bulk copy.  warp 1: epilogue.  warps 2-3: idle (the register split needs a full warpgroup).
+__device__ __forceinline__ void ws_tma_issuer(const WsParams& wp, double2* sRing, unsigned long long* full, unsigned long long* empty) {
     const PostParams& p = wp.p;
-    const int NB = p.NB, TB = p.TB, T = p.T, Npad = 8 * p.NB;
-    const int q = lane & 3, tl = lane >> 2;
-    const unsigned group_bytes = (unsigned)(kGroupK * TB * 512);
-    const size_t group_elems = (size_t)kGroupK * TB * 32;
+    const unsigned group_bytes = (unsigned)(kGroupK * p.TB * 512);
+    const size_t group_elems = (size_t)kGroupK * p.TB * 32;
     int pslot = 0;
     unsigned pwrap = 0;
+    for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        const int64_t gt = wp.first_tile + tile;
+        const int j = (int)(gt % wp.tpb);
+        const double2* src = wp.PfFrag + (size_t)j * wp.gpt * group_elems;
+        for (int gi = 0; gi < wp.gpt; ++gi) {
+            mbar_wait(&empty[pslot], (pwrap & 1u) ^ 1u);
+            mbar_expect_tx(&full[pslot], group_bytes);
+            tma_bulk_g2s(sRing + (size_t)pslot * group_elems, src + (size_t)gi * group_elems, group_bytes, &full[pslot]);
+            if (++pslot == wp.Rg) { pslot = 0; ++pwrap; }
+        }
+    }
+}
+
+// Finalises a tile from the consumers' partials: |V|^2 summed over the RG row groups, mean summed over the NB k-blocks
+// (both in fixed order => bit-reproducible), then var, l/u (separate multiply and add roundings like NumPy) and the S bit.
+__device__ __forceinline__ void ws_epilogue_warp(const WsParams& wp, const double* sMeanK, const double* sSS,
+                                                 unsigned long long* tilefull, unsigned long long* tileempty, int lane) {
+    const PostParams& p = wp.p;
+    const int T = p.T, RG = p.RG, NB = p.NB;
     int it = 0;
     for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
         const int par = it & 1;
         const int64_t gt = wp.first_tile + tile;
         const int64_t si = gt / wp.tpb;
         const int j = (int)(gt - si * wp.tpb);
-        const double2* w2 = reinterpret_cast<const double2*>(wp.Wslow + (size_t)si * Npad) + q;
-        const double2* src = wp.PfFrag + (size_t)j * wp.gpt * group_elems;
-        double m[8];
-#pragma unroll
-        for (int ct = 0; ct < 8; ++ct) m[ct] = 0.0;
-        for (int gi = 0; gi < wp.gpt; ++gi) {
-            const int slot = pslot;
-            const unsigned par_full = pwrap & 1u;
-            if (pw == 0 && lane == 0) {
-                mbar_wait(&empty[slot], par_full ^ 1u);
-                mbar_expect_tx(&full[slot], group_bytes);
-                tma_bulk_g2s(sRing + (size_t)slot * group_elems, src + (size_t)gi * group_elems, group_bytes, &full[slot]);
+        const int64_t tile_row0 = si * wp.fast_rows + (int64_t)j * T - p.row0;
+        const int64_t left = wp.fast_rows - (int64_t)j * T;
+        const int valid_cols = left < T ? (int)left : T;
+        mbar_wait(&tilefull[par], ((unsigned)(it >> 1)) & 1u);
+        const double* ssp = sSS + (size_t)par * RG * T;
+        const double* mkp = sMeanK + (size_t)par * NB * T;
+        for (int t = lane; t < T; t += 32) {
+            const int64_t row = tile_row0 + t;
+            if (t >= valid_cols || row < 0 || row >= p.M) continue;
+            double sumsq = 0.0, mu = 0.0;
+            for (int g = 0; g < RG; ++g) sumsq += ssp[(size_t)g * T + t];
+            for (int kb = 0; kb < NB; ++kb) mu += mkp[(size_t)kb * T + t];
+            double v = p.variance - sumsq;
+            v = v > SO_VAR_FLOOR ? v : SO_VAR_FLOOR;
+            const double sd = sqrt(v);
+            const double bs = __dmul_rn(p.beta, sd);
+            const double lo = __dsub_rn(mu, bs), up = __dadd_rn(mu, bs);
+            if (p.mean) p.mean[row] = mu;
+            if (p.var) p.var[row] = v;
+            if (p.Q) {
+                double* qp = p.Q + (size_t)row * p.q_stride + p.q_col;
+                if ((p.q_stride & 1) == 0 && (p.q_col & 1) == 0) *reinterpret_cast<double2*>(qp) = make_double2(lo, up);
+                else { qp[0] = lo; qp[1] = up; }
             }
-            if (++pslot == wp.Rg) { pslot = 0; ++pwrap; }
-            const int kb = gi * kGroupK + pw;
-            mbar_wait(&full[slot], par_full);
-            if (kb < NB) {
-                const double2 wv = __ldg(w2 + 4 * kb);
-                const double2* srcs = sRing + ((size_t)slot * kGroupK + pw) * TB * 32 + lane;
-#pragma unroll
-                for (int ct = 0; ct < 8; ++ct)
-                    if (ct < TB) {
-                        const double2 v = srcs[ct * 32];
-                        m[ct] = fma(v.x, wv.x, m[ct]);
-                        m[ct] = fma(v.y, wv.y, m[ct]);
-                    }
+            if (p.safe_mode != SO_SAFE_NONE && p.S) {
+                const uint8_t safe = lo > p.fmin ? 1 : 0;
+                p.S[row] = p.safe_mode == SO_SAFE_WRITE ? safe : (uint8_t)(p.S[row] & safe);
             }
-            mbar_arrive(&empty[slot]);
         }
-        mbar_wait(&meanempty[par], (((unsigned)(it >> 1)) & 1u) ^ 1u);
-#pragma unroll
-        for (int ct = 0; ct < 8; ++ct)
-            if (ct < TB) {
-                double v = m[ct];
-                v += __shfl_xor_sync(0xffffffffu, v, 1);
-                v += __shfl_xor_sync(0xffffffffu, v, 2);
-                if (q == 0) sMeanP[((size_t)par * kProducerWarps + pw) * T + ct * 8 + tl] = v;
-            }
-        mbar_arrive(&meanfull[par]);
+        mbar_arrive(&tileempty[par]);
     }
 }
 
@@ -340,10 +349,16 @@ struct RingCursor {           // position of group 0 of the current tile in the 
     }
 };
 
-template <int BT, int ROWS, int FIRST>
+struct MeanSink {              // TMA mode: where a consumer warp leaves the mean contribution of its own k-blocks
+    const double2* w2;         // Wslow[s] as double2, + (lane & 3)
+    unsigned base;             // shared address of sMeanK[par][0][this warp's first column + lane/4]
+    unsigned kb_stride;        // bytes between k-blocks (T * 8)
+};
+
+template <int BT, int ROWS, int FIRST, bool MEAN>
 __device__ __forceinline__ void ws_segment(double (&acc)[ROWS][BT][2], double2 (&a)[ROWS], const double2* __restrict__ Afrag,
                                            const unsigned (&abase)[ROWS], const RingCursor& rc, int kb_lo, int kb_hi,
-                                           bool release, int NB, int& next_release) {
+                                           bool release, int NB, int& next_release, const MeanSink& ms, int lane) {
     int slot = 0;
     unsigned parity = 0;
     for (int kb = kb_lo; kb <= kb_hi; ++kb) {
@@ -367,6 +382,20 @@ __device__ __forceinline__ void ws_segment(double (&acc)[ROWS][BT][2], double2 (
         }
 #pragma unroll
         for (int s = FIRST; s < ROWS; ++s) a[s] = an[s];
+        if (MEAN && kb == kb_hi) {
+            // kb_hi is the block row that slot FIRST owns: every k-block index is owned by exactly one (warp, pass, slot),
+            // so the mean k.w is assembled from per-k-block partials without any cross-warp accumulation
+            const double2 wv = __ldg(ms.w2 + 4 * kb);
+#pragma unroll
+            for (int c = 0; c < BT; ++c) {
+                const double2 b = lds_f64x2(bp + c * 512u);
+                double v = fma(b.y, wv.y, b.x * wv.x);
+                v += __shfl_xor_sync(0xffffffffu, v, 1);
+                v += __shfl_xor_sync(0xffffffffu, v, 2);
+                if ((lane & 3) == 0)
+                    asm volatile("st.shared.f64 [%0], %1;\n" ::"r"(ms.base + (unsigned)kb * ms.kb_stride + c * 64u), "d"(v) : "memory");
+            }
+        }
         if (release && ((kb & 3) == 3 || kb == NB - 1)) {
             mbar_arrive_u32(rc.empty0 + 8u * slot);
             next_release = gi + 1;
@@ -399,6 +428,8 @@ __device__ __forceinline__ void ws_consumer(const WsParams& wp, const double2* s
         int next_release = 0;
         int64_t tile_row0 = tile * T;         // local row of column 0 of this tile
         int valid_cols = T;
+        MeanSink ms;
+        ms.w2 = nullptr; ms.base = 0; ms.kb_stride = 0;
         if (TMA) {
             const int64_t gt = wp.first_tile + tile;
             const int64_t si = gt / wp.tpb;
@@ -407,6 +438,11 @@ __device__ __forceinline__ void ws_consumer(const WsParams& wp, const double2* s
             tile_row0 = si * wp.fast_rows + (int64_t)j * T - p.row0;
             const int64_t left = wp.fast_rows - (int64_t)j * T;
             valid_cols = left < T ? (int)left : T;
+            // the epilogue warp must have consumed the buffers of tile it-2 before they are written again
+            mbar_wait(&meanempty[par], (((unsigned)(it >> 1)) & 1u) ^ 1u);
+            ms.w2 = reinterpret_cast<const double2*>(wp.Wslow + (size_t)si * 8 * NB) + (lane & 3);
+            ms.base = smem_u32(sMeanP + (size_t)par * NB * T + (size_t)(cg * BT) * 8 + (lane >> 2));
+            ms.kb_stride = (unsigned)T * 8u;
         }
         for (int pass = 0; pass < p.npass; ++pass) {
             const bool release = pass == p.npass - 1;
@@ -435,11 +471,11 @@ __device__ __forceinline__ void ws_consumer(const WsParams& wp, const double2* s
             double2 a[ROWS];
 #pragma unroll
             for (int s = 0; s < ROWS; ++s) a[s] = ldg_stream(Afrag + abase[s]);
-            ws_segment<BT, ROWS, 0>(acc, a, Afrag, abase, rc, 0, ext[0], release, NB, next_release);
-            ws_segment<BT, ROWS, 1>(acc, a, Afrag, abase, rc, ext[0] + 1, ext[1], release, NB, next_release);
+            ws_segment<BT, ROWS, 0, TMA>(acc, a, Afrag, abase, rc, 0, ext[0], release, NB, next_release, ms, lane);
+            ws_segment<BT, ROWS, 1, TMA>(acc, a, Afrag, abase, rc, ext[0] + 1, ext[1], release, NB, next_release, ms, lane);
             if (ROWS == 4) {
-                ws_segment<BT, ROWS, (ROWS == 4 ? 2 : 1)>(acc, a, Afrag, abase, rc, ext[1] + 1, ext[ROWS == 4 ? 2 : 1], release, NB, next_release);
-                ws_segment<BT, ROWS, (ROWS == 4 ? 3 : 1)>(acc, a, Afrag, abase, rc, ext[ROWS == 4 ? 2 : 1] + 1, ext[ROWS - 1], release, NB, next_release);
+                ws_segment<BT, ROWS, (ROWS == 4 ? 2 : 1), TMA>(acc, a, Afrag, abase, rc, ext[1] + 1, ext[ROWS == 4 ? 2 : 1], release, NB, next_release, ms, lane);
+                ws_segment<BT, ROWS, (ROWS == 4 ? 3 : 1), TMA>(acc, a, Afrag, abase, rc, ext[ROWS == 4 ? 2 : 1] + 1, ext[ROWS - 1], release, NB, next_release, ms, lane);
             }
             // column sums of squares of this pass: over the 4 slots, then over the 8 rows of a block
             // (lane bits 2..4, fixed tree => deterministic); accumulated across passes in this warp's own
@@ -475,6 +511,11 @@ __device__ __forceinline__ void ws_consumer(const WsParams& wp, const double2* s
         // advance the ring cursor by one tile
         rc.slot0 += wp.gpt;
         while (rc.slot0 >= rc.Rg) { rc.slot0 -= rc.Rg; ++rc.wrap0; }
+        if (TMA) {
+            // no consumer-side barrier or epilogue: hand the partial sums to the epilogue warp and move on
+            mbar_arrive(&meanfull[par]);
+            continue;
+        }
         named_bar_sync(1, CW * 32);
         if (ctid < T) {
             mbar_wait(&meanfull[par], ((unsigned)(it >> 1)) & 1u);
@@ -513,7 +554,7 @@ __global__ void __launch_bounds__(WsShape<CW>::kThreads, 1) k_posterior_ws(const
     constexpr bool TMA = MODE == kModeTma;
     const PostParams& p = wp.p;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const WsSmem L = ws_smem(p.NB, p.T, p.d, p.RG, wp.Rg, GRID);
+    const WsSmem L = ws_smem(p.NB, p.T, p.d, p.RG, wp.Rg, GRID, TMA);
     double2* sRing = reinterpret_cast<double2*>(smem_raw + L.ring_off);
     double* sAlpha = reinterpret_cast<double*>(smem_raw + L.alpha_off);
     double* sXs = reinterpret_cast<double*>(smem_raw + L.xs_off);
@@ -535,12 +576,15 @@ __global__ void __launch_bounds__(WsShape<CW>::kThreads, 1) k_posterior_ws(const
         for (int s = 0; s < wp.Rg; ++s) {
             // kModeTma: one expect_tx arrival + the TMA byte count complete `full`; the producer warps also read the
             // slot (mean) and therefore take part in `empty`
+            // kModeTma: one expect_tx arrival + the TMA byte count complete `full`
             mbar_init(&full[s], TMA ? 1 : kProducerWarps * 32);
-            mbar_init(&empty[s], TMA ? (CW + kProducerWarps) * 32 : CW * 32);
+            mbar_init(&empty[s], CW * 32);
         }
         for (int s = 0; s < 2; ++s) {
-            mbar_init(&meanfull[s], kProducerWarps * 32);
-            mbar_init(&meanempty[s], CW * 32);
+            // compute modes: producers publish the mean (meanfull), consumers hand the buffer back (meanempty);
+            // kModeTma: consumers publish their partials (tilefull = meanfull), the epilogue warp hands them back
+            mbar_init(&meanfull[s], TMA ? CW * 32 : kProducerWarps * 32);
+            mbar_init(&meanempty[s], TMA ? 32 : CW * 32);
         }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
@@ -548,8 +592,10 @@ __global__ void __launch_bounds__(WsShape<CW>::kThreads, 1) k_posterior_ws(const
 
     if (warp < kProducerWarps) {
         reg_dealloc<WsShape<CW>::kProducerRegs>();
-        if (TMA) ws_producer_tma(wp, sRing, sMeanP, full, empty, meanfull, meanempty, warp, lane);
-        else ws_producer<KIND, GRID>(wp, sRing, sAlpha, sXs, sXt, sMeanP, full, empty, meanfull, meanempty, warp, lane);
+        if (TMA) {
+            if (warp == 0 && lane == 0) ws_tma_issuer(wp, sRing, full, empty);
+            else if (warp == 1) ws_epilogue_warp(wp, sMeanP, sSS, meanfull, meanempty, lane);
+        } else ws_producer<KIND, GRID>(wp, sRing, sAlpha, sXs, sXt, sMeanP, full, empty, meanfull, meanempty, warp, lane);
     } else {
         reg_alloc<WsShape<CW>::kConsumerRegs>();
         ws_consumer<BT, CW, TMA>(wp, sRing, sMeanP, sSS, full, empty, meanfull, meanempty, warp - kProducerWarps, lane);
