@@ -83,8 +83,8 @@ __host__ __device__ inline WsSmem ws_smem(int NB, int T, int d, int RG, int Rg, 
     L.alpha_off = off; off += Npad * sizeof(double);
     L.xs_off = off; off += grid ? 0 : Npad * d * sizeof(double);
     L.xt_off = off; off += grid ? 0 : 2 * (size_t)T * d * sizeof(double);
-    // mean partials: per producer warp (compute modes) or per k-block (TMA mode, written by the consumers)
-    L.meanp_off = off; off += 2 * (size_t)(tma ? NB : kProducerWarps) * T * sizeof(double);
+    // mean partials: per producer warp (compute modes) or per consumer row group (TMA mode, written by the consumers)
+    L.meanp_off = off; off += 2 * (size_t)(tma ? RG : kProducerWarps) * T * sizeof(double);
     L.ss_off = off; off += 2 * (size_t)RG * T * sizeof(double);
     L.bar_off = off; off += (2 * (size_t)Rg + 4) * sizeof(unsigned long long);
     L.total = off;
@@ -247,7 +247,8 @@ __device__ __forceinline__ void ws_producer(const WsParams& wp, double2* sRing, 
 
 // ---------------------------------------------------------------- producer group, kModeTma
 // warp 0 (one lane): walks the tiles ahead of the consumers and moves each 16 KB group of the fragment-ordered fast table
-// into the ring with one bulk copy.  warp 1: epilogue.  warps 2-3: idle (the register split needs a full warpgroup).
+// into the ring with one bulk copy.  warps 1-2: epilogue (one row per lane).  warp 3: idle (the register split needs a
+// full warpgroup).
 __device__ __forceinline__ void ws_tma_issuer(const WsParams& wp, double2* sRing, unsigned long long* full, unsigned long long* empty) {
     const PostParams& p = wp.p;
     const unsigned group_bytes = (unsigned)(kGroupK * p.TB * 512);
@@ -269,10 +270,10 @@ __device__ __forceinline__ void ws_tma_issuer(const WsParams& wp, double2* sRing
 
 // Finalises a tile from the consumers' partials: |V|^2 summed over the RG row groups, mean summed over the NB k-blocks
 // (both in fixed order => bit-reproducible), then var, l/u (separate multiply and add roundings like NumPy) and the S bit.
-__device__ __forceinline__ void ws_epilogue_warp(const WsParams& wp, const double* sMeanK, const double* sSS,
-                                                 unsigned long long* tilefull, unsigned long long* tileempty, int lane) {
+__device__ __forceinline__ void ws_epilogue_warp(const WsParams& wp, const double* sMeanG, const double* sSS,
+                                                 unsigned long long* tilefull, unsigned long long* tileempty, int elane) {
     const PostParams& p = wp.p;
-    const int T = p.T, RG = p.RG, NB = p.NB;
+    const int T = p.T, RG = p.RG;
     int it = 0;
     for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
         const int par = it & 1;
@@ -284,13 +285,12 @@ __device__ __forceinline__ void ws_epilogue_warp(const WsParams& wp, const doubl
         const int valid_cols = left < T ? (int)left : T;
         mbar_wait(&tilefull[par], ((unsigned)(it >> 1)) & 1u);
         const double* ssp = sSS + (size_t)par * RG * T;
-        const double* mkp = sMeanK + (size_t)par * NB * T;
-        for (int t = lane; t < T; t += 32) {
+        const double* mgp = sMeanG + (size_t)par * RG * T;
+        for (int t = elane; t < T; t += 64) {
             const int64_t row = tile_row0 + t;
             if (t >= valid_cols || row < 0 || row >= p.M) continue;
             double sumsq = 0.0, mu = 0.0;
-            for (int g = 0; g < RG; ++g) sumsq += ssp[(size_t)g * T + t];
-            for (int kb = 0; kb < NB; ++kb) mu += mkp[(size_t)kb * T + t];
+            for (int g = 0; g < RG; ++g) { sumsq += ssp[(size_t)g * T + t]; mu += mgp[(size_t)g * T + t]; }
             double v = p.variance - sumsq;
             v = v > SO_VAR_FLOOR ? v : SO_VAR_FLOOR;
             const double sd = sqrt(v);
@@ -349,16 +349,16 @@ struct RingCursor {           // position of group 0 of the current tile in the 
     }
 };
 
-struct MeanSink {              // TMA mode: where a consumer warp leaves the mean contribution of its own k-blocks
+struct MeanSink {              // TMA mode: where a consumer warp accumulates the mean contribution of its own k-blocks
     const double2* w2;         // Wslow[s] as double2, + (lane & 3)
-    unsigned base;             // shared address of sMeanK[par][0][this warp's first column + lane/4]
-    unsigned kb_stride;        // bytes between k-blocks (T * 8)
+    unsigned base;             // shared address of sMeanG[par][g][this warp's first column + lane/4]
+    bool first;                // no contribution stored yet in this tile
 };
 
 template <int BT, int ROWS, int FIRST, bool MEAN>
 __device__ __forceinline__ void ws_segment(double (&acc)[ROWS][BT][2], double2 (&a)[ROWS], const double2* __restrict__ Afrag,
                                            const unsigned (&abase)[ROWS], const RingCursor& rc, int kb_lo, int kb_hi,
-                                           bool release, int NB, int& next_release, const MeanSink& ms, int lane) {
+                                           bool release, int NB, int& next_release, MeanSink& ms, int lane) {
     int slot = 0;
     unsigned parity = 0;
     for (int kb = kb_lo; kb <= kb_hi; ++kb) {
@@ -392,9 +392,17 @@ __device__ __forceinline__ void ws_segment(double (&acc)[ROWS][BT][2], double2 (
                 double v = fma(b.y, wv.y, b.x * wv.x);
                 v += __shfl_xor_sync(0xffffffffu, v, 1);
                 v += __shfl_xor_sync(0xffffffffu, v, 2);
-                if ((lane & 3) == 0)
-                    asm volatile("st.shared.f64 [%0], %1;\n" ::"r"(ms.base + (unsigned)kb * ms.kb_stride + c * 64u), "d"(v) : "memory");
+                if ((lane & 3) == 0) {
+                    const unsigned addr = ms.base + c * 64u;
+                    if (!ms.first) {
+                        double prev;
+                        asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(prev) : "r"(addr) : "memory");
+                        v += prev;
+                    }
+                    asm volatile("st.shared.f64 [%0], %1;\n" ::"r"(addr), "d"(v) : "memory");
+                }
             }
+            ms.first = false;
         }
         if (release && ((kb & 3) == 3 || kb == NB - 1)) {
             mbar_arrive_u32(rc.empty0 + 8u * slot);
@@ -429,7 +437,7 @@ __device__ __forceinline__ void ws_consumer(const WsParams& wp, const double2* s
         int64_t tile_row0 = tile * T;         // local row of column 0 of this tile
         int valid_cols = T;
         MeanSink ms;
-        ms.w2 = nullptr; ms.base = 0; ms.kb_stride = 0;
+        ms.w2 = nullptr; ms.base = 0; ms.first = true;
         if (TMA) {
             const int64_t gt = wp.first_tile + tile;
             const int64_t si = gt / wp.tpb;
@@ -441,8 +449,8 @@ __device__ __forceinline__ void ws_consumer(const WsParams& wp, const double2* s
             // the epilogue warp must have consumed the buffers of tile it-2 before they are written again
             mbar_wait(&meanempty[par], (((unsigned)(it >> 1)) & 1u) ^ 1u);
             ms.w2 = reinterpret_cast<const double2*>(wp.Wslow + (size_t)si * 8 * NB) + (lane & 3);
-            ms.base = smem_u32(sMeanP + (size_t)par * NB * T + (size_t)(cg * BT) * 8 + (lane >> 2));
-            ms.kb_stride = (unsigned)T * 8u;
+            ms.base = smem_u32(sMeanP + ((size_t)par * RG + g) * T + (size_t)(cg * BT) * 8 + (lane >> 2));
+            ms.first = true;
         }
         for (int pass = 0; pass < p.npass; ++pass) {
             const bool release = pass == p.npass - 1;
@@ -584,7 +592,7 @@ __global__ void __launch_bounds__(WsShape<CW>::kThreads, 1) k_posterior_ws(const
             // compute modes: producers publish the mean (meanfull), consumers hand the buffer back (meanempty);
             // kModeTma: consumers publish their partials (tilefull = meanfull), the epilogue warp hands them back
             mbar_init(&meanfull[s], TMA ? CW * 32 : kProducerWarps * 32);
-            mbar_init(&meanempty[s], TMA ? 32 : CW * 32);
+            mbar_init(&meanempty[s], TMA ? 64 : CW * 32);
         }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
@@ -594,7 +602,7 @@ __global__ void __launch_bounds__(WsShape<CW>::kThreads, 1) k_posterior_ws(const
         reg_dealloc<WsShape<CW>::kProducerRegs>();
         if (TMA) {
             if (warp == 0 && lane == 0) ws_tma_issuer(wp, sRing, full, empty);
-            else if (warp == 1) ws_epilogue_warp(wp, sMeanP, sSS, meanfull, meanempty, lane);
+            else if (warp == 1 || warp == 2) ws_epilogue_warp(wp, sMeanP, sSS, meanfull, meanempty, (warp - 1) * 32 + lane);
         } else ws_producer<KIND, GRID>(wp, sRing, sAlpha, sXs, sXt, sMeanP, full, empty, meanfull, meanempty, warp, lane);
     } else {
         reg_alloc<WsShape<CW>::kConsumerRegs>();
