@@ -40,7 +40,7 @@ struct GPState {
     double* Wslow = nullptr;
     size_t capWslow = 0;
     size_t a_stride = 0;
-    int tma_T = 0, tma_tpb = 0;
+    int tma_T = 0, tma_tpb = 0, tma_BT = 0, tma_RG = 0, tma_CG = 0, tma_kb_pad = 0;
     bool tma_ready = false;
     bool grid_ready = false;
 };

@@ -15,7 +15,7 @@
 //         with separate multiply and add roundings (NumPy does not contract), S bit.
 // Algorithmic work per row and GP: N^2/2 FMA (contraction) + N kernel evaluations; algorithmic HBM
 // bytes: d*8 in (0 on the grid path) + 32 out (mean, var, l, u) + 1 (S).  See DESIGN.md section 3.
-#include "posterior_ws.cuh"
+#include "posterior_tma.cuh"
 #include <cstdlib>
 
 namespace {
@@ -344,10 +344,50 @@ int launch_ws_bt(so_handle* h, const WsParams& wp, const WsPlan& pl, cudaStream_
     }
 }
 
+// ---- TMA double-buffer variant (grid path default) -----------------------------------------------
+struct TmaPlan { int BT, RG, CG, T, TB, npass, kb_pad; size_t smem; };
+
+int plan_tma(so_handle* h, const GPState& g, TmaPlan& tp) {
+    const int NB = g.NB;
+    if (NB >= 32) { tp.RG = 8; tp.CG = 1; }
+    else if (NB >= 16) { tp.RG = 4; tp.CG = 2; }
+    else if (NB >= 8) { tp.RG = 2; tp.CG = 4; }
+    else { tp.RG = 1; tp.CG = 8; }
+    tp.npass = (NB + 4 * tp.RG - 1) / (4 * tp.RG);
+    tp.kb_pad = kGroupK * ((NB + kGroupK - 1) / kGroupK);
+    const int options[3] = {6, 4, 2};
+    for (int k = 0; k < 3; ++k) {
+        const int bt = options[k];
+        const TmaSmem L = tma_smem(tp.kb_pad, bt * tp.CG, tp.RG, 8 * bt * tp.CG);
+        if (L.total <= (size_t)h->smem_optin) {
+            tp.BT = bt; tp.TB = bt * tp.CG; tp.T = 8 * bt * tp.CG; tp.smem = L.total;
+            return SO_OK;
+        }
+    }
+    return SO_ERR_CAPACITY;
+}
+
+template <int BT>
+int launch_tma_one(so_handle* h, const TmaParams& tp, size_t smem, cudaStream_t stream) {
+    static int configured_for = -1;
+    if (configured_for != h->device) {
+        SO_CUDA(h, cudaFuncSetAttribute(k_posterior_tma<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
+        configured_for = h->device;
+    }
+    const int grid = (int)(tp.p.ntiles < (int64_t)h->num_sms ? tp.p.ntiles : (int64_t)h->num_sms);
+    k_posterior_tma<BT><<<grid, kThreads, smem, stream>>>(tp);
+    SO_CHECK_LAUNCH(h, "k_posterior_tma");
+    return SO_OK;
+}
+
 // SO_K2_VARIANT=bulk selects the bulk-synchronous kernel (kept for A/B measurements); default = warp-specialised.
-bool use_bulk_variant() {
+// SO_K2_VARIANT: "tma" (default: TMA double buffer on the grid path, bulk kernel for explicit rows), "bulk" (bulk kernel
+// everywhere), "ws" (warp-specialised producer/consumer kernels everywhere) -- for A/B measurements.
+int k2_variant() {
     const char* v = std::getenv("SO_K2_VARIANT");
-    return v && std::string(v) == "bulk";
+    if (v && std::string(v) == "bulk") return 1;
+    if (v && std::string(v) == "ws") return 2;
+    return 0;
 }
 
 int run_posterior(so_handle* h, int gp, const double* Xstar_d, bool grid, int64_t row0, int64_t M, double beta, double fmin,
@@ -372,18 +412,21 @@ int run_posterior(so_handle* h, int gp, const double* Xstar_d, bool grid, int64_
     }
     DeviceGuard guard(h->device);
     cudaStream_t stream = (cudaStream_t)stream_;
-    const bool bulk = use_bulk_variant();
+    const int variant = k2_variant();
+    const bool tma2 = grid && variant == 0 && g.tma_ready;
+    const bool bulk = !tma2 && variant != 2;
     LaunchPlan lp;
     WsPlan pl;
-    const bool tma = grid && !bulk && g.tma_ready && std::getenv("SO_K2_NO_TMA") == nullptr;
-    // the TMA-mode tables are laid out for one tile size, so the few-tiles heuristic is skipped there
-    int rc = bulk ? plan_launch(h, g, M, grid, lp) : plan_ws(h, g, tma ? (int64_t)1 << 60 : M, grid, pl, tma && std::getenv("SO_K2_NARROW") == nullptr, tma);
+    const bool tma = grid && !bulk && !tma2 && false;
+    int rc = SO_OK;
+    if (tma2) { lp.RG = g.tma_RG; lp.CG = g.tma_CG; lp.T = g.tma_T; lp.TB = g.tma_BT * g.tma_CG; lp.BT = g.tma_BT;
+                lp.npass = (g.NB + 4 * lp.RG - 1) / (4 * lp.RG); lp.smem = 0; }
+    else rc = bulk ? plan_launch(h, g, M, grid, lp) : plan_ws(h, g, M, grid, pl);
     if (rc) return rc;
-    if (tma && pl.T != g.tma_T) return so_fail(h, SO_ERR_BAD_ARG, "posterior_grid: tile size differs from the prepared tables");
     WsParams wp;
     PostParams& p = wp.p;
     p.N = g.N; p.NB = g.NB; p.d = g.d; p.kind = g.kind;
-    if (bulk) { p.RG = lp.RG; p.CG = lp.CG; p.T = lp.T; p.TB = lp.TB; p.npass = lp.npass; }
+    if (bulk || tma2) { p.RG = lp.RG; p.CG = lp.CG; p.T = lp.T; p.TB = lp.TB; p.npass = lp.npass; }
     else { p.RG = pl.RG; p.CG = pl.CG; p.T = pl.T; p.TB = pl.TB; p.npass = pl.npass; }
     p.Afrag = g.Afrag; p.alpha = g.alpha; p.Xs = g.Xs;
     for (int j = 0; j < SO_MAX_DIM; ++j) p.inv_ls[j] = g.inv_ls[j];
@@ -397,6 +440,24 @@ int run_posterior(so_handle* h, int gp, const double* Xstar_d, bool grid, int64_
     }
     p.beta = beta; p.fmin = fmin;
     p.mean = mean_d; p.var = var_d; p.Q = Q_d; p.q_stride = q_stride; p.q_col = q_col; p.S = S_d; p.safe_mode = safe_mode;
+    if (tma2) {
+        // tiles are aligned to the slow blocks of the product grid: global tile = (row / F) * tpb + (row % F) / T
+        TmaParams tp;
+        tp.p = p;
+        tp.PfFrag = g.PfFrag; tp.Aprime = g.Aprime; tp.Wslow = g.Wslow; tp.a_stride = g.a_stride;
+        tp.fast_rows = h->grid.fast_rows; tp.tpb = g.tma_tpb; tp.kb_pad = g.tma_kb_pad;
+        const int64_t F = h->grid.fast_rows, last_row = row0 + M - 1;
+        const int64_t t0 = (row0 / F) * g.tma_tpb + (row0 % F) / lp.T;
+        const int64_t t1 = (last_row / F) * g.tma_tpb + (last_row % F) / lp.T;
+        tp.first_tile = t0;
+        tp.p.ntiles = t1 - t0 + 1;
+        const size_t smem = tma_smem(g.tma_kb_pad, lp.TB, lp.RG, lp.T).total;
+        switch (lp.BT) {
+            case 6: return launch_tma_one<6>(h, tp, smem, stream);
+            case 4: return launch_tma_one<4>(h, tp, smem, stream);
+            default: return launch_tma_one<2>(h, tp, smem, stream);
+        }
+    }
     if (bulk) {
         if (grid) return launch_bt<SO_KERNEL_RBF, true>(h, p, lp, stream);
         switch (g.kind) {
@@ -409,18 +470,8 @@ int run_posterior(so_handle* h, int gp, const double* Xstar_d, bool grid, int64_
     wp.fast_rows = h->grid.fast_rows;
     wp.Pfast = g.P2;
     wp.Pslow = g.P2 ? g.P2 + (size_t)h->grid.fast_rows * 8 * g.NB : nullptr;
-    wp.PfFrag = g.PfFrag; wp.Aprime = g.Aprime; wp.Wslow = g.Wslow; wp.a_stride = g.a_stride; wp.tpb = g.tma_tpb;
-    wp.first_tile = 0;
-    if (tma) {
-        // tiles are aligned to the slow blocks of the product grid: global tile = (row / F) * tpb + (row % F) / T
-        const int64_t F = h->grid.fast_rows;
-        const int64_t last_row = row0 + M - 1;
-        const int64_t t0 = (row0 / F) * g.tma_tpb + (row0 % F) / pl.T;
-        const int64_t t1 = (last_row / F) * g.tma_tpb + (last_row % F) / pl.T;
-        wp.first_tile = t0;
-        p.ntiles = t1 - t0 + 1;
-        return launch_ws_bt<SO_KERNEL_RBF, kModeTma>(h, wp, pl, stream);
-    }
+    wp.PfFrag = nullptr; wp.Aprime = nullptr; wp.Wslow = nullptr; wp.a_stride = 0; wp.tpb = 1; wp.first_tile = 0;
+    (void)tma;
     if (grid) return launch_ws_bt<SO_KERNEL_RBF, kModeGrid>(h, wp, pl, stream);
     switch (g.kind) {
         case SO_KERNEL_RBF: return launch_ws_bt<SO_KERNEL_RBF, kModeRows>(h, wp, pl, stream);
@@ -576,9 +627,9 @@ extern "C" int so_grid_prepare(so_handle* h, int gp, void* stream_) {
     // ---- TMA-mode tables (fragment-ordered fast table, scaled operands, Wslow)
     g.tma_ready = false;
     {
-        WsPlan pl;
-        if (plan_ws(h, g, (int64_t)1 << 60, true, pl, std::getenv("SO_K2_NARROW") == nullptr, true) == SO_OK) {
-            const int T = pl.T, TB = pl.TB, gpt = pl.gpt;
+        TmaPlan pl;
+        if (plan_tma(h, g, pl) == SO_OK) {
+            const int T = pl.T, TB = pl.TB, gpt = pl.kb_pad / kGroupK;
             const int tpb = (int)((gs.fast_rows + T - 1) / T);
             const size_t pf_elems = (size_t)tpb * gpt * kGroupK * TB * 32;
             const size_t a_stride = (tri_blocks(g.NB) + 1) * 32;
@@ -617,7 +668,8 @@ extern "C" int so_grid_prepare(so_handle* h, int gp, void* stream_) {
                 k_aprime<<<grd, 256, 0, stream>>>(g.Afrag, Pslow, g.alpha, g.Aprime, g.Wslow, g.NB, a_stride);
                 SO_CHECK_LAUNCH(h, "k_aprime");
                 SO_CUDA(h, cudaMemsetAsync(g.Aprime + (size_t)gs.slow_rows * a_stride, 0, sizeof(double2) * 64, stream));
-                g.a_stride = a_stride; g.tma_T = T; g.tma_tpb = tpb; g.tma_ready = true;
+                g.a_stride = a_stride; g.tma_T = T; g.tma_tpb = tpb; g.tma_BT = pl.BT; g.tma_RG = pl.RG; g.tma_CG = pl.CG;
+                g.tma_kb_pad = pl.kb_pad; g.tma_ready = true;
             }
         }
     }
