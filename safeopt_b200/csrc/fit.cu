@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(256) k_trinv(const double* __restrict__ L, dou
 
 // alpha = Linv^T (Linv y), one CTA; padding entries are zero.
 __global__ void __launch_bounds__(1024) k_alpha(const double* __restrict__ Linv, const double* __restrict__ Y,
-                                                double* __restrict__ alpha, int N, int Npad) {
+                                                double* __restrict__ alpha, double* __restrict__ zvec, int N, int Npad) {
     extern __shared__ double w[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     for (int i = warp; i < N; i += nwarps) {
@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(1024) k_alpha(const double* __restrict__ Linv,
         if (c < N)
             for (int i = c; i < N; ++i) s = fma(Linv[(size_t)i * Npad + c], w[i], s);
         alpha[c] = s;
+        zvec[c] = c < N ? w[c] : 0.0;
     }
 }
 
@@ -178,6 +179,7 @@ extern "C" int so_fit(so_handle* h, int gp, const double* X_h, const double* Y_h
         if ((rc = grow(h, g.K, (size_t)cap * cap))) return rc;
         if ((rc = grow(h, g.Linv, (size_t)cap * cap))) return rc;
         if ((rc = grow(h, g.alpha, (size_t)cap))) return rc;
+        if ((rc = grow(h, g.zvec, (size_t)cap))) return rc;
         if ((rc = grow(h, g.Afrag, (tri_blocks(capNB) + 2) * 32))) return rc;
         g.capN = cap;
     }
@@ -205,7 +207,7 @@ extern "C" int so_fit(so_handle* h, int gp, const double* X_h, const double* Y_h
         }
         k_trinv<<<(N + warps - 1) / warps, warps * 32, smem, stream>>>(g.K, g.Linv, N, Npad);
     }
-    k_alpha<<<1, 1024, sizeof(double) * Npad, stream>>>(g.Linv, g.Y, g.alpha, N, Npad);
+    k_alpha<<<1, 1024, sizeof(double) * Npad, stream>>>(g.Linv, g.Y, g.alpha, g.zvec, N, Npad);
     SO_CUDA(h, cudaMemsetAsync(g.Afrag, 0, sizeof(double2) * (tri_blocks(NB) + 2) * 32, stream));
     k_pack_afrag<<<dim3(NB, NB), 32, 0, stream>>>(g.Linv, g.Afrag, N, Npad);
     SO_CHECK_LAUNCH(h, "so_fit kernels");

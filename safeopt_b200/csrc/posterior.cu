@@ -444,7 +444,7 @@ int run_posterior(so_handle* h, int gp, const double* Xstar_d, bool grid, int64_
         // tiles are aligned to the slow blocks of the product grid: global tile = (row / F) * tpb + (row % F) / T
         TmaParams tp;
         tp.p = p;
-        tp.PfFrag = g.PfFrag; tp.Aprime = g.Aprime; tp.Wslow = g.Wslow; tp.a_stride = g.a_stride;
+        tp.PfFrag = g.PfFrag; tp.Aprime = g.Aprime; tp.zvec = g.zvec; tp.a_stride = g.a_stride;
         tp.fast_rows = h->grid.fast_rows; tp.tpb = g.tma_tpb; tp.kb_pad = g.tma_kb_pad;
         const int64_t F = h->grid.fast_rows, last_row = row0 + M - 1;
         const int64_t t0 = (row0 / F) * g.tma_tpb + (row0 % F) / lp.T;

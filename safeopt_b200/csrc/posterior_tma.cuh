@@ -22,7 +22,7 @@ struct TmaParams {
     PostParams p;
     const double2* PfFrag;            // [tile in slow block][k-block][col tile][lane] double2, zero padded
     const double2* Aprime;            // slow_rows packed scaled operands, a_stride double2 apart
-    const double* Wslow;              // slow_rows x Npad: Pslow[s][n] * alpha[n]
+    const double* zvec;               // Npad: z = L^-1 y
     size_t a_stride;
     int64_t fast_rows;
     int64_t first_tile;
@@ -42,11 +42,41 @@ __host__ __device__ inline TmaSmem tma_smem(int kb_pad, int TB, int RG, int T) {
     return L;
 }
 
+// Recursive-halving reduction of K values per lane over the 8 lanes that hold the rows of one 8x8 block (lane bits
+// 4,3,2): after the three stages every lane owns K/8 fully reduced values, at 7K/8 shuffle+add pairs per lane instead of
+// 3K for a butterfly.  Scalar fp64 instructions are precious here: they share the one FP64 pipe with DMMA and are
+// served behind it (profiles/r01_k2_variants.md).  Lane (b4,b3,b2) ends up with original indices
+// b4*K/2 + b3*K/4 + b2*K/8 + [0, K/8).
+template <int K>
+__device__ __forceinline__ void halving_reduce(double (&v)[K], int lane) {
+    static_assert(K % 8 == 0, "K must be a multiple of 8");
+#pragma unroll
+    for (int i = 0; i < K / 2; ++i) {
+        const bool up = (lane & 16) != 0;
+        const double send = up ? v[i] : v[i + K / 2];
+        const double keep = up ? v[i + K / 2] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < K / 4; ++i) {
+        const bool up = (lane & 8) != 0;
+        const double send = up ? v[i] : v[i + K / 4];
+        const double keep = up ? v[i + K / 4] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+#pragma unroll
+    for (int i = 0; i < K / 8; ++i) {
+        const bool up = (lane & 4) != 0;
+        const double send = up ? v[i] : v[i + K / 8];
+        const double keep = up ? v[i + K / 8] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+}
+
 template <int BT, int FIRST>
 __device__ __forceinline__ void tma_segment(double (&acc)[4][BT][2], double2 (&a)[4], const double2* __restrict__ Afrag,
                                             const size_t (&abase)[4], const double2* __restrict__ sB, int TB, int kb_lo,
-                                            int kb_hi, const double2* __restrict__ w2, double* __restrict__ mean_slot,
-                                            bool& mean_first, int lane) {
+                                            int kb_hi) {
     for (int kb = kb_lo; kb <= kb_hi; ++kb) {
         double2 an[4];
 #pragma unroll
@@ -63,23 +93,6 @@ __device__ __forceinline__ void tma_segment(double (&acc)[4][BT][2], double2 (&a
         }
 #pragma unroll
         for (int s = FIRST; s < 4; ++s) a[s] = an[s];
-    }
-    if (kb_hi >= kb_lo) {
-        // kb_hi is the block row slot FIRST owns: its k-block's share of the mean is added here, once
-        const double2 wv = __ldg(w2 + 4 * kb_hi);
-        const double2* bp = sB + (size_t)kb_hi * TB * 32;
-#pragma unroll
-        for (int c = 0; c < BT; ++c) {
-            const double2 b = bp[c * 32];
-            double v = fma(b.y, wv.y, b.x * wv.x);
-            v += __shfl_xor_sync(0xffffffffu, v, 1);
-            v += __shfl_xor_sync(0xffffffffu, v, 2);
-            if ((lane & 3) == 0) {
-                double* dst = mean_slot + c * 8;
-                *dst = mean_first ? v : *dst + v;
-            }
-        }
-        mean_first = false;
     }
 }
 
@@ -130,29 +143,26 @@ __global__ void __launch_bounds__(kThreads, 1) k_posterior_tma(const __grid_cons
         const int64_t si = gt / tp.tpb;
         const int j = (int)(gt - si * tp.tpb);
         const double2* Afrag = tp.Aprime + (size_t)si * tp.a_stride + lane;
-        const double2* w2 = reinterpret_cast<const double2*>(tp.Wslow + (size_t)si * Npad) + (lane & 3);
         const double2* sB = sBuf + (size_t)b * buf_elems + (size_t)(cg * BT) * 32 + lane;
         double* sSST = sSS + (size_t)b * RG * T;
-        double* mean_slot = sMeanG + ((size_t)b * RG + g) * T + (size_t)(cg * BT) * 8 + (lane >> 2);
-        bool mean_first = true;
+        double* sMeanT = sMeanG + (size_t)b * RG * T;
 
         mbar_wait(&full[b], ((unsigned)(it >> 1)) & 1u);
 
-        double ss[BT][2];
-#pragma unroll
-        for (int c = 0; c < BT; ++c) { ss[c][0] = 0.0; ss[c][1] = 0.0; }
         for (int pass = 0; pass < p.npass; ++pass) {
             const int base = 4 * RG * pass;
             const int r0 = base + g, r1 = base + 2 * RG - 1 - g, r2 = base + 2 * RG + g, r3 = base + 4 * RG - 1 - g;
             const int na = (r0 < NB) + (r1 < NB) + (r2 < NB) + (r3 < NB);
             int ext[4];
             size_t abase[4];
+            double zs[4];              // z = L^-1 y at this lane's row of each slot's block (0 for inactive slots)
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
                 const int src = s - (4 - na);
                 const int r = src >= 0 ? pick4(r0, r1, r2, r3, src) : -1;
                 ext[s] = r;
                 abase[s] = r >= 0 ? (size_t)r * (r + 1) / 2 * 32 : 0;
+                zs[s] = r >= 0 ? __ldg(tp.zvec + 8 * r + (lane >> 2)) : 0.0;
             }
             double acc[4][BT][2];
 #pragma unroll
@@ -162,35 +172,37 @@ __global__ void __launch_bounds__(kThreads, 1) k_posterior_tma(const __grid_cons
             double2 a[4];
 #pragma unroll
             for (int s = 0; s < 4; ++s) a[s] = __ldg(Afrag + abase[s]);
-            tma_segment<BT, 0>(acc, a, Afrag, abase, sB, TB, 0, ext[0], w2, mean_slot, mean_first, lane);
-            tma_segment<BT, 1>(acc, a, Afrag, abase, sB, TB, ext[0] + 1, ext[1], w2, mean_slot, mean_first, lane);
-            tma_segment<BT, 2>(acc, a, Afrag, abase, sB, TB, ext[1] + 1, ext[2], w2, mean_slot, mean_first, lane);
-            tma_segment<BT, 3>(acc, a, Afrag, abase, sB, TB, ext[2] + 1, ext[3], w2, mean_slot, mean_first, lane);
-#pragma unroll
-            for (int s = 0; s < 4; ++s)
-#pragma unroll
-                for (int c = 0; c < BT; ++c) {
-                    ss[c][0] = fma(acc[s][c][0], acc[s][c][0], ss[c][0]);
-                    ss[c][1] = fma(acc[s][c][1], acc[s][c][1], ss[c][1]);
-                }
-        }
-        if (mean_first && (lane & 3) == 0) {
-            // a warp without an active row in this tile (NB not a multiple of the row groups) contributes zero
-#pragma unroll
-            for (int c = 0; c < BT; ++c) mean_slot[c * 8] = 0.0;
-        }
-#pragma unroll
-        for (int c = 0; c < BT; ++c) {
-#pragma unroll
-            for (int o = 4; o < 32; o <<= 1) {
-                ss[c][0] += __shfl_xor_sync(0xffffffffu, ss[c][0], o);
-                ss[c][1] += __shfl_xor_sync(0xffffffffu, ss[c][1], o);
-            }
-        }
-        if (lane < 4) {
+            tma_segment<BT, 0>(acc, a, Afrag, abase, sB, TB, 0, ext[0]);
+            tma_segment<BT, 1>(acc, a, Afrag, abase, sB, TB, ext[0] + 1, ext[1]);
+            tma_segment<BT, 2>(acc, a, Afrag, abase, sB, TB, ext[1] + 1, ext[2]);
+            tma_segment<BT, 3>(acc, a, Afrag, abase, sB, TB, ext[2] + 1, ext[3]);
+            // |V|^2 and V.z of this warp's rows: red[c*2+h] = sum of squares, red[2BT + c*2+h] = mean share, for column
+            // 8c + 2(lane%4) + h of this warp's column group; then across the 8 row lanes by recursive halving
+            double red[4 * BT];
 #pragma unroll
             for (int c = 0; c < BT; ++c)
-                *reinterpret_cast<double2*>(sSST + (size_t)g * T + (cg * BT + c) * 8 + 2 * lane) = make_double2(ss[c][0], ss[c][1]);
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    double q2 = 0.0, mz = 0.0;
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) {
+                        q2 = fma(acc[s][c][hh], acc[s][c][hh], q2);
+                        mz = fma(acc[s][c][hh], zs[s], mz);
+                    }
+                    red[c * 2 + hh] = q2;
+                    red[2 * BT + c * 2 + hh] = mz;
+                }
+            halving_reduce<4 * BT>(red, lane);
+            // lane (b4,b3,b2) owns original indices first + [0, BT/2)
+            const int first = ((lane >> 4) & 1) * (2 * BT) + ((lane >> 3) & 1) * BT + ((lane >> 2) & 1) * (BT / 2);
+#pragma unroll
+            for (int i = 0; i < BT / 2; ++i) {
+                const int idx = first + i;
+                const bool is_mean = idx >= 2 * BT;
+                const int ch = is_mean ? idx - 2 * BT : idx;           // c*2 + h
+                double* dst = (is_mean ? sMeanT : sSST) + (size_t)g * T + (size_t)(cg * BT + (ch >> 1)) * 8 + 2 * (lane & 3) + (ch & 1);
+                *dst = pass == 0 ? red[i] : *dst + red[i];
+            }
         }
         __syncthreads();
 
