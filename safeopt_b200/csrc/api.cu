@@ -48,7 +48,7 @@ int so_create(int device, int max_gps, so_handle** out) {
 
 static void free_gp(GPState& g) {
     cudaFree(g.X); cudaFree(g.Xs); cudaFree(g.Y); cudaFree(g.K); cudaFree(g.Linv);
-    cudaFree(g.alpha); cudaFree(g.zvec); cudaFree(g.Afrag); cudaFree(g.E); cudaFree(g.P2); cudaFree(g.PfFrag); cudaFree(g.Aprime); cudaFree(g.Wslow);
+    cudaFree(g.alpha); cudaFree(g.zvec); cudaFree(g.Afrag); cudaFree(g.E); cudaFree(g.P2); cudaFree(g.PfFrag); cudaFree(g.Aprime);
     g = GPState();
 }
 

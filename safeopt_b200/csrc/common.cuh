@@ -33,13 +33,11 @@ struct GPState {
     // two-level product tables (warp-specialised kernel): fast_rows + slow_rows rows of Npad doubles
     double* P2 = nullptr;
     size_t capP2 = 0;
-    // TMA-mode tables: fragment-ordered fast table, scaled operands A'(s), Wslow (see posterior_ws.cuh)
+    // tables of the TMA kernel: fragment-ordered fast table, scaled operands A'(s) (see posterior_tma.cuh)
     double2* PfFrag = nullptr;
     size_t capPfFrag = 0;
     double2* Aprime = nullptr;
     size_t capAprime = 0;
-    double* Wslow = nullptr;
-    size_t capWslow = 0;
     size_t a_stride = 0;
     int tma_T = 0, tma_tpb = 0, tma_BT = 0, tma_RG = 0, tma_CG = 0, tma_kb_pad = 0;
     bool tma_ready = false;

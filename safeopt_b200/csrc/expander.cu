@@ -84,17 +84,14 @@ __global__ void __launch_bounds__(256) k_expander_prep(const double* __restrict_
 template <int KIND, bool GRID>
 __global__ void __launch_bounds__(kThreads, 1) k_expander(const __grid_constant__ ExpParams ep) {
     const PostParams& p = ep.p;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const SmemLayout L = smem_layout(p.NB, p.T, p.d, p.RG, GRID);
     double2* sK = reinterpret_cast<double2*>(smem_raw);
-    double* sAlpha = reinterpret_cast<double*>(smem_raw + L.alpha_off);
     double* sXs = reinterpret_cast<double*>(smem_raw + L.xs_off);
     double* sXt = reinterpret_cast<double*>(smem_raw + L.xt_off);
-    double* sMean = reinterpret_cast<double*>(smem_raw + L.mean_off);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int Npad = 8 * p.NB, T = p.T, TB = p.TB, NB = p.NB, d = p.d;
 
-    for (int i = threadIdx.x; i < Npad; i += kThreads) sAlpha[i] = p.alpha[i];
     if (!GRID)
         for (int i = threadIdx.x; i < Npad * d; i += kThreads) sXs[i] = p.Xs[i];
     __syncthreads();
@@ -109,8 +106,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_expander(const __grid_constant_
         }
         if (!GRID) load_tile_rows(p, sXt, tile_local0);
         if (!__syncthreads_or(any)) continue;   // uniform across the CTA
-        if (GRID) gen_grid(p, sK, sAlpha, sMean, p.row0 + tile_local0, warp, lane);
-        else gen_rows<KIND>(p, sK, sAlpha, sXs, sXt, sMean, warp, lane);
+        if (GRID) gen_grid(p, sK, p.row0 + tile_local0, warp, lane);
+        else gen_rows<KIND>(p, sK, sXs, sXt, warp, lane);
         __syncthreads();
 
         for (int ct = warp; ct < TB; ct += kWarps) {
@@ -260,7 +257,7 @@ extern "C" int so_expander_check(so_handle* h, int gp, const double* Xstar_d, in
     while (T >= 16 && smem_layout(NB, T, d, 1, grid).total > (size_t)h->smem_optin) T >>= 1;
     if (T < 16) return so_fail(h, SO_ERR_CAPACITY, "expander: N too large for the shared-memory tile");
     p.N = g.N; p.NB = NB; p.d = d; p.RG = 1; p.CG = 8; p.T = T; p.TB = T / 8; p.npass = 1; p.kind = g.kind;
-    p.Afrag = g.Afrag; p.alpha = g.alpha; p.Xs = g.Xs;
+    p.Afrag = g.Afrag; p.zvec = g.zvec; p.Xs = g.Xs;
     for (int j = 0; j < SO_MAX_DIM; ++j) p.inv_ls[j] = g.inv_ls[j];
     p.variance = g.variance;
     p.Xstar = Xstar_d; p.M = M; p.row0 = row0; p.ntiles = (M + T - 1) / T;

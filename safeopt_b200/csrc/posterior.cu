@@ -1,136 +1,35 @@
-// K2 -- fused GP posterior over candidate rows: kernel-row build, the dense triangular
-// contraction V = L^-1 k on the fp64 tensor pipe (DMMA.8x8x4), predictive mean/variance,
-// confidence bounds and the safe bit.  Stands in for `gp.predict_noiseless(self.inputs)`
-// (safeopt/gp_opt.py:469) + :471-476 + this GP's factor of :481.  Nothing of size N x M ever
-// reaches HBM (the reference materialises three such temporaries).
+// K2 -- fused GP posterior over candidate rows: kernel-row build, the dense triangular contraction V = L^-1 k on the
+// fp64 tensor pipe (DMMA.8x8x4), predictive mean/variance, confidence bounds and the safe bit.  Stands in for
+// `gp.predict_noiseless(self.inputs)` (safeopt/gp_opt.py:469) + :471-476 + this GP's factor of :481.  Nothing of size
+// N x M ever reaches HBM (the reference materialises three such temporaries).
 //
-// Persistent kernel, one 256-thread CTA per SM, looping over tiles of T candidate rows:
-//   gen : k(x*, X) for the tile, written to shared memory directly in DMMA B-fragment order;
-//         the mean k.alpha is accumulated on the way (deterministic shuffle reduction).
-//   mma : warp (g, cg) owns block rows {g, 2RG-1-g, 2RG+g, 4RG-1-g} (+4RG per pass) of L^-1 --
-//         a pairing that balances the triangular work -- and BT column tiles; A fragments stream
-//         from L2 (each is used by exactly one warp per tile, so staging them in shared memory
-//         would add traffic without reuse), B fragments come from shared memory (LDS.128).
-//   epi : column sums of squares -> var = max(k** - |V|^2, 1e-15), l/u = mean -/+ beta*sqrt(var)
-//         with separate multiply and add roundings (NumPy does not contract), S bit.
-// Algorithmic work per row and GP: N^2/2 FMA (contraction) + N kernel evaluations; algorithmic HBM
-// bytes: d*8 in (0 on the grid path) + 32 out (mean, var, l, u) + 1 (S).  See DESIGN.md section 3.
+// Two persistent kernels, one 256-thread CTA per SM, looping over tiles of T candidate rows:
+//   k_posterior      (explicit rows, any stationary kernel; also the fallback of the grid path)
+//       gen : k(x*, X) for the tile, written to shared memory directly in DMMA B-fragment order (distance + exp or
+//             Matern profile per value; on a grid: product of per-axis table entries)
+//       mma : contract_tile (posterior_core.cuh)   epi : finalize_row
+//   k_posterior_tma  (product grids with an RBF kernel -- the headline path, posterior_tma.cuh)
+//       no generation phase at all: scaled operands A'(s) + TMA double buffer of the fragment-ordered fast table.
+// Algorithmic work per row and GP: N^2/2 FMA (contraction) + N kernel evaluations; algorithmic HBM bytes: d*8 in (0 on
+// the grid path) + 32 out (mean, var, l, u) + 1 (S).  See DESIGN.md section 3.
 #include "posterior_tma.cuh"
 #include <cstdlib>
 
 namespace {
 
-template <int BT>
-__device__ __forceinline__ void mma_phase(const PostParams& p, const double2* __restrict__ sK, double* __restrict__ sSS,
-                                          int warp, int lane) {
-    const int RG = p.RG, NB = p.NB, TB = p.TB, T = p.T;
-    const int g = warp % RG, cg = warp / RG;
-    const double2* sB = sK + (size_t)(cg * BT) * 32 + lane;
-    const double2* Afrag = p.Afrag + lane;
-    double ss[BT][2];
-#pragma unroll
-    for (int c = 0; c < BT; ++c) { ss[c][0] = 0.0; ss[c][1] = 0.0; }
-
-    for (int pass = 0; pass < p.npass; ++pass) {
-        const int base = 4 * RG * pass;
-        const int r0 = base + g, r1 = base + 2 * RG - 1 - g, r2 = base + 2 * RG + g, r3 = base + 4 * RG - 1 - g;
-        // rows are ascending; the ones beyond NB (inactive) form a suffix.  Slots are ordered by
-        // K extent, inactive slots (extent -1) first, so that "slots FIRST..3 active" holds per segment.
-        const int na = (r0 < NB) + (r1 < NB) + (r2 < NB) + (r3 < NB);
-        int ext[4];
-        size_t abase[4];
-#pragma unroll
-        for (int s = 0; s < 4; ++s) {
-            const int src = s - (4 - na);
-            const int r = src >= 0 ? pick4(r0, r1, r2, r3, src) : -1;
-            ext[s] = r;
-            abase[s] = r >= 0 ? (size_t)r * (r + 1) / 2 * 32 : 0;
-        }
-        double acc[4][BT][2];
-#pragma unroll
-        for (int s = 0; s < 4; ++s)
-#pragma unroll
-            for (int c = 0; c < BT; ++c) { acc[s][c][0] = 0.0; acc[s][c][1] = 0.0; }
-        double2 a[4];
-#pragma unroll
-        for (int s = 0; s < 4; ++s) a[s] = __ldg(Afrag + abase[s]);
-        mma_segment<BT, 0>(acc, a, Afrag, abase, sB, TB, 0, ext[0]);
-        mma_segment<BT, 1>(acc, a, Afrag, abase, sB, TB, ext[0] + 1, ext[1]);
-        mma_segment<BT, 2>(acc, a, Afrag, abase, sB, TB, ext[1] + 1, ext[2]);
-        mma_segment<BT, 3>(acc, a, Afrag, abase, sB, TB, ext[2] + 1, ext[3]);
-#pragma unroll
-        for (int s = 0; s < 4; ++s)
-#pragma unroll
-            for (int c = 0; c < BT; ++c) {
-                ss[c][0] = fma(acc[s][c][0], acc[s][c][0], ss[c][0]);
-                ss[c][1] = fma(acc[s][c][1], acc[s][c][1], ss[c][1]);
-            }
-    }
-    // sum over the 8 rows of a block (lane bits 2..4), fixed tree => deterministic
-#pragma unroll
-    for (int c = 0; c < BT; ++c) {
-#pragma unroll
-        for (int o = 4; o < 32; o <<= 1) {
-            ss[c][0] += __shfl_xor_sync(0xffffffffu, ss[c][0], o);
-            ss[c][1] += __shfl_xor_sync(0xffffffffu, ss[c][1], o);
-        }
-    }
-    if (lane < 4) {
-#pragma unroll
-        for (int c = 0; c < BT; ++c) {
-            double2* dst = reinterpret_cast<double2*>(sSS + (size_t)g * T + (cg * BT + c) * 8 + 2 * lane);
-            *dst = make_double2(ss[c][0], ss[c][1]);
-        }
-    }
-}
-
-// ---------------------------------------------------------------- epilogue
-__device__ __forceinline__ void epilogue(const PostParams& p, const double* __restrict__ sMean, const double* __restrict__ sSS,
-                                         int64_t tile_local0) {
-    const int T = p.T, RG = p.RG;
-    for (int t = threadIdx.x; t < T; t += kThreads) {
-        const int64_t row = tile_local0 + t;
-        if (row >= p.M) continue;
-        double sumsq = 0.0;
-        for (int g = 0; g < RG; ++g) sumsq += sSS[(size_t)g * T + t];
-        const double mu = sMean[t];
-        double v = p.variance - sumsq;
-        v = v > SO_VAR_FLOOR ? v : SO_VAR_FLOOR;
-        const double sd = sqrt(v);
-        const double bs = __dmul_rn(p.beta, sd);
-        const double lo = __dsub_rn(mu, bs), up = __dadd_rn(mu, bs);
-        if (p.mean) p.mean[row] = mu;
-        if (p.var) p.var[row] = v;
-        if (p.Q) {
-            double* qp = p.Q + (size_t)row * p.q_stride + p.q_col;
-            if ((p.q_stride & 1) == 0 && (p.q_col & 1) == 0) {
-                *reinterpret_cast<double2*>(qp) = make_double2(lo, up);
-            } else {
-                qp[0] = lo;
-                qp[1] = up;
-            }
-        }
-        if (p.safe_mode != SO_SAFE_NONE && p.S) {
-            const uint8_t safe = lo > p.fmin ? 1 : 0;
-            p.S[row] = p.safe_mode == SO_SAFE_WRITE ? safe : (uint8_t)(p.S[row] & safe);
-        }
-    }
-}
-
 template <int BT, int KIND, bool GRID>
 __global__ void __launch_bounds__(kThreads, 1) k_posterior(const __grid_constant__ PostParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const SmemLayout L = smem_layout(p.NB, p.T, p.d, p.RG, GRID);
     double2* sK = reinterpret_cast<double2*>(smem_raw);
-    double* sAlpha = reinterpret_cast<double*>(smem_raw + L.alpha_off);
     double* sXs = reinterpret_cast<double*>(smem_raw + L.xs_off);
     double* sXt = reinterpret_cast<double*>(smem_raw + L.xt_off);
-    double* sMean = reinterpret_cast<double*>(smem_raw + L.mean_off);
     double* sSS = reinterpret_cast<double*>(smem_raw + L.ss_off);
+    double* sMean = reinterpret_cast<double*>(smem_raw + L.mean_off);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int Npad = 8 * p.NB, T = p.T;
+    const int Npad = 8 * p.NB, T = p.T, RG = p.RG;
+    const int g = warp % RG, cg = warp / RG;
 
-    for (int i = threadIdx.x; i < Npad; i += kThreads) sAlpha[i] = p.alpha[i];
     if (!GRID) {
         for (int i = threadIdx.x; i < Npad * p.d; i += kThreads) sXs[i] = p.Xs[i];
         if ((int64_t)blockIdx.x < p.ntiles) load_tile_rows(p, sXt, (int64_t)blockIdx.x * T);
@@ -140,18 +39,24 @@ __global__ void __launch_bounds__(kThreads, 1) k_posterior(const __grid_constant
     int par = 0;
     for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, par ^= 1) {
         const int64_t tile_local0 = tile * T;
-        double* sMeanT = sMean + par * T;
-        double* sSST = sSS + (size_t)par * p.RG * T;
-        if (GRID) gen_grid(p, sK, sAlpha, sMeanT, p.row0 + tile_local0, warp, lane);
-        else gen_rows<KIND>(p, sK, sAlpha, sXs, sXt + (size_t)par * T * p.d, sMeanT, warp, lane);
+        double* sSST = sSS + (size_t)par * RG * T;
+        double* sMeanT = sMean + (size_t)par * RG * T;
+        if (GRID) gen_grid(p, sK, p.row0 + tile_local0, warp, lane);
+        else gen_rows<KIND>(p, sK, sXs, sXt + (size_t)par * T * p.d, warp, lane);
         __syncthreads();
         if (!GRID) {
+            // the next tile's candidate rows are fetched under the contraction
             const int64_t next = tile + gridDim.x;
             if (next < p.ntiles) load_tile_rows(p, sXt + (size_t)(par ^ 1) * T * p.d, next * T);
         }
-        mma_phase<BT>(p, sK, sSST, warp, lane);
+        contract_tile<BT>(p, p.Afrag + lane, sK + (size_t)(cg * BT) * 32 + lane, sSST, sMeanT, g, cg, lane);
         __syncthreads();
-        epilogue(p, sMeanT, sSST, tile_local0);
+        for (int t = threadIdx.x; t < T; t += kThreads) {
+            const int64_t row = tile_local0 + t;
+            if (row < p.M) finalize_row(p, sSST, sMeanT, t, row);
+        }
+        // the partial-sum buffers alternate with `par`; sK is rewritten only after the barrier at the top of the next
+        // iteration's contraction, which every thread reaches after its epilogue
     }
 }
 
@@ -240,12 +145,16 @@ __global__ void k_grid_rows(GridDecode gd, const double* __restrict__ axis, int6
 // ---------------------------------------------------------------- host
 struct LaunchPlan { int BT, RG, CG, T, TB, npass; size_t smem; };
 
+void row_groups(int NB, int& RG, int& CG) {
+    if (NB >= 32) { RG = 8; CG = 1; }
+    else if (NB >= 16) { RG = 4; CG = 2; }
+    else if (NB >= 8) { RG = 2; CG = 4; }
+    else { RG = 1; CG = 8; }
+}
+
 int plan_launch(so_handle* h, const GPState& g, int64_t M, bool grid, LaunchPlan& lp) {
     const int NB = g.NB;
-    if (NB >= 32) { lp.RG = 8; lp.CG = 1; }
-    else if (NB >= 16) { lp.RG = 4; lp.CG = 2; }
-    else if (NB >= 8) { lp.RG = 2; lp.CG = 4; }
-    else { lp.RG = 1; lp.CG = 8; }
+    row_groups(NB, lp.RG, lp.CG);
     const size_t limit = (size_t)h->smem_optin;
     int BT = 8;
     while (BT >= 2 && smem_layout(NB, 8 * BT * lp.CG, g.d, lp.RG, grid).total > limit) BT >>= 1;
@@ -282,79 +191,14 @@ int launch_bt(so_handle* h, const PostParams& p, const LaunchPlan& lp, cudaStrea
     }
 }
 
-// ---- warp-specialised variant -------------------------------------------------------------------
-struct WsPlan { int BT, RG, CG, T, TB, npass, gpt, Rg, CW; size_t smem; };
-
-int plan_ws(so_handle* h, const GPState& g, int64_t M, bool grid, WsPlan& wp, bool wide = false, bool tma = false) {
-    const int NB = g.NB;
-    // wide: 16 consumer warps x 2 block rows (TMA mode, NB >= 32); else 8 consumer warps x 4 block rows
-    wp.CW = (wide && NB >= 32) ? 16 : 8;
-    const int rows = wp.CW == 16 ? 2 : 4;
-    if (NB >= 32) { wp.RG = wp.CW; wp.CG = 1; }
-    else if (NB >= 16) { wp.RG = 4; wp.CG = 2; }
-    else if (NB >= 8) { wp.RG = 2; wp.CG = 4; }
-    else { wp.RG = 1; wp.CG = 8; }
-    wp.npass = (NB + rows * wp.RG - 1) / (rows * wp.RG);
-    wp.gpt = (NB + kGroupK - 1) / kGroupK;
-    const size_t limit = (size_t)h->smem_optin;
-    const int min_groups = wp.npass > 1 ? wp.gpt : 2;
-    int BT = 8 / wp.CG;
-    auto fit = [&](int bt) {
-        int rg = wp.gpt + 2;
-        while (rg >= min_groups && ws_smem(NB, 8 * bt * wp.CG, g.d, wp.RG, rg, grid, tma).total > limit) --rg;
-        return rg >= min_groups ? rg : 0;
-    };
-    while (BT >= 1 && fit(BT) == 0) BT >>= 1;
-    if (BT < 1) return so_fail(h, SO_ERR_CAPACITY, "posterior: N too large for the shared-memory ring");
-    while (BT > 1 && (M + 8 * BT * wp.CG - 1) / (8 * BT * wp.CG) < 2 * (int64_t)h->num_sms) BT >>= 1;
-    wp.BT = BT;
-    wp.T = 8 * BT * wp.CG;
-    wp.TB = BT * wp.CG;
-    wp.Rg = fit(BT);
-    wp.smem = ws_smem(NB, wp.T, g.d, wp.RG, wp.Rg, grid, tma).total;
-    return SO_OK;
-}
-
-template <int BT, int KIND, int MODE, int CW>
-int launch_ws_cw(so_handle* h, const WsParams& wp, const WsPlan& pl, cudaStream_t stream) {
-    static int configured_for = -1;
-    if (configured_for != h->device) {
-        SO_CUDA(h, cudaFuncSetAttribute(k_posterior_ws<BT, KIND, MODE, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
-        configured_for = h->device;
-    }
-    const int grid = (int)(wp.p.ntiles < (int64_t)h->num_sms ? wp.p.ntiles : (int64_t)h->num_sms);
-    k_posterior_ws<BT, KIND, MODE, CW><<<grid, WsShape<CW>::kThreads, pl.smem, stream>>>(wp);
-    SO_CHECK_LAUNCH(h, "k_posterior_ws");
-    return SO_OK;
-}
-
-template <int BT, int KIND, int MODE>
-int launch_ws_one(so_handle* h, const WsParams& wp, const WsPlan& pl, cudaStream_t stream) {
-    if (MODE == kModeTma && BT == 8 && pl.CW == 16) return launch_ws_cw<BT, KIND, MODE, (MODE == kModeTma && BT == 8) ? 16 : 8>(h, wp, pl, stream);
-    return launch_ws_cw<BT, KIND, MODE, 8>(h, wp, pl, stream);
-}
-
-template <int KIND, int MODE>
-int launch_ws_bt(so_handle* h, const WsParams& wp, const WsPlan& pl, cudaStream_t stream) {
-    switch (pl.BT) {
-        case 8: return launch_ws_one<8, KIND, MODE>(h, wp, pl, stream);
-        case 4: return launch_ws_one<4, KIND, MODE>(h, wp, pl, stream);
-        case 2: return launch_ws_one<2, KIND, MODE>(h, wp, pl, stream);
-        default: return launch_ws_one<1, KIND, MODE>(h, wp, pl, stream);
-    }
-}
-
-// ---- TMA double-buffer variant (grid path default) -----------------------------------------------
+// ---- TMA double-buffer kernel (grid path default) ----------------------------------------------------------------
 struct TmaPlan { int BT, RG, CG, T, TB, npass, kb_pad; size_t smem; };
 
 int plan_tma(so_handle* h, const GPState& g, TmaPlan& tp) {
     const int NB = g.NB;
-    if (NB >= 32) { tp.RG = 8; tp.CG = 1; }
-    else if (NB >= 16) { tp.RG = 4; tp.CG = 2; }
-    else if (NB >= 8) { tp.RG = 2; tp.CG = 4; }
-    else { tp.RG = 1; tp.CG = 8; }
+    row_groups(NB, tp.RG, tp.CG);
     tp.npass = (NB + 4 * tp.RG - 1) / (4 * tp.RG);
-    tp.kb_pad = kGroupK * ((NB + kGroupK - 1) / kGroupK);
+    tp.kb_pad = kChunkK * ((NB + kChunkK - 1) / kChunkK);
     const int options[3] = {6, 4, 2};
     for (int k = 0; k < 3; ++k) {
         const int bt = options[k];
@@ -380,14 +224,10 @@ int launch_tma_one(so_handle* h, const TmaParams& tp, size_t smem, cudaStream_t 
     return SO_OK;
 }
 
-// SO_K2_VARIANT=bulk selects the bulk-synchronous kernel (kept for A/B measurements); default = warp-specialised.
-// SO_K2_VARIANT: "tma" (default: TMA double buffer on the grid path, bulk kernel for explicit rows), "bulk" (bulk kernel
-// everywhere), "ws" (warp-specialised producer/consumer kernels everywhere) -- for A/B measurements.
-int k2_variant() {
+// SO_K2_VARIANT=bulk forces the generate-then-contract kernel on the grid path too (A/B measurements).
+bool force_bulk() {
     const char* v = std::getenv("SO_K2_VARIANT");
-    if (v && std::string(v) == "bulk") return 1;
-    if (v && std::string(v) == "ws") return 2;
-    return 0;
+    return v && std::string(v) == "bulk";
 }
 
 int run_posterior(so_handle* h, int gp, const double* Xstar_d, bool grid, int64_t row0, int64_t M, double beta, double fmin,
@@ -412,26 +252,15 @@ int run_posterior(so_handle* h, int gp, const double* Xstar_d, bool grid, int64_
     }
     DeviceGuard guard(h->device);
     cudaStream_t stream = (cudaStream_t)stream_;
-    const int variant = k2_variant();
-    const bool tma2 = grid && variant == 0 && g.tma_ready;
-    const bool bulk = !tma2 && variant != 2;
-    LaunchPlan lp;
-    WsPlan pl;
-    const bool tma = grid && !bulk && !tma2 && false;
-    int rc = SO_OK;
-    if (tma2) { lp.RG = g.tma_RG; lp.CG = g.tma_CG; lp.T = g.tma_T; lp.TB = g.tma_BT * g.tma_CG; lp.BT = g.tma_BT;
-                lp.npass = (g.NB + 4 * lp.RG - 1) / (4 * lp.RG); lp.smem = 0; }
-    else rc = bulk ? plan_launch(h, g, M, grid, lp) : plan_ws(h, g, M, grid, pl);
-    if (rc) return rc;
-    WsParams wp;
-    PostParams& p = wp.p;
+    const bool tma = grid && g.tma_ready && !force_bulk();
+
+    TmaParams tp;
+    PostParams& p = tp.p;
     p.N = g.N; p.NB = g.NB; p.d = g.d; p.kind = g.kind;
-    if (bulk || tma2) { p.RG = lp.RG; p.CG = lp.CG; p.T = lp.T; p.TB = lp.TB; p.npass = lp.npass; }
-    else { p.RG = pl.RG; p.CG = pl.CG; p.T = pl.T; p.TB = pl.TB; p.npass = pl.npass; }
-    p.Afrag = g.Afrag; p.alpha = g.alpha; p.Xs = g.Xs;
+    p.Afrag = g.Afrag; p.zvec = g.zvec; p.Xs = g.Xs;
     for (int j = 0; j < SO_MAX_DIM; ++j) p.inv_ls[j] = g.inv_ls[j];
     p.variance = g.variance;
-    p.Xstar = Xstar_d; p.M = M; p.row0 = row0; p.ntiles = (M + p.T - 1) / p.T;
+    p.Xstar = Xstar_d; p.M = M; p.row0 = row0;
     p.gd = 0; p.E = g.E;
     for (int j = 0; j < kGridMaxDim; ++j) { p.gn[j] = 1; p.goff[j] = 0; p.gstride[j] = 1; }
     if (grid) {
@@ -440,43 +269,35 @@ int run_posterior(so_handle* h, int gp, const double* Xstar_d, bool grid, int64_
     }
     p.beta = beta; p.fmin = fmin;
     p.mean = mean_d; p.var = var_d; p.Q = Q_d; p.q_stride = q_stride; p.q_col = q_col; p.S = S_d; p.safe_mode = safe_mode;
-    if (tma2) {
-        // tiles are aligned to the slow blocks of the product grid: global tile = (row / F) * tpb + (row % F) / T
-        TmaParams tp;
-        tp.p = p;
-        tp.PfFrag = g.PfFrag; tp.Aprime = g.Aprime; tp.zvec = g.zvec; tp.a_stride = g.a_stride;
+
+    if (tma) {
+        p.RG = g.tma_RG; p.CG = g.tma_CG; p.T = g.tma_T; p.TB = g.tma_BT * g.tma_CG;
+        p.npass = (g.NB + 4 * p.RG - 1) / (4 * p.RG);
+        tp.PfFrag = g.PfFrag; tp.Aprime = g.Aprime; tp.a_stride = g.a_stride;
         tp.fast_rows = h->grid.fast_rows; tp.tpb = g.tma_tpb; tp.kb_pad = g.tma_kb_pad;
+        // tiles are aligned to the slow blocks of the product grid: global tile = (row / F) * tpb + (row % F) / T
         const int64_t F = h->grid.fast_rows, last_row = row0 + M - 1;
-        const int64_t t0 = (row0 / F) * g.tma_tpb + (row0 % F) / lp.T;
-        const int64_t t1 = (last_row / F) * g.tma_tpb + (last_row % F) / lp.T;
+        const int64_t t0 = (row0 / F) * g.tma_tpb + (row0 % F) / p.T;
+        const int64_t t1 = (last_row / F) * g.tma_tpb + (last_row % F) / p.T;
         tp.first_tile = t0;
-        tp.p.ntiles = t1 - t0 + 1;
-        const size_t smem = tma_smem(g.tma_kb_pad, lp.TB, lp.RG, lp.T).total;
-        switch (lp.BT) {
+        p.ntiles = t1 - t0 + 1;
+        const size_t smem = tma_smem(g.tma_kb_pad, p.TB, p.RG, p.T).total;
+        switch (g.tma_BT) {
             case 6: return launch_tma_one<6>(h, tp, smem, stream);
             case 4: return launch_tma_one<4>(h, tp, smem, stream);
             default: return launch_tma_one<2>(h, tp, smem, stream);
         }
     }
-    if (bulk) {
-        if (grid) return launch_bt<SO_KERNEL_RBF, true>(h, p, lp, stream);
-        switch (g.kind) {
-            case SO_KERNEL_RBF: return launch_bt<SO_KERNEL_RBF, false>(h, p, lp, stream);
-            case SO_KERNEL_MATERN32: return launch_bt<SO_KERNEL_MATERN32, false>(h, p, lp, stream);
-            default: return launch_bt<SO_KERNEL_MATERN52, false>(h, p, lp, stream);
-        }
-    }
-    wp.gpt = pl.gpt; wp.Rg = pl.Rg;
-    wp.fast_rows = h->grid.fast_rows;
-    wp.Pfast = g.P2;
-    wp.Pslow = g.P2 ? g.P2 + (size_t)h->grid.fast_rows * 8 * g.NB : nullptr;
-    wp.PfFrag = nullptr; wp.Aprime = nullptr; wp.Wslow = nullptr; wp.a_stride = 0; wp.tpb = 1; wp.first_tile = 0;
-    (void)tma;
-    if (grid) return launch_ws_bt<SO_KERNEL_RBF, kModeGrid>(h, wp, pl, stream);
+    LaunchPlan lp;
+    int rc = plan_launch(h, g, M, grid, lp);
+    if (rc) return rc;
+    p.RG = lp.RG; p.CG = lp.CG; p.T = lp.T; p.TB = lp.TB; p.npass = lp.npass;
+    p.ntiles = (M + p.T - 1) / p.T;
+    if (grid) return launch_bt<SO_KERNEL_RBF, true>(h, p, lp, stream);
     switch (g.kind) {
-        case SO_KERNEL_RBF: return launch_ws_bt<SO_KERNEL_RBF, kModeRows>(h, wp, pl, stream);
-        case SO_KERNEL_MATERN32: return launch_ws_bt<SO_KERNEL_MATERN32, kModeRows>(h, wp, pl, stream);
-        default: return launch_ws_bt<SO_KERNEL_MATERN52, kModeRows>(h, wp, pl, stream);
+        case SO_KERNEL_RBF: return launch_bt<SO_KERNEL_RBF, false>(h, p, lp, stream);
+        case SO_KERNEL_MATERN32: return launch_bt<SO_KERNEL_MATERN32, false>(h, p, lp, stream);
+        default: return launch_bt<SO_KERNEL_MATERN52, false>(h, p, lp, stream);
     }
 }
 
@@ -583,6 +404,7 @@ extern "C" int so_grid_prepare(so_handle* h, int gp, void* stream_) {
     DeviceGuard guard(h->device);
     cudaStream_t stream = (cudaStream_t)stream_;
     const int Npad = 8 * g.NB;
+    // ---- per-axis factor tables (expander kernel, fallback posterior kernel)
     const size_t need = (size_t)gs.total * g.capN + SO_MAX_DIM;
     if (need > g.capE) {
         SO_CUDA(h, cudaStreamSynchronize(stream));
@@ -597,11 +419,17 @@ extern "C" int so_grid_prepare(so_handle* h, int gp, void* stream_) {
     k_grid_tables<<<grd, 128, 0, stream>>>(gs.axis, g.Xs, g.E, gs.total, g.N, Npad, g.d,
                                            reinterpret_cast<const int*>(gs.axis + gs.cap), g.variance, inv_ls_d);
     SO_CHECK_LAUNCH(h, "k_grid_tables");
-    {
-        const int64_t trows = gs.fast_rows + gs.slow_rows;
+
+    // ---- tables of the TMA kernel: product tables -> fragment-ordered fast table + scaled operands A'(s)
+    g.tma_ready = false;
+    TmaPlan pl;
+    const int64_t trows = gs.fast_rows + gs.slow_rows;
+    const size_t a_stride = (tri_blocks(g.NB) + 1) * 32;
+    const size_t ap_elems = (size_t)gs.slow_rows * a_stride + 64;
+    const bool fits = plan_tma(h, g, pl) == SO_OK && trows <= 2147483647 && gs.slow_rows <= 65535 &&
+                      (size_t)trows * Npad * sizeof(double) <= ((size_t)4 << 30) && ap_elems * sizeof(double2) <= ((size_t)8 << 30);
+    if (fits) {
         const size_t need2 = (size_t)trows * Npad;
-        if (need2 * sizeof(double) > ((size_t)4 << 30))
-            return so_fail(h, SO_ERR_CAPACITY, "so_grid_prepare: product tables would exceed 4 GiB; use explicit rows");
         if (need2 > g.capP2) {
             SO_CUDA(h, cudaStreamSynchronize(stream));
             if (g.P2) cudaFree(g.P2);
@@ -619,59 +447,38 @@ extern "C" int so_grid_prepare(so_handle* h, int gp, void* stream_) {
             ts.in_fast[j] = j < gs.d ? gs.in_fast[j] : 0;
         }
         ts.fast_rows = gs.fast_rows; ts.slow_rows = gs.slow_rows;
-        if (trows > 2147483647) return so_fail(h, SO_ERR_CAPACITY, "so_grid_prepare: too many table rows");
-        k_grid_tables2<<<(unsigned)trows, 128, 0, stream>>>(ts, gs.axis, g.Xs, g.P2, g.P2 + (size_t)gs.fast_rows * Npad, g.N, Npad,
-                                                             g.d, g.variance, inv_ls_d);
+        double* Pfast = g.P2;
+        double* Pslow = g.P2 + (size_t)gs.fast_rows * Npad;
+        k_grid_tables2<<<(unsigned)trows, 128, 0, stream>>>(ts, gs.axis, g.Xs, Pfast, Pslow, g.N, Npad, g.d, g.variance, inv_ls_d);
         SO_CHECK_LAUNCH(h, "k_grid_tables2");
-    }
-    // ---- TMA-mode tables (fragment-ordered fast table, scaled operands, Wslow)
-    g.tma_ready = false;
-    {
-        TmaPlan pl;
-        if (plan_tma(h, g, pl) == SO_OK) {
-            const int T = pl.T, TB = pl.TB, gpt = pl.kb_pad / kGroupK;
-            const int tpb = (int)((gs.fast_rows + T - 1) / T);
-            const size_t pf_elems = (size_t)tpb * gpt * kGroupK * TB * 32;
-            const size_t a_stride = (tri_blocks(g.NB) + 1) * 32;
-            const size_t ap_elems = (size_t)gs.slow_rows * a_stride + 64;
-            const size_t w_elems = (size_t)gs.slow_rows * Npad;
-            const size_t limit = (size_t)8 << 30;       // 8 GiB of scaled operands at most, else kModeGrid
-            if (ap_elems * sizeof(double2) <= limit && gs.slow_rows <= 65535) {
-                if (pf_elems > g.capPfFrag) {
-                    SO_CUDA(h, cudaStreamSynchronize(stream));
-                    if (g.PfFrag) cudaFree(g.PfFrag);
-                    g.PfFrag = nullptr;
-                    SO_CUDA(h, cudaMalloc(&g.PfFrag, sizeof(double2) * pf_elems * 2));
-                    g.capPfFrag = pf_elems * 2;
-                }
-                if (ap_elems > g.capAprime) {
-                    SO_CUDA(h, cudaStreamSynchronize(stream));
-                    if (g.Aprime) cudaFree(g.Aprime);
-                    g.Aprime = nullptr;
-                    const size_t cap = ap_elems + ap_elems / 4;
-                    SO_CUDA(h, cudaMalloc(&g.Aprime, sizeof(double2) * cap));
-                    g.capAprime = cap;
-                }
-                if (w_elems > g.capWslow) {
-                    SO_CUDA(h, cudaStreamSynchronize(stream));
-                    if (g.Wslow) cudaFree(g.Wslow);
-                    g.Wslow = nullptr;
-                    SO_CUDA(h, cudaMalloc(&g.Wslow, sizeof(double) * w_elems * 2));
-                    g.capWslow = w_elems * 2;
-                }
-                const double* Pfast = g.P2;
-                const double* Pslow = g.P2 + (size_t)gs.fast_rows * Npad;
-                k_pffrag<<<(unsigned)((pf_elems + 255) / 256 < 4096 ? (pf_elems + 255) / 256 : 4096), 256, 0, stream>>>(
-                    Pfast, g.PfFrag, gs.fast_rows, g.N, Npad, T, TB, gpt, tpb);
-                SO_CHECK_LAUNCH(h, "k_pffrag");
-                dim3 grd((unsigned)((a_stride + 255) / 256), (unsigned)gs.slow_rows);
-                k_aprime<<<grd, 256, 0, stream>>>(g.Afrag, Pslow, g.alpha, g.Aprime, g.Wslow, g.NB, a_stride);
-                SO_CHECK_LAUNCH(h, "k_aprime");
-                SO_CUDA(h, cudaMemsetAsync(g.Aprime + (size_t)gs.slow_rows * a_stride, 0, sizeof(double2) * 64, stream));
-                g.a_stride = a_stride; g.tma_T = T; g.tma_tpb = tpb; g.tma_BT = pl.BT; g.tma_RG = pl.RG; g.tma_CG = pl.CG;
-                g.tma_kb_pad = pl.kb_pad; g.tma_ready = true;
-            }
+
+        const int tpb = (int)((gs.fast_rows + pl.T - 1) / pl.T);
+        const size_t pf_elems = (size_t)tpb * pl.kb_pad * pl.TB * 32;
+        if (pf_elems > g.capPfFrag) {
+            SO_CUDA(h, cudaStreamSynchronize(stream));
+            if (g.PfFrag) cudaFree(g.PfFrag);
+            g.PfFrag = nullptr;
+            SO_CUDA(h, cudaMalloc(&g.PfFrag, sizeof(double2) * pf_elems * 2));
+            g.capPfFrag = pf_elems * 2;
         }
+        if (ap_elems > g.capAprime) {
+            SO_CUDA(h, cudaStreamSynchronize(stream));
+            if (g.Aprime) cudaFree(g.Aprime);
+            g.Aprime = nullptr;
+            const size_t cap = ap_elems + ap_elems / 4;
+            SO_CUDA(h, cudaMalloc(&g.Aprime, sizeof(double2) * cap));
+            g.capAprime = cap;
+        }
+        const size_t pf_blocks = (pf_elems + 255) / 256;
+        k_pffrag<<<(unsigned)(pf_blocks < 4096 ? pf_blocks : 4096), 256, 0, stream>>>(Pfast, g.PfFrag, gs.fast_rows, g.N, Npad, pl.T,
+                                                                                      pl.TB, pl.kb_pad, tpb);
+        SO_CHECK_LAUNCH(h, "k_pffrag");
+        dim3 grd2((unsigned)((a_stride + 255) / 256), (unsigned)gs.slow_rows);
+        k_aprime<<<grd2, 256, 0, stream>>>(g.Afrag, Pslow, g.Aprime, g.NB, a_stride);
+        SO_CHECK_LAUNCH(h, "k_aprime");
+        SO_CUDA(h, cudaMemsetAsync(g.Aprime + (size_t)gs.slow_rows * a_stride, 0, sizeof(double2) * 64, stream));
+        g.a_stride = a_stride; g.tma_T = pl.T; g.tma_tpb = tpb; g.tma_BT = pl.BT; g.tma_RG = pl.RG; g.tma_CG = pl.CG;
+        g.tma_kb_pad = pl.kb_pad; g.tma_ready = true;
     }
     g.grid_ready = true;
     return SO_OK;

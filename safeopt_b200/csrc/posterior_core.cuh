@@ -1,6 +1,6 @@
-// Device building blocks shared by the posterior kernel (posterior.cu) and the batched expander
-// test (expander.cu): tile parameters, shared-memory layout, the two kernel-row generators that
-// write the k(x*, X) tile straight into DMMA B-fragment order, and the DMMA K-segment loop.
+// Device building blocks shared by the posterior kernels (posterior.cu, posterior_tma.cuh) and the batched expander
+// test (expander.cu): tile parameters, shared-memory layout, the kernel-row generators that write the k(x*, X) tile
+// straight into DMMA B-fragment order, the DMMA K-segment loop and the tile-end reduction.
 #pragma once
 #include "common.cuh"
 
@@ -12,18 +12,18 @@ constexpr int kGridMaxDim = 6;   // grid fast path (larger d uses explicit rows)
 
 struct PostParams {
     int N, NB, d, RG, CG, T, TB, npass, kind;
-    const double2* Afrag;
-    const double* alpha;
-    const double* Xs;
+    const double2* Afrag;        // L^-1 packed in DMMA A-fragment order (fit.cu: k_pack_afrag)
+    const double* zvec;          // z = L^-1 y, zero padded to 8*NB: mean(x*) = (L^-1 k).z
+    const double* Xs;            // training inputs scaled by 1/lengthscale, 8*NB x d
     double inv_ls[SO_MAX_DIM];
     double variance;
-    const double* Xstar;
+    const double* Xstar;         // explicit candidate rows (M x d) or nullptr
     int64_t M, row0, ntiles;
-    int gd;
+    int gd;                      // grid description (so_grid_define) for the index-generated rows
     int gn[kGridMaxDim];
     int goff[kGridMaxDim];
     int64_t gstride[kGridMaxDim];
-    const double* E;
+    const double* E;             // per-axis factor tables, (sum n_j) x 8*NB
     double beta, fmin;
     double* mean;
     double* var;
@@ -34,33 +34,32 @@ struct PostParams {
 };
 
 struct SmemLayout {
-    size_t k_bytes, alpha_off, xs_off, xt_off, mean_off, ss_off, total;
+    size_t k_bytes, xs_off, xt_off, ss_off, mean_off, total;
 };
 
+// [ Kx tile | scaled training inputs | two tiles of candidate rows | |V|^2 partials x2 | mean partials x2 ]
 __host__ __device__ inline SmemLayout smem_layout(int NB, int T, int d, int RG, bool grid) {
     SmemLayout L;
     const size_t Npad = 8 * (size_t)NB;
     L.k_bytes = Npad * T * sizeof(double);
-    L.alpha_off = L.k_bytes;
-    L.xs_off = L.alpha_off + Npad * sizeof(double);
+    L.xs_off = L.k_bytes;
     L.xt_off = L.xs_off + (grid ? 0 : Npad * d * sizeof(double));
-    L.mean_off = L.xt_off + (grid ? 0 : 2 * (size_t)T * d * sizeof(double));
-    L.ss_off = L.mean_off + 2 * (size_t)T * sizeof(double);
-    L.total = L.ss_off + 2 * (size_t)RG * T * sizeof(double);
+    L.ss_off = L.xt_off + (grid ? 0 : 2 * (size_t)T * d * sizeof(double));
+    L.mean_off = L.ss_off + 2 * (size_t)RG * T * sizeof(double);
+    L.total = L.mean_off + 2 * (size_t)RG * T * sizeof(double);
     return L;
 }
 
 // ---------------------------------------------------------------- gen: explicit rows
+// Lane l of the warp that owns column tile ct produces, for every k-block kb, the pair
+// (k(x*_t, x_n0), k(x*_t, x_n0+1)) with t = 8 ct + l/4, n0 = 8 kb + 2 (l%4) -- exactly its slot of the B fragment.
 template <int KIND>
-__device__ __forceinline__ void gen_rows(const PostParams& p, double2* __restrict__ sK, const double* __restrict__ sAlpha,
-                                         const double* __restrict__ sXs, const double* __restrict__ sXt,
-                                         double* __restrict__ sMean, int warp, int lane) {
+__device__ __forceinline__ void gen_rows(const PostParams& p, double2* __restrict__ sK, const double* __restrict__ sXs,
+                                         const double* __restrict__ sXt, int warp, int lane) {
     const int d = p.d, N = p.N, NB = p.NB, TB = p.TB;
     const int q = lane & 3, tl = lane >> 2;
     for (int ct = warp; ct < TB; ct += kWarps) {
-        const int t = ct * 8 + tl;
-        const double* xt = sXt + t * d;
-        double m = 0.0;
+        const double* xt = sXt + (ct * 8 + tl) * d;
         for (int kb = 0; kb < NB; ++kb) {
             const int n0 = 8 * kb + 2 * q;
             const double* x0 = sXs + n0 * d;
@@ -73,29 +72,22 @@ __device__ __forceinline__ void gen_rows(const PostParams& p, double2* __restric
             }
             const double k0 = n0 < N ? kernel_of_r2<KIND>(r0, p.variance) : 0.0;
             const double k1 = n0 + 1 < N ? kernel_of_r2<KIND>(r1, p.variance) : 0.0;
-            m = fma(k0, sAlpha[n0], m);
-            m = fma(k1, sAlpha[n0 + 1], m);
             sK[(kb * TB + ct) * 32 + lane] = make_double2(k0, k1);
         }
-        m += __shfl_xor_sync(0xffffffffu, m, 1);
-        m += __shfl_xor_sync(0xffffffffu, m, 2);
-        if (q == 0) sMean[t] = m;
     }
 }
 
-// ---------------------------------------------------------------- gen: separable RBF on a grid
-// k(x*, x_n) = prod_j E_j[idx_j(row)][n]; the tables (sum_j n_j rows of Npad doubles, built once per
-// fit by k_grid_tables) replace N fp64 exp() per row by (d-1) multiplies -- exp costs ~21 FMA
-// slots of the one FP64 pipe the contraction also needs (profiles/r01_fp64_rates_b200.jsonl).
-__device__ __forceinline__ void gen_grid(const PostParams& p, double2* __restrict__ sK, const double* __restrict__ sAlpha,
-                                         double* __restrict__ sMean, int64_t tile_row0, int warp, int lane) {
+// ---------------------------------------------------------------- gen: separable RBF on a grid (per-axis tables)
+// k(x*, x_n) = prod_j E_j[idx_j(row)][n]; the tables (sum_j n_j rows of 8*NB doubles, built once per fit by
+// k_grid_tables) replace N fp64 exp() per row by (d-1) multiplies -- exp costs ~21 FMA slots of the one FP64 pipe the
+// contraction also needs (profiles/r01_fp64_rates_b200.jsonl).  Used by the expander kernel and as the fallback of the
+// grid path when the scaled-operand tables of the TMA kernel would not fit.
+__device__ __forceinline__ void gen_grid(const PostParams& p, double2* __restrict__ sK, int64_t tile_row0, int warp, int lane) {
     const int NB = p.NB, TB = p.TB, Npad = 8 * p.NB;
     const int q = lane & 3, tl = lane >> 2;
-    const double2* sA2 = reinterpret_cast<const double2*>(sAlpha);
     const int64_t last = p.row0 + p.M - 1;
     for (int ct = warp; ct < TB; ct += kWarps) {
-        const int t = ct * 8 + tl;
-        int64_t row = tile_row0 + t;
+        int64_t row = tile_row0 + ct * 8 + tl;
         if (row > last) row = last;
         const double2* e[kGridMaxDim];
 #pragma unroll
@@ -107,7 +99,6 @@ __device__ __forceinline__ void gen_grid(const PostParams& p, double2* __restric
                 e[j] = nullptr;
             }
         }
-        double m = 0.0;
         for (int kb = 0; kb < NB; ++kb) {
             double2 v = __ldg(e[0] + 4 * kb);
 #pragma unroll
@@ -118,20 +109,14 @@ __device__ __forceinline__ void gen_grid(const PostParams& p, double2* __restric
                     v.y *= w.y;
                 }
             }
-            const double2 a = sA2[4 * kb + q];
-            m = fma(v.x, a.x, m);
-            m = fma(v.y, a.y, m);
             sK[(kb * TB + ct) * 32 + lane] = v;
         }
-        m += __shfl_xor_sync(0xffffffffu, m, 1);
-        m += __shfl_xor_sync(0xffffffffu, m, 2);
-        if (q == 0) sMean[t] = m;
     }
 }
 
-// ---------------------------------------------------------------- mma
-// One K segment: accumulator slots FIRST..3 are active.  `a` holds the fragments of the current
-// k-block on entry and those of k-block kb_hi+1 on exit (software prefetch, distance one block).
+// ---------------------------------------------------------------- contraction
+// One K segment: accumulator slots FIRST..3 are active.  `a` holds the fragments of the current k-block on entry and
+// those of k-block kb_hi+1 on exit (software prefetch, distance one block; the packed operand has a block of slack).
 template <int BT, int FIRST>
 __device__ __forceinline__ void mma_segment(double (&acc)[4][BT][2], double2 (&a)[4], const double2* __restrict__ Afrag,
                                             const size_t (&abase)[4], const double2* __restrict__ sB, int TB,
@@ -157,6 +142,130 @@ __device__ __forceinline__ void mma_segment(double (&acc)[4][BT][2], double2 (&a
 
 __device__ __forceinline__ int pick4(int r0, int r1, int r2, int r3, int i) {
     return i == 0 ? r0 : (i == 1 ? r1 : (i == 2 ? r2 : r3));
+}
+
+// Recursive-halving reduction of K values per lane over the 8 lanes that hold the rows of one 8x8 block (lane bits
+// 4,3,2): after the three stages every lane owns K/8 fully reduced values, at 7K/8 shuffle+add pairs per lane instead of
+// 3K for a butterfly.  Scalar fp64 instructions are precious here: they share the one FP64 pipe with DMMA and are served
+// behind it (profiles/r01_k2_variants.md).  Lane (b4,b3,b2) ends up with original indices b4*K/2 + b3*K/4 + b2*K/8 + [0, K/8).
+template <int K>
+__device__ __forceinline__ void halving_reduce(double (&v)[K], int lane) {
+    static_assert(K % 8 == 0, "K must be a multiple of 8");
+#pragma unroll
+    for (int i = 0; i < K / 2; ++i) {
+        const bool up = (lane & 16) != 0;
+        const double send = up ? v[i] : v[i + K / 2];
+        const double keep = up ? v[i + K / 2] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < K / 4; ++i) {
+        const bool up = (lane & 8) != 0;
+        const double send = up ? v[i] : v[i + K / 4];
+        const double keep = up ? v[i + K / 4] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+#pragma unroll
+    for (int i = 0; i < K / 8; ++i) {
+        const bool up = (lane & 4) != 0;
+        const double send = up ? v[i] : v[i + K / 8];
+        const double keep = up ? v[i + K / 8] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+}
+
+// The whole contraction of one tile for one warp: V = A.B over the warp's block rows (pairing {g, 2RG-1-g, 2RG+g,
+// 4RG-1-g} per pass, which equalises the triangular work) and its BT column tiles, then per column
+//     |V|^2 partial (sum of squares of this warp's rows)  and  V.z partial (the mean's share, z = L^-1 y)
+// taken from the accumulators in one pass, reduced over the 8 row lanes by recursive halving and left in this row
+// group's slot of sSS / sMean (fixed order everywhere => bit-reproducible).
+template <int BT>
+__device__ __forceinline__ void contract_tile(const PostParams& p, const double2* __restrict__ Afrag_lane,
+                                              const double2* __restrict__ sB, double* __restrict__ sSST,
+                                              double* __restrict__ sMeanT, int g, int cg, int lane) {
+    static_assert(BT % 2 == 0, "BT must be even");
+    const int RG = p.RG, NB = p.NB, TB = p.TB, T = p.T;
+    for (int pass = 0; pass < p.npass; ++pass) {
+        const int base = 4 * RG * pass;
+        const int r0 = base + g, r1 = base + 2 * RG - 1 - g, r2 = base + 2 * RG + g, r3 = base + 4 * RG - 1 - g;
+        // rows are ascending; the ones beyond NB (inactive) form a suffix.  Slots are ordered by K extent, inactive
+        // slots (extent -1) first, so that "slots FIRST..3 active" holds in every segment.
+        const int na = (r0 < NB) + (r1 < NB) + (r2 < NB) + (r3 < NB);
+        int ext[4];
+        size_t abase[4];
+        double zs[4];              // z at this lane's row of each slot's block (0 for inactive slots)
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            const int src = s - (4 - na);
+            const int r = src >= 0 ? pick4(r0, r1, r2, r3, src) : -1;
+            ext[s] = r;
+            abase[s] = r >= 0 ? (size_t)r * (r + 1) / 2 * 32 : 0;
+            zs[s] = r >= 0 ? __ldg(p.zvec + 8 * r + (lane >> 2)) : 0.0;
+        }
+        double acc[4][BT][2];
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+#pragma unroll
+            for (int c = 0; c < BT; ++c) { acc[s][c][0] = 0.0; acc[s][c][1] = 0.0; }
+        double2 a[4];
+#pragma unroll
+        for (int s = 0; s < 4; ++s) a[s] = __ldg(Afrag_lane + abase[s]);
+        mma_segment<BT, 0>(acc, a, Afrag_lane, abase, sB, TB, 0, ext[0]);
+        mma_segment<BT, 1>(acc, a, Afrag_lane, abase, sB, TB, ext[0] + 1, ext[1]);
+        mma_segment<BT, 2>(acc, a, Afrag_lane, abase, sB, TB, ext[1] + 1, ext[2]);
+        mma_segment<BT, 3>(acc, a, Afrag_lane, abase, sB, TB, ext[2] + 1, ext[3]);
+        // red[c*2+h] = sum of squares, red[2BT + c*2+h] = mean share, for column 8c + 2(lane%4) + h of this column group
+        double red[4 * BT];
+#pragma unroll
+        for (int c = 0; c < BT; ++c)
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                double q2 = 0.0, mz = 0.0;
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    q2 = fma(acc[s][c][hh], acc[s][c][hh], q2);
+                    mz = fma(acc[s][c][hh], zs[s], mz);
+                }
+                red[c * 2 + hh] = q2;
+                red[2 * BT + c * 2 + hh] = mz;
+            }
+        halving_reduce<4 * BT>(red, lane);
+        // lane (b4,b3,b2) owns original indices first + [0, BT/2)
+        const int first = ((lane >> 4) & 1) * (2 * BT) + ((lane >> 3) & 1) * BT + ((lane >> 2) & 1) * (BT / 2);
+#pragma unroll
+        for (int i = 0; i < BT / 2; ++i) {
+            const int idx = first + i;
+            const bool is_mean = idx >= 2 * BT;
+            const int ch = is_mean ? idx - 2 * BT : idx;           // c*2 + h
+            double* dst = (is_mean ? sMeanT : sSST) + (size_t)g * T + (size_t)(cg * BT + (ch >> 1)) * 8 + 2 * (lane & 3) + (ch & 1);
+            *dst = pass == 0 ? red[i] : *dst + red[i];
+        }
+    }
+}
+
+// Finalise one row from the per-row-group partials: var = max(k** - |V|^2, 1e-15), l/u = mean -/+ beta sqrt(var) with
+// separate multiply and add roundings (NumPy does not contract, gp_opt.py:475-476), S bit (strict >, gp_opt.py:481).
+__device__ __forceinline__ void finalize_row(const PostParams& p, const double* __restrict__ sSST, const double* __restrict__ sMeanT,
+                                             int t, int64_t row) {
+    const int T = p.T, RG = p.RG;
+    double sumsq = 0.0, mu = 0.0;
+    for (int g = 0; g < RG; ++g) { sumsq += sSST[(size_t)g * T + t]; mu += sMeanT[(size_t)g * T + t]; }
+    double v = p.variance - sumsq;
+    v = v > SO_VAR_FLOOR ? v : SO_VAR_FLOOR;
+    const double sd = sqrt(v);
+    const double bs = __dmul_rn(p.beta, sd);
+    const double lo = __dsub_rn(mu, bs), up = __dadd_rn(mu, bs);
+    if (p.mean) p.mean[row] = mu;
+    if (p.var) p.var[row] = v;
+    if (p.Q) {
+        double* qp = p.Q + (size_t)row * p.q_stride + p.q_col;
+        if ((p.q_stride & 1) == 0 && (p.q_col & 1) == 0) *reinterpret_cast<double2*>(qp) = make_double2(lo, up);
+        else { qp[0] = lo; qp[1] = up; }
+    }
+    if (p.safe_mode != SO_SAFE_NONE && p.S) {
+        const uint8_t safe = lo > p.fmin ? 1 : 0;
+        p.S[row] = p.safe_mode == SO_SAFE_WRITE ? safe : (uint8_t)(p.S[row] & safe);
+    }
 }
 
 __device__ __forceinline__ void load_tile_rows(const PostParams& p, double* __restrict__ sXt, int64_t tile_local0) {

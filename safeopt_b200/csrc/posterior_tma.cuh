@@ -1,28 +1,53 @@
-// K2, grid path, final form ("tma"): the bulk-synchronous contraction loop of posterior.cu -- whose MMA phase was
-// measured at 92% of the DMMA peak -- with the kernel-row generation phase removed altogether:
+// K2, grid path ("tma" kernel): the contraction loop of posterior_core.cuh with the kernel-row generation phase removed.
 //
-//   * the slow-axis factor of the separable RBF kernel is folded into the A operand, A'(s) = L^-1 diag(Pslow[s])
-//     (one packed 270 KB matrix per slow index, L2-resident while its 2500 rows are being processed), so the B tile of
-//     a row block is a plain contiguous slice of the fragment-ordered fast table;
-//   * one thread moves the NEXT tile's slice (T = 48 rows x N: 96 KB) with cp.async.bulk (TMA) into the second half of a
-//     double buffer while all eight warps contract the current one; completion is an mbarrier transaction count;
-//   * the mean k.(Pslow*alpha) is picked up inside the contraction loop: warp (g, pass, slot) adds the contribution of
-//     k-block kb == its own block row, so every k-block is counted exactly once with ~1% extra fp64 work.
+//   * The slow-axis factor of the separable RBF kernel is folded into the A operand, A'(s) = L^-1 diag(Pslow[s]) -- one
+//     packed 270 KB matrix per slow index (N = 256), L2-resident while its block of fast rows is processed -- so the B
+//     tile of a row block is a plain contiguous slice of the fragment-ordered fast table: V = L^-1 k = A'(s) Pfast.
+//   * One thread moves the NEXT tile's slice (T = 48 rows x N: 96 KB) with cp.async.bulk (TMA, SASS UBLKCP) into the
+//     other half of a shared-memory double buffer while all eight warps contract the current one; completion is an
+//     mbarrier transaction count.  No fp64 instruction is spent on generating kernel rows: DMMA saturates the one FP64
+//     pipe and scalar fp64 work is served behind it (profiles/r01_k2_variants.md).
+//   * Mean and variance both come out of the accumulators: |V|^2 and V.z with z = L^-1 y.
 //
-// Per tile: one mbarrier wait, the contraction, one __syncthreads, a 48-thread epilogue.  The warp-specialised
-// producer/consumer variants (posterior_ws.cuh) stay available for comparison (SO_K2_VARIANT=ws); they lose ~20% in
-// their consumer loop to per-group barrier traffic and the smaller register budget
-// (profiles/r01_k2_variants.md).
+// Per tile: one mbarrier wait, the contraction, one __syncthreads, a T-thread epilogue.  Tiles are aligned to the slow
+// blocks of the grid (tile = (row / F) * tpb + (row % F) / T); rows outside the rank's shard are masked in the epilogue.
+// Algorithmic HBM bytes per row: 33 written (mean, var, l, u, S); the A' table adds slow_rows * 270 KB of reads per
+// launch (676 MB at C4 = 0.1 ms at 6.5 TB/s against a 14 ms kernel).
 #pragma once
-#include "posterior_ws.cuh"
+#include "posterior_core.cuh"
 
 namespace {
+
+constexpr int kChunkK = 4;            // k-blocks per TMA bulk copy
+
+// ---- mbarrier / TMA primitives (PTX; SASS: SYNCS.*, UBLKCP) -----------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}\n" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
 
 struct TmaParams {
     PostParams p;
     const double2* PfFrag;            // [tile in slow block][k-block][col tile][lane] double2, zero padded
     const double2* Aprime;            // slow_rows packed scaled operands, a_stride double2 apart
-    const double* zvec;               // Npad: z = L^-1 y
     size_t a_stride;
     int64_t fast_rows;
     int64_t first_tile;
@@ -42,60 +67,6 @@ __host__ __device__ inline TmaSmem tma_smem(int kb_pad, int TB, int RG, int T) {
     return L;
 }
 
-// Recursive-halving reduction of K values per lane over the 8 lanes that hold the rows of one 8x8 block (lane bits
-// 4,3,2): after the three stages every lane owns K/8 fully reduced values, at 7K/8 shuffle+add pairs per lane instead of
-// 3K for a butterfly.  Scalar fp64 instructions are precious here: they share the one FP64 pipe with DMMA and are
-// served behind it (profiles/r01_k2_variants.md).  Lane (b4,b3,b2) ends up with original indices
-// b4*K/2 + b3*K/4 + b2*K/8 + [0, K/8).
-template <int K>
-__device__ __forceinline__ void halving_reduce(double (&v)[K], int lane) {
-    static_assert(K % 8 == 0, "K must be a multiple of 8");
-#pragma unroll
-    for (int i = 0; i < K / 2; ++i) {
-        const bool up = (lane & 16) != 0;
-        const double send = up ? v[i] : v[i + K / 2];
-        const double keep = up ? v[i + K / 2] : v[i];
-        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-    }
-#pragma unroll
-    for (int i = 0; i < K / 4; ++i) {
-        const bool up = (lane & 8) != 0;
-        const double send = up ? v[i] : v[i + K / 4];
-        const double keep = up ? v[i + K / 4] : v[i];
-        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-    }
-#pragma unroll
-    for (int i = 0; i < K / 8; ++i) {
-        const bool up = (lane & 4) != 0;
-        const double send = up ? v[i] : v[i + K / 8];
-        const double keep = up ? v[i + K / 8] : v[i];
-        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-    }
-}
-
-template <int BT, int FIRST>
-__device__ __forceinline__ void tma_segment(double (&acc)[4][BT][2], double2 (&a)[4], const double2* __restrict__ Afrag,
-                                            const size_t (&abase)[4], const double2* __restrict__ sB, int TB, int kb_lo,
-                                            int kb_hi) {
-    for (int kb = kb_lo; kb <= kb_hi; ++kb) {
-        double2 an[4];
-#pragma unroll
-        for (int s = FIRST; s < 4; ++s) an[s] = __ldg(Afrag + abase[s] + (size_t)(kb + 1) * 32);
-        const double2* bp = sB + (size_t)kb * TB * 32;
-#pragma unroll
-        for (int c = 0; c < BT; ++c) {
-            const double2 b = bp[c * 32];
-#pragma unroll
-            for (int s = FIRST; s < 4; ++s) {
-                dmma884(acc[s][c][0], acc[s][c][1], a[s].x, b.x);
-                dmma884(acc[s][c][0], acc[s][c][1], a[s].y, b.y);
-            }
-        }
-#pragma unroll
-        for (int s = FIRST; s < 4; ++s) a[s] = an[s];
-    }
-}
-
 template <int BT>
 __global__ void __launch_bounds__(kThreads, 1) k_posterior_tma(const __grid_constant__ TmaParams tp) {
     const PostParams& p = tp.p;
@@ -103,14 +74,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_posterior_tma(const __grid_cons
     const TmaSmem L = tma_smem(tp.kb_pad, p.TB, p.RG, p.T);
     double2* sBuf = reinterpret_cast<double2*>(smem_raw);
     double* sSS = reinterpret_cast<double*>(smem_raw + L.ss_off);
-    double* sMeanG = reinterpret_cast<double*>(smem_raw + L.mean_off);
+    double* sMean = reinterpret_cast<double*>(smem_raw + L.mean_off);
     unsigned long long* full = reinterpret_cast<unsigned long long*>(smem_raw + L.bar_off);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int RG = p.RG, NB = p.NB, TB = p.TB, T = p.T, Npad = 8 * p.NB;
+    const int RG = p.RG, T = p.T, TB = p.TB;
     const int g = warp % RG, cg = warp / RG;
     const size_t buf_elems = L.buf_bytes / sizeof(double2);
-    const unsigned chunk_bytes = (unsigned)(kGroupK * TB * 512);
-    const int nchunks = tp.kb_pad / kGroupK;
+    const unsigned chunk_bytes = (unsigned)(kChunkK * TB * 512);
+    const int nchunks = tp.kb_pad / kChunkK;
 
     if (threadIdx.x == 0) {
         mbar_init(&full[0], 1);
@@ -145,94 +116,104 @@ __global__ void __launch_bounds__(kThreads, 1) k_posterior_tma(const __grid_cons
         const double2* Afrag = tp.Aprime + (size_t)si * tp.a_stride + lane;
         const double2* sB = sBuf + (size_t)b * buf_elems + (size_t)(cg * BT) * 32 + lane;
         double* sSST = sSS + (size_t)b * RG * T;
-        double* sMeanT = sMeanG + (size_t)b * RG * T;
+        double* sMeanT = sMean + (size_t)b * RG * T;
 
         mbar_wait(&full[b], ((unsigned)(it >> 1)) & 1u);
-
-        for (int pass = 0; pass < p.npass; ++pass) {
-            const int base = 4 * RG * pass;
-            const int r0 = base + g, r1 = base + 2 * RG - 1 - g, r2 = base + 2 * RG + g, r3 = base + 4 * RG - 1 - g;
-            const int na = (r0 < NB) + (r1 < NB) + (r2 < NB) + (r3 < NB);
-            int ext[4];
-            size_t abase[4];
-            double zs[4];              // z = L^-1 y at this lane's row of each slot's block (0 for inactive slots)
-#pragma unroll
-            for (int s = 0; s < 4; ++s) {
-                const int src = s - (4 - na);
-                const int r = src >= 0 ? pick4(r0, r1, r2, r3, src) : -1;
-                ext[s] = r;
-                abase[s] = r >= 0 ? (size_t)r * (r + 1) / 2 * 32 : 0;
-                zs[s] = r >= 0 ? __ldg(tp.zvec + 8 * r + (lane >> 2)) : 0.0;
-            }
-            double acc[4][BT][2];
-#pragma unroll
-            for (int s = 0; s < 4; ++s)
-#pragma unroll
-                for (int c = 0; c < BT; ++c) { acc[s][c][0] = 0.0; acc[s][c][1] = 0.0; }
-            double2 a[4];
-#pragma unroll
-            for (int s = 0; s < 4; ++s) a[s] = __ldg(Afrag + abase[s]);
-            tma_segment<BT, 0>(acc, a, Afrag, abase, sB, TB, 0, ext[0]);
-            tma_segment<BT, 1>(acc, a, Afrag, abase, sB, TB, ext[0] + 1, ext[1]);
-            tma_segment<BT, 2>(acc, a, Afrag, abase, sB, TB, ext[1] + 1, ext[2]);
-            tma_segment<BT, 3>(acc, a, Afrag, abase, sB, TB, ext[2] + 1, ext[3]);
-            // |V|^2 and V.z of this warp's rows: red[c*2+h] = sum of squares, red[2BT + c*2+h] = mean share, for column
-            // 8c + 2(lane%4) + h of this warp's column group; then across the 8 row lanes by recursive halving
-            double red[4 * BT];
-#pragma unroll
-            for (int c = 0; c < BT; ++c)
-#pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                    double q2 = 0.0, mz = 0.0;
-#pragma unroll
-                    for (int s = 0; s < 4; ++s) {
-                        q2 = fma(acc[s][c][hh], acc[s][c][hh], q2);
-                        mz = fma(acc[s][c][hh], zs[s], mz);
-                    }
-                    red[c * 2 + hh] = q2;
-                    red[2 * BT + c * 2 + hh] = mz;
-                }
-            halving_reduce<4 * BT>(red, lane);
-            // lane (b4,b3,b2) owns original indices first + [0, BT/2)
-            const int first = ((lane >> 4) & 1) * (2 * BT) + ((lane >> 3) & 1) * BT + ((lane >> 2) & 1) * (BT / 2);
-#pragma unroll
-            for (int i = 0; i < BT / 2; ++i) {
-                const int idx = first + i;
-                const bool is_mean = idx >= 2 * BT;
-                const int ch = is_mean ? idx - 2 * BT : idx;           // c*2 + h
-                double* dst = (is_mean ? sMeanT : sSST) + (size_t)g * T + (size_t)(cg * BT + (ch >> 1)) * 8 + 2 * (lane & 3) + (ch & 1);
-                *dst = pass == 0 ? red[i] : *dst + red[i];
-            }
-        }
+        contract_tile<BT>(p, Afrag, sB, sSST, sMeanT, g, cg, lane);
         __syncthreads();
 
-        // epilogue: tiles are aligned to the slow blocks of the grid, rows outside this rank's shard are masked
         const int64_t tile_row0 = si * tp.fast_rows + (int64_t)j * T - p.row0;
         const int64_t left = tp.fast_rows - (int64_t)j * T;
         const int valid_cols = left < T ? (int)left : T;
         for (int t = threadIdx.x; t < T; t += kThreads) {
             const int64_t row = tile_row0 + t;
-            if (t >= valid_cols || row < 0 || row >= p.M) continue;
-            double sumsq = 0.0, mu = 0.0;
-            const double* mg = sMeanG + (size_t)b * RG * T;
-            for (int gg = 0; gg < RG; ++gg) { sumsq += sSST[(size_t)gg * T + t]; mu += mg[(size_t)gg * T + t]; }
-            double v = p.variance - sumsq;
-            v = v > SO_VAR_FLOOR ? v : SO_VAR_FLOOR;
-            const double sd = sqrt(v);
-            const double bs = __dmul_rn(p.beta, sd);
-            const double lo = __dsub_rn(mu, bs), up = __dadd_rn(mu, bs);
-            if (p.mean) p.mean[row] = mu;
-            if (p.var) p.var[row] = v;
-            if (p.Q) {
-                double* qp = p.Q + (size_t)row * p.q_stride + p.q_col;
-                if ((p.q_stride & 1) == 0 && (p.q_col & 1) == 0) *reinterpret_cast<double2*>(qp) = make_double2(lo, up);
-                else { qp[0] = lo; qp[1] = up; }
-            }
-            if (p.safe_mode != SO_SAFE_NONE && p.S) {
-                const uint8_t safe = lo > p.fmin ? 1 : 0;
-                p.S[row] = p.safe_mode == SO_SAFE_WRITE ? safe : (uint8_t)(p.S[row] & safe);
+            if (t < valid_cols && row >= 0 && row < p.M) finalize_row(p, sSST, sMeanT, t, row);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- tables of the grid path
+// Product tables: row r of the fast table is the product over the fast (low-order) axes of exp(-0.5 ((x_j - X_nj)/l_j)^2)
+// for grid row r (< fast_rows); row s of the slow table the same over the slow axes for grid row s * fast_rows, times the
+// signal variance.  Padding columns n >= N are zero.
+struct TableSpec {
+    int d;
+    int n[kGridMaxDim];
+    int off[kGridMaxDim];
+    int64_t stride[kGridMaxDim];
+    int in_fast[kGridMaxDim];
+    int64_t fast_rows, slow_rows;
+};
+
+__global__ void k_grid_tables2(TableSpec ts, const double* __restrict__ axis, const double* __restrict__ Xs,
+                               double* __restrict__ Pfast, double* __restrict__ Pslow, int N, int Npad, int d,
+                               double variance, const double* __restrict__ inv_ls_d) {
+    const int64_t r = blockIdx.x;             // one table row per block
+    const bool fast = r < ts.fast_rows;
+    const int64_t tr = fast ? r : r - ts.fast_rows;
+    const int64_t grow = fast ? tr : tr * ts.fast_rows;
+    for (int n = threadIdx.x; n < Npad; n += blockDim.x) {
+        double v = 0.0;
+        if (n < N) {
+            v = fast ? 1.0 : variance;
+            for (int j = 0; j < ts.d; ++j) {
+                if ((ts.in_fast[j] != 0) != fast) continue;
+                const int idx = (int)((grow / ts.stride[j]) % ts.n[j]);
+                const double t = axis[ts.off[j] + idx] * inv_ls_d[j] - Xs[(size_t)n * d + j];
+                v *= exp(-0.5 * (t * t));
             }
         }
+        (fast ? Pfast : Pslow)[(size_t)tr * Npad + n] = v;
+    }
+}
+
+// PfFrag: the fast table re-ordered so that the bytes a tile needs are contiguous and already in B-fragment order:
+// [tile j of a slow block][k-block][col tile][lane] double2, lane l -> rows j*T + 8ct + l/4, training points
+// 8kb + 2(l%4) + {0,1}; zero beyond fast_rows / N.
+__global__ void k_pffrag(const double* __restrict__ Pfast, double2* __restrict__ PfFrag, int64_t fast_rows, int N, int Npad,
+                         int T, int TB, int kb_pad, int tpb) {
+    const size_t total = (size_t)tpb * kb_pad * TB * 32;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int lane = (int)(e & 31);
+        size_t r = e >> 5;
+        const int ct = (int)(r % TB); r /= TB;
+        const int kb = (int)(r % kb_pad);
+        const int j = (int)(r / kb_pad);
+        const int64_t row = (int64_t)j * T + ct * 8 + (lane >> 2);
+        const int n0 = 8 * kb + 2 * (lane & 3);
+        double2 v = make_double2(0.0, 0.0);
+        if (row < fast_rows) {
+            if (n0 < N) v.x = Pfast[(size_t)row * Npad + n0];
+            if (n0 + 1 < N) v.y = Pfast[(size_t)row * Npad + n0 + 1];
+        }
+        PfFrag[e] = v;
+    }
+}
+
+// A'(s) = L^-1 diag(Pslow[s]) in the packed fragment order of Afrag.
+__global__ void k_aprime(const double2* __restrict__ Afrag, const double* __restrict__ Pslow, double2* __restrict__ Aprime,
+                         int NB, size_t a_stride) {
+    const int64_t si = blockIdx.y;
+    const int Npad = 8 * NB;
+    const double* ps = Pslow + (size_t)si * Npad;
+    const size_t nfrag = tri_blocks(NB) * 32;
+    double2* dst = Aprime + (size_t)si * a_stride;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < a_stride; e += (size_t)gridDim.x * blockDim.x) {
+        double2 v = make_double2(0.0, 0.0);
+        if (e < nfrag) {
+            const size_t blk = e >> 5;
+            const int lane = (int)(e & 31);
+            // block index -> (i, kb) with blk = i(i+1)/2 + kb
+            int i = (int)((sqrt(8.0 * (double)blk + 1.0) - 1.0) * 0.5);
+            while ((size_t)(i + 1) * (i + 2) / 2 <= blk) ++i;
+            while ((size_t)i * (i + 1) / 2 > blk) --i;
+            const int kb = (int)(blk - (size_t)i * (i + 1) / 2);
+            const int c0 = 8 * kb + 2 * (lane & 3);
+            const double2 a = Afrag[e];
+            v.x = a.x * ps[c0];
+            v.y = a.y * ps[c0 + 1];
+        }
+        dst[e] = v;
     }
 }
 
