@@ -133,7 +133,7 @@ class DeviceEngine:
 
     def prepare_grid(self, gp: int):
         self._check(self.lib.so_grid_prepare(self.handle, gp, self._stream()), "so_grid_prepare")
-        self.launches += 1
+        self.launches += 4
 
     def grid_rows(self, row0: int, M: int):
         d = len(self._grid_axes)
