@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libsafeopt_b200.so")
+# SAFEOPT_B200_LIB points at an alternative build of the same ABI (A/B measurements of kernel variants)
+LIB_PATH = os.environ.get("SAFEOPT_B200_LIB") or os.path.join(HERE, "csrc", "libsafeopt_b200.so")
 
 SO_OK = 0
 SO_ERR_BAD_ARG = -1

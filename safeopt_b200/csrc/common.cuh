@@ -26,7 +26,7 @@ struct GPState {
     double* Linv = nullptr;      // Npad x Npad lower, row-major
     double* alpha = nullptr;     // Npad (padding = 0)
     double* zvec = nullptr;      // Npad: z = L^-1 y (padding = 0); mean(x*) = (L^-1 k).z, taken from the same accumulators as |L^-1 k|^2
-    double2* Afrag = nullptr;    // L^-1 packed in DMMA A-fragment order (+1 block of slack)
+    double2* Afrag = nullptr;    // L^-1 packed in DMMA A-fragment order (+4 blocks of slack for the prefetch)
     // grid tables (grid fast path): per axis j, E_j[i][n], i < n_j, n < Npad
     double* E = nullptr;
     size_t capE = 0;

@@ -180,7 +180,7 @@ extern "C" int so_fit(so_handle* h, int gp, const double* X_h, const double* Y_h
         if ((rc = grow(h, g.Linv, (size_t)cap * cap))) return rc;
         if ((rc = grow(h, g.alpha, (size_t)cap))) return rc;
         if ((rc = grow(h, g.zvec, (size_t)cap))) return rc;
-        if ((rc = grow(h, g.Afrag, (tri_blocks(capNB) + 2) * 32))) return rc;
+        if ((rc = grow(h, g.Afrag, (tri_blocks(capNB) + 4) * 32))) return rc;
         g.capN = cap;
     }
     g.fitted = false;
@@ -208,7 +208,7 @@ extern "C" int so_fit(so_handle* h, int gp, const double* X_h, const double* Y_h
         k_trinv<<<(N + warps - 1) / warps, warps * 32, smem, stream>>>(g.K, g.Linv, N, Npad);
     }
     k_alpha<<<1, 1024, sizeof(double) * Npad, stream>>>(g.Linv, g.Y, g.alpha, g.zvec, N, Npad);
-    SO_CUDA(h, cudaMemsetAsync(g.Afrag, 0, sizeof(double2) * (tri_blocks(NB) + 2) * 32, stream));
+    SO_CUDA(h, cudaMemsetAsync(g.Afrag, 0, sizeof(double2) * (tri_blocks(NB) + 4) * 32, stream));
     k_pack_afrag<<<dim3(NB, NB), 32, 0, stream>>>(g.Linv, g.Afrag, N, Npad);
     SO_CHECK_LAUNCH(h, "so_fit kernels");
     SO_CUDA(h, cudaMemcpyAsync(h->h_status, h->d_status, sizeof(int), cudaMemcpyDeviceToHost, stream));

@@ -425,7 +425,7 @@ extern "C" int so_grid_prepare(so_handle* h, int gp, void* stream_) {
     TmaPlan pl;
     const int64_t trows = gs.fast_rows + gs.slow_rows;
     const size_t a_stride = (tri_blocks(g.NB) + 1) * 32;
-    const size_t ap_elems = (size_t)gs.slow_rows * a_stride + 64;
+    const size_t ap_elems = (size_t)gs.slow_rows * a_stride + 128;   // the A prefetch runs up to 3 blocks past a row
     const bool fits = plan_tma(h, g, pl) == SO_OK && trows <= 2147483647 && gs.slow_rows <= 65535 &&
                       (size_t)trows * Npad * sizeof(double) <= ((size_t)4 << 30) && ap_elems * sizeof(double2) <= ((size_t)8 << 30);
     if (fits) {
@@ -476,7 +476,7 @@ extern "C" int so_grid_prepare(so_handle* h, int gp, void* stream_) {
         dim3 grd2((unsigned)((a_stride + 255) / 256), (unsigned)gs.slow_rows);
         k_aprime<<<grd2, 256, 0, stream>>>(g.Afrag, Pslow, g.Aprime, g.NB, a_stride);
         SO_CHECK_LAUNCH(h, "k_aprime");
-        SO_CUDA(h, cudaMemsetAsync(g.Aprime + (size_t)gs.slow_rows * a_stride, 0, sizeof(double2) * 64, stream));
+        SO_CUDA(h, cudaMemsetAsync(g.Aprime + (size_t)gs.slow_rows * a_stride, 0, sizeof(double2) * 128, stream));
         g.a_stride = a_stride; g.tma_T = pl.T; g.tma_tpb = tpb; g.tma_BT = pl.BT; g.tma_RG = pl.RG; g.tma_CG = pl.CG;
         g.tma_kb_pad = pl.kb_pad; g.tma_ready = true;
     }
