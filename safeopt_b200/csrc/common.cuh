@@ -5,6 +5,7 @@
 #include <string>
 #include <vector>
 #include "../../include/safeopt_b200.h"
+#include "fastexp.cuh"
 
 #define SO_MAX_DIM 16            // max input dimension (parameters + contexts)
 #define SO_JITTER 1e-8           // GPy adds this to the noise variance
@@ -122,6 +123,31 @@ __device__ __forceinline__ double kernel_of_r2(double r2, double variance) {
         double r = sqrt(r2);
         return variance * (1.0 + s5 * r + (5.0 / 3.0) * r2) * exp(-s5 * r);
     }
+}
+
+// Same value through so_exp_neg (fastexp.cuh): ~11 fp64 operations per exp instead of libdevice's ~21.  `T` is the 64-entry
+// 2^(j/64) table in shared memory (load_exp_table).  Used by the per-row generators; one-off kernels keep exp().
+template <int KIND>
+__device__ __forceinline__ double kernel_of_r2_fast(double r2, double variance, const double* __restrict__ T) {
+    if (KIND == SO_KERNEL_RBF) {
+        return variance * so_exp_neg(-0.5 * r2, T);
+    } else if (KIND == SO_KERNEL_MATERN32) {
+        const double s3 = 1.7320508075688772;
+        double r = sqrt(r2);
+        return variance * (1.0 + s3 * r) * so_exp_neg(-s3 * r, T);
+    } else {
+        const double s5 = 2.23606797749979;
+        double r = sqrt(r2);
+        return variance * (1.0 + s5 * r + (5.0 / 3.0) * r2) * so_exp_neg(-s5 * r, T);
+    }
+}
+
+static __constant__ double c_exp_table[64] = {SO_EXP_TABLE_VALUES};
+
+// Copies the exp table into shared memory (divergent table indices would serialise on the constant cache).
+// The caller synchronises the block before the first use.
+__device__ __forceinline__ void load_exp_table(double* __restrict__ sT) {
+    if (threadIdx.x < 64) sT[threadIdx.x] = c_exp_table[threadIdx.x];
 }
 
 // Number of DMMA A-fragment blocks in the packed lower triangle of an NB x NB block matrix.

@@ -92,6 +92,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_expander(const __grid_constant_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int Npad = 8 * p.NB, T = p.T, TB = p.TB, NB = p.NB, d = p.d;
 
+    double* sExpT = reinterpret_cast<double*>(smem_raw + L.exp_off);
+    load_exp_table(sExpT);
     if (!GRID)
         for (int i = threadIdx.x; i < Npad * d; i += kThreads) sXs[i] = p.Xs[i];
     __syncthreads();
@@ -107,7 +109,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_expander(const __grid_constant_
         if (!GRID) load_tile_rows(p, sXt, tile_local0);
         if (!__syncthreads_or(any)) continue;   // uniform across the CTA
         if (GRID) gen_grid(p, sK, p.row0 + tile_local0, warp, lane);
-        else gen_rows<KIND>(p, sK, sXs, sXt, warp, lane);
+        else gen_rows<KIND>(p, sK, sXs, sXt, sExpT, warp, lane);
         __syncthreads();
 
         for (int ct = warp; ct < TB; ct += kWarps) {
@@ -165,7 +167,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_expander(const __grid_constant_
                                 r2 = fma(df, df, r2);
                             }
                         }
-                        const double kxc = kernel_of_r2<KIND>(r2, p.variance);
+                        const double kxc = kernel_of_r2_fast<KIND>(r2, p.variance, sExpT);
                         const double c = kxc - acc[bb][hh];
                         const CandInfo ci = ep.cinfo[b];
                         const double mean2 = fma(c, ci.coef, mu);

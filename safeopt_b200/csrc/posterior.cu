@@ -29,8 +29,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_posterior(const __grid_constant
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int Npad = 8 * p.NB, T = p.T, RG = p.RG;
     const int g = warp % RG, cg = warp / RG;
+    double* sExpT = reinterpret_cast<double*>(smem_raw + L.exp_off);
 
     if (!GRID) {
+        load_exp_table(sExpT);
         for (int i = threadIdx.x; i < Npad * p.d; i += kThreads) sXs[i] = p.Xs[i];
         if ((int64_t)blockIdx.x < p.ntiles) load_tile_rows(p, sXt, (int64_t)blockIdx.x * T);
     }
@@ -42,7 +44,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_posterior(const __grid_constant
         double* sSST = sSS + (size_t)par * RG * T;
         double* sMeanT = sMean + (size_t)par * RG * T;
         if (GRID) gen_grid(p, sK, p.row0 + tile_local0, warp, lane);
-        else gen_rows<KIND>(p, sK, sXs, sXt + (size_t)par * T * p.d, warp, lane);
+        else gen_rows<KIND>(p, sK, sXs, sXt + (size_t)par * T * p.d, sExpT, warp, lane);
         __syncthreads();
         if (!GRID) {
             // the next tile's candidate rows are fetched under the contraction

@@ -34,10 +34,10 @@ struct PostParams {
 };
 
 struct SmemLayout {
-    size_t k_bytes, xs_off, xt_off, ss_off, mean_off, total;
+    size_t k_bytes, xs_off, xt_off, ss_off, mean_off, exp_off, total;
 };
 
-// [ Kx tile | scaled training inputs | two tiles of candidate rows | |V|^2 partials x2 | mean partials x2 ]
+// [ Kx tile | scaled training inputs | two tiles of candidate rows | |V|^2 partials x2 | mean partials x2 | exp table ]
 __host__ __device__ inline SmemLayout smem_layout(int NB, int T, int d, int RG, bool grid) {
     SmemLayout L;
     const size_t Npad = 8 * (size_t)NB;
@@ -46,34 +46,72 @@ __host__ __device__ inline SmemLayout smem_layout(int NB, int T, int d, int RG, 
     L.xt_off = L.xs_off + (grid ? 0 : Npad * d * sizeof(double));
     L.ss_off = L.xt_off + (grid ? 0 : 2 * (size_t)T * d * sizeof(double));
     L.mean_off = L.ss_off + 2 * (size_t)RG * T * sizeof(double);
-    L.total = L.mean_off + 2 * (size_t)RG * T * sizeof(double);
+    L.exp_off = L.mean_off + 2 * (size_t)RG * T * sizeof(double);
+    L.total = L.exp_off + 64 * sizeof(double);
     return L;
 }
 
 // ---------------------------------------------------------------- gen: explicit rows
 // Lane l of the warp that owns column tile ct produces, for every k-block kb, the pair
 // (k(x*_t, x_n0), k(x*_t, x_n0+1)) with t = 8 ct + l/4, n0 = 8 kb + 2 (l%4) -- exactly its slot of the B fragment.
-template <int KIND>
-__device__ __forceinline__ void gen_rows(const PostParams& p, double2* __restrict__ sK, const double* __restrict__ sXs,
-                                         const double* __restrict__ sXt, int warp, int lane) {
-    const int d = p.d, N = p.N, NB = p.NB, TB = p.TB;
+// The generator is bound by the fp64 dependency chain (distance -> exp -> scale), not by the pipe: with 8 warps per SM
+// only ILP hides the latency, so the body is branch-free and works on two k-blocks = four kernel values at a time, with
+// the candidate row held in registers (D = compile-time dimension; D = 0 keeps the runtime loop for d > 6).
+template <int KIND, int D>
+__device__ __forceinline__ void gen_rows_d(const PostParams& p, double2* __restrict__ sK, const double* __restrict__ sXs,
+                                           const double* __restrict__ sXt, const double* __restrict__ sExpT, int warp, int lane) {
+    const int d = D ? D : p.d, N = p.N, NB = p.NB, TB = p.TB;
     const int q = lane & 3, tl = lane >> 2;
+    const double variance = p.variance;
     for (int ct = warp; ct < TB; ct += kWarps) {
         const double* xt = sXt + (ct * 8 + tl) * d;
-        for (int kb = 0; kb < NB; ++kb) {
-            const int n0 = 8 * kb + 2 * q;
+        double xr[D ? D : 1];
+#pragma unroll
+        for (int j = 0; j < D; ++j) xr[j] = xt[j];
+        for (int kb = 0; kb < NB; kb += 2) {
+            const int kb1 = kb + 1 < NB ? kb + 1 : kb;        // odd NB: the last pass recomputes block kb (same store)
+            const int n0 = 8 * kb + 2 * q, n1 = 8 * kb1 + 2 * q;
             const double* x0 = sXs + n0 * d;
-            double r0 = 0.0, r1 = 0.0;
-            for (int j = 0; j < d; ++j) {
-                const double xv = xt[j];
-                const double t0 = xv - x0[j], t1 = xv - x0[d + j];
-                r0 = fma(t0, t0, r0);
-                r1 = fma(t1, t1, r1);
+            const double* x1 = sXs + n1 * d;
+            double r00 = 0.0, r01 = 0.0, r10 = 0.0, r11 = 0.0;
+            if (D) {
+#pragma unroll
+                for (int j = 0; j < D; ++j) {
+                    const double a = xr[j] - x0[j], b = xr[j] - x0[D + j], c = xr[j] - x1[j], e = xr[j] - x1[D + j];
+                    r00 = fma(a, a, r00); r01 = fma(b, b, r01); r10 = fma(c, c, r10); r11 = fma(e, e, r11);
+                }
+            } else {
+                for (int j = 0; j < d; ++j) {
+                    const double xv = xt[j];
+                    const double a = xv - x0[j], b = xv - x0[d + j], c = xv - x1[j], e = xv - x1[d + j];
+                    r00 = fma(a, a, r00); r01 = fma(b, b, r01); r10 = fma(c, c, r10); r11 = fma(e, e, r11);
+                }
             }
-            const double k0 = n0 < N ? kernel_of_r2<KIND>(r0, p.variance) : 0.0;
-            const double k1 = n0 + 1 < N ? kernel_of_r2<KIND>(r1, p.variance) : 0.0;
-            sK[(kb * TB + ct) * 32 + lane] = make_double2(k0, k1);
+            double k00 = kernel_of_r2_fast<KIND>(r00, variance, sExpT);
+            double k01 = kernel_of_r2_fast<KIND>(r01, variance, sExpT);
+            double k10 = kernel_of_r2_fast<KIND>(r10, variance, sExpT);
+            double k11 = kernel_of_r2_fast<KIND>(r11, variance, sExpT);
+            k00 = n0 < N ? k00 : 0.0;                          // zero padding of the last k-block
+            k01 = n0 + 1 < N ? k01 : 0.0;
+            k10 = n1 < N ? k10 : 0.0;
+            k11 = n1 + 1 < N ? k11 : 0.0;
+            sK[(kb * TB + ct) * 32 + lane] = make_double2(k00, k01);
+            sK[(kb1 * TB + ct) * 32 + lane] = make_double2(k10, k11);
         }
+    }
+}
+
+template <int KIND>
+__device__ __forceinline__ void gen_rows(const PostParams& p, double2* __restrict__ sK, const double* __restrict__ sXs,
+                                         const double* __restrict__ sXt, const double* __restrict__ sExpT, int warp, int lane) {
+    switch (p.d) {
+        case 1: gen_rows_d<KIND, 1>(p, sK, sXs, sXt, sExpT, warp, lane); break;
+        case 2: gen_rows_d<KIND, 2>(p, sK, sXs, sXt, sExpT, warp, lane); break;
+        case 3: gen_rows_d<KIND, 3>(p, sK, sXs, sXt, sExpT, warp, lane); break;
+        case 4: gen_rows_d<KIND, 4>(p, sK, sXs, sXt, sExpT, warp, lane); break;
+        case 5: gen_rows_d<KIND, 5>(p, sK, sXs, sXt, sExpT, warp, lane); break;
+        case 6: gen_rows_d<KIND, 6>(p, sK, sXs, sXt, sExpT, warp, lane); break;
+        default: gen_rows_d<KIND, 0>(p, sK, sXs, sXt, sExpT, warp, lane); break;
     }
 }
 

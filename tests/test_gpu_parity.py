@@ -132,6 +132,17 @@ def test_grid_path_equals_rows_path(d, n, N):
     eng.close()
 
 
+def _check_argmax(row, row_ref, values_ref, mask_ref, tol):
+    """`row` must be the reference's argmax row; if the reference's values tie within 100*tol, any tied row passes."""
+    cand = np.flatnonzero(mask_ref)
+    top = np.sort(values_ref[cand])[::-1]
+    gap = top[0] - top[1] if top.size > 1 else np.inf
+    if gap > 100 * tol:
+        assert row == row_ref
+    else:
+        assert mask_ref[row] and abs(values_ref[row] - values_ref[row_ref]) < tol
+
+
 # ---------------------------------------------------------------- golden fixtures produced by the reference
 @pytest.mark.parametrize("explicit", [False, True])
 @pytest.mark.parametrize("name", GRID_CASES)
@@ -156,13 +167,20 @@ def test_safeopt_matches_golden(name, explicit, monkeypatch):
     assert np.array_equal(opt.S, unpack_mask(g["S"], n_rows))
     assert np.array_equal(opt.M, unpack_mask(g["M"], n_rows))
     assert np.array_equal(opt.G, unpack_mask(g["G"], n_rows))
-    assert opt.last_query_row == int(g["row_next"])
-    assert np.array_equal(x, g["x_next"])
+    # argmax rows: identical whenever the reference's own best/second-best gap is decidable at this tolerance; the 1-D
+    # doctest fixture is mirror symmetric (rows 27 and 72 tie EXACTLY in the reference, which then takes the first), so
+    # there any row whose reference value ties with the reference's pick within `tol` is accepted
+    S_ref, M_ref, G_ref = (unpack_mask(g[k], n_rows) for k in "SMG")
+    width = ((g["Q"][:, 1::2] - g["Q"][:, ::2]) / opt.scaling).max(axis=1)
+    _check_argmax(opt.last_query_row, int(g["row_next"]), width, M_ref | G_ref, tol)
+    assert np.array_equal(x, grid[opt.last_query_row])
     mx = opt.get_maximum()
     assert abs(mx[1] - float(g["max_val"])) < tol
-    assert np.array_equal(mx[0], g["max_x"])
+    lower0 = g["Q"][:, 0]
+    _check_argmax(int(np.flatnonzero((grid == mx[0]).all(axis=1))[0]), int(np.flatnonzero((grid == g["max_x"]).all(axis=1))[0]),
+                  lower0, S_ref, tol)
     opt.optimize(ucb=True)
-    assert opt.last_query_row == int(g["row_ucb"])
+    _check_argmax(opt.last_query_row, int(g["row_ucb"]), g["Q"][:, 1], S_ref, tol)
 
 
 @pytest.mark.parametrize("name", ["context_1p1c", "context_1p1c_lipschitz"])
