@@ -47,56 +47,161 @@ __global__ void k_build_ky(const double* __restrict__ Xs, double* __restrict__ K
     K[(size_t)i * Npad + j] = v;
 }
 
-// In-place right-looking Cholesky of the leading N x N block (lower triangle), one CTA.
-__global__ void __launch_bounds__(1024) k_cholesky(double* __restrict__ K, int N, int ld, int* status) {
-    extern __shared__ double col[];
-    __shared__ int bad;
-    const int tid = threadIdx.x, nt = blockDim.x;
-    const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
-    if (tid == 0) bad = 0;
-    __syncthreads();
-    for (int j = 0; j < N; ++j) {
-        if (tid == 0) {
-            double dj = K[(size_t)j * ld + j];
-            if (!(dj > 0.0) || isinf(dj)) bad = 1; else K[(size_t)j * ld + j] = sqrt(dj);
-        }
-        __syncthreads();
-        if (bad) break;
-        const double ljj = K[(size_t)j * ld + j];
-        for (int i = j + 1 + tid; i < N; i += nt) {
-            double v = K[(size_t)i * ld + j] / ljj;
-            K[(size_t)i * ld + j] = v;
-            col[i] = v;
-        }
-        __syncthreads();
-        for (int i = j + 1 + warp; i < N; i += nwarps) {
-            const double ci = col[i];
-            double* row = K + (size_t)i * ld;
-            for (int k = j + 1 + lane; k <= i; k += 32) row[k] = fma(-ci, col[k], row[k]);
-        }
-        __syncthreads();
+// ---------------------------------------------------------------- blocked Cholesky + triangular inverse
+// Right-looking, panel width 32, on the identity-padded Npad x Npad matrix.  Per panel P (rows/cols p0 .. p0+nb):
+//   k_chol_panel : every CTA re-factors the 32x32 diagonal block in registers (one warp, shuffles; ~2 us, cheaper than
+//                  a grid-wide dependency), then the CTAs share (b) L[R,P] = A[R,P] L_PP^-T by forward substitution,
+//                  one thread per row, and (c) W[P, 0:p0] <- L_PP^-1 W[P, 0:p0], one thread per column.  CTA 0 also
+//                  writes L_PP and W[P,P] = L_PP^-1 (substitution on the identity).
+//   k_chol_update: 32x32 tiles over all SMs:  A[R,R] -= L[R,P] L[R,P]^T  (lower tiles)  and
+//                  W[R, 0:p0+nb] -= L[R,P] W[P, 0:p0+nb]  -- forward substitution on the identity done right-looking,
+//                  so W ends as L^-1.  Both updates have the same shape and run in the same launch.
+// N = 256: 15 launches, ~0.1 ms (the previous single-CTA column-by-column factorisation + per-column inverse: 1.25 ms).
+constexpr int kPB = 32;
+
+__device__ __forceinline__ void chol_diag_block(const double* __restrict__ K, double* __restrict__ W, int ld, int p0, int nb,
+                                                double (*sL)[kPB + 1], double* __restrict__ sRinv, bool write_back, int* status) {
+    const int lane = threadIdx.x & 31;
+    double row[kPB];
+#pragma unroll
+    for (int k = 0; k < kPB; ++k) {
+        double v = (k == lane) ? 1.0 : 0.0;
+        if (lane < nb && k <= lane) v = K[(size_t)(p0 + lane) * ld + p0 + k];
+        row[k] = v;
     }
-    if (tid == 0) *status = bad ? SO_ERR_NOT_PD : SO_OK;
+    int bad = 0;
+#pragma unroll
+    for (int j = 0; j < kPB; ++j) {
+        double djj = __shfl_sync(0xffffffffu, row[j], j);
+        if (!(djj > 0.0) || isinf(djj)) { bad = 1; djj = 1.0; }
+        const double ljj = sqrt(djj);
+        row[j] = (lane == j) ? ljj : row[j] / ljj;
+#pragma unroll
+        for (int k = j + 1; k < kPB; ++k) {
+            const double lkj = __shfl_sync(0xffffffffu, row[j], k);
+            row[k] = fma(-row[j], lkj, row[k]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kPB; ++k) {
+        sL[lane][k] = (k <= lane) ? row[k] : 0.0;
+        if (k == lane) sRinv[lane] = 1.0 / row[k];      // static register index
+    }
+    if (bad && lane == 0 && write_back) *status = SO_ERR_NOT_PD;
+    __syncwarp();
+    if (!write_back) return;
+#pragma unroll
+    for (int k = 0; k < kPB; ++k)
+        if (lane < nb && k <= lane) const_cast<double*>(K)[(size_t)(p0 + lane) * ld + p0 + k] = row[k];
+    // W[P,P] = L_PP^-1: lane c solves L_PP x = e_c
+    double x[kPB];
+#pragma unroll
+    for (int i = 0; i < kPB; ++i) {
+        double s0 = (i == lane) ? 1.0 : 0.0, s1 = 0.0;
+#pragma unroll
+        for (int k = 0; k + 1 < i; k += 2) {
+            s0 = fma(-sL[i][k], x[k], s0);
+            s1 = fma(-sL[i][k + 1], x[k + 1], s1);
+        }
+        if (i & 1) s0 = fma(-sL[i][i - 1], x[i - 1], s0);
+        x[i] = (s0 + s1) / sL[i][i];
+    }
+#pragma unroll
+    for (int i = 0; i < kPB; ++i)
+        if (i < nb && lane < nb) W[(size_t)(p0 + i) * ld + p0 + lane] = x[i];
 }
 
-// L^-1 by forward substitution, one warp per column (columns are independent).
-__global__ void __launch_bounds__(256) k_trinv(const double* __restrict__ L, double* __restrict__ Linv, int N, int ld) {
-    extern __shared__ double xs_all[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int c = blockIdx.x * (blockDim.x >> 5) + warp;
-    if (c >= N) return;
-    double* xs = xs_all + (size_t)warp * ld;
-    for (int i = c; i < N; ++i) {
-        const double* row = L + (size_t)i * ld;
-        double part = 0.0;
-        for (int k = c + lane; k < i; k += 32) part = fma(row[k], xs[k], part);
+__global__ void __launch_bounds__(256) k_chol_panel(double* __restrict__ K, double* __restrict__ W, int Npad, int p0, int nb,
+                                                    int* status) {
+    __shared__ double sL[kPB][kPB + 1];
+    __shared__ double sRinv[kPB];
+    const int ld = Npad;
+    if (threadIdx.x < 32) chol_diag_block(K, W, ld, p0, nb, sL, sRinv, blockIdx.x == 0, status);
+    __syncthreads();
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = p0 + nb + t;
+    if (r < Npad) {                 // only reached with nb == 32 (a narrower panel is the last one)
+        double* arow = K + (size_t)r * ld + p0;
+        double x[kPB];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-        double xi = ((i == c ? 1.0 : 0.0) - part) / row[i];
-        if (lane == 0) xs[i] = xi;
-        __syncwarp();
+        for (int c = 0; c < kPB; c += 2) {
+            const double2 v = *reinterpret_cast<const double2*>(arow + c);
+            x[c] = v.x; x[c + 1] = v.y;
+        }
+#pragma unroll
+        for (int c = 0; c < kPB; ++c) {
+            double s0 = x[c], s1 = 0.0;
+#pragma unroll
+            for (int k = 0; k + 1 < c; k += 2) {
+                s0 = fma(-sL[c][k], x[k], s0);
+                s1 = fma(-sL[c][k + 1], x[k + 1], s1);
+            }
+            if (c & 1) s0 = fma(-sL[c][c - 1], x[c - 1], s0);
+            x[c] = (s0 + s1) * sRinv[c];
+        }
+#pragma unroll
+        for (int c = 0; c < kPB; c += 2) *reinterpret_cast<double2*>(arow + c) = make_double2(x[c], x[c + 1]);
     }
-    for (int i = c + lane; i < N; i += 32) Linv[(size_t)i * ld + c] = xs[i];
+    if (t < p0) {                   // column t of W[P, 0:p0]
+        double x[kPB];
+#pragma unroll
+        for (int i = 0; i < kPB; ++i) x[i] = i < nb ? W[(size_t)(p0 + i) * ld + t] : 0.0;
+#pragma unroll
+        for (int i = 0; i < kPB; ++i) {
+            double s0 = x[i], s1 = 0.0;
+#pragma unroll
+            for (int k = 0; k + 1 < i; k += 2) {
+                s0 = fma(-sL[i][k], x[k], s0);
+                s1 = fma(-sL[i][k + 1], x[k + 1], s1);
+            }
+            if (i & 1) s0 = fma(-sL[i][i - 1], x[i - 1], s0);
+            x[i] = (s0 + s1) * sRinv[i];
+        }
+#pragma unroll
+        for (int i = 0; i < kPB; ++i)
+            if (i < nb) W[(size_t)(p0 + i) * ld + t] = x[i];
+    }
+}
+
+// One 32x32 output tile per CTA.  blockIdx.y = row block below the panel, blockIdx.x = column block (<= row block).
+__global__ void __launch_bounds__(256) k_chol_update(double* __restrict__ K, double* __restrict__ W, int Npad, int p0) {
+    const int pblk = p0 / kPB;
+    const int rb = pblk + 1 + blockIdx.y, cb = blockIdx.x;
+    if (cb > rb) return;
+    __shared__ double sA[kPB][kPB + 1];     // L[rb rows, P]
+    __shared__ double sB[kPB][kPB + 1];     // [k][j]: L[cb rows, P]^T (A tiles) or W[P, cb cols] (W tiles)
+    const int ld = Npad, tid = threadIdx.x;
+    const bool a_tile = cb > pblk;
+    for (int e = tid; e < kPB * kPB; e += 256) {
+        const int i = e >> 5, k = e & 31;
+        const int r = rb * kPB + i;
+        sA[i][k] = r < Npad ? K[(size_t)r * ld + p0 + k] : 0.0;
+        if (a_tile) {
+            const int rc = cb * kPB + i;
+            sB[k][i] = rc < Npad ? K[(size_t)rc * ld + p0 + k] : 0.0;
+        } else {
+            const int c = cb * kPB + k;      // here e = (row i of the panel, column k of the tile)
+            sB[i][k] = (c < Npad && (cb < pblk || k <= i)) ? W[(size_t)(p0 + i) * ld + c] : 0.0;
+        }
+    }
+    __syncthreads();
+    const int i = tid >> 3, j0 = (tid & 7) * 4;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int k = 0; k < kPB; ++k) {
+        const double a = sA[i][k];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[u] = fma(a, sB[k][j0 + u], acc[u]);
+    }
+    const int r = rb * kPB + i;
+    if (r >= Npad) return;
+    double* dst = (a_tile ? K : W) + (size_t)r * ld + cb * kPB + j0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        if (cb * kPB + j0 + u >= Npad) break;
+        if (!a_tile && cb == pblk) dst[u] = -acc[u];          // first touch of W[R, P]: starts from zero
+        else dst[u] -= acc[u];
+    }
 }
 
 // alpha = Linv^T (Linv y), one CTA; padding entries are zero.
@@ -195,17 +300,18 @@ extern "C" int so_fit(so_handle* h, int gp, const double* X_h, const double* Y_h
     k_scale_x<<<(Npad * d + 255) / 256, 256, 0, stream>>>(g.X, g.Xs, N, Npad, d, il);
     dim3 blk(16, 16), grd((Npad + 15) / 16, (Npad + 15) / 16);
     k_build_ky<<<grd, blk, 0, stream>>>(g.Xs, g.K, N, Npad, d, kernel_kind, variance, noise_var + SO_JITTER);
-    k_cholesky<<<1, 1024, sizeof(double) * Npad, stream>>>(g.K, N, Npad, h->d_status);
+    SO_CUDA(h, cudaMemsetAsync(h->d_status, 0, sizeof(int), stream));
+    static_assert(SO_OK == 0, "status word is cleared with memset");
     SO_CUDA(h, cudaMemsetAsync(g.Linv, 0, sizeof(double) * (size_t)Npad * Npad, stream));
-    {
-        const int warps = 8;
-        size_t smem = sizeof(double) * (size_t)warps * Npad;
-        static bool attr_set = false;
-        if (!attr_set) {
-            SO_CUDA(h, cudaFuncSetAttribute(k_trinv, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            attr_set = true;
+    for (int p0 = 0; p0 < Npad; p0 += kPB) {
+        const int nb = Npad - p0 < kPB ? Npad - p0 : kPB;
+        const int below = Npad - p0 - nb;
+        const int work = below > p0 ? below : p0;
+        k_chol_panel<<<work > 0 ? (work + 255) / 256 : 1, 256, 0, stream>>>(g.K, g.Linv, Npad, p0, nb, h->d_status);
+        if (below > 0) {
+            const int nrb = (below + kPB - 1) / kPB, ncb = (Npad + kPB - 1) / kPB;
+            k_chol_update<<<dim3(ncb, nrb), 256, 0, stream>>>(g.K, g.Linv, Npad, p0);
         }
-        k_trinv<<<(N + warps - 1) / warps, warps * 32, smem, stream>>>(g.K, g.Linv, N, Npad);
     }
     k_alpha<<<1, 1024, sizeof(double) * Npad, stream>>>(g.Linv, g.Y, g.alpha, g.zvec, N, Npad);
     SO_CUDA(h, cudaMemsetAsync(g.Afrag, 0, sizeof(double2) * (tri_blocks(NB) + 4) * 32, stream));

@@ -115,7 +115,8 @@ class DeviceEngine:
         rc = self.lib.so_fit(self.handle, gp, _hptr(X), _hptr(Y), N, d, kind, _hptr(ls), float(variance),
                              float(noise_var), self._stream())
         self._check(rc, "so_fit")
-        self.launches += 6
+        panels = (8 * ((N + 7) // 8) + 31) // 32           # fit.cu: k_chol_panel per panel, k_chol_update between panels
+        self.launches += 4 + 2 * panels - 1
 
     def fit_export(self, gp: int, N: int):
         L = np.empty((N, N))

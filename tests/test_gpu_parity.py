@@ -30,7 +30,8 @@ def _problem(N, d, seed):
 
 
 # ---------------------------------------------------------------- K1
-@pytest.mark.parametrize("N,d,kind", [(1, 1, 0), (5, 1, 0), (7, 2, 1), (64, 2, 0), (100, 3, 1), (256, 4, 0), (300, 2, 2), (512, 6, 0)])
+@pytest.mark.parametrize("N,d,kind", [(1, 1, 0), (5, 1, 0), (7, 2, 1), (33, 2, 0), (64, 2, 0), (100, 3, 1), (256, 4, 0), (300, 2, 2), (512, 6, 0),
+                                      (1000, 3, 0), (2048, 4, 0)])
 def test_fit_matches_lapack(N, d, kind):
     X, Y, ls, _ = _problem(N, d, N)
     eng = DeviceEngine(max_gps=1)
