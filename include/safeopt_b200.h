@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SO_ABI_VERSION 1
+#define SO_ABI_VERSION 2
 
 /* status codes */
 #define SO_OK                  0
@@ -195,10 +195,37 @@ int so_swarm_step(so_handle* h, int64_t P, int d, double* pos_d, double* vel_d,
                   double inertia, const double* velocity_scale_h, const double* bounds_h,
                   void* stream);
 /* personal/global best update of safeopt/swarm.py:132-146; writes argmax of best_values
- * (first index) to *best_idx_d. */
+ * (first index) to *best_idx_d.  When the swarm is sharded over ranks this rank holds particles
+ * [p0, p0+P); if rec_d != NULL the kernel also leaves the record
+ *   rec_d[0] = best value, rec_d[1] = (double)(p0 + argmax), rec_d[2..2+d) = that best position
+ * (SO_SWARM_REC_DOUBLES doubles) for the cross-rank exchange. */
+#define SO_SWARM_REC_DOUBLES 18
 int so_swarm_update_best(so_handle* h, int64_t P, int d, const double* pos_d, const double* values_d,
                          const uint8_t* safe_d, double* best_pos_d, double* best_values_d,
-                         int64_t* best_idx_d, void* stream);
+                         int64_t* best_idx_d, int64_t p0, double* rec_d, void* stream);
+/* `global_best = best_positions[argmax(best_values)]` (safeopt/swarm.py:146) over the records of
+ * all ranks (recs_d: n_ranks x SO_SWARM_REC_DOUBLES, as all-gathered): largest value, ties to the
+ * lowest global particle index.  Writes global_best_d (d) and, if not NULL, global_rec_d[0..1] =
+ * {value, index}.  Stream-ordered, no host involvement: a PSO iteration has no host sync. */
+int so_swarm_combine_best(so_handle* h, const double* recs_d, int n_ranks, int d,
+                          double* global_best_d, double* global_rec_d, void* stream);
+
+/* ------------------------------------------------------------------ f1: swarm safe-set maintenance
+ * Stands in for the dense correlation test of safeopt/gp_opt.py:1088-1110
+ *   covariance = gp.kern.K(best_positions, vstack(S, best_positions)) / scaling[0]**2
+ *   for j in range(n): accept j iff all(covariance[j, already in the set] <= 0.95)
+ * without the P x (|S| + P) matrix.  corr(x,x') = k(x,x') / scale2 with the kernel of GP `gp`.
+ * so_safeset_filter: keep_d[j] = all_i corr(cand_j, ref_i) <= thresh   (n candidates x m references,
+ *   both row-major x d; overwrites keep_d; rows may be any shard of the candidates).
+ * so_safeset_insert: the sequential walk over ALL n candidates in index order, restricted to those
+ *   with keep_d[j] != 0: accept_d[j] = keep_d[j] && corr(cand_j, cand_i) <= thresh for every accepted
+ *   i < j.  keep_d is used as scratch (cleared for rejected candidates).  Accepted rows are appended
+ *   in index order to accepted_pos_d (capacity n x d) and counted in *n_accept_d (device). */
+int so_safeset_filter(so_handle* h, int gp, const double* cand_d, int64_t n, const double* ref_d, int64_t m,
+                      double scale2, double thresh, uint8_t* keep_d, void* stream);
+int so_safeset_insert(so_handle* h, int gp, const double* cand_d, int64_t n, uint8_t* keep_d,
+                      double scale2, double thresh, uint8_t* accept_d, double* accepted_pos_d,
+                      int64_t* n_accept_d, void* stream);
 
 #ifdef __cplusplus
 }

@@ -120,6 +120,56 @@ def swarm_case(ref, GPy, name):
     print("%-28s velocities %s" % (name, opt.optimal_velocities))
 
 
+def swarm_query_case(ref, GPy, name, kind="rbf", swarm_size=48, iters=25):
+    """SafeOptSwarm.optimize() unrolled (gp_opt.py:1136-1177) with the global NumPy stream seeded: per swarm
+    the safe set before/after, the swarm's best positions (input of the insertion step, gp_opt.py:1088-1110),
+    the returned point and value.  The GPU tests replay the insertion on the stored best positions and the
+    whole trajectory with the same seed."""
+    rs = np.random.RandomState(11)
+    d, N, G = 2, 12, 2
+    X = rs.uniform(-0.4, 0.4, size=(N, d))
+    f = 1.0 - 0.3 * np.sum(X * X, axis=1)
+    Y = np.stack([f + 0.05 * np.random.RandomState(12 + i).randn(N) for i in range(G)], axis=1)
+    ls = np.array([0.8, 1.1])
+    gps = [GPy.models.GPRegression(X, Y[:, [i]], kernel=kernel_of(GPy, kind, d, 2.0, ls), noise_var=0.05 ** 2) for i in range(G)]
+    fmin = [0.0, 0.2]
+    opt = ref.SafeOptSwarm(gps, fmin, bounds=[(-1.5, 1.5)] * d, beta=2.0, swarm_size=swarm_size)
+    opt.max_iters = iters
+    np.random.seed(5)
+    out = {}
+    for stage in ["greedy", "maximizers", "expanders"]:
+        out[stage + "_S_before"] = opt.S.copy()
+        x, v = opt.get_new_query_point(stage)
+        if stage == "greedy":
+            opt.greedy, opt.best_lower_bound = x, v
+        out[stage + "_x"] = np.asarray(x, dtype=float)
+        out[stage + "_v"] = np.asarray(v, dtype=float)
+        out[stage + "_best_positions"] = opt.swarms[stage].best_positions.copy()
+        out[stage + "_best_values"] = opt.swarms[stage].best_values.copy()
+        out[stage + "_S_after"] = opt.S.copy()
+        # the insertion must not have been preceded by a pruning of S in this fixture
+        assert np.array_equal(out[stage + "_S_after"][:out[stage + "_S_before"].shape[0]], out[stage + "_S_before"])
+    # decision margins of the insertion step (knife-edge fixtures would be useless for parity)
+    from oracle import safeopt_port as port
+    margins = []
+    for stage in ["maximizers", "expanders"]:
+        acc, margin = port.select_new_safe_points(gps[0].kern, out[stage + "_S_before"], out[stage + "_best_positions"], opt.scaling[0])
+        assert np.array_equal(out[stage + "_best_positions"][acc], out[stage + "_S_after"][out[stage + "_S_before"].shape[0]:])
+        margins.append(margin)
+    # a full optimize() from the same seed (fresh optimiser)
+    gps2 = [GPy.models.GPRegression(X, Y[:, [i]], kernel=kernel_of(GPy, kind, d, 2.0, ls), noise_var=0.05 ** 2) for i in range(G)]
+    opt2 = ref.SafeOptSwarm(gps2, fmin, bounds=[(-1.5, 1.5)] * d, beta=2.0, swarm_size=swarm_size)
+    opt2.max_iters = iters
+    np.random.seed(5)
+    x_next = opt2.optimize()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), X=X, Y=Y, fmin=np.asarray(fmin), beta=2.0, variance=2.0, lengthscale=ls,
+                        noise_var=0.05 ** 2, kind=KINDS[kind], bounds=np.asarray([(-1.5, 1.5)] * d), swarm_size=swarm_size,
+                        max_iters=iters, seed=5, scaling=opt.scaling, insertion_margin=np.asarray(margins), x_next=np.asarray(x_next),
+                        S_final=opt2.S, **out)
+    print("%-28s |S| %d -> %d -> %d, insertion margins %s, next %s" % (
+        name, out["maximizers_S_before"].shape[0], out["maximizers_S_after"].shape[0], out["expanders_S_after"].shape[0], margins, x_next))
+
+
 def context_case(ref, GPy, name, lipschitz=None, threshold=5.0):
     """examples/context_example.ipynb shape: 1 parameter + 1 context, product of RBF kernels on disjoint dims.
     (With the GP-based expander test and candidates present the reference raises IndexError -- gp_opt.py:585-588
@@ -179,6 +229,8 @@ def main():
     grid_case(ref, GPy, "matern52_2d_g2", X, Y, "mat52", 2.0, [1.2, 0.7], 0.05 ** 2, [(-4.0, 4.0)] * 2, [31, 45], [-np.inf, 0.4], 2.0, 0.05)
     loop_case(ref, GPy, "bo_loop_2d")
     swarm_case(ref, GPy, "swarm_fitness_3d")
+    swarm_query_case(ref, GPy, "swarm_query_2d")
+    swarm_query_case(ref, GPy, "swarm_query_2d_mat32", kind="mat32", swarm_size=40, iters=15)
     # Lipschitz expander rule (gp_opt.py:558-576) and contexts (gp_opt.py:424-451)
     X, Y = synth(0, 40, 2, 1, 2.5)
     grid_case(ref, GPy, "lipschitz_g1", X, Y, "rbf", 2.0, [1.0, 1.0], 0.05 ** 2, [(-5.0, 5.0)] * 2, 40, [0.5], 2.0, 0.05, lipschitz=2.0)

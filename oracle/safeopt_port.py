@@ -304,3 +304,23 @@ def pso_step(positions, velocities, best_positions, best_values, global_best, r1
     best_positions = np.where(upd[:, None], positions, best_positions)
     global_best = best_positions[np.argmax(best_values)].copy()
     return positions, velocities, best_positions, best_values, global_best
+
+
+def select_new_safe_points(kern, S, best_positions, scaling0, limit=0.95):
+    """Swarm safe-set insertion (gp_opt.py:1088-1110): particle j joins iff its prior correlation
+    ``k(x_j, .) / scaling0**2`` with every old safe point and every particle accepted before it is
+    ``<= limit``.  Returns (accepted mask over the particles, min |corr - limit| over the pairs compared).
+
+    Row-at-a-time restatement (the reference builds the full P x (|S|+P) matrix first); the comparison
+    set and order are the reference's."""
+    S = np.asarray(S, dtype=float)
+    best_positions = np.asarray(best_positions, dtype=float)
+    accepted = np.zeros(best_positions.shape[0], dtype=bool)
+    margin = np.inf
+    for j in range(best_positions.shape[0]):
+        pool = np.vstack((S, best_positions[accepted]))
+        corr = kern.K(best_positions[[j]], pool)[0] / scaling0 ** 2
+        margin = min(margin, float(np.min(np.abs(corr - limit)))) if corr.size else margin
+        if np.all(corr <= limit):
+            accepted[j] = True
+    return accepted, margin

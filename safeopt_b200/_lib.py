@@ -28,7 +28,8 @@ SWARM_GREEDY, SWARM_MAXIMIZERS, SWARM_EXPANDERS, SWARM_SAFE_SET = 0, 1, 2, 3
 SWARM_KINDS = {"greedy": SWARM_GREEDY, "maximizers": SWARM_MAXIMIZERS, "expanders": SWARM_EXPANDERS,
                "safe_set": SWARM_SAFE_SET}
 EXPANDER_MAX_BATCH = 32
-ABI_VERSION = 1
+ABI_VERSION = 2
+SWARM_REC_DOUBLES = 18
 
 
 class NativeLibraryError(RuntimeError):
@@ -80,7 +81,10 @@ SIGNATURES = {
     "so_expander_lipschitz": (_i, [_P, _P, _i, _i64, _i64, _P, _P, _P, _i, _dbl, _dbl, _P, _P]),
     "so_swarm_fitness": (_i, [_P, _i, _i, _i64, _P, _P, _dbl, _P, _P, _dbl, _P, _P, _P]),
     "so_swarm_step": (_i, [_P, _i64, _i, _P, _P, _P, _P, _P, _dbl, _P, _P, _P]),
-    "so_swarm_update_best": (_i, [_P, _i64, _i, _P, _P, _P, _P, _P, _P, _P]),
+    "so_swarm_update_best": (_i, [_P, _i64, _i, _P, _P, _P, _P, _P, _P, _i64, _P, _P]),
+    "so_swarm_combine_best": (_i, [_P, _P, _i, _i, _P, _P, _P]),
+    "so_safeset_filter": (_i, [_P, _i, _P, _i64, _P, _i64, _dbl, _dbl, _P, _P]),
+    "so_safeset_insert": (_i, [_P, _i, _P, _i64, _P, _dbl, _dbl, _P, _P, _P, _P]),
 }
 
 _lib = None

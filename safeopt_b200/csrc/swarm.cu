@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(kThreads) k_swarm_update_best(int64_t P, int d
                                                                const double* __restrict__ values, const uint8_t* __restrict__ safe,
                                                                double* __restrict__ best_pos, double* __restrict__ best_values,
                                                                BestPartial* __restrict__ part, unsigned int* __restrict__ counter,
-                                                               int64_t* __restrict__ best_idx) {
+                                                               int64_t* __restrict__ best_idx, int64_t p0, double* __restrict__ rec) {
     BestPartial acc = {-INFINITY, -1};
     for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < P; i += (int64_t)gridDim.x * kThreads) {
         double bv = best_values[i];
@@ -148,7 +148,31 @@ __global__ void __launch_bounds__(kThreads) k_swarm_update_best(int64_t P, int d
         }
         *best_idx = t.idx;
         *counter = 0;
+        if (rec) {
+            // every personal best of this launch was written before the owning block took its ticket
+            rec[0] = t.v;
+            rec[1] = (double)(p0 + t.idx);
+            for (int j = 0; j < d; ++j) rec[2 + j] = best_pos[(size_t)t.idx * d + j];
+        }
     }
+}
+
+// Global best over the R per-rank records {value, global index, position[d]} (stride SO_SWARM_REC_DOUBLES):
+// largest value, ties to the lowest global particle index (np.argmax over the unsharded swarm, swarm.py:146).
+__global__ void k_swarm_combine_best(const double* __restrict__ recs, int R, int d, double* __restrict__ gbest,
+                                     double* __restrict__ grec) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int best = -1;
+    for (int r = 0; r < R; ++r) {
+        const double v = recs[(size_t)r * SO_SWARM_REC_DOUBLES], i = recs[(size_t)r * SO_SWARM_REC_DOUBLES + 1];
+        if (i < 0.0) continue;
+        if (best < 0 || v > recs[(size_t)best * SO_SWARM_REC_DOUBLES] ||
+            (v == recs[(size_t)best * SO_SWARM_REC_DOUBLES] && i < recs[(size_t)best * SO_SWARM_REC_DOUBLES + 1])) best = r;
+    }
+    if (best < 0) return;
+    const double* b = recs + (size_t)best * SO_SWARM_REC_DOUBLES;
+    for (int j = 0; j < d; ++j) gbest[j] = b[2 + j];
+    if (grec) { grec[0] = b[0]; grec[1] = b[1]; }
 }
 
 }  // namespace
@@ -190,14 +214,24 @@ extern "C" int so_swarm_step(so_handle* h, int64_t P, int d, double* pos_d, doub
 
 extern "C" int so_swarm_update_best(so_handle* h, int64_t P, int d, const double* pos_d, const double* values_d,
                                     const uint8_t* safe_d, double* best_pos_d, double* best_values_d, int64_t* best_idx_d,
-                                    void* stream) {
+                                    int64_t p0, double* rec_d, void* stream) {
     if (!h || !pos_d || !values_d || !safe_d || !best_pos_d || !best_values_d || !best_idx_d || P < 1) return SO_ERR_BAD_ARG;
     if (d < 1 || d > SO_MAX_DIM) return so_fail(h, SO_ERR_UNSUPPORTED, "swarm_update_best: 1 <= d <= 16");
     DeviceGuard guard(h->device);
     int64_t blocks = (P + kThreads - 1) / kThreads;
     if (blocks > SO_WS_MAX_BLOCKS) blocks = SO_WS_MAX_BLOCKS;
     k_swarm_update_best<<<(unsigned)blocks, kThreads, 0, (cudaStream_t)stream>>>(
-        P, d, pos_d, values_d, safe_d, best_pos_d, best_values_d, (BestPartial*)h->ws_partials, h->ws_counter, best_idx_d);
+        P, d, pos_d, values_d, safe_d, best_pos_d, best_values_d, (BestPartial*)h->ws_partials, h->ws_counter, best_idx_d, p0, rec_d);
     SO_CHECK_LAUNCH(h, "k_swarm_update_best");
+    return SO_OK;
+}
+
+extern "C" int so_swarm_combine_best(so_handle* h, const double* recs_d, int n_ranks, int d, double* global_best_d,
+                                     double* global_rec_d, void* stream) {
+    if (!h || !recs_d || !global_best_d || n_ranks < 1) return SO_ERR_BAD_ARG;
+    if (d < 1 || d > SO_MAX_DIM) return so_fail(h, SO_ERR_UNSUPPORTED, "swarm_combine_best: 1 <= d <= 16");
+    DeviceGuard guard(h->device);
+    k_swarm_combine_best<<<1, 32, 0, (cudaStream_t)stream>>>(recs_d, n_ranks, d, global_best_d, global_rec_d);
+    SO_CHECK_LAUNCH(h, "k_swarm_combine_best");
     return SO_OK;
 }

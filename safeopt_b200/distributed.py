@@ -79,6 +79,18 @@ class Comm:
             out = torch.stack(parts, dim=0)
         return out.cpu().numpy()
 
+    def all_gather_into(self, out, t):
+        """Device-side all-gather with no host involvement: ``out[r] = t`` of rank r (``out``: (world, *t.shape))."""
+        if not self.active:
+            out[0].copy_(t)
+            return out
+        try:
+            self._dist.all_gather_into_tensor(out, t.contiguous())
+        except (RuntimeError, AttributeError, NotImplementedError):
+            parts = [out[r] for r in range(self.world)]
+            self._dist.all_gather(parts, t.contiguous())
+        return out
+
     def gather_records(self, rec_u8, dtype: np.dtype) -> np.ndarray:
         """All ranks' copies of a device-resident record (uint8 tensor of dtype.itemsize bytes)."""
         raw = self.all_gather_tensor(rec_u8)
@@ -143,6 +155,27 @@ def gather_row_blocks(comm: Comm, local: np.ndarray, n_rows: int) -> np.ndarray:
     pad[:local.shape[0]] = local
     allr = comm.all_gather(pad)
     return allr.reshape((-1,) + local.shape[1:])[:n_rows]
+
+
+def gather_padded_rows(comm: Comm, local, total: int):
+    """Reassemble a row-sharded torch tensor (blocks from shard_bounds) on every rank without leaving the
+    device: blocks are padded to ceil(total/world) rows, all-gathered with one collective and trimmed.
+    Works for CUDA tensors over NCCL and CPU tensors over gloo."""
+    if not comm.active:
+        return local
+    import torch
+    per = -(-int(total) // comm.world)
+    pad = torch.zeros((per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[:local.shape[0]] = local
+    out = torch.empty((comm.world,) + tuple(pad.shape), dtype=local.dtype, device=local.device)
+    comm.all_gather_into(out, pad)
+    return out.reshape((-1,) + tuple(local.shape[1:]))[:total]
+
+
+def shard_stacked_blocks(full: np.ndarray, blocks: int, total: int, lo: int, hi: int) -> np.ndarray:
+    """``full`` is ``blocks`` stacked (total, d) arrays (how the reference draws its PSO randoms,
+    swarm.py:105: ``rand(2 * swarm_size, ndim)``); returns rows [lo, hi) of each block, stacked."""
+    return np.concatenate([full[b * total + lo: b * total + hi] for b in range(blocks)], axis=0)
 
 
 def order_candidates(comm: Comm, rows_sorted: np.ndarray, keys_sorted: np.ndarray) -> np.ndarray:

@@ -218,12 +218,34 @@ class DeviceEngine:
         self._check(rc, "so_swarm_step")
         self.launches += 1
 
-    def swarm_update_best(self, pos, values, safe, best_pos, best_values, best_idx):
+    def swarm_update_best(self, pos, values, safe, best_pos, best_values, best_idx, p0=0, rec=None):
         P, d = pos.shape
         rc = self.lib.so_swarm_update_best(self.handle, P, d, _ptr(pos), _ptr(values), _ptr(safe), _ptr(best_pos),
-                                           _ptr(best_values), _ptr(best_idx), self._stream())
+                                           _ptr(best_values), _ptr(best_idx), int(p0), _ptr(rec), self._stream())
         self._check(rc, "so_swarm_update_best")
         self.launches += 1
+
+    def swarm_combine_best(self, recs, d, global_best, global_rec=None):
+        rc = self.lib.so_swarm_combine_best(self.handle, _ptr(recs), int(recs.shape[0]), int(d), _ptr(global_best),
+                                            _ptr(global_rec), self._stream())
+        self._check(rc, "so_swarm_combine_best")
+        self.launches += 1
+
+    # ------------------------------------------------------------------ f1: swarm safe-set maintenance
+    def safeset_filter(self, gp, cand, ref, scale2, thresh, keep):
+        n, m = cand.shape[0], ref.shape[0]
+        rc = self.lib.so_safeset_filter(self.handle, gp, _ptr(cand), n, _ptr(ref) if m else C.c_void_p(0), m, float(scale2),
+                                        float(thresh), _ptr(keep), self._stream())
+        self._check(rc, "so_safeset_filter")
+        self.launches += (1 + (1 if m else 0)) if n else 0
+
+    def safeset_insert(self, gp, cand, keep, scale2, thresh, accept, accepted_pos, n_accept):
+        n = cand.shape[0]
+        rc = self.lib.so_safeset_insert(self.handle, gp, _ptr(cand), n, _ptr(keep), float(scale2), float(thresh),
+                                        _ptr(accept), _ptr(accepted_pos), _ptr(n_accept), self._stream())
+        self._check(rc, "so_safeset_insert")
+        blocks = (n + 1023) // 1024
+        self.launches += max(0, 2 * blocks - 1)
 
     # ------------------------------------------------------------------ records
     def read_record(self, rec, dtype):

@@ -21,11 +21,11 @@ from typing import List, Optional
 import numpy as np
 
 from . import _lib
-from .distributed import (Comm, combine_max_first, gather_ragged, gather_row_blocks, order_candidates,
+from .distributed import (Comm, combine_max_first, gather_padded_rows, gather_ragged, gather_row_blocks, order_candidates,
                           reduce_max_records, reduce_safe_records, shard_bounds)
 from .engine import MAX_REC_DTYPE, SAFE_REC_DTYPE, DeviceEngine
 from .gpmodel import extract_hyper, fingerprint
-from .swarm import SwarmOptimization
+from .swarm import DeviceSwarm, SwarmOptimization
 from .utilities import detect_grid, grid_rows_from_index, linearly_spaced_combinations
 
 __all__ = ["SafeOpt", "SafeOptSwarm", "GaussianProcessOptimization"]
@@ -568,12 +568,24 @@ class SafeOptSwarm(GaussianProcessOptimization):
     """SafeOpt for higher dimensions with particle swarms (reference: gp_opt.py:715-1192).
 
     Parameters are the reference's (``gp, fmin, bounds, beta=2, scaling='auto', threshold=0,
-    swarm_size=20``) plus ``device``.  No Lipschitz constant, no contexts (as in the reference).
-    The particle posterior + fitness runs on the GPU; particle initialisation and the sequential
-    safe-set insertion stay in host NumPy exactly as in the reference.
+    swarm_size=20``) plus ``device``, ``swarm_backend`` and ``rng``.  No Lipschitz constant, no contexts
+    (as in the reference).
+
+    The particle posterior + fitness and the safe-set maintenance of ``get_new_query_point`` (the
+    correlation-filtered insertion of gp_opt.py:1088-1110) run on the GPU.
+    ``swarm_backend``: ``'host'`` keeps the swarm state in the reference's ``SwarmOptimization`` (NumPy
+    state, fitness on the GPU; bit-for-bit the reference's random stream), ``'device'`` keeps it in HBM
+    (:class:`DeviceSwarm`, sharded over the ranks of ``torch.distributed`` when initialised), ``'auto'``
+    picks ``'device'`` from ``DEVICE_SWARM_MIN`` particles.  ``rng`` is passed to :class:`DeviceSwarm`.
+    In a multi-rank run every rank must construct the optimiser identically and seed ``np.random``
+    identically (particles are sampled from the replicated safe set with the host generator).
     """
 
-    def __init__(self, gp, fmin, bounds, beta=2, scaling="auto", threshold=0, swarm_size=20, device=None):
+    DEVICE_SWARM_MIN = 2048
+    CORRELATION_LIMIT = 0.95        # gp_opt.py:1105
+
+    def __init__(self, gp, fmin, bounds, beta=2, scaling="auto", threshold=0, swarm_size=20, device=None,
+                 swarm_backend="auto", rng="host", seed=0):
         super(SafeOptSwarm, self).__init__(gp, fmin=fmin, beta=beta, num_contexts=0, threshold=threshold,
                                            scaling=scaling)
         self.S = np.asarray(self.gps[0].X)
@@ -583,13 +595,24 @@ class SafeOptSwarm(GaussianProcessOptimization):
         self.best_lower_bound = -np.inf
         self.greedy_point = self.S[0, :]
 
+        if swarm_backend not in ("auto", "host", "device"):
+            raise ValueError("swarm_backend must be 'auto', 'host' or 'device'")
+        if swarm_backend == "auto":
+            swarm_backend = "device" if swarm_size >= self.DEVICE_SWARM_MIN else "host"
+        self.swarm_backend = swarm_backend
         self._engine = DeviceEngine(device, max_gps=len(self.gps))
+        self._comm = Comm(self._engine.device)
         self._fits = _DeviceFits(self._engine, self.gps)
         self.optimal_velocities = self.optimize_particle_velocity()
         swarm_types = ["greedy", "maximizers", "expanders"]
-        self.swarms = {kind: SwarmOptimization(swarm_size, self.optimal_velocities,
-                                               partial(self._compute_particle_fitness, kind), bounds=self.bounds)
-                       for kind in swarm_types}
+        if swarm_backend == "device":
+            self.swarms = {kind: DeviceSwarm(self._engine, self.optimal_velocities, partial(self._fitness_device, kind),
+                                             bounds=self.bounds, rng=rng, seed=seed + 1000 * k, comm=self._comm)
+                           for k, kind in enumerate(swarm_types)}
+        else:
+            self.swarms = {kind: SwarmOptimization(swarm_size, self.optimal_velocities,
+                                                   partial(self._compute_particle_fitness, kind), bounds=self.bounds)
+                           for kind in swarm_types}
 
     def optimize_particle_velocity(self):
         """Per-dimension velocities at which the prior correlation drops to ~0.95 (gp_opt.py:818-872).
@@ -684,34 +707,56 @@ class SafeOptSwarm(GaussianProcessOptimization):
         swarm = self.swarms[swarm_type]
         swarm.init_swarm(particles)
         swarm.run_swarm(self.max_iters)
+        on_device = isinstance(swarm, DeviceSwarm)
+        global_best = swarm.global_best                      # host array in both backends
+        best_value = swarm.global_best_value if on_device else np.max(swarm.best_values)
 
         if swarm_type != "greedy":
-            num_added = 0
-            covariance = self.gp.kern.K(swarm.best_positions, np.vstack((self.S, swarm.best_positions)))
-            covariance /= self.scaling[0] ** 2
-            initial_safe = len(self.S)
-            n, m = np.shape(covariance)
-            mask = np.zeros(m, dtype=bool)
-            mask[:initial_safe] = True
-            for j in range(n):
-                if np.all(covariance[j, mask] <= 0.95):
-                    self.S = np.vstack((self.S, swarm.best_positions[[j], :]))
-                    num_added += 1
-                    mask[initial_safe + j] = True
-            logging.debug("At the end of swarm {}, {} points were appended to the safeset".format(swarm_type, num_added))
+            new_rows = self._select_new_safe_points(swarm.best_positions, sharded=on_device)
+            if new_rows.shape[0]:
+                self.S = np.vstack((self.S, new_rows))
+            logging.debug("At the end of swarm {}, {} points were appended to the safeset".format(swarm_type,
+                                                                                                   new_rows.shape[0]))
         else:
             mean, var = self._posterior_host(0, self.greedy_point[None, :])
             lower_bound = mean.squeeze() - beta * np.sqrt(var.squeeze())
-            if lower_bound < np.max(swarm.best_values):
-                self.greedy_point = swarm.global_best.copy()
+            if lower_bound < best_value:
+                self.greedy_point = global_best.copy()
 
         if swarm_type == "greedy":
-            return swarm.global_best.copy(), np.max(swarm.best_values)
+            return global_best.copy(), best_value
 
         var = np.empty(len(self.gps), dtype=float)
         for i in range(len(self.gps)):
-            var[i] = self._posterior_host(i, swarm.global_best[None, :])[1].squeeze()
-        return swarm.global_best, np.sqrt(var)
+            var[i] = self._posterior_host(i, global_best[None, :])[1].squeeze()
+        return global_best, np.sqrt(var)
+
+    def _select_new_safe_points(self, best_positions, sharded=False):
+        """Rows of ``best_positions`` that join the safe set (reference: gp_opt.py:1088-1110).
+
+        The reference materialises ``K(best_positions, vstack(S, best_positions)) / scaling[0]**2`` and walks
+        the particles in index order, accepting one iff its prior correlation with every point already in the
+        set is ``<= 0.95``.  Here: a tiled filter against the old safe set (each rank on its own particles when
+        the swarm is sharded), one all-gather of (position, keep) over the ranks, then the blocked sequential
+        walk over the survivors (``so_safeset_insert``, run redundantly on every rank so that ``S`` stays
+        replicated and identical).  Returns the accepted positions as a host array, in particle order."""
+        eng = self._engine
+        t = eng.torch
+        self._fits.refresh()
+        cand = best_positions if t.is_tensor(best_positions) else eng.to_device(np.ascontiguousarray(best_positions, dtype=float))
+        n_local, d = cand.shape
+        scale2 = float(self.scaling[0]) ** 2
+        keep = eng.empty((max(n_local, 1),), "u8")[:n_local]
+        eng.safeset_filter(0, cand, eng.to_device(np.ascontiguousarray(self.S, dtype=float)), scale2,
+                           self.CORRELATION_LIMIT, keep)
+        if sharded and self._comm.active:
+            cand = gather_padded_rows(self._comm, cand, self.swarm_size)
+            keep = gather_padded_rows(self._comm, keep, self.swarm_size)
+        n = cand.shape[0]
+        accept, acc_pos, n_acc = eng.empty((max(n, 1),), "u8"), eng.empty((max(n, 1), d)), eng.zeros((1,), "i64")
+        eng.safeset_insert(0, cand, keep, scale2, self.CORRELATION_LIMIT, accept, acc_pos, n_acc)
+        count = int(n_acc.item())
+        return acc_pos[:count].cpu().numpy()
 
     def _posterior_host(self, i, X):
         """Posterior of GP ``i`` at a few host points through the device path."""

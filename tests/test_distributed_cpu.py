@@ -116,6 +116,50 @@ def test_sharded_record_reduction_gloo(fixture, tmp_path):
     assert all(os.path.exists(os.path.join(str(tmp_path), "ok_%d" % r)) for r in range(world))
 
 
+def _swarm_worker(rank, world, port, out_dir):
+    """Host logic of the sharded swarm: random-block slicing, padded row gather (positions + keep flags of the
+    safe-set insertion) and the best-record exchange, with CPU tensors over gloo."""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from safeopt_b200 import _lib
+        from safeopt_b200 import distributed as D
+        comm = D.Comm()
+        P, d = 11, 3                                     # odd size: the last block is short
+        p0, p1 = D.shard_bounds(P, world, rank)
+        np.random.seed(9)                                # every rank draws the same stream
+        full = np.random.rand(2 * P, d)
+        mine = D.shard_stacked_blocks(full, 2, P, p0, p1)
+        assert mine.shape == (2 * (p1 - p0), d)
+        assert np.array_equal(mine[:p1 - p0], full[p0:p1]) and np.array_equal(mine[p1 - p0:], full[P + p0:P + p1])
+        pos = np.arange(P * d, dtype=float).reshape(P, d)
+        keep = (np.arange(P) % 3 != 0).astype(np.uint8)
+        got_pos = D.gather_padded_rows(comm, torch.from_numpy(pos[p0:p1].copy()), P).numpy()
+        got_keep = D.gather_padded_rows(comm, torch.from_numpy(keep[p0:p1].copy()), P).numpy()
+        assert np.array_equal(got_pos, pos) and np.array_equal(got_keep, keep)
+        # best-record exchange: {value, global index, position}; equal values -> lowest global index wins
+        rec = torch.zeros(_lib.SWARM_REC_DOUBLES, dtype=torch.float64)
+        rec[0], rec[1] = 2.5, float(p0 + 1)
+        rec[2:2 + d] = torch.from_numpy(pos[p0 + 1])
+        recs = torch.zeros((world, _lib.SWARM_REC_DOUBLES), dtype=torch.float64)
+        comm.all_gather_into(recs, rec)
+        r = recs.numpy()
+        assert np.array_equal(r[:, 1], [D.shard_bounds(P, world, k)[0] + 1 for k in range(world)])
+        v, idx = D.combine_max_first(r[:, 0], r[:, 1].astype(np.int64))
+        assert (v, idx) == (2.5, 1) and np.array_equal(r[0, 2:2 + d], pos[1])
+        open(os.path.join(out_dir, "ok_%d" % rank), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_swarm_host_logic_gloo(tmp_path):
+    world = 2
+    mp.spawn(_swarm_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(os.path.join(str(tmp_path), "ok_%d" % r)) for r in range(world))
+
+
 def test_single_rank_comm_is_identity():
     from safeopt_b200 import distributed as D
     comm = D.Comm()

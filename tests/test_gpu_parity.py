@@ -17,6 +17,7 @@ if not torch.cuda.is_available():  # pragma: no cover - the CPU run deselects th
 
 import safeopt_b200 as sb  # noqa: E402
 from safeopt_b200 import _lib, workloads  # noqa: E402
+from safeopt_b200 import distributed as D  # noqa: E402
 from safeopt_b200.engine import DeviceEngine  # noqa: E402
 from oracle import gpy_lite, safeopt_port as port  # noqa: E402
 
@@ -319,7 +320,100 @@ def test_device_swarm_large_matches_host_swarm_logic():
     ds.run_swarm(5)
     assert np.abs(ds.positions.cpu().numpy() - hs.positions).max() < 1e-9
     assert np.abs(ds.best_values.cpu().numpy() - hs.best_values).max() < 1e-8
-    assert np.abs(ds.global_best.cpu().numpy() - hs.global_best).max() < 1e-9
+    assert np.abs(ds.global_best - hs.global_best).max() < 1e-9
+
+
+def _swarm_query_problem(g, **kw):
+    X, Y = g["X"], g["Y"]
+    d = X.shape[1]
+    cls = {0: sb.RBF, 1: sb.Matern32, 2: sb.Matern52}[int(g["kind"])]
+    gps = [sb.GPRegression(X, Y[:, [i]], kernel=cls(d, variance=float(g["variance"]), lengthscale=g["lengthscale"], ARD=True),
+                           noise_var=float(g["noise_var"])) for i in range(Y.shape[1])]
+    opt = sb.SafeOptSwarm(gps, list(g["fmin"]), bounds=[tuple(b) for b in g["bounds"]], beta=float(g["beta"]),
+                          swarm_size=int(g["swarm_size"]), **kw)
+    opt.max_iters = int(g["max_iters"])
+    return opt
+
+
+@pytest.mark.parametrize("name", ["swarm_query_2d", "swarm_query_2d_mat32"])
+def test_safeset_insertion_matches_golden(name):
+    """f1: the device insertion kernels on the reference's own swarms (gp_opt.py:1088-1110)."""
+    g = load_golden(name)
+    opt = _swarm_query_problem(g)
+    for stage in ["maximizers", "expanders"]:
+        before, after = g[stage + "_S_before"], g[stage + "_S_after"]
+        opt.S = before.copy()
+        new = opt._select_new_safe_points(g[stage + "_best_positions"])
+        assert np.array_equal(new, after[before.shape[0]:]), stage
+
+
+@pytest.mark.parametrize("kind,d,n,m", [(0, 3, 3000, 500), (1, 6, 2500, 0), (2, 2, 1024, 300), (0, 16, 1500, 40), (0, 1, 5, 3)])
+def test_safeset_kernels_match_port(kind, d, n, m):
+    """Filter + blocked sequential walk vs the port on random candidates spanning several 1024-blocks."""
+    rs = np.random.RandomState(100 + d)
+    ls = rs.uniform(0.5, 1.5, d)
+    X, Y = rs.uniform(-1, 1, (8, d)), rs.randn(8)
+    eng = DeviceEngine(max_gps=1)
+    eng.fit(0, X, Y, kind, ls, 1.7, 0.01)
+    kern = oracle_kernel(kind, d, 1.7, ls)
+    spread = {1: 8.0, 2: 6.0, 3: 2.5, 6: 0.9, 16: 0.16}[d]        # dense enough that a good share is rejected
+    cand, ref = rs.uniform(-spread, spread, (n, d)), rs.uniform(-spread, spread, (m, d))
+    scale0 = np.sqrt(1.7)
+    acc_ref, margin = port.select_new_safe_points(kern, ref, cand, scale0)
+    assert margin > 1e-9
+    cand_d = eng.to_device(cand)
+    keep = eng.empty((n,), "u8")
+    eng.safeset_filter(0, cand_d, eng.to_device(ref) if m else eng.empty((0, d)), scale0 ** 2, 0.95, keep)
+    if m:
+        keep_ref = np.all(kern.K(cand, ref) / scale0 ** 2 <= 0.95, axis=1)
+        assert np.array_equal(keep.cpu().numpy().astype(bool), keep_ref)
+    accept, pos, cnt = eng.empty((n,), "u8"), eng.empty((n, d)), eng.zeros((1,), "i64")
+    eng.safeset_insert(0, cand_d, keep, scale0 ** 2, 0.95, accept, pos, cnt)
+    acc = accept.cpu().numpy().astype(bool)
+    assert 0 < acc_ref.sum() < n or n < 10
+    assert np.array_equal(acc, acc_ref)
+    assert int(cnt.item()) == acc_ref.sum() and np.array_equal(pos[:int(cnt.item())].cpu().numpy(), cand[acc_ref])
+    eng.close()
+
+
+@pytest.mark.parametrize("name", ["swarm_query_2d", "swarm_query_2d_mat32"])
+@pytest.mark.parametrize("backend", ["host", "device"])
+def test_safeoptswarm_trajectory_matches_golden(name, backend):
+    """SafeOptSwarm.optimize() unrolled like gp_opt.py:1136-1177 with the reference's random stream: every
+    swarm's best positions, the safe-set growth and the returned points follow the reference."""
+    g = load_golden(name)
+    opt = _swarm_query_problem(g, swarm_backend=backend, rng="host")
+    np.random.seed(int(g["seed"]))
+    for stage in ["greedy", "maximizers", "expanders"]:
+        assert np.array_equal(opt.S, g[stage + "_S_before"]), stage
+        x, v = opt.get_new_query_point(stage)
+        if stage == "greedy":
+            opt.greedy, opt.best_lower_bound = x, v
+        sw = opt.swarms[stage]
+        bp = sw.best_positions.cpu().numpy() if backend == "device" else sw.best_positions
+        assert np.abs(bp - g[stage + "_best_positions"]).max() < 1e-7, stage
+        assert np.abs(np.asarray(x) - g[stage + "_x"]).max() < 1e-7 and np.abs(np.asarray(v) - g[stage + "_v"]).max() < 1e-7, stage
+        assert opt.S.shape == g[stage + "_S_after"].shape and np.abs(opt.S - g[stage + "_S_after"]).max() < 1e-7, stage
+    opt2 = _swarm_query_problem(g, swarm_backend=backend, rng="host")
+    np.random.seed(int(g["seed"]))
+    assert np.abs(opt2.optimize() - g["x_next"]).max() < 1e-7
+    assert opt2.S.shape == g["S_final"].shape
+
+
+def test_device_swarm_device_rng_runs():
+    g = load_golden("swarm_query_2d")
+    opt = _swarm_query_problem(g, swarm_backend="device", rng="device", seed=3)
+    opt.swarm_size = 4096
+    np.random.seed(0)
+    x = opt.optimize()
+    assert x.shape == (2,) and np.all(np.abs(x) <= 1.5)
+    _, safe = opt._compute_particle_fitness("safe_set", opt.S)
+    assert opt.S.shape[0] > g["X"].shape[0]
+    # every pair of points in the grown safe set respects the correlation limit (gp_opt.py:1105)
+    kern = oracle_kernel(0, 2, float(g["variance"]), g["lengthscale"])
+    C = kern.K(opt.S[g["X"].shape[0]:], opt.S) / float(g["variance"])
+    np.fill_diagonal(C[:, g["X"].shape[0]:], 0.0)
+    assert C.max() <= 0.95 + 1e-12
 
 
 # ---------------------------------------------------------------- full-size properties (BASELINE config 4 and 2)
@@ -392,6 +486,44 @@ def _nccl_worker(rank, world, port_no, out):
         open(os.path.join(out, "ok_%d" % rank), "w").write("1" if ok else "0")
     finally:
         dist.destroy_process_group()
+
+
+def _nccl_swarm_worker(rank, world, port_no, out):
+    import os
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port_no)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        ok = True
+        for name in ["swarm_query_2d", "swarm_query_2d_mat32"]:
+            g = load_golden(name)
+            opt = _swarm_query_problem(g, swarm_backend="device", rng="host", device=torch.device("cuda", rank))
+            np.random.seed(int(g["seed"]))
+            x = opt.optimize()
+            sw = opt.swarms["expanders"]
+            ok = ok and sw.comm.world == world and sw.p1 - sw.p0 < int(g["swarm_size"])
+            ok = ok and np.abs(x - g["x_next"]).max() < 1e-7 and opt.S.shape == g["S_final"].shape
+            ok = ok and np.abs(opt.S - g["S_final"]).max() < 1e-7
+            full = D.gather_padded_rows(sw.comm, sw.best_positions, int(g["swarm_size"])).cpu().numpy()
+            ok = ok and np.abs(full - g["expanders_best_positions"]).max() < 1e-7
+        open(os.path.join(out, "ok_%d" % rank), "w").write("1" if ok else "0")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_sharded_swarm_matches_golden(tmp_path):
+    import os
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port_no = s.getsockname()[1]
+    s.close()
+    mp.spawn(_nccl_swarm_worker, args=(2, port_no, str(tmp_path)), nprocs=2, join=True)
+    assert all(open(os.path.join(str(tmp_path), "ok_%d" % r)).read() == "1" for r in range(2))
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")

@@ -3,7 +3,7 @@ the reference's own package (build container only) and the committed golden fixt
 import numpy as np
 import pytest
 
-from conftest import GRID_CASES, golden_lipschitz, golden_problem, load_golden, unpack_mask
+from conftest import GRID_CASES, golden_lipschitz, golden_problem, load_golden, oracle_kernel, unpack_mask
 from oracle import gpy_lite, safeopt_port as port
 
 
@@ -128,6 +128,18 @@ def test_port_swarm_fitness_golden():
                                      best_lower_bound=float(g["best_lower_bound"]))
         assert np.allclose(v, g["values_" + kind], rtol=1e-13, atol=1e-13)
         assert np.array_equal(s, g["safe_" + kind])
+
+
+@pytest.mark.parametrize("name", ["swarm_query_2d", "swarm_query_2d_mat32"])
+def test_port_swarm_insertion_golden(name):
+    """select_new_safe_points == the reference's safe-set growth (gp_opt.py:1088-1110) on the stored swarms."""
+    g = load_golden(name)
+    kern = oracle_kernel(int(g["kind"]), 2, float(g["variance"]), g["lengthscale"])
+    for stage in ["maximizers", "expanders"]:
+        before, after, best = g[stage + "_S_before"], g[stage + "_S_after"], g[stage + "_best_positions"]
+        acc, margin = port.select_new_safe_points(kern, before, best, float(g["scaling"][0]))
+        assert np.array_equal(best[acc], after[before.shape[0]:])
+        assert margin > 1e-6
 
 
 def test_port_bo_loop_golden():
