@@ -95,6 +95,17 @@ int         so_num_sms(const so_handle* h);
 int so_fit(so_handle* h, int gp, const double* X_h, const double* Y_h, int N, int d,
            int kernel_kind, const double* lengthscale_h, double variance, double noise_var,
            void* stream);
+/* f4 -- one-point updates of an existing fit (same hyper-parameters), O(N^2) instead of O(N^3):
+ * so_fit_append stands in for the `set_XY(vstack(X, x), vstack(Y, y))` of
+ * safeopt/gp_opt.py:227 (`_add_data_point`, reached from add_new_data_point :230-255):
+ * bordered Cholesky row l = L^-1 k_new, new row of L^-1, alpha and z updated in place, one
+ * fragment block row re-packed.  x_new_h: d doubles.  Returns SO_ERR_CAPACITY when the
+ * handle's buffers are full and SO_ERR_NOT_PD when the bordered matrix is not positive
+ * definite -- in both cases the caller falls back to so_fit on the full data.
+ * so_fit_remove_last stands in for `set_XY(X[:-1], Y[:-1])` (gp_opt.py:267, :275).
+ * After either call so_grid_prepare must run again (like after so_fit). */
+int so_fit_append(so_handle* h, int gp, const double* x_new_h, double y_new, void* stream);
+int so_fit_remove_last(so_handle* h, int gp, void* stream);
 /* Test/diagnostic read-back (synchronous): any of the outputs may be NULL.
  *   L_h, Linv_h: N x N row-major; alpha_h: N. */
 int so_fit_export(so_handle* h, int gp, double* L_h, double* Linv_h, double* alpha_h);

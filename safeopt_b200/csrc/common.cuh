@@ -18,13 +18,14 @@ struct GPState {
     int N = 0, d = 0, kind = 0;
     int NB = 0;                  // number of 8-row blocks, Npad = 8*NB
     int capN = 0;                // allocated for this many padded rows
+    int ld = 0;                  // leading dimension of K / Linv (= capN: stays put while points are appended)
     double variance = 0, noise = 0;
     double inv_ls[SO_MAX_DIM];   // 1 / lengthscale_j
     double* X = nullptr;         // N x d raw training inputs
     double* Xs = nullptr;        // Npad x d, scaled by 1/lengthscale (padding rows = 0)
     double* Y = nullptr;         // N
-    double* K = nullptr;         // Npad x Npad work / L (lower, row-major, ld = Npad)
-    double* Linv = nullptr;      // Npad x Npad lower, row-major
+    double* K = nullptr;         // Npad x Npad work / L (lower, row-major, leading dimension ld)
+    double* Linv = nullptr;      // Npad x Npad lower, row-major, leading dimension ld
     double* alpha = nullptr;     // Npad (padding = 0)
     double* zvec = nullptr;      // Npad: z = L^-1 y (padding = 0); mean(x*) = (L^-1 k).z, taken from the same accumulators as |L^-1 k|^2
     double2* Afrag = nullptr;    // L^-1 packed in DMMA A-fragment order (+4 blocks of slack for the prefetch)

@@ -32,7 +32,7 @@ struct ExpParams {
 
 // z_b = Ky^-1 k_cb = Linv^T (Linv k_cb), written in fragment order; one CTA per candidate.
 __global__ void __launch_bounds__(256) k_expander_prep(const double* __restrict__ Linv, const double* __restrict__ Xs,
-                                                       int N, int NB, int d, int kind, double variance, double noise_j,
+                                                       int N, int NB, int ld, int d, int kind, double variance, double noise_j,
                                                        const double* __restrict__ inv_ls_d, const double* __restrict__ xc,
                                                        const double* __restrict__ mean_c, const double* __restrict__ var_c,
                                                        const double* __restrict__ u_c, double* __restrict__ Zfrag,
@@ -59,14 +59,14 @@ __global__ void __launch_bounds__(256) k_expander_prep(const double* __restrict_
     __syncthreads();
     for (int n = threadIdx.x; n < N; n += blockDim.x) {
         double acc = 0.0;
-        const double* row = Linv + (size_t)n * Npad;
+        const double* row = Linv + (size_t)n * ld;
         for (int m = 0; m <= n; ++m) acc = fma(row[m], kc[m], acc);
         v[n] = acc;
     }
     __syncthreads();
     for (int c = threadIdx.x; c < N; c += blockDim.x) {
         double acc = 0.0;
-        for (int i = c; i < N; ++i) acc = fma(Linv[(size_t)i * Npad + c], v[i], acc);
+        for (int i = c; i < N; ++i) acc = fma(Linv[(size_t)i * ld + c], v[i], acc);
         const int kb = c >> 3, q = (c & 7) >> 1, half = c & 1;
         const int lane = (b & 7) * 4 + q, bb = b >> 3;
         Zfrag[(((size_t)bb * NB + kb) * 32 + lane) * 2 + half] = acc;
@@ -247,7 +247,7 @@ extern "C" int so_expander_check(so_handle* h, int gp, const double* Xstar_d, in
     double* inv_ls_d = xcs + (size_t)kMaxBatch * SO_MAX_DIM;
     SO_CUDA(h, cudaMemsetAsync(Zfrag, 0, sizeof(double) * z_doubles, stream));
     SO_CUDA(h, cudaMemcpyAsync(inv_ls_d, g.inv_ls, sizeof(double) * SO_MAX_DIM, cudaMemcpyHostToDevice, stream));
-    k_expander_prep<<<B, 256, sizeof(double) * 2 * Npad, stream>>>(g.Linv, g.Xs, g.N, NB, d, g.kind, g.variance,
+    k_expander_prep<<<B, 256, sizeof(double) * 2 * Npad, stream>>>(g.Linv, g.Xs, g.N, NB, g.ld, d, g.kind, g.variance,
                                                                    g.noise + SO_JITTER, inv_ls_d, xc_d, mean_c_d, var_c_d,
                                                                    u_c_d, Zfrag, cinfo, xcs);
     SO_CHECK_LAUNCH(h, "k_expander_prep");

@@ -27,7 +27,7 @@ __global__ void k_scale_x(const double* __restrict__ X, double* __restrict__ Xs,
 }
 
 // Ky (padded with an identity block so the factorisation of the padded matrix is trivial there).
-__global__ void k_build_ky(const double* __restrict__ Xs, double* __restrict__ K, int N, int Npad, int d,
+__global__ void k_build_ky(const double* __restrict__ Xs, double* __restrict__ K, int N, int Npad, int ld, int d,
                            int kind, double variance, double diag_add) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     int i = blockIdx.y * blockDim.y + threadIdx.y;
@@ -44,7 +44,7 @@ __global__ void k_build_ky(const double* __restrict__ Xs, double* __restrict__ K
     } else {
         v = (i == j) ? 1.0 : 0.0;
     }
-    K[(size_t)i * Npad + j] = v;
+    K[(size_t)i * ld + j] = v;
 }
 
 // ---------------------------------------------------------------- blocked Cholesky + triangular inverse
@@ -111,11 +111,10 @@ __device__ __forceinline__ void chol_diag_block(const double* __restrict__ K, do
         if (i < nb && lane < nb) W[(size_t)(p0 + i) * ld + p0 + lane] = x[i];
 }
 
-__global__ void __launch_bounds__(256) k_chol_panel(double* __restrict__ K, double* __restrict__ W, int Npad, int p0, int nb,
-                                                    int* status) {
+__global__ void __launch_bounds__(256) k_chol_panel(double* __restrict__ K, double* __restrict__ W, int Npad, int ld, int p0,
+                                                    int nb, int* status) {
     __shared__ double sL[kPB][kPB + 1];
     __shared__ double sRinv[kPB];
-    const int ld = Npad;
     if (threadIdx.x < 32) chol_diag_block(K, W, ld, p0, nb, sL, sRinv, blockIdx.x == 0, status);
     __syncthreads();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -164,13 +163,13 @@ __global__ void __launch_bounds__(256) k_chol_panel(double* __restrict__ K, doub
 }
 
 // One 32x32 output tile per CTA.  blockIdx.y = row block below the panel, blockIdx.x = column block (<= row block).
-__global__ void __launch_bounds__(256) k_chol_update(double* __restrict__ K, double* __restrict__ W, int Npad, int p0) {
+__global__ void __launch_bounds__(256) k_chol_update(double* __restrict__ K, double* __restrict__ W, int Npad, int ld, int p0) {
     const int pblk = p0 / kPB;
     const int rb = pblk + 1 + blockIdx.y, cb = blockIdx.x;
     if (cb > rb) return;
     __shared__ double sA[kPB][kPB + 1];     // L[rb rows, P]
     __shared__ double sB[kPB][kPB + 1];     // [k][j]: L[cb rows, P]^T (A tiles) or W[P, cb cols] (W tiles)
-    const int ld = Npad, tid = threadIdx.x;
+    const int tid = threadIdx.x;
     const bool a_tile = cb > pblk;
     for (int e = tid; e < kPB * kPB; e += 256) {
         const int i = e >> 5, k = e & 31;
@@ -206,11 +205,11 @@ __global__ void __launch_bounds__(256) k_chol_update(double* __restrict__ K, dou
 
 // alpha = Linv^T (Linv y), one CTA; padding entries are zero.
 __global__ void __launch_bounds__(1024) k_alpha(const double* __restrict__ Linv, const double* __restrict__ Y,
-                                                double* __restrict__ alpha, double* __restrict__ zvec, int N, int Npad) {
+                                                double* __restrict__ alpha, double* __restrict__ zvec, int N, int Npad, int ld) {
     extern __shared__ double w[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     for (int i = warp; i < N; i += nwarps) {
-        const double* row = Linv + (size_t)i * Npad;
+        const double* row = Linv + (size_t)i * ld;
         double part = 0.0;
         for (int k = lane; k <= i; k += 32) part = fma(row[k], Y[k], part);
 #pragma unroll
@@ -221,7 +220,7 @@ __global__ void __launch_bounds__(1024) k_alpha(const double* __restrict__ Linv,
     for (int c = tid; c < Npad; c += blockDim.x) {
         double s = 0.0;
         if (c < N)
-            for (int i = c; i < N; ++i) s = fma(Linv[(size_t)i * Npad + c], w[i], s);
+            for (int i = c; i < N; ++i) s = fma(Linv[(size_t)i * ld + c], w[i], s);
         alpha[c] = s;
         zvec[c] = c < N ? w[c] : 0.0;
     }
@@ -231,15 +230,15 @@ __global__ void __launch_bounds__(1024) k_alpha(const double* __restrict__ Linv,
 // holds 32 double2: lane l -> (Linv[8i + l/4][8kb + 2(l%4)], Linv[8i + l/4][8kb + 2(l%4) + 1]).
 // The k permutation inside an 8-block (even slots in MMA step 0, odd slots in step 1) is shared
 // with the B operand built by the posterior kernel, so a lane's two values are adjacent doubles.
-__global__ void k_pack_afrag(const double* __restrict__ Linv, double2* __restrict__ Afrag, int N, int Npad) {
-    const int i = blockIdx.y, kb = blockIdx.x;
+__global__ void k_pack_afrag(const double* __restrict__ Linv, double2* __restrict__ Afrag, int N, int ld, int i0) {
+    const int i = i0 + blockIdx.y, kb = blockIdx.x;
     if (kb > i) return;
     const int lane = threadIdx.x;
     const int r = 8 * i + (lane >> 2), c0 = 8 * kb + 2 * (lane & 3);
     double v0 = 0.0, v1 = 0.0;
     if (r < N) {
-        if (c0 < N && c0 <= r) v0 = Linv[(size_t)r * Npad + c0];
-        if (c0 + 1 < N && c0 + 1 <= r) v1 = Linv[(size_t)r * Npad + c0 + 1];
+        if (c0 < N && c0 <= r) v0 = Linv[(size_t)r * ld + c0];
+        if (c0 + 1 < N && c0 + 1 <= r) v1 = Linv[(size_t)r * ld + c0 + 1];
     }
     Afrag[((size_t)i * (i + 1) / 2 + kb) * 32 + lane] = make_double2(v0, v1);
 }
@@ -287,7 +286,9 @@ extern "C" int so_fit(so_handle* h, int gp, const double* X_h, const double* Y_h
         if ((rc = grow(h, g.zvec, (size_t)cap))) return rc;
         if ((rc = grow(h, g.Afrag, (tri_blocks(capNB) + 4) * 32))) return rc;
         g.capN = cap;
+        g.ld = cap;
     }
+    const int ld = g.ld;
     g.fitted = false;
     g.grid_ready = false;
     g.N = N; g.d = d; g.kind = kernel_kind; g.NB = NB;
@@ -299,23 +300,23 @@ extern "C" int so_fit(so_handle* h, int gp, const double* X_h, const double* Y_h
     SO_CUDA(h, cudaMemcpyAsync(g.Y, Y_h, sizeof(double) * N, cudaMemcpyHostToDevice, stream));
     k_scale_x<<<(Npad * d + 255) / 256, 256, 0, stream>>>(g.X, g.Xs, N, Npad, d, il);
     dim3 blk(16, 16), grd((Npad + 15) / 16, (Npad + 15) / 16);
-    k_build_ky<<<grd, blk, 0, stream>>>(g.Xs, g.K, N, Npad, d, kernel_kind, variance, noise_var + SO_JITTER);
+    k_build_ky<<<grd, blk, 0, stream>>>(g.Xs, g.K, N, Npad, ld, d, kernel_kind, variance, noise_var + SO_JITTER);
     SO_CUDA(h, cudaMemsetAsync(h->d_status, 0, sizeof(int), stream));
     static_assert(SO_OK == 0, "status word is cleared with memset");
-    SO_CUDA(h, cudaMemsetAsync(g.Linv, 0, sizeof(double) * (size_t)Npad * Npad, stream));
+    SO_CUDA(h, cudaMemsetAsync(g.Linv, 0, sizeof(double) * (size_t)Npad * ld, stream));
     for (int p0 = 0; p0 < Npad; p0 += kPB) {
         const int nb = Npad - p0 < kPB ? Npad - p0 : kPB;
         const int below = Npad - p0 - nb;
         const int work = below > p0 ? below : p0;
-        k_chol_panel<<<work > 0 ? (work + 255) / 256 : 1, 256, 0, stream>>>(g.K, g.Linv, Npad, p0, nb, h->d_status);
+        k_chol_panel<<<work > 0 ? (work + 255) / 256 : 1, 256, 0, stream>>>(g.K, g.Linv, Npad, ld, p0, nb, h->d_status);
         if (below > 0) {
             const int nrb = (below + kPB - 1) / kPB, ncb = (Npad + kPB - 1) / kPB;
-            k_chol_update<<<dim3(ncb, nrb), 256, 0, stream>>>(g.K, g.Linv, Npad, p0);
+            k_chol_update<<<dim3(ncb, nrb), 256, 0, stream>>>(g.K, g.Linv, Npad, ld, p0);
         }
     }
-    k_alpha<<<1, 1024, sizeof(double) * Npad, stream>>>(g.Linv, g.Y, g.alpha, g.zvec, N, Npad);
+    k_alpha<<<1, 1024, sizeof(double) * Npad, stream>>>(g.Linv, g.Y, g.alpha, g.zvec, N, Npad, ld);
     SO_CUDA(h, cudaMemsetAsync(g.Afrag, 0, sizeof(double2) * (tri_blocks(NB) + 4) * 32, stream));
-    k_pack_afrag<<<dim3(NB, NB), 32, 0, stream>>>(g.Linv, g.Afrag, N, Npad);
+    k_pack_afrag<<<dim3(NB, NB), 32, 0, stream>>>(g.Linv, g.Afrag, N, ld, 0);
     SO_CHECK_LAUNCH(h, "so_fit kernels");
     SO_CUDA(h, cudaMemcpyAsync(h->h_status, h->d_status, sizeof(int), cudaMemcpyDeviceToHost, stream));
     SO_CUDA(h, cudaStreamSynchronize(stream));
@@ -331,14 +332,185 @@ extern "C" int so_fit_export(so_handle* h, int gp, double* L_h, double* Linv_h, 
     if (!g.fitted) return so_fail(h, SO_ERR_NOT_FITTED, "so_fit_export: GP not fitted");
     DeviceGuard guard(h->device);
     SO_CUDA(h, cudaDeviceSynchronize());
-    const int N = g.N, Npad = 8 * g.NB;
+    const int N = g.N, ld = g.ld;
     if (L_h) {
-        SO_CUDA(h, cudaMemcpy2D(L_h, sizeof(double) * N, g.K, sizeof(double) * Npad, sizeof(double) * N, N, cudaMemcpyDeviceToHost));
+        SO_CUDA(h, cudaMemcpy2D(L_h, sizeof(double) * N, g.K, sizeof(double) * ld, sizeof(double) * N, N, cudaMemcpyDeviceToHost));
         for (int i = 0; i < N; ++i)
             for (int j = i + 1; j < N; ++j) L_h[(size_t)i * N + j] = 0.0;
     }
     if (Linv_h)
-        SO_CUDA(h, cudaMemcpy2D(Linv_h, sizeof(double) * N, g.Linv, sizeof(double) * Npad, sizeof(double) * N, N, cudaMemcpyDeviceToHost));
+        SO_CUDA(h, cudaMemcpy2D(Linv_h, sizeof(double) * N, g.Linv, sizeof(double) * ld, sizeof(double) * N, N, cudaMemcpyDeviceToHost));
     if (alpha_h) SO_CUDA(h, cudaMemcpy(alpha_h, g.alpha, sizeof(double) * N, cudaMemcpyDeviceToHost));
+    return SO_OK;
+}
+
+// ---------------------------------------------------------------- f4: one-point append / removal
+// `add_new_data_point` (safeopt/gp_opt.py:230-255) grows the data by one row per iteration; GPy refits from
+// scratch (O(N^3)).  With L and W = L^-1 resident, the bordered factorisation is O(N^2):
+//   l   = W k_new                     (new row of L)          k_append_row    one warp per entry
+//   lnn = sqrt(k(x,x) + noise + 1e-8 - |l|^2)
+//   W[N, c] = -(sum_{i>=c} l_i W[i, c]) / lnn , W[N,N] = 1/lnn   k_append_finish one thread per column
+//   z_N = W[N, :] y ;  alpha += W[N, :]^T z_N                  k_append_alpha
+// followed by re-packing the one fragment block row that changed.  Removing the last point keeps the
+// leading blocks of L and W as they are (they do not depend on later rows).
+namespace {
+
+__global__ void __launch_bounds__(256) k_append_row(const double* __restrict__ W, const double* __restrict__ Xs,
+                                                    double* __restrict__ Lrow, int N, int ld, int d, int kind, double variance) {
+    extern __shared__ double kv[];                      // k(x_new, X_i), i < N (every CTA builds its own copy)
+    const double* xn = Xs + (size_t)N * d;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        double r2 = 0.0;
+        for (int c = 0; c < d; ++c) {
+            const double t = xn[c] - Xs[(size_t)i * d + c];
+            r2 = fma(t, t, r2);
+        }
+        kv[i] = kernel_switch(kind, r2, variance);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= N) return;
+    const double* row = W + (size_t)i * ld;
+    double part = 0.0;
+    for (int k = lane; k <= i; k += 32) part = fma(row[k], kv[k], part);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == 0) Lrow[i] = part;
+}
+
+// Deterministic block-wide sum (same tree in every CTA, so every CTA derives the same lnn).
+__device__ __forceinline__ double block_sum_256(double v, double* red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += red[w];
+    __syncthreads();
+    return s;
+}
+
+__global__ void __launch_bounds__(256) k_append_finish(double* __restrict__ K, double* __restrict__ W, int N, int ld, double kss,
+                                                       int* status) {
+    __shared__ double red[8];
+    const double* l = K + (size_t)N * ld;               // new row of L, entries 0..N-1
+    double part = 0.0;
+    for (int i = threadIdx.x; i < N; i += 256) part = fma(l[i], l[i], part);
+    const double s = block_sum_256(part, red);
+    double dnn = kss - s;
+    if (!(dnn > 0.0) || isinf(dnn)) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) *status = SO_ERR_NOT_PD;
+        dnn = 1.0;
+    }
+    const double lnn = sqrt(dnn);
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c < N) {
+        double acc0 = 0.0, acc1 = 0.0;
+        int i = c;
+        for (; i + 1 < N; i += 2) {
+            acc0 = fma(l[i], W[(size_t)i * ld + c], acc0);
+            acc1 = fma(l[i + 1], W[(size_t)(i + 1) * ld + c], acc1);
+        }
+        if (i < N) acc0 = fma(l[i], W[(size_t)i * ld + c], acc0);
+        W[(size_t)N * ld + c] = -(acc0 + acc1) / lnn;
+    } else if (c == N) {
+        W[(size_t)N * ld + N] = 1.0 / lnn;
+        K[(size_t)N * ld + N] = lnn;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_append_alpha(const double* __restrict__ W, const double* __restrict__ Y,
+                                                      double* __restrict__ alpha, double* __restrict__ zvec, int N, int ld) {
+    __shared__ double red[8];
+    const double* w = W + (size_t)N * ld;
+    double part = 0.0;
+    for (int c = threadIdx.x; c <= N; c += 256) part = fma(w[c], Y[c], part);
+    const double zn = block_sum_256(part, red);
+    for (int c = threadIdx.x; c <= N; c += 256) alpha[c] = c < N ? fma(w[c], zn, alpha[c]) : w[c] * zn;
+    if (threadIdx.x == 0) zvec[N] = zn;
+}
+
+// Rows [r0, r1) of the per-point arrays become padding: zero coordinates / targets / alpha / z.
+__global__ void k_clear_rows(double* __restrict__ Xs, double* __restrict__ Y, double* __restrict__ alpha,
+                             double* __restrict__ zvec, int r0, int r1, int d) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = r0 + idx / (d + 3), j = idx % (d + 3);
+    if (n >= r1) return;
+    if (j < d) Xs[(size_t)n * d + j] = 0.0;
+    else if (j == d) Y[n] = 0.0;
+    else if (j == d + 1) alpha[n] = 0.0;
+    else zvec[n] = 0.0;
+}
+
+}  // namespace
+
+extern "C" int so_fit_append(so_handle* h, int gp, const double* x_new_h, double y_new, void* stream_) {
+    if (!h || !x_new_h) return SO_ERR_BAD_ARG;
+    if (gp < 0 || gp >= h->max_gps) return so_fail(h, SO_ERR_BAD_ARG, "so_fit_append: gp index out of range");
+    GPState& g = h->gps[gp];
+    if (!g.fitted) return so_fail(h, SO_ERR_NOT_FITTED, "so_fit_append: GP not fitted");
+    const int N = g.N, d = g.d;
+    const int NB1 = (N + 8) / 8, Npad1 = 8 * NB1;
+    if (Npad1 > g.capN || N + 1 > 2048) return so_fail(h, SO_ERR_CAPACITY, "so_fit_append: capacity exhausted, refit with so_fit");
+    DeviceGuard guard(h->device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int ld = g.ld;
+    g.fitted = false;
+    g.grid_ready = false;
+    g.tma_ready = false;
+    if (NB1 != g.NB) {
+        // a new block of 8 rows starts: its 7 other rows are padding (finite zeros), its fragment blocks start empty
+        const int cells = 8 * (d + 3);
+        k_clear_rows<<<(cells + 127) / 128, 128, 0, stream>>>(g.Xs, g.Y, g.alpha, g.zvec, N, Npad1, d);
+        SO_CUDA(h, cudaMemsetAsync(g.Afrag + tri_blocks(g.NB) * 32, 0, sizeof(double2) * ((size_t)NB1 + 4) * 32, stream));
+    }
+    double xs[SO_MAX_DIM + 1];
+    for (int j = 0; j < d; ++j) xs[j] = x_new_h[j] * g.inv_ls[j];
+    xs[d] = y_new;
+    // small synchronous-safe staging: cudaMemcpyAsync from pageable memory copies before returning
+    SO_CUDA(h, cudaMemcpyAsync(g.X + (size_t)N * d, x_new_h, sizeof(double) * d, cudaMemcpyHostToDevice, stream));
+    SO_CUDA(h, cudaMemcpyAsync(g.Xs + (size_t)N * d, xs, sizeof(double) * d, cudaMemcpyHostToDevice, stream));
+    SO_CUDA(h, cudaMemcpyAsync(g.Y + N, xs + d, sizeof(double), cudaMemcpyHostToDevice, stream));
+    SO_CUDA(h, cudaMemsetAsync(h->d_status, 0, sizeof(int), stream));
+    SO_CUDA(h, cudaMemsetAsync(g.K + (size_t)N * ld, 0, sizeof(double) * Npad1, stream));
+    SO_CUDA(h, cudaMemsetAsync(g.Linv + (size_t)N * ld, 0, sizeof(double) * Npad1, stream));
+    k_append_row<<<(N + 7) / 8, 256, sizeof(double) * N, stream>>>(g.Linv, g.Xs, g.K + (size_t)N * ld, N, ld, d, g.kind, g.variance);
+    const double kss = g.variance + g.noise + SO_JITTER;      // Kdiag = variance for every stationary family
+    k_append_finish<<<(N + 1 + 255) / 256, 256, 0, stream>>>(g.K, g.Linv, N, ld, kss, h->d_status);
+    k_append_alpha<<<1, 256, 0, stream>>>(g.Linv, g.Y, g.alpha, g.zvec, N, ld);
+    k_pack_afrag<<<dim3(NB1, 1), 32, 0, stream>>>(g.Linv, g.Afrag, N + 1, ld, NB1 - 1);
+    SO_CHECK_LAUNCH(h, "so_fit_append kernels");
+    SO_CUDA(h, cudaMemcpyAsync(h->h_status, h->d_status, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    SO_CUDA(h, cudaStreamSynchronize(stream));
+    if (*h->h_status != SO_OK)
+        return so_fail(h, SO_ERR_NOT_PD, "so_fit_append: bordered matrix is not positive definite; refit with so_fit");
+    g.N = N + 1;
+    g.NB = NB1;
+    g.fitted = true;
+    return SO_OK;
+}
+
+extern "C" int so_fit_remove_last(so_handle* h, int gp, void* stream_) {
+    if (!h) return SO_ERR_BAD_ARG;
+    if (gp < 0 || gp >= h->max_gps) return so_fail(h, SO_ERR_BAD_ARG, "so_fit_remove_last: gp index out of range");
+    GPState& g = h->gps[gp];
+    if (!g.fitted) return so_fail(h, SO_ERR_NOT_FITTED, "so_fit_remove_last: GP not fitted");
+    if (g.N < 2) return so_fail(h, SO_ERR_BAD_ARG, "so_fit_remove_last: at least one point must remain");
+    DeviceGuard guard(h->device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int N1 = g.N - 1, d = g.d, ld = g.ld;
+    const int NB1 = (N1 + 7) / 8, Npad1 = 8 * NB1;
+    g.grid_ready = false;
+    g.tma_ready = false;
+    // row N1 becomes padding; alpha / z are rebuilt from the leading block of L^-1 (exactly what a refit would use)
+    k_clear_rows<<<(d + 3 + 127) / 128, 128, 0, stream>>>(g.Xs, g.Y, g.alpha, g.zvec, N1, N1 + 1, d);
+    k_alpha<<<1, 1024, sizeof(double) * Npad1, stream>>>(g.Linv, g.Y, g.alpha, g.zvec, N1, Npad1, ld);
+    k_pack_afrag<<<dim3(NB1, 1), 32, 0, stream>>>(g.Linv, g.Afrag, N1, ld, NB1 - 1);
+    if (NB1 != g.NB)        // the dropped block row: the posterior kernels prefetch a few blocks past the end, keep them finite
+        SO_CUDA(h, cudaMemsetAsync(g.Afrag + tri_blocks(NB1) * 32, 0, sizeof(double2) * ((size_t)g.NB + 4) * 32, stream));
+    SO_CHECK_LAUNCH(h, "so_fit_remove_last kernels");
+    g.N = N1;
+    g.NB = NB1;
     return SO_OK;
 }

@@ -118,6 +118,21 @@ class DeviceEngine:
         panels = (8 * ((N + 7) // 8) + 31) // 32           # fit.cu: k_chol_panel per panel, k_chol_update between panels
         self.launches += 4 + 2 * panels - 1
 
+    def fit_append(self, gp: int, x_new, y_new: float) -> bool:
+        """One-point update of an existing fit (f4).  Returns False when the device asks for a full refit
+        (buffers full, or the bordered matrix lost positive definiteness)."""
+        x = _np_f64(x_new).reshape(-1)
+        rc = self.lib.so_fit_append(self.handle, gp, _hptr(x), float(y_new), self._stream())
+        if rc in (_lib.SO_ERR_CAPACITY, _lib.SO_ERR_NOT_PD):
+            return False
+        self._check(rc, "so_fit_append")
+        self.launches += 4
+        return True
+
+    def fit_remove_last(self, gp: int):
+        self._check(self.lib.so_fit_remove_last(self.handle, gp, self._stream()), "so_fit_remove_last")
+        self.launches += 3
+
     def fit_export(self, gp: int, N: int):
         L = np.empty((N, N))
         Linv = np.empty((N, N))

@@ -149,30 +149,60 @@ class GaussianProcessOptimization(object):
 
 
 class _DeviceFits:
-    """Keeps the device-side fit of each GP in step with the user's model objects."""
+    """Keeps the device-side fit of each GP in step with the user's model objects.
+
+    The user's objects stay the source of truth (``set_XY`` is still called on them); before
+    every device pass their data and hyper-parameters are fingerprinted.  A change that is exactly "one row
+    appended" or "last row removed" under unchanged hyper-parameters -- what ``add_new_data_point`` /
+    ``remove_last_data_point`` do (gp_opt.py:230-278) -- is applied to the resident factorisation in O(N^2)
+    (``so_fit_append`` / ``so_fit_remove_last``); anything else refits from scratch (``so_fit``).
+    ``SAFEOPT_B200_INCREMENTAL_FIT=0`` disables the incremental path."""
 
     def __init__(self, engine: DeviceEngine, gps):
         self.engine = engine
         self.gps = gps
         self._fp = [None] * len(gps)
+        self._data = [None] * len(gps)        # (X, Y, hyper key) the device fit was built from
         self.hypers = [None] * len(gps)
         self.refits = 0
+        self.appends = 0
+        self.removals = 0
+        self.incremental = os.environ.get("SAFEOPT_B200_INCREMENTAL_FIT", "1") != "0"
 
     def refresh(self, after_fit=None):
         for i, gp in enumerate(self.gps):
             hyper = extract_hyper(gp)
             fp = fingerprint(gp, hyper)
-            if fp != self._fp[i]:
-                Y = np.asarray(gp.Y, dtype=float)
-                self.engine.fit(i, gp.X, Y[:, 0], hyper.kind, hyper.lengthscale, hyper.variance, hyper.noise_var)
-                self._fp[i] = fp
-                self.hypers[i] = hyper
+            if fp == self._fp[i]:
+                continue
+            X = np.ascontiguousarray(np.asarray(gp.X, dtype=float))
+            Y = np.ascontiguousarray(np.asarray(gp.Y, dtype=float)[:, 0])
+            key = (hyper.kind, hyper.lengthscale.tobytes(), hyper.variance, hyper.noise_var)
+            done = False
+            prev = self._data[i]
+            if self.incremental and prev is not None and prev[2] == key and prev[0].shape[1] == X.shape[1]:
+                Xp, Yp = prev[0], prev[1]
+                if X.shape[0] == Xp.shape[0] + 1 and np.array_equal(X[:-1], Xp) and np.array_equal(Y[:-1], Yp):
+                    done = self.engine.fit_append(i, X[-1], Y[-1])
+                    self.appends += int(done)
+                elif X.shape[0] == Xp.shape[0] - 1 and X.shape[0] >= 1 and np.array_equal(X, Xp[:-1]) \
+                        and np.array_equal(Y, Yp[:-1]):
+                    self.engine.fit_remove_last(i)
+                    self.removals += 1
+                    done = True
+            if not done:
+                self.engine.fit(i, X, Y, hyper.kind, hyper.lengthscale, hyper.variance, hyper.noise_var)
                 self.refits += 1
-                if after_fit is not None:
-                    after_fit(i, hyper)
+            self._fp[i] = fp
+            self._data[i] = (X.copy(), Y.copy(), key)
+            self.hypers[i] = hyper
+            if after_fit is not None:
+                after_fit(i, hyper)
 
     def invalidate(self):
+        """Forget the resident fits: the next refresh refits every GP from scratch."""
         self._fp = [None] * len(self.gps)
+        self._data = [None] * len(self.gps)
 
 
 class SafeOpt(GaussianProcessOptimization):

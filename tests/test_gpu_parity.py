@@ -45,6 +45,75 @@ def test_fit_matches_lapack(N, d, kind):
     eng.close()
 
 
+@pytest.mark.parametrize("N0,steps,d,kind", [(1, 20, 1, 0), (5, 30, 2, 0), (60, 12, 3, 1), (255, 4, 4, 0), (500, 3, 6, 2)])
+def test_fit_append_and_remove_match_refit(N0, steps, d, kind):
+    """f4: one-point appends (bordered Cholesky, gp_opt.py:227) and removals (:267, :275) reproduce the
+    from-scratch factorisation of the same data; buffers are grown by a refit when the capacity is hit."""
+    import scipy.linalg as sla
+    X, Y, ls, _ = _problem(N0 + steps, d, seed=7 + N0)
+    var, noise = 2.0, 0.05 ** 2
+    eng = DeviceEngine(max_gps=1)
+    eng.fit(0, X[:N0], Y[:N0], kind, ls, var, noise)
+    kern = oracle_kernel(kind, d, var, ls)
+    Xq = np.random.RandomState(1).uniform(-2, 2, size=(300, d))
+    n = N0
+    appended = 0
+    for _ in range(steps):
+        if eng.fit_append(0, X[n], Y[n]):
+            appended += 1
+        else:                                   # capacity: the host's fallback
+            eng.fit(0, X[:n + 1], Y[:n + 1], kind, ls, var, noise)
+        n += 1
+        if n in (N0 + 1, N0 + steps) or n % 8 in (0, 1):
+            L, Linv, alpha = eng.fit_export(0, n)
+            Ky = kern.K(X[:n]) + (noise + 1e-8) * np.eye(n)
+            Lr = np.linalg.cholesky(Ky)
+            assert np.abs(L - Lr).max() < 1e-11 * np.abs(Lr).max()
+            Lir = sla.solve_triangular(Lr, np.eye(n), lower=True)
+            assert np.abs(Linv - Lir).max() < 1e-9 * np.abs(Lir).max()
+            assert np.abs(alpha - sla.cho_solve((Lr, True), Y[:n])).max() < 1e-8 * max(1.0, np.abs(alpha).max())
+            go = gpy_lite.GPRegression(X[:n], Y[:n, None], kernel=kern, noise_var=noise)
+            mo, vo = go.predict_noiseless(Xq)
+            mean, varr = eng.empty((300,)), eng.empty((300,))
+            eng.posterior_rows(0, eng.to_device(Xq), 2.0, -np.inf, mean=mean, var=varr)
+            assert np.abs(mean.cpu().numpy() - mo[:, 0]).max() < 1e-9 * max(1.0, np.abs(Y).max())
+            assert np.abs(varr.cpu().numpy() - vo[:, 0]).max() < 1e-9 * var
+    assert appended >= steps - 2
+    for _ in range(min(steps, 10)):
+        eng.fit_remove_last(0)
+        n -= 1
+    go = gpy_lite.GPRegression(X[:n], Y[:n, None], kernel=kern, noise_var=noise)
+    mo, vo = go.predict_noiseless(Xq)
+    mean, varr = eng.empty((300,)), eng.empty((300,))
+    eng.posterior_rows(0, eng.to_device(Xq), 2.0, -np.inf, mean=mean, var=varr)
+    assert np.abs(mean.cpu().numpy() - mo[:, 0]).max() < 1e-9 * max(1.0, np.abs(Y).max())
+    assert np.abs(varr.cpu().numpy() - vo[:, 0]).max() < 1e-9 * var
+    _, _, alpha = eng.fit_export(0, n)
+    assert np.abs(alpha - go.woodbury_vector[:, 0]).max() < 1e-8 * max(1.0, np.abs(alpha).max())
+    eng.close()
+
+
+def test_device_fits_use_incremental_updates():
+    """add_new_data_point / remove_last_data_point reach the device as append / removal, anything else refits."""
+    g = load_golden("expander_g1")
+    gps, grid, fmin = golden_problem(g, "gpu")
+    opt = sb.SafeOpt(gps, grid, fmin, beta=float(g["beta"]), threshold=float(g["threshold"]))
+    x = opt.optimize()
+    assert (opt._fits.refits, opt._fits.appends) == (1, 0)
+    opt.add_new_data_point(x, np.array([[1.0]]))
+    x2 = opt.optimize()
+    assert (opt._fits.refits, opt._fits.appends) == (1, 1)
+    Q_inc = opt.Q.copy()
+    opt._fits.invalidate()
+    opt.optimize()
+    assert opt._fits.refits == 2 and np.abs(opt.Q - Q_inc).max() < 1e-10
+    opt.remove_last_data_point()
+    assert np.array_equal(opt.optimize(), x) and opt._fits.removals == 1
+    opt.gps[0].kern.variance = 2.5                   # hyper-parameter change: full refit
+    opt.optimize()
+    assert opt._fits.refits == 3
+
+
 def test_fit_reports_not_positive_definite():
     eng = DeviceEngine(max_gps=1)
     X = np.zeros((3, 1))            # three identical points, zero noise -> singular even with the 1e-8 jitter in fp64? no: jitter keeps it PD
@@ -231,7 +300,8 @@ def test_bo_loop_matches_golden():
         assert opt.last_query_row == int(row_ref), "trajectory diverged at iteration %d" % it
         assert int(opt.G.sum()) == int(g["n_expanders"][it])
         opt.add_new_data_point(x, np.array([[g["ys"][it]]]))
-    assert opt.t == 6 + len(g["rows"]) and opt._fits.refits == len(g["rows"])
+    # one from-scratch fit, then one-point appends (f4) -- the trajectory above is the parity check of both
+    assert opt.t == 6 + len(g["rows"]) and opt._fits.refits + opt._fits.appends == len(g["rows"]) and opt._fits.appends >= 15
 
 
 def test_no_safe_points_raises_like_reference():
