@@ -8,8 +8,11 @@ A *step* is one ``SafeOpt.optimize()`` over the whole candidate grid: GP posteri
 (kernel rows, L^-1 contraction, mean/var), confidence bounds, safe set, maximisers, expander
 candidates / search and the query-point argmax.  Workload = BASELINE config 4 (the configuration
 the metric is quoted on): d=4, 50^4 = 6.25e6 rows, N_train=256, 1 GP (objective = constraint),
-fp64, synthetic RBF problem of SURVEY.md section 8d.  With N ranks the fixed grid is split into N
-contiguous row blocks ("strong" scaling, as the config says "sharded 8xB200").
+fp64, synthetic RBF problem of SURVEY.md section 8d.  With N ranks the candidate rows are split into
+N contiguous row blocks.  ``--scaling weak`` (default): every rank keeps a full config-4 block, i.e.
+the grid becomes 50 x (50 N) x 50 x 50 (axis 1 is the slowest axis of the reference's row order, so
+rank r owns axis-1 indices [50 r, 50 (r+1))) -- at N=1 this IS config 4.  ``--scaling strong``: the
+fixed 50^4 grid is split N ways (the config's "sharded 8xB200" reading).
 
 Reported: ``value`` (device-resident throughput, fit cached), ``e2e`` (through the public API
 with host inputs: refit from host X/Y every step + optimize + result read-back), ``roofline`` of
@@ -47,6 +50,8 @@ def parse_args():
     ap.add_argument("--cpu-sample-rows", type=int, default=400_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--explicit-rows", action="store_true", help="force the explicit-rows kernel path (no grid tables)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: per-GPU rows fixed (grid axis 1 grows with N); strong: the 50^4 grid is split N ways")
     return ap.parse_args()
 
 
@@ -117,19 +122,21 @@ class ClockSampler:
 def cpu_port_run(w, sample_rows, steps=1, warmup=0):
     """Time the oracle port (NumPy/SciPy restatement of the reference path) on a bounded row sample."""
     from oracle import gpy_lite, safeopt_port as port
-    grid = port.linearly_spaced_combinations(w.bounds, w.num_samples)
-    M = grid.shape[0]
+    M = w.n_rows
     take = min(sample_rows, M)
     # contiguous block around the training data (the block contains safe, unsafe and boundary rows)
     start = max(0, M // 2 - take // 2)
-    sub = np.ascontiguousarray(grid[start:start + take])
+    sub = port.grid_rows(w.bounds, w.num_samples, np.arange(start, start + take))
     gps = [gpy_lite.GPRegression(w.X, w.Y[:, [i]], kernel=gpy_lite.RBF(w.d, variance=w.variance, lengthscale=w.lengthscale, ARD=True),
                                  noise_var=w.noise_var) for i in range(w.n_gps)]
     prob = port.GridProblem.create(gps, sub, w.fmin, beta=w.beta, threshold=w.threshold)
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
-        prob.optimize(chunk=100_000)
+        try:
+            prob.optimize(chunk=100_000)
+        except port.NoSafePoints:       # a small sample block may hold no safe row; the posterior + set passes ran
+            pass
         times.append(time.perf_counter() - t0)
     times = times[warmup:]
     return take, times
@@ -145,7 +152,7 @@ def run_reference(args, w, rank, world):
     value = take * len(times) / total
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "strong",
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(w, args, grid_path=None),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
@@ -158,9 +165,10 @@ def run_reference(args, w, rank, world):
 
 
 def workload_config(w, args, grid_path):
-    return {"workload": "%s: %dD RBF-ARD, %d constraint GP(s), %d^%d=%d grid rows, N_train=%d, %s, beta=%g, fmin=0, threshold=%g" % (
-        w.name, w.d, w.n_gps, w.num_samples, w.d, w.n_rows, w.n_train, w.dtype, w.beta, w.threshold),
-        "rows": w.n_rows, "n_train": w.n_train, "d": w.d, "n_gps": w.n_gps, "parallelism": "rows sharded x%d" % args.gpus,
+    return {"workload": "%s: %dD RBF-ARD, %d constraint GP(s), %s=%d grid rows, N_train=%d, %s, beta=%g, fmin=0, threshold=%g" % (
+        w.name, w.d, w.n_gps, "x".join(str(n) for n in w.samples_per_axis), w.n_rows, w.n_train, w.dtype, w.beta, w.threshold),
+        "rows": w.n_rows, "rows_per_gpu": -(-w.n_rows // args.gpus), "n_train": w.n_train, "d": w.d, "n_gps": w.n_gps,
+        "parallelism": "rows sharded x%d (%s scaling)" % (args.gpus, args.scaling),
         "candidate_path": None if grid_path is None else ("grid rows generated on device" if grid_path else "explicit rows in HBM"),
         "l2": "each step streams 33 B/row of outputs (206 MB at C4, > 126 MB L2) and re-derives everything else; "
               "operands (L^-1, tables, 0.8 MB) are meant to stay cache-resident"}
@@ -302,7 +310,7 @@ def run_b200(args, w, rank, world, local_rank):
                          "oracle/gpy_lite.py, NumPy/OpenBLAS default threads, 100k-row chunks), %.1f s" % (take, rows, times[0])}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": workload_config(w, args, grid_path),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e_ms / args.steps,
@@ -342,6 +350,12 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     from safeopt_b200 import workloads
     w = workloads.config(args.config, num_samples=args.num_samples)
+    if args.scaling == "weak" and args.gpus > 1 and w.d >= 2:
+        # per-GPU work fixed: axis 1 (slowest in the reference row order) gets N times the points
+        per_axis = w.samples_per_axis
+        per_axis[1] *= args.gpus
+        w.num_samples = per_axis
+        w.name = "%s x%d (weak)" % (w.name, args.gpus)
     if args.impl == "reference":
         run_reference(args, w, rank, world)
         return

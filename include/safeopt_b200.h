@@ -121,6 +121,9 @@ int so_fit_export(so_handle* h, int gp, double* L_h, double* Linv_h, double* alp
  * (it rebuilds the per-axis kernel factor tables); synchronous on `stream` order. */
 int so_grid_define(so_handle* h, int d, const int32_t* n_h, const double* axis_values_h, void* stream);
 int so_grid_prepare(so_handle* h, int gp, void* stream);
+/* Same, building the large per-slow-index operand table only for grid rows [row0, row0+M) -- the
+ * row block a rank evaluates with so_posterior_grid (contiguous row blocks). */
+int so_grid_prepare_rows(so_handle* h, int gp, int64_t row0, int64_t M, void* stream);
 
 /* ------------------------------------------------------------------ K2: posterior + bounds + safe bit
  * Stands in for `gp.predict_noiseless(self.inputs)` (safeopt/gp_opt.py:469) fused with

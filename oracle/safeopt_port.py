@@ -42,6 +42,24 @@ def linearly_spaced_combinations(bounds, num_samples):
 
 
 # --------------------------------------------------------------------------- CI + S (a4, a7)
+def grid_rows(bounds, num_samples, rows):
+    """Rows ``rows`` of ``linearly_spaced_combinations(bounds, num_samples)`` without building the whole grid
+    (bit-identical: meshgrid only replicates the linspace values; row order of utilities.py:50-54:
+    variable 1 slowest, then variable 0, then variables 2..d-1)."""
+    d = len(bounds)
+    if not isinstance(num_samples, Sequence):
+        num_samples = [num_samples] * d
+    axes = [np.linspace(b[0], b[1], int(n)) for b, n in zip(bounds, num_samples)]
+    rows = np.asarray(rows, dtype=np.int64)
+    order = [0] if d == 1 else [1, 0] + list(range(2, d))       # slowest ... fastest
+    out = np.empty((rows.size, d))
+    stride = 1
+    for j in reversed(order):
+        out[:, j] = axes[j][(rows // stride) % len(axes[j])]
+        stride *= len(axes[j])
+    return out
+
+
 def confidence_intervals(gps, inputs, beta, chunk: Optional[int] = None):
     """Q[:, 2i] = mean_i - beta*std_i, Q[:, 2i+1] = mean_i + beta*std_i  (gp_opt.py:453-476)."""
     M = inputs.shape[0]

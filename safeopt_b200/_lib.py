@@ -72,6 +72,7 @@ SIGNATURES = {
     "so_fit_export": (_i, [_P, _i, _P, _P, _P]),
     "so_grid_define": (_i, [_P, _i, _P, _P, _P]),
     "so_grid_prepare": (_i, [_P, _i, _P]),
+    "so_grid_prepare_rows": (_i, [_P, _i, _i64, _i64, _P]),
     "so_posterior_rows": (_i, [_P, _i, _P, _i64, _dbl, _dbl, _P, _P, _P, _i, _i, _P, _i, _P]),
     "so_posterior_grid": (_i, [_P, _i, _i64, _i64, _dbl, _dbl, _P, _P, _P, _i, _i, _P, _i, _P]),
     "so_posterior_rows_simple": (_i, [_P, _i, _P, _i64, _P, _P, _P]),

@@ -275,7 +275,9 @@ int run_posterior(so_handle* h, int gp, const double* Xstar_d, bool grid, int64_
     if (tma) {
         p.RG = g.tma_RG; p.CG = g.tma_CG; p.T = g.tma_T; p.TB = g.tma_BT * g.tma_CG;
         p.npass = (g.NB + 4 * p.RG - 1) / (4 * p.RG);
-        tp.PfFrag = g.PfFrag; tp.Aprime = g.Aprime; tp.a_stride = g.a_stride;
+        tp.PfFrag = g.PfFrag; tp.Aprime = g.Aprime; tp.a_stride = g.a_stride; tp.s0 = g.ap_s0;
+        if (row0 / h->grid.fast_rows < g.ap_s0 || (row0 + M - 1) / h->grid.fast_rows >= g.ap_s1)
+            return so_fail(h, SO_ERR_NOT_FITTED, "posterior_grid: rows outside the range given to so_grid_prepare_rows");
         tp.fast_rows = h->grid.fast_rows; tp.tpb = g.tma_tpb; tp.kb_pad = g.tma_kb_pad;
         // tiles are aligned to the slow blocks of the product grid: global tile = (row / F) * tpb + (row % F) / T
         const int64_t F = h->grid.fast_rows, last_row = row0 + M - 1;
@@ -396,10 +398,16 @@ extern "C" int so_grid_define(so_handle* h, int d, const int32_t* n_h, const dou
 }
 
 extern "C" int so_grid_prepare(so_handle* h, int gp, void* stream_) {
+    if (!h) return SO_ERR_BAD_ARG;
+    return so_grid_prepare_rows(h, gp, 0, h->grid.defined ? h->grid.rows : 0, stream_);
+}
+
+extern "C" int so_grid_prepare_rows(so_handle* h, int gp, int64_t row0, int64_t M, void* stream_) {
     if (!h || gp < 0 || gp >= h->max_gps) return SO_ERR_BAD_ARG;
     GPState& g = h->gps[gp];
     GridSpec& gs = h->grid;
     if (!gs.defined) return so_fail(h, SO_ERR_BAD_ARG, "so_grid_prepare: no grid defined");
+    if (row0 < 0 || M < 0 || row0 + M > gs.rows) return so_fail(h, SO_ERR_BAD_ARG, "so_grid_prepare_rows: rows outside the grid");
     if (!g.fitted) return so_fail(h, SO_ERR_NOT_FITTED, "so_grid_prepare: GP not fitted");
     if (g.kind != SO_KERNEL_RBF) return so_fail(h, SO_ERR_UNSUPPORTED, "so_grid_prepare: separable tables need an RBF kernel");
     if (g.d != gs.d) return so_fail(h, SO_ERR_BAD_ARG, "so_grid_prepare: grid dimension differs from the GP input dimension");
@@ -427,8 +435,12 @@ extern "C" int so_grid_prepare(so_handle* h, int gp, void* stream_) {
     TmaPlan pl;
     const int64_t trows = gs.fast_rows + gs.slow_rows;
     const size_t a_stride = (tri_blocks(g.NB) + 1) * 32;
-    const size_t ap_elems = (size_t)gs.slow_rows * a_stride + 128;   // the A prefetch runs up to 3 blocks past a row
-    const bool fits = plan_tma(h, g, pl) == SO_OK && trows <= 2147483647 && gs.slow_rows <= 65535 &&
+    // scaled operands only for the slow indices the caller's rows touch (a rank's row block)
+    const int64_t s_lo = M > 0 ? row0 / gs.fast_rows : 0;
+    const int64_t s_hi = M > 0 ? (row0 + M - 1) / gs.fast_rows + 1 : 0;
+    const int64_t n_slow = s_hi - s_lo;
+    const size_t ap_elems = (size_t)n_slow * a_stride + 128;   // the A prefetch runs up to 3 blocks past a row
+    const bool fits = plan_tma(h, g, pl) == SO_OK && trows <= 2147483647 && n_slow <= 65535 &&
                       (size_t)trows * Npad * sizeof(double) <= ((size_t)4 << 30) && ap_elems * sizeof(double2) <= ((size_t)8 << 30);
     if (fits) {
         const size_t need2 = (size_t)trows * Npad;
@@ -475,10 +487,13 @@ extern "C" int so_grid_prepare(so_handle* h, int gp, void* stream_) {
         k_pffrag<<<(unsigned)(pf_blocks < 4096 ? pf_blocks : 4096), 256, 0, stream>>>(Pfast, g.PfFrag, gs.fast_rows, g.N, Npad, pl.T,
                                                                                       pl.TB, pl.kb_pad, tpb);
         SO_CHECK_LAUNCH(h, "k_pffrag");
-        dim3 grd2((unsigned)((a_stride + 255) / 256), (unsigned)gs.slow_rows);
-        k_aprime<<<grd2, 256, 0, stream>>>(g.Afrag, Pslow, g.Aprime, g.NB, a_stride);
-        SO_CHECK_LAUNCH(h, "k_aprime");
-        SO_CUDA(h, cudaMemsetAsync(g.Aprime + (size_t)gs.slow_rows * a_stride, 0, sizeof(double2) * 128, stream));
+        if (n_slow > 0) {
+            dim3 grd2((unsigned)((a_stride + 255) / 256), (unsigned)n_slow);
+            k_aprime<<<grd2, 256, 0, stream>>>(g.Afrag, Pslow, g.Aprime, g.NB, a_stride, s_lo);
+            SO_CHECK_LAUNCH(h, "k_aprime");
+        }
+        SO_CUDA(h, cudaMemsetAsync(g.Aprime + (size_t)n_slow * a_stride, 0, sizeof(double2) * 128, stream));
+        g.ap_s0 = s_lo; g.ap_s1 = s_hi;
         g.a_stride = a_stride; g.tma_T = pl.T; g.tma_tpb = tpb; g.tma_BT = pl.BT; g.tma_RG = pl.RG; g.tma_CG = pl.CG;
         g.tma_kb_pad = pl.kb_pad; g.tma_ready = true;
     }

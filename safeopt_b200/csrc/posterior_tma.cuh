@@ -49,6 +49,7 @@ struct TmaParams {
     const double2* PfFrag;            // [tile in slow block][k-block][col tile][lane] double2, zero padded
     const double2* Aprime;            // slow_rows packed scaled operands, a_stride double2 apart
     size_t a_stride;
+    int64_t s0;                       // slow index of the first operand resident in Aprime
     int64_t fast_rows;
     int64_t first_tile;
     int tpb;                          // tiles per slow block
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_posterior_tma(const __grid_cons
         const int64_t gt = tp.first_tile + tile;
         const int64_t si = gt / tp.tpb;
         const int j = (int)(gt - si * tp.tpb);
-        const double2* Afrag = tp.Aprime + (size_t)si * tp.a_stride + lane;
+        const double2* Afrag = tp.Aprime + (size_t)(si - tp.s0) * tp.a_stride + lane;
         const double2* sB = sBuf + (size_t)b * buf_elems + (size_t)(cg * BT) * 32 + lane;
         double* sSST = sSS + (size_t)b * RG * T;
         double* sMeanT = sMean + (size_t)b * RG * T;
@@ -192,12 +193,12 @@ __global__ void k_pffrag(const double* __restrict__ Pfast, double2* __restrict__
 
 // A'(s) = L^-1 diag(Pslow[s]) in the packed fragment order of Afrag.
 __global__ void k_aprime(const double2* __restrict__ Afrag, const double* __restrict__ Pslow, double2* __restrict__ Aprime,
-                         int NB, size_t a_stride) {
-    const int64_t si = blockIdx.y;
+                         int NB, size_t a_stride, int64_t s0) {
+    const int64_t si = s0 + blockIdx.y;
     const int Npad = 8 * NB;
     const double* ps = Pslow + (size_t)si * Npad;
     const size_t nfrag = tri_blocks(NB) * 32;
-    double2* dst = Aprime + (size_t)si * a_stride;
+    double2* dst = Aprime + (size_t)blockIdx.y * a_stride;
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < a_stride; e += (size_t)gridDim.x * blockDim.x) {
         double2 v = make_double2(0.0, 0.0);
         if (e < nfrag) {

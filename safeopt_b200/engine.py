@@ -147,8 +147,13 @@ class DeviceEngine:
         self._check(self.lib.so_grid_define(self.handle, len(axes), _hptr(n), _hptr(vals), self._stream()), "so_grid_define")
         self._grid_axes = [np.asarray(a, dtype=np.float64) for a in axes]
 
-    def prepare_grid(self, gp: int):
-        self._check(self.lib.so_grid_prepare(self.handle, gp, self._stream()), "so_grid_prepare")
+    def prepare_grid(self, gp: int, row0: Optional[int] = None, n_rows: Optional[int] = None):
+        """Grid tables of GP ``gp``; with a row range, the per-slow-index operands only for that row block."""
+        if row0 is None:
+            self._check(self.lib.so_grid_prepare(self.handle, gp, self._stream()), "so_grid_prepare")
+        else:
+            self._check(self.lib.so_grid_prepare_rows(self.handle, gp, int(row0), int(n_rows), self._stream()),
+                        "so_grid_prepare_rows")
         self.launches += 4
 
     def grid_rows(self, row0: int, M: int):

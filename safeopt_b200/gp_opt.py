@@ -227,10 +227,20 @@ class SafeOpt(GaussianProcessOptimization):
         super(SafeOpt, self).__init__(gp, fmin=fmin, beta=beta, num_contexts=num_contexts, threshold=threshold,
                                       scaling=scaling)
         parameter_set = np.asarray(parameter_set, dtype=float)
+        # SAFEOPT_B200_GRID_FAST_PATH=0 forces the explicit-rows kernels (tests / A-B measurements)
+        axes = None
+        if self.num_contexts == 0 and os.environ.get("SAFEOPT_B200_GRID_FAST_PATH", "1") != "0":
+            axes = detect_grid(parameter_set)
         if self.num_contexts > 0:
             zeros = np.zeros((parameter_set.shape[0], self.num_contexts), dtype=parameter_set.dtype)
             self.inputs = np.hstack((parameter_set, zeros))
             self.parameter_set = self.inputs[:, :-self.num_contexts]
+        elif axes is not None:
+            # a verified product grid: bounds and num_samples (gp_opt.py:414-422) follow from the axes, without
+            # the per-column np.unique sorts over all M rows
+            self.inputs = self._parameter_set = parameter_set
+            self.bounds = [(np.min(a), np.max(a)) for a in axes]
+            self.num_samples = [len(a) for a in axes]
         else:
             self.inputs = self.parameter_set = parameter_set
 
@@ -248,11 +258,8 @@ class SafeOpt(GaussianProcessOptimization):
         n_rows = self.inputs.shape[0]
         self._row0, self._row1 = shard_bounds(n_rows, self._comm.world, self._comm.rank)
         m_local = self._row1 - self._row0
-        self._grid_axes = None
+        self._grid_axes = axes
         self._rows_d = None
-        # SAFEOPT_B200_GRID_FAST_PATH=0 forces the explicit-rows kernels (tests / A-B measurements)
-        if self.num_contexts == 0 and os.environ.get("SAFEOPT_B200_GRID_FAST_PATH", "1") != "0":
-            self._grid_axes = detect_grid(self.inputs)
         if self._grid_axes is not None:
             self._engine.define_grid(self._grid_axes)
         else:
@@ -370,7 +377,7 @@ class SafeOpt(GaussianProcessOptimization):
     # ------------------------------------------------------------------ hot path
     def _after_fit(self, i, hyper):
         if self._grid_axes is not None and hyper.kind == _lib.KERNEL_RBF:
-            self._engine.prepare_grid(i)
+            self._engine.prepare_grid(i, self._row0, self._row1 - self._row0)
 
     def _use_grid_kernel(self, i) -> bool:
         return self._grid_axes is not None and self._fits.hypers[i].kind == _lib.KERNEL_RBF

@@ -21,7 +21,7 @@ import numpy as np
 class GridWorkload:
     name: str
     d: int
-    num_samples: int          # per axis
+    num_samples: object       # per axis: int, or a list with one entry per axis
     n_train: int
     n_gps: int
     dtype: str
@@ -37,7 +37,13 @@ class GridWorkload:
 
     @property
     def n_rows(self) -> int:
-        return self.num_samples ** self.d
+        return int(np.prod(self.samples_per_axis))
+
+    @property
+    def samples_per_axis(self) -> List[int]:
+        if isinstance(self.num_samples, (list, tuple)):
+            return [int(n) for n in self.num_samples]
+        return [int(self.num_samples)] * self.d
 
 
 def _objective(X: np.ndarray) -> np.ndarray:
@@ -60,7 +66,7 @@ def grid_workload(name: str, d: int, num_samples: int, n_train: int, n_gps: int 
                         noise_var=0.05 ** 2, fmin=[0.0] * n_gps, beta=2.0, threshold=0.2)
 
 
-def config(name: str, seed: int = 0, num_samples: int | None = None) -> GridWorkload:
+def config(name: str, seed: int = 0, num_samples=None) -> GridWorkload:
     table = {
         "C1": dict(d=1, num_samples=100, n_train=5, n_gps=1, dtype="fp64"),
         "C2": dict(d=2, num_samples=200, n_train=64, n_gps=1, dtype="fp64"),
