@@ -170,6 +170,19 @@ int so_sets_candidates(so_handle* h, const double* Q_d, int n_gps, int64_t M, in
                        uint8_t* cand_mask_d, double* cand_key_d, int64_t* cand_row_d,
                        int64_t cap, int64_t* n_cand_d, void* stream);
 
+/* Chained variants: the scalar linking two passes is taken from device memory instead of the host --
+ * max_l0 = max_r safe_recs_d[r].max_l0 and max_var = max_r max_recs_d[r].max_width0 / scaling_h[0] over the
+ * n_recs per-rank records of the previous pass (as all-gathered; n_recs = 1 on a single GPU).  The three
+ * passes then run back to back on the stream and the host reads every record with one copy at the end. */
+int so_sets_maximizers_chain(so_handle* h, const double* Q_d, int n_gps, int64_t M, int64_t row0,
+                             const uint8_t* S_d, const so_safe_record* safe_recs_d, int n_recs,
+                             const double* scaling_h, uint8_t* Mmask_d, so_max_record* rec_d, void* stream);
+int so_sets_candidates_chain(so_handle* h, const double* Q_d, int n_gps, int64_t M, int64_t row0,
+                             const uint8_t* S_d, const uint8_t* Mmask_d, const so_max_record* max_recs_d,
+                             int n_recs, const double* scaling_h, const double* thr_h,
+                             uint8_t* cand_mask_d, double* cand_key_d, int64_t* cand_row_d,
+                             int64_t cap, int64_t* n_cand_d, void* stream);
+
 /* ------------------------------------------------------------------ K4: batched expander test
  * Stands in for the refit/predict/refit loop of safeopt/gp_opt.py:579-606 for B
  * candidates at once, through the rank-1 identity:

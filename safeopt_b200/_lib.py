@@ -80,6 +80,8 @@ SIGNATURES = {
     "so_sets_reduce_safe": (_i, [_P, _P, _i, _i64, _i64, _P, _P, _P]),
     "so_sets_maximizers": (_i, [_P, _P, _i, _i64, _i64, _P, _dbl, _P, _P, _P, _P]),
     "so_sets_candidates": (_i, [_P, _P, _i, _i64, _i64, _P, _P, _dbl, _P, _P, _P, _P, _P, _i64, _P, _P]),
+    "so_sets_maximizers_chain": (_i, [_P, _P, _i, _i64, _i64, _P, _P, _i, _P, _P, _P, _P]),
+    "so_sets_candidates_chain": (_i, [_P, _P, _i, _i64, _i64, _P, _P, _P, _i, _P, _P, _P, _P, _P, _i64, _P, _P]),
     "so_expander_check": (_i, [_P, _i, _P, _i64, _i64, _P, _P, _P, _P, _P, _P, _P, _i, _dbl, _dbl, _P, _P]),
     "so_expander_lipschitz": (_i, [_P, _P, _i, _i64, _i64, _P, _P, _P, _i, _dbl, _dbl, _P, _P]),
     "so_swarm_fitness": (_i, [_P, _i, _i, _i64, _P, _P, _dbl, _P, _P, _dbl, _P, _P, _P]),

@@ -1,189 +1,289 @@
 // K3 -- the set logic of SafeOpt.compute_sets as HBM-streaming passes over Q (fp64, row-major,
-// 2G columns) and the byte masks.  Each pass is one coalesced sweep (16*G + 1..3 bytes per row)
-// with a warp-shuffle + shared-memory block reduction and a last-block-done final combine, so
-// results are deterministic (first-row tie-breaks follow NumPy's argmax, gp_opt.py:635,:644,:710).
+// 2G columns) and the byte masks.  Each pass is one coalesced sweep: a thread takes 16 consecutive rows,
+// reads their 16 mask bytes with one 128-bit load and touches Q only for rows that are in the set
+// (16*G + 1..3 bytes per row at most); warp-shuffle + shared-memory block reduction, and the last block
+// to finish combines the per-block partials in parallel, so results are deterministic (first-row
+// tie-breaks follow NumPy's argmax, gp_opt.py:635,:644,:710).
 //   so_sets_reduce_safe : gp_opt.py:504 (any S), :512 (max l0[S]), :634-636, :708-712
 //   so_sets_maximizers  : gp_opt.py:511-513 and the M part of :642-644
 //   so_sets_candidates  : gp_opt.py:531-536 and the sort key of :551
+// The *_chain variants take the scalar that links two passes (max l0[S]; max width over M) from the
+// records of the previous pass in device memory -- one record per rank, as all-gathered -- so the three
+// passes run back to back on the stream and the host reads all results with a single copy.
 #include "common.cuh"
 
 namespace {
 
 constexpr int kThreads = 256;
 constexpr int kMaxBlocks = SO_WS_MAX_BLOCKS;
+constexpr int kRows = 16;                      // rows per thread and step: one uint4 of mask bytes
 
 struct SafePartial { long long n; double max_l; long long arg_l; double max_u; long long arg_u; };
 struct MaxPartial { long long n; double max_w0; double best; long long best_row; };
+struct Scal { double v[64]; };
 
 __device__ __forceinline__ void take_max_first(double& v, long long& r, double ov, long long orow) {
     // keep the larger value; on ties keep the smaller (global) row; row < 0 means "empty"
     if (orow >= 0 && (r < 0 || ov > v || (ov == v && orow < r))) { v = ov; r = orow; }
 }
 
-__global__ void __launch_bounds__(kThreads) k_reduce_safe(const double* __restrict__ Q, int q_stride, int64_t M, int64_t row0,
-                                                         const uint8_t* __restrict__ S, SafePartial* __restrict__ part,
-                                                         unsigned int* __restrict__ counter, so_safe_record* __restrict__ out) {
-    SafePartial acc = {0, -INFINITY, -1, -INFINITY, -1};
-    for (int64_t r = (int64_t)blockIdx.x * kThreads + threadIdx.x; r < M; r += (int64_t)gridDim.x * kThreads) {
-        if (S[r]) {
-            const double l = Q[(size_t)r * q_stride], u = Q[(size_t)r * q_stride + 1];
-            acc.n += 1;
-            take_max_first(acc.max_l, acc.arg_l, l, row0 + r);
-            take_max_first(acc.max_u, acc.arg_u, u, row0 + r);
-        }
-    }
-    __shared__ SafePartial sm[kThreads / 32];
-    __shared__ bool last;
+__device__ __forceinline__ void merge(SafePartial& a, const SafePartial& o) {
+    a.n += o.n;
+    take_max_first(a.max_l, a.arg_l, o.max_l, o.arg_l);
+    take_max_first(a.max_u, a.arg_u, o.max_u, o.arg_u);
+}
+__device__ __forceinline__ void merge(MaxPartial& a, const MaxPartial& o) {
+    a.n += o.n;
+    a.max_w0 = o.max_w0 > a.max_w0 ? o.max_w0 : a.max_w0;
+    take_max_first(a.best, a.best_row, o.best, o.best_row);
+}
+__device__ __forceinline__ SafePartial shfl_xor(const SafePartial& a, int o) {
+    SafePartial r;
+    r.n = __shfl_xor_sync(0xffffffffu, a.n, o);
+    r.max_l = __shfl_xor_sync(0xffffffffu, a.max_l, o);
+    r.arg_l = __shfl_xor_sync(0xffffffffu, a.arg_l, o);
+    r.max_u = __shfl_xor_sync(0xffffffffu, a.max_u, o);
+    r.arg_u = __shfl_xor_sync(0xffffffffu, a.arg_u, o);
+    return r;
+}
+__device__ __forceinline__ MaxPartial shfl_xor(const MaxPartial& a, int o) {
+    MaxPartial r;
+    r.n = __shfl_xor_sync(0xffffffffu, a.n, o);
+    r.max_w0 = __shfl_xor_sync(0xffffffffu, a.max_w0, o);
+    r.best = __shfl_xor_sync(0xffffffffu, a.best, o);
+    r.best_row = __shfl_xor_sync(0xffffffffu, a.best_row, o);
+    return r;
+}
+
+// Block reduction of `acc` (all operations are order-independent: integer sums, max with lowest-row ties);
+// the result is valid in thread 0.
+template <typename P>
+__device__ __forceinline__ P block_reduce(P acc, P* sm) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        SafePartial other;
-        other.n = __shfl_xor_sync(0xffffffffu, acc.n, o);
-        other.max_l = __shfl_xor_sync(0xffffffffu, acc.max_l, o);
-        other.arg_l = __shfl_xor_sync(0xffffffffu, acc.arg_l, o);
-        other.max_u = __shfl_xor_sync(0xffffffffu, acc.max_u, o);
-        other.arg_u = __shfl_xor_sync(0xffffffffu, acc.arg_u, o);
-        acc.n += other.n;
-        take_max_first(acc.max_l, acc.arg_l, other.max_l, other.arg_l);
-        take_max_first(acc.max_u, acc.arg_u, other.max_u, other.arg_u);
-    }
+    for (int o = 16; o > 0; o >>= 1) merge(acc, shfl_xor(acc, o));
     if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
     __syncthreads();
+    if (threadIdx.x < 32) {
+        P t = sm[threadIdx.x < kThreads / 32 ? threadIdx.x : 0];
+        if (threadIdx.x >= kThreads / 32) t = sm[0];          // duplicates of entry 0 do not change max / are not summed:
+        if (threadIdx.x >= kThreads / 32) t.n = 0;            // only their counts must not be added twice
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) merge(t, shfl_xor(t, o));
+        acc = t;
+    }
+    __syncthreads();
+    return acc;
+}
+
+// Publishes this block's partial; the last block to arrive reduces all partials (in parallel) and returns true
+// in thread 0 with the total in `acc`.
+template <typename P>
+__device__ __forceinline__ bool grid_reduce(P& acc, P* __restrict__ part, unsigned int* __restrict__ counter, P identity) {
+    __shared__ P sm[kThreads / 32];
+    __shared__ bool last;
+    acc = block_reduce(acc, sm);
     if (threadIdx.x == 0) {
-        SafePartial t = sm[0];
-        for (int w = 1; w < kThreads / 32; ++w) {
-            t.n += sm[w].n;
-            take_max_first(t.max_l, t.arg_l, sm[w].max_l, sm[w].arg_l);
-            take_max_first(t.max_u, t.arg_u, sm[w].max_u, sm[w].arg_u);
-        }
-        part[blockIdx.x] = t;
+        part[blockIdx.x] = acc;
         __threadfence();
         last = atomicAdd(counter, 1u) == gridDim.x - 1;
     }
     __syncthreads();
-    if (last && threadIdx.x == 0) {
-        __threadfence();
-        SafePartial t = {0, -INFINITY, -1, -INFINITY, -1};
-        for (unsigned b = 0; b < gridDim.x; ++b) {
-            const SafePartial o = part[b];
-            t.n += o.n;
-            take_max_first(t.max_l, t.arg_l, o.max_l, o.arg_l);
-            take_max_first(t.max_u, t.arg_u, o.max_u, o.arg_u);
-        }
-        out->n_safe = t.n; out->max_l0 = t.max_l; out->argmax_l0 = t.arg_l; out->max_u0 = t.max_u; out->argmax_u0 = t.arg_u;
-        out->reserved[0] = out->reserved[1] = out->reserved[2] = 0;
-        *counter = 0;
+    if (!last) return false;
+    __threadfence();
+    P t = identity;
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += kThreads) merge(t, part[b]);
+    acc = block_reduce(t, sm);
+    if (threadIdx.x == 0) *counter = 0;
+    return threadIdx.x == 0;
+}
+
+// 16 mask bytes of rows [r0, r0+16): one 128-bit load when the block is whole and aligned, bytes otherwise
+// (rows >= M read as 0).
+__device__ __forceinline__ void load_mask16(const uint8_t* __restrict__ m, int64_t r0, int64_t M, bool aligned, uint8_t (&b)[kRows]) {
+    if (aligned && r0 + kRows <= M) {
+        const uint4 v = *reinterpret_cast<const uint4*>(m + r0);
+        const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < kRows; ++k) b[k] = (uint8_t)((w[k >> 2] >> (8 * (k & 3))) & 0xffu);
+    } else {
+#pragma unroll
+        for (int k = 0; k < kRows; ++k) b[k] = (r0 + k < M) ? m[r0 + k] : (uint8_t)0;
+    }
+}
+__device__ __forceinline__ bool any16(const uint8_t (&b)[kRows]) {
+    unsigned acc = 0;
+#pragma unroll
+    for (int k = 0; k < kRows; ++k) acc |= b[k];
+    return acc != 0;
+}
+__device__ __forceinline__ void store_mask16(uint8_t* __restrict__ m, int64_t r0, int64_t M, bool aligned, const uint8_t (&b)[kRows]) {
+    if (aligned && r0 + kRows <= M) {
+        unsigned w[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int k = 0; k < kRows; ++k) w[k >> 2] |= (unsigned)b[k] << (8 * (k & 3));
+        *reinterpret_cast<uint4*>(m + r0) = make_uint4(w[0], w[1], w[2], w[3]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < kRows; ++k)
+            if (r0 + k < M) m[r0 + k] = b[k];
     }
 }
 
-struct Scal { double v[64]; };
+__global__ void __launch_bounds__(kThreads) k_reduce_safe(const double* __restrict__ Q, int q_stride, int64_t M, int64_t row0,
+                                                         const uint8_t* __restrict__ S, SafePartial* __restrict__ part,
+                                                         unsigned int* __restrict__ counter, so_safe_record* __restrict__ out) {
+    const SafePartial identity = {0, -INFINITY, -1, -INFINITY, -1};
+    SafePartial acc = identity;
+    const bool aligned = (reinterpret_cast<uintptr_t>(S) & 15) == 0;
+    const int64_t nchunks = (M + kRows - 1) / kRows;
+    for (int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x; c < nchunks; c += (int64_t)gridDim.x * kThreads) {
+        const int64_t r0 = c * kRows;
+        uint8_t s[kRows];
+        load_mask16(S, r0, M, aligned, s);
+        if (!any16(s)) continue;
+#pragma unroll
+        for (int k = 0; k < kRows; ++k) {
+            if (!s[k]) continue;
+            const int64_t r = r0 + k;
+            const double2 lu = *reinterpret_cast<const double2*>(Q + (size_t)r * q_stride);
+            acc.n += 1;
+            take_max_first(acc.max_l, acc.arg_l, lu.x, row0 + r);
+            take_max_first(acc.max_u, acc.arg_u, lu.y, row0 + r);
+        }
+    }
+    if (grid_reduce(acc, part, counter, identity)) {
+        out->n_safe = acc.n; out->max_l0 = acc.max_l; out->argmax_l0 = acc.arg_l; out->max_u0 = acc.max_u; out->argmax_u0 = acc.arg_u;
+        out->reserved[0] = out->reserved[1] = out->reserved[2] = 0;
+    }
+}
 
 __global__ void __launch_bounds__(kThreads) k_maximizers(const double* __restrict__ Q, int G, int64_t M, int64_t row0,
-                                                        const uint8_t* __restrict__ S, double max_l0, Scal scaling,
+                                                        const uint8_t* __restrict__ S, double max_l0,
+                                                        const so_safe_record* __restrict__ safe_recs, int n_recs, Scal scaling,
                                                         uint8_t* __restrict__ Mmask, MaxPartial* __restrict__ part,
                                                         unsigned int* __restrict__ counter, so_max_record* __restrict__ out) {
-    MaxPartial acc = {0, -INFINITY, -INFINITY, -1};
+    if (safe_recs) {                            // chained: max over the ranks' records of max l0[S] (-inf where a rank has none)
+        max_l0 = -INFINITY;
+        for (int r = 0; r < n_recs; ++r) max_l0 = safe_recs[r].max_l0 > max_l0 ? safe_recs[r].max_l0 : max_l0;
+    }
+    const MaxPartial identity = {0, -INFINITY, -INFINITY, -1};
+    MaxPartial acc = identity;
     const int qs = 2 * G;
-    for (int64_t r = (int64_t)blockIdx.x * kThreads + threadIdx.x; r < M; r += (int64_t)gridDim.x * kThreads) {
-        uint8_t m = 0;
-        if (S[r]) {
-            const double* q = Q + (size_t)r * qs;
-            if (q[1] >= max_l0) {
-                m = 1;
-                acc.n += 1;
-                const double w0 = q[1] - q[0];
-                acc.max_w0 = w0 > acc.max_w0 ? w0 : acc.max_w0;
-                double val = w0 / scaling.v[0];
-                for (int i = 1; i < G; ++i) {
-                    const double wi = (q[2 * i + 1] - q[2 * i]) / scaling.v[i];
-                    val = wi > val ? wi : val;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(S) | reinterpret_cast<uintptr_t>(Mmask)) & 15) == 0;
+    const int64_t nchunks = (M + kRows - 1) / kRows;
+    for (int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x; c < nchunks; c += (int64_t)gridDim.x * kThreads) {
+        const int64_t r0 = c * kRows;
+        uint8_t s[kRows], m[kRows];
+        load_mask16(S, r0, M, aligned, s);
+#pragma unroll
+        for (int k = 0; k < kRows; ++k) m[k] = 0;
+        if (any16(s)) {
+#pragma unroll
+            for (int k = 0; k < kRows; ++k) {
+                if (!s[k]) continue;
+                const int64_t r = r0 + k;
+                const double* q = Q + (size_t)r * qs;
+                const double2 lu = *reinterpret_cast<const double2*>(q);
+                if (lu.y >= max_l0) {
+                    m[k] = 1;
+                    acc.n += 1;
+                    const double w0 = lu.y - lu.x;
+                    acc.max_w0 = w0 > acc.max_w0 ? w0 : acc.max_w0;
+                    double val = w0 / scaling.v[0];
+                    for (int i = 1; i < G; ++i) {
+                        const double wi = (q[2 * i + 1] - q[2 * i]) / scaling.v[i];
+                        val = wi > val ? wi : val;
+                    }
+                    take_max_first(acc.best, acc.best_row, val, row0 + r);
                 }
-                take_max_first(acc.best, acc.best_row, val, row0 + r);
             }
         }
-        Mmask[r] = m;
+        store_mask16(Mmask, r0, M, aligned, m);
     }
-    __shared__ MaxPartial sm[kThreads / 32];
-    __shared__ bool last;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        MaxPartial other;
-        other.n = __shfl_xor_sync(0xffffffffu, acc.n, o);
-        other.max_w0 = __shfl_xor_sync(0xffffffffu, acc.max_w0, o);
-        other.best = __shfl_xor_sync(0xffffffffu, acc.best, o);
-        other.best_row = __shfl_xor_sync(0xffffffffu, acc.best_row, o);
-        acc.n += other.n;
-        acc.max_w0 = other.max_w0 > acc.max_w0 ? other.max_w0 : acc.max_w0;
-        take_max_first(acc.best, acc.best_row, other.best, other.best_row);
-    }
-    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        MaxPartial t = sm[0];
-        for (int w = 1; w < kThreads / 32; ++w) {
-            t.n += sm[w].n;
-            t.max_w0 = sm[w].max_w0 > t.max_w0 ? sm[w].max_w0 : t.max_w0;
-            take_max_first(t.best, t.best_row, sm[w].best, sm[w].best_row);
-        }
-        part[blockIdx.x] = t;
-        __threadfence();
-        last = atomicAdd(counter, 1u) == gridDim.x - 1;
-    }
-    __syncthreads();
-    if (last && threadIdx.x == 0) {
-        __threadfence();
-        MaxPartial t = {0, -INFINITY, -INFINITY, -1};
-        for (unsigned b = 0; b < gridDim.x; ++b) {
-            const MaxPartial o = part[b];
-            t.n += o.n;
-            t.max_w0 = o.max_w0 > t.max_w0 ? o.max_w0 : t.max_w0;
-            take_max_first(t.best, t.best_row, o.best, o.best_row);
-        }
-        out->n_max = t.n; out->max_width0 = t.max_w0; out->best_value = t.best; out->best_row = t.best_row;
+    if (grid_reduce(acc, part, counter, identity)) {
+        out->n_max = acc.n; out->max_width0 = acc.max_w0; out->best_value = acc.best; out->best_row = acc.best_row;
         out->reserved[0] = out->reserved[1] = out->reserved[2] = out->reserved[3] = 0;
-        *counter = 0;
     }
 }
 
 __global__ void __launch_bounds__(kThreads) k_candidates(const double* __restrict__ Q, int G, int64_t M, int64_t row0,
                                                         const uint8_t* __restrict__ S, const uint8_t* __restrict__ Mmask,
-                                                        double max_var, Scal scaling, Scal thr, uint8_t* __restrict__ cmask,
+                                                        double max_var, const so_max_record* __restrict__ max_recs, int n_recs,
+                                                        Scal scaling, Scal thr, uint8_t* __restrict__ cmask,
                                                         double* __restrict__ ckey, int64_t* __restrict__ crow, int64_t cap,
                                                         unsigned long long* __restrict__ n_cand) {
+    if (max_recs) {                             // chained: gp_opt.py:513 from the ranks' maximiser records
+        double w = -INFINITY;
+        for (int r = 0; r < n_recs; ++r) w = max_recs[r].max_width0 > w ? max_recs[r].max_width0 : w;
+        max_var = w / scaling.v[0];
+    }
     const int qs = 2 * G;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(S) | reinterpret_cast<uintptr_t>(Mmask) | reinterpret_cast<uintptr_t>(cmask)) & 15) == 0;
+    const int64_t nchunks = (M + kRows - 1) / kRows;
+    const unsigned lane = threadIdx.x & 31;
     // whole warps iterate together (the append below uses full-mask warp collectives)
-    for (int64_t base = (int64_t)blockIdx.x * kThreads; base < M; base += (int64_t)gridDim.x * kThreads) {
-        const int64_t r = base + threadIdx.x;
-        uint8_t c = 0;
-        double key = 0.0;
-        if (r < M && S[r] && !Mmask[r]) {
-            const double* q = Q + (size_t)r * qs;
-            double smax = -INFINITY, wmax = -INFINITY;
-            bool over = false;
-            for (int i = 0; i < G; ++i) {
-                const double w = q[2 * i + 1] - q[2 * i];
-                const double ws = w / scaling.v[i];
-                smax = ws > smax ? ws : smax;
-                wmax = w > wmax ? w : wmax;
-                over = over || (w > thr.v[i]);
+    for (int64_t cbase = (int64_t)blockIdx.x * kThreads; cbase < nchunks; cbase += (int64_t)gridDim.x * kThreads) {
+        const int64_t c = cbase + threadIdx.x;
+        const int64_t r0 = c * kRows;
+        uint8_t s[kRows], m[kRows], cnd[kRows];
+        unsigned bits = 0;
+#pragma unroll
+        for (int k = 0; k < kRows; ++k) cnd[k] = 0;
+        if (c < nchunks) {
+            load_mask16(S, r0, M, aligned, s);
+            if (any16(s)) {
+                load_mask16(Mmask, r0, M, aligned, m);
+#pragma unroll
+                for (int k = 0; k < kRows; ++k) {
+                    if (!s[k] || m[k]) continue;
+                    const double* q = Q + (size_t)(r0 + k) * qs;
+                    double smax = -INFINITY;
+                    bool over = false;
+                    for (int i = 0; i < G; ++i) {
+                        const double w = q[2 * i + 1] - q[2 * i];
+                        const double ws = w / scaling.v[i];
+                        smax = ws > smax ? ws : smax;
+                        over = over || (w > thr.v[i]);
+                    }
+                    if (smax > max_var && over) { cnd[k] = 1; bits |= 1u << k; }
+                }
             }
-            if (smax > max_var && over) { c = 1; key = wmax; }
+            if (cmask) store_mask16(cmask, r0, M, aligned, cnd);
         }
-        if (cmask && r < M) cmask[r] = c;
-        const unsigned ballot = __ballot_sync(0xffffffffu, c);
-        if (ballot) {
-            const unsigned lane = threadIdx.x & 31;
-            const int leader = __ffs(ballot) - 1;
-            unsigned long long slot0 = 0;
-            if ((int)lane == leader) slot0 = atomicAdd(n_cand, (unsigned long long)__popc(ballot));
-            slot0 = __shfl_sync(0xffffffffu, slot0, leader);
-            const unsigned long long slot = slot0 + __popc(ballot & ((1u << lane) - 1));
-            if (c && (int64_t)slot < cap) { ckey[slot] = key; crow[slot] = row0 + r; }
+        // warp-aggregated append: exclusive scan of the per-lane counts, one atomic per warp
+        const int cnt = __popc(bits);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)lane >= o) incl += v;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total == 0) continue;
+        unsigned long long slot0 = 0;
+        if (lane == 31) slot0 = atomicAdd(n_cand, (unsigned long long)total);
+        slot0 = __shfl_sync(0xffffffffu, slot0, 31);
+        unsigned long long slot = slot0 + (unsigned long long)(incl - cnt);
+        while (bits) {
+            const int k = __ffs(bits) - 1;
+            bits &= bits - 1;
+            if ((int64_t)slot < cap) {
+                const double* q = Q + (size_t)(r0 + k) * qs;
+                double wmax = -INFINITY;                  // sort key of gp_opt.py:551: unscaled width
+                for (int i = 0; i < G; ++i) {
+                    const double w = q[2 * i + 1] - q[2 * i];
+                    wmax = w > wmax ? w : wmax;
+                }
+                ckey[slot] = wmax;
+                crow[slot] = row0 + r0 + k;
+            }
+            ++slot;
         }
     }
 }
 
 int grid_for(const so_handle* h, int64_t M) {
-    int64_t blocks = (M + kThreads - 1) / kThreads;
+    int64_t blocks = ((M + kRows - 1) / kRows + kThreads - 1) / kThreads;
     int64_t cap = (int64_t)h->num_sms * 8;
     if (cap > kMaxBlocks) cap = kMaxBlocks;
     if (blocks > cap) blocks = cap;
@@ -204,22 +304,35 @@ extern "C" int so_sets_reduce_safe(so_handle* h, const double* Q_d, int n_gps, i
     return SO_OK;
 }
 
-extern "C" int so_sets_maximizers(so_handle* h, const double* Q_d, int n_gps, int64_t M, int64_t row0, const uint8_t* S_d,
-                                  double max_l0, const double* scaling_h, uint8_t* Mmask_d, so_max_record* rec_d, void* stream) {
+static int run_maximizers(so_handle* h, const double* Q_d, int n_gps, int64_t M, int64_t row0, const uint8_t* S_d, double max_l0,
+                          const so_safe_record* safe_recs_d, int n_recs, const double* scaling_h, uint8_t* Mmask_d,
+                          so_max_record* rec_d, void* stream) {
     if (!h || !Q_d || !S_d || !scaling_h || !Mmask_d || !rec_d || n_gps < 1 || n_gps > 64 || M < 0) return SO_ERR_BAD_ARG;
     DeviceGuard guard(h->device);
     Scal sc;
     for (int i = 0; i < 64; ++i) sc.v[i] = i < n_gps ? scaling_h[i] : 1.0;
-    k_maximizers<<<grid_for(h, M), kThreads, 0, (cudaStream_t)stream>>>(Q_d, n_gps, M, row0, S_d, max_l0, sc, Mmask_d,
-                                                                        (MaxPartial*)h->ws_partials, h->ws_counter, rec_d);
+    k_maximizers<<<grid_for(h, M), kThreads, 0, (cudaStream_t)stream>>>(Q_d, n_gps, M, row0, S_d, max_l0, safe_recs_d, n_recs, sc,
+                                                                        Mmask_d, (MaxPartial*)h->ws_partials, h->ws_counter, rec_d);
     SO_CHECK_LAUNCH(h, "k_maximizers");
     return SO_OK;
 }
 
-extern "C" int so_sets_candidates(so_handle* h, const double* Q_d, int n_gps, int64_t M, int64_t row0, const uint8_t* S_d,
-                                  const uint8_t* Mmask_d, double max_var, const double* scaling_h, const double* thr_h,
-                                  uint8_t* cand_mask_d, double* cand_key_d, int64_t* cand_row_d, int64_t cap,
-                                  int64_t* n_cand_d, void* stream) {
+extern "C" int so_sets_maximizers(so_handle* h, const double* Q_d, int n_gps, int64_t M, int64_t row0, const uint8_t* S_d,
+                                  double max_l0, const double* scaling_h, uint8_t* Mmask_d, so_max_record* rec_d, void* stream) {
+    return run_maximizers(h, Q_d, n_gps, M, row0, S_d, max_l0, nullptr, 0, scaling_h, Mmask_d, rec_d, stream);
+}
+
+extern "C" int so_sets_maximizers_chain(so_handle* h, const double* Q_d, int n_gps, int64_t M, int64_t row0, const uint8_t* S_d,
+                                        const so_safe_record* safe_recs_d, int n_recs, const double* scaling_h,
+                                        uint8_t* Mmask_d, so_max_record* rec_d, void* stream) {
+    if (!safe_recs_d || n_recs < 1) return SO_ERR_BAD_ARG;
+    return run_maximizers(h, Q_d, n_gps, M, row0, S_d, 0.0, safe_recs_d, n_recs, scaling_h, Mmask_d, rec_d, stream);
+}
+
+static int run_candidates(so_handle* h, const double* Q_d, int n_gps, int64_t M, int64_t row0, const uint8_t* S_d,
+                          const uint8_t* Mmask_d, double max_var, const so_max_record* max_recs_d, int n_recs,
+                          const double* scaling_h, const double* thr_h, uint8_t* cand_mask_d, double* cand_key_d,
+                          int64_t* cand_row_d, int64_t cap, int64_t* n_cand_d, void* stream) {
     if (!h || !Q_d || !S_d || !Mmask_d || !scaling_h || !thr_h || !n_cand_d || n_gps < 1 || n_gps > 64 || M < 0 || cap < 0)
         return SO_ERR_BAD_ARG;
     if (cap > 0 && (!cand_key_d || !cand_row_d)) return SO_ERR_BAD_ARG;
@@ -227,9 +340,26 @@ extern "C" int so_sets_candidates(so_handle* h, const double* Q_d, int n_gps, in
     Scal sc, th;
     for (int i = 0; i < 64; ++i) { sc.v[i] = i < n_gps ? scaling_h[i] : 1.0; th.v[i] = i < n_gps ? thr_h[i] : 0.0; }
     SO_CUDA(h, cudaMemsetAsync(n_cand_d, 0, sizeof(int64_t), (cudaStream_t)stream));
-    k_candidates<<<grid_for(h, M), kThreads, 0, (cudaStream_t)stream>>>(Q_d, n_gps, M, row0, S_d, Mmask_d, max_var, sc, th, cand_mask_d,
-                                                                        cand_key_d, cand_row_d, cap,
+    k_candidates<<<grid_for(h, M), kThreads, 0, (cudaStream_t)stream>>>(Q_d, n_gps, M, row0, S_d, Mmask_d, max_var, max_recs_d, n_recs,
+                                                                        sc, th, cand_mask_d, cand_key_d, cand_row_d, cap,
                                                                         reinterpret_cast<unsigned long long*>(n_cand_d));
     SO_CHECK_LAUNCH(h, "k_candidates");
     return SO_OK;
+}
+
+extern "C" int so_sets_candidates(so_handle* h, const double* Q_d, int n_gps, int64_t M, int64_t row0, const uint8_t* S_d,
+                                  const uint8_t* Mmask_d, double max_var, const double* scaling_h, const double* thr_h,
+                                  uint8_t* cand_mask_d, double* cand_key_d, int64_t* cand_row_d, int64_t cap,
+                                  int64_t* n_cand_d, void* stream) {
+    return run_candidates(h, Q_d, n_gps, M, row0, S_d, Mmask_d, max_var, nullptr, 0, scaling_h, thr_h, cand_mask_d, cand_key_d,
+                          cand_row_d, cap, n_cand_d, stream);
+}
+
+extern "C" int so_sets_candidates_chain(so_handle* h, const double* Q_d, int n_gps, int64_t M, int64_t row0, const uint8_t* S_d,
+                                        const uint8_t* Mmask_d, const so_max_record* max_recs_d, int n_recs,
+                                        const double* scaling_h, const double* thr_h, uint8_t* cand_mask_d, double* cand_key_d,
+                                        int64_t* cand_row_d, int64_t cap, int64_t* n_cand_d, void* stream) {
+    if (!max_recs_d || n_recs < 1) return SO_ERR_BAD_ARG;
+    return run_candidates(h, Q_d, n_gps, M, row0, S_d, Mmask_d, 0.0, max_recs_d, n_recs, scaling_h, thr_h, cand_mask_d, cand_key_d,
+                          cand_row_d, cap, n_cand_d, stream);
 }

@@ -206,6 +206,22 @@ class DeviceEngine:
                                                 _ptr(cand_row), cap, _ptr(n_cand), self._stream()), "so_sets_candidates")
         self.launches += 1
 
+    def maximizers_chain(self, Q, n_gps, row0, S, safe_recs, n_recs, scaling, Mmask, rec):
+        sc = _np_f64(scaling)
+        self._check(self.lib.so_sets_maximizers_chain(self.handle, _ptr(Q), n_gps, Q.shape[0], int(row0), _ptr(S),
+                                                      _ptr(safe_recs), int(n_recs), _hptr(sc), _ptr(Mmask), _ptr(rec),
+                                                      self._stream()), "so_sets_maximizers_chain")
+        self.launches += 1
+
+    def candidates_chain(self, Q, n_gps, row0, S, Mmask, max_recs, n_recs, scaling, thr, cand_mask, cand_key, cand_row, n_cand):
+        sc, th = _np_f64(scaling), _np_f64(thr)
+        cap = 0 if cand_key is None else cand_key.shape[0]
+        self._check(self.lib.so_sets_candidates_chain(self.handle, _ptr(Q), n_gps, Q.shape[0], int(row0), _ptr(S), _ptr(Mmask),
+                                                      _ptr(max_recs), int(n_recs), _hptr(sc), _hptr(th), _ptr(cand_mask),
+                                                      _ptr(cand_key), _ptr(cand_row), cap, _ptr(n_cand), self._stream()),
+                    "so_sets_candidates_chain")
+        self.launches += 1
+
     # ------------------------------------------------------------------ K4
     def expander_check(self, gp, Xstar, row0, M, S, mean, var, xc, mean_c, var_c, u_c, beta, fmin, flags):
         B = xc.shape[0]

@@ -426,43 +426,77 @@ class SafeOpt(GaussianProcessOptimization):
         self._safe_info = reduce_safe_records(self._comm.gather_records(self._rec_safe_d, SAFE_REC_DTYPE))
         self._invalidate_host("S")
 
+    def _record_buffers(self):
+        """Device buffer holding every rank's records of the three set passes back to back
+        ([world x safe record][world x max record][world x candidate count]) so the host needs one copy.
+        On a single GPU the kernels write straight into it; with several ranks each pass is followed by a
+        stream-ordered all-gather of the 64-byte record."""
+        if getattr(self, "_recs_all_d", None) is None:
+            eng, world, t = self._engine, self._comm.world, self._engine.torch
+            self._recs_all_d = eng.zeros((world * 136,), "u8")
+            self._safe_all_d = self._recs_all_d[:world * 64].view(world, 64)
+            self._max_all_d = self._recs_all_d[world * 64:world * 128].view(world, 64)
+            self._ncand_all_d = self._recs_all_d[world * 128:].view(t.int64)
+            if world == 1:
+                self._rec_safe_l, self._rec_max_l, self._n_cand_l = self._safe_all_d[0], self._max_all_d[0], self._ncand_all_d
+            else:
+                self._rec_safe_l, self._rec_max_l, self._n_cand_l = self._rec_safe_d, self._rec_max_d, self._n_cand_d
+        return self._recs_all_d
+
+    def _share(self, all_d, local_d):
+        if self._comm.active:
+            self._comm.all_gather_into(all_d, local_d)
+
     def compute_sets(self, full_sets=False):
-        """Safe set, maximisers ``M`` and expanders ``G`` (reference: gp_opt.py:483-615)."""
+        """Safe set, maximisers ``M`` and expanders ``G`` (reference: gp_opt.py:483-615).
+
+        The three streaming passes (safe-set record, maximisers, expander candidates) are chained on the
+        device: each takes the scalar it depends on (``max l0[S]``, ``max width(M)``) from the previous pass's
+        records in device memory, so the host waits once, for a single 136-byte copy per rank."""
         beta = self.beta(self.t)
-        self.compute_safe_set()
+        if self._ci_beta is None:
+            raise RuntimeError("call update_confidence_intervals() first")
+        if not np.array_equal(self._ci_fmin, self.fmin):
+            self.update_confidence_intervals(context=self.context)
         eng = self._engine
         G = len(self.gps)
+        world = self._comm.world
         self._G_rows = []
         self._max_info = None
         self.last_trace = {}
-        self._invalidate_host("M")
-        if self._safe_info["n_safe"] == 0:
-            self._M_d.zero_()
-            return
-
-        eng.maximizers(self._Q_d, G, self._row0, self._S_d, self._safe_info["max_l0"], self.scaling, self._M_d,
-                       self._rec_max_d)
-        self._max_info = reduce_max_records(self._comm.gather_records(self._rec_max_d, MAX_REC_DTYPE), self.scaling[0])
-        max_var = self._max_info["max_var"]
-
+        self._invalidate_host("S", "M")
+        recs = self._record_buffers()
         m_local = self._row1 - self._row0
-        if self._cand_key_d is None:
-            self._cand_key_d = eng.empty((max(m_local, 1),))
-            self._cand_row_d = eng.empty((max(m_local, 1),), "i64")
         thr = np.broadcast_to(np.asarray(self.threshold, dtype=float), (G,)) * beta
+
+        eng.reduce_safe(self._Q_d, G, self._row0, self._S_d, self._rec_safe_l)
+        self._share(self._safe_all_d, self._rec_safe_l)
+        eng.maximizers_chain(self._Q_d, G, self._row0, self._S_d, self._safe_all_d, world, self.scaling, self._M_d,
+                             self._rec_max_l)
+        self._share(self._max_all_d, self._rec_max_l)
+        if not full_sets:
+            if self._cand_key_d is None:
+                self._cand_key_d = eng.empty((max(m_local, 1),))
+                self._cand_row_d = eng.empty((max(m_local, 1),), "i64")
+            eng.candidates_chain(self._Q_d, G, self._row0, self._S_d, self._M_d, self._max_all_d, world, self.scaling, thr,
+                                 None, self._cand_key_d, self._cand_row_d, self._n_cand_l)
+            self._share(self._ncand_all_d, self._n_cand_l)
+        host = recs.cpu().numpy()                                   # the one host wait of compute_sets
+        self._safe_info = reduce_safe_records(host[:world * 64].view(SAFE_REC_DTYPE).reshape(-1))
+        if self._safe_info["n_safe"] == 0:                          # gp_opt.py:504-507 (M is already all-False: M is a subset of S)
+            return
+        self._max_info = reduce_max_records(host[world * 64:world * 128].view(MAX_REC_DTYPE).reshape(-1), self.scaling[0])
+        max_var = self._max_info["max_var"]
         if full_sets:
             # every safe point is a candidate, natural order (gp_opt.py:527-528, :555)
             rows_local = eng.torch.nonzero(self._S_d, as_tuple=False).reshape(-1) + self._row0
             keys_local = None
+            counts = self._comm.all_gather(np.array([rows_local.shape[0]], dtype=np.int64)).reshape(-1)
         else:
-            eng.candidates(self._Q_d, G, self._row0, self._S_d, self._M_d, max_var, self.scaling, thr, None,
-                           self._cand_key_d, self._cand_row_d, self._n_cand_d)
-            counts = self._comm.all_gather_tensor(self._n_cand_d).reshape(-1)
+            counts = host[world * 128:].view(np.int64).reshape(-1)
             n_local = int(counts[self._comm.rank])
             rows_local = self._cand_row_d[:n_local]
             keys_local = self._cand_key_d[:n_local]
-        if full_sets:
-            counts = self._comm.all_gather(np.array([rows_local.shape[0]], dtype=np.int64)).reshape(-1)
         n_total = int(counts.sum())
         self.last_trace = dict(max_l=self._safe_info["max_l0"], max_var=max_var, n_candidates=n_total)
         if n_total == 0:
