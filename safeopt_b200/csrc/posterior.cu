@@ -194,36 +194,58 @@ int launch_bt(so_handle* h, const PostParams& p, const LaunchPlan& lp, cudaStrea
 }
 
 // ---- TMA double-buffer kernel (grid path default) ----------------------------------------------------------------
-struct TmaPlan { int BT, RG, CG, T, TB, npass, kb_pad; size_t smem; };
+struct TmaPlan { int BT, RG, CG, T, TB, npass, kb_pad, warps; size_t smem; };
+
+// 8 warps per CTA (four block rows per warp) by default; SO_K2_WARPS=16 selects the 16-warp variant (two block rows per
+// warp, four warps per scheduler) for A/B measurements -- measured 13.55 vs 13.40 ms at config 4, pipe 84.7 % vs 85.5 %
+// busy (profiles/r01_k2_variants.md): the extra warps do not buy back what the doubled B-fragment traffic costs.
+int tma_warps() {
+    const char* v = std::getenv("SO_K2_WARPS");
+    return v && std::string(v) == "16" ? 16 : 8;
+}
 
 int plan_tma(so_handle* h, const GPState& g, TmaPlan& tp) {
     const int NB = g.NB;
-    row_groups(NB, tp.RG, tp.CG);
-    tp.npass = (NB + 4 * tp.RG - 1) / (4 * tp.RG);
     tp.kb_pad = kChunkK * ((NB + kChunkK - 1) / kChunkK);
     const int options[3] = {6, 4, 2};
-    for (int k = 0; k < 3; ++k) {
-        const int bt = options[k];
-        const TmaSmem L = tma_smem(tp.kb_pad, bt * tp.CG, tp.RG, 8 * bt * tp.CG);
-        if (L.total <= (size_t)h->smem_optin) {
-            tp.BT = bt; tp.TB = bt * tp.CG; tp.T = 8 * bt * tp.CG; tp.smem = L.total;
-            return SO_OK;
+    for (int warps = tma_warps(); warps >= 8; warps -= 8) {
+        const int ns = warps == 16 ? 2 : 4;
+        int rg = 1;
+        while (rg < warps && ns * rg < NB) rg *= 2;       // row groups: enough warps to cover the block rows in one pass
+        tp.warps = warps; tp.RG = rg; tp.CG = warps / rg;
+        tp.npass = (NB + ns * rg - 1) / (ns * rg);
+        for (int k = 0; k < 3; ++k) {
+            const int bt = options[k];
+            const TmaSmem L = tma_smem(tp.kb_pad, bt * tp.CG, tp.RG, 8 * bt * tp.CG);
+            if (L.total <= (size_t)h->smem_optin) {
+                tp.BT = bt; tp.TB = bt * tp.CG; tp.T = 8 * bt * tp.CG; tp.smem = L.total;
+                return SO_OK;
+            }
         }
     }
     return SO_ERR_CAPACITY;
 }
 
-template <int BT>
+template <int BT, int WARPS>
 int launch_tma_one(so_handle* h, const TmaParams& tp, size_t smem, cudaStream_t stream) {
     static int configured_for = -1;
     if (configured_for != h->device) {
-        SO_CUDA(h, cudaFuncSetAttribute(k_posterior_tma<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
+        SO_CUDA(h, cudaFuncSetAttribute(k_posterior_tma<BT, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
         configured_for = h->device;
     }
     const int grid = (int)(tp.p.ntiles < (int64_t)h->num_sms ? tp.p.ntiles : (int64_t)h->num_sms);
-    k_posterior_tma<BT><<<grid, kThreads, smem, stream>>>(tp);
+    k_posterior_tma<BT, WARPS><<<grid, WARPS * 32, smem, stream>>>(tp);
     SO_CHECK_LAUNCH(h, "k_posterior_tma");
     return SO_OK;
+}
+
+template <int WARPS>
+int launch_tma(so_handle* h, int bt, const TmaParams& tp, size_t smem, cudaStream_t stream) {
+    switch (bt) {
+        case 6: return launch_tma_one<6, WARPS>(h, tp, smem, stream);
+        case 4: return launch_tma_one<4, WARPS>(h, tp, smem, stream);
+        default: return launch_tma_one<2, WARPS>(h, tp, smem, stream);
+    }
 }
 
 // SO_K2_VARIANT=bulk forces the generate-then-contract kernel on the grid path too (A/B measurements).
@@ -274,7 +296,8 @@ int run_posterior(so_handle* h, int gp, const double* Xstar_d, bool grid, int64_
 
     if (tma) {
         p.RG = g.tma_RG; p.CG = g.tma_CG; p.T = g.tma_T; p.TB = g.tma_BT * g.tma_CG;
-        p.npass = (g.NB + 4 * p.RG - 1) / (4 * p.RG);
+        const int ns = g.tma_warps == 16 ? 2 : 4;
+        p.npass = (g.NB + ns * p.RG - 1) / (ns * p.RG);
         tp.PfFrag = g.PfFrag; tp.Aprime = g.Aprime; tp.a_stride = g.a_stride; tp.s0 = g.ap_s0;
         if (row0 / h->grid.fast_rows < g.ap_s0 || (row0 + M - 1) / h->grid.fast_rows >= g.ap_s1)
             return so_fail(h, SO_ERR_NOT_FITTED, "posterior_grid: rows outside the range given to so_grid_prepare_rows");
@@ -286,11 +309,7 @@ int run_posterior(so_handle* h, int gp, const double* Xstar_d, bool grid, int64_
         tp.first_tile = t0;
         p.ntiles = t1 - t0 + 1;
         const size_t smem = tma_smem(g.tma_kb_pad, p.TB, p.RG, p.T).total;
-        switch (g.tma_BT) {
-            case 6: return launch_tma_one<6>(h, tp, smem, stream);
-            case 4: return launch_tma_one<4>(h, tp, smem, stream);
-            default: return launch_tma_one<2>(h, tp, smem, stream);
-        }
+        return g.tma_warps == 16 ? launch_tma<16>(h, g.tma_BT, tp, smem, stream) : launch_tma<8>(h, g.tma_BT, tp, smem, stream);
     }
     LaunchPlan lp;
     int rc = plan_launch(h, g, M, grid, lp);
@@ -495,7 +514,7 @@ extern "C" int so_grid_prepare_rows(so_handle* h, int gp, int64_t row0, int64_t 
         SO_CUDA(h, cudaMemsetAsync(g.Aprime + (size_t)n_slow * a_stride, 0, sizeof(double2) * 128, stream));
         g.ap_s0 = s_lo; g.ap_s1 = s_hi;
         g.a_stride = a_stride; g.tma_T = pl.T; g.tma_tpb = tpb; g.tma_BT = pl.BT; g.tma_RG = pl.RG; g.tma_CG = pl.CG;
-        g.tma_kb_pad = pl.kb_pad; g.tma_ready = true;
+        g.tma_kb_pad = pl.kb_pad; g.tma_warps = pl.warps; g.tma_ready = true;
     }
     g.grid_ready = true;
     return SO_OK;

@@ -153,32 +153,64 @@ __device__ __forceinline__ void gen_grid(const PostParams& p, double2* __restric
 }
 
 // ---------------------------------------------------------------- contraction
-// One K segment: accumulator slots FIRST..3 are active.  `a` holds the fragments of the current k-block on entry and
-// those of k-block kb_hi+1 on exit (software prefetch, distance one block; the packed operand has a block of slack).
-template <int BT, int FIRST>
-__device__ __forceinline__ void mma_segment(double (&acc)[4][BT][2], double2 (&a)[4], const double2* __restrict__ Afrag,
-                                            const size_t (&abase)[4], const double2* __restrict__ sB, int TB,
+// One K segment: accumulator slots FIRST..NS-1 are active.  `a` holds the fragments of the current k-block on entry and
+// those of k-block kb_hi+1 on exit (software prefetch into registers, distance one block; the packed operand has slack
+// blocks behind it).  The fragments of k-block kb + SO_K2_A_PF_L1 are pulled from L2 into L1 meanwhile (CCTL.PF1, no
+// registers held): the A stream has no reuse, so without it every register prefetch pays a full L2 round trip and with
+// two to four warps per scheduler those waits coincide often enough to idle the FP64 pipe (measured: 14.0 -> 13.4 ms).
+#ifndef SO_K2_A_PF_L1
+#define SO_K2_A_PF_L1 2
+#endif
+template <int BT, int NS, int FIRST>
+__device__ __forceinline__ void mma_segment(double (&acc)[NS][BT][2], double2 (&a)[NS], const double2* __restrict__ Afrag,
+                                            const size_t (&abase)[NS], const double2* __restrict__ sB, int TB,
                                             int kb_lo, int kb_hi) {
     for (int kb = kb_lo; kb <= kb_hi; ++kb) {
-        double2 an[4];
+        double2 an[NS];
 #pragma unroll
-        for (int s = FIRST; s < 4; ++s) an[s] = __ldg(Afrag + abase[s] + (size_t)(kb + 1) * 32);
+        for (int s = FIRST; s < NS; ++s) an[s] = __ldg(Afrag + abase[s] + (size_t)(kb + 1) * 32);
+#if SO_K2_A_PF_L1 > 0
+#pragma unroll
+        for (int s = FIRST; s < NS; ++s)
+            asm volatile("prefetch.global.L1 [%0];\n" ::"l"(Afrag + abase[s] + (size_t)(kb + SO_K2_A_PF_L1) * 32));
+#endif
         const double2* bp = sB + (size_t)kb * TB * 32;
 #pragma unroll
         for (int c = 0; c < BT; ++c) {
             const double2 b = bp[c * 32];
 #pragma unroll
-            for (int s = FIRST; s < 4; ++s) {
+            for (int s = FIRST; s < NS; ++s) {
                 dmma884(acc[s][c][0], acc[s][c][1], a[s].x, b.x);
                 dmma884(acc[s][c][0], acc[s][c][1], a[s].y, b.y);
             }
         }
 #pragma unroll
-        for (int s = FIRST; s < 4; ++s) a[s] = an[s];
+        for (int s = FIRST; s < NS; ++s) a[s] = an[s];
     }
 }
 
-__device__ __forceinline__ int pick4(int r0, int r1, int r2, int r3, int i) {
+template <int BT, int NS, int FIRST>
+struct SegmentChain {       // segments FIRST..NS-1 in order; segment s covers k-blocks ext[s-1]+1 .. ext[s]
+    static __device__ __forceinline__ void run(double (&acc)[NS][BT][2], double2 (&a)[NS], const double2* __restrict__ Afrag,
+                                               const size_t (&abase)[NS], const double2* __restrict__ sB, int TB,
+                                               const int (&ext)[NS]) {
+        mma_segment<BT, NS, FIRST>(acc, a, Afrag, abase, sB, TB, FIRST == 0 ? 0 : ext[FIRST > 0 ? FIRST - 1 : 0] + 1, ext[FIRST]);
+        SegmentChain<BT, NS, FIRST + 1>::run(acc, a, Afrag, abase, sB, TB, ext);
+    }
+};
+template <int BT, int NS>
+struct SegmentChain<BT, NS, NS> {
+    static __device__ __forceinline__ void run(double (&)[NS][BT][2], double2 (&)[NS], const double2* __restrict__,
+                                               const size_t (&)[NS], const double2* __restrict__, int, const int (&)[NS]) {}
+};
+
+// Block rows of a warp in one pass, ascending: {g, 2RG-1-g} (NS = 2) or {g, 2RG-1-g, 2RG+g, 4RG-1-g} (NS = 4) above
+// base = NS * RG * pass -- a pairing that gives every warp the same triangular work.
+template <int NS>
+__device__ __forceinline__ int warp_row(int base, int RG, int g, int i) {
+    const int r0 = base + g, r1 = base + 2 * RG - 1 - g;
+    if (NS == 2) return i == 0 ? r0 : r1;
+    const int r2 = base + 2 * RG + g, r3 = base + 4 * RG - 1 - g;
     return i == 0 ? r0 : (i == 1 ? r1 : (i == 2 ? r2 : r3));
 }
 
@@ -212,46 +244,46 @@ __device__ __forceinline__ void halving_reduce(double (&v)[K], int lane) {
     }
 }
 
-// The whole contraction of one tile for one warp: V = A.B over the warp's block rows (pairing {g, 2RG-1-g, 2RG+g,
-// 4RG-1-g} per pass, which equalises the triangular work) and its BT column tiles, then per column
+// The whole contraction of one tile for one warp: V = A.B over the warp's NS block rows per pass (warp_row) and its BT
+// column tiles, then per column
 //     |V|^2 partial (sum of squares of this warp's rows)  and  V.z partial (the mean's share, z = L^-1 y)
 // taken from the accumulators in one pass, reduced over the 8 row lanes by recursive halving and left in this row
-// group's slot of sSS / sMean (fixed order everywhere => bit-reproducible).
-template <int BT>
+// group's slot of sSS / sMean (fixed order everywhere => bit-reproducible).  NS = 4 with 8 warps per CTA, NS = 2 with 16
+// (half the accumulators per warp, twice the warps per scheduler to cover each other's waits).
+template <int BT, int NS = 4>
 __device__ __forceinline__ void contract_tile(const PostParams& p, const double2* __restrict__ Afrag_lane,
                                               const double2* __restrict__ sB, double* __restrict__ sSST,
                                               double* __restrict__ sMeanT, int g, int cg, int lane) {
     static_assert(BT % 2 == 0, "BT must be even");
+    static_assert(NS == 2 || NS == 4, "two or four block rows per warp and pass");
     const int RG = p.RG, NB = p.NB, TB = p.TB, T = p.T;
     for (int pass = 0; pass < p.npass; ++pass) {
-        const int base = 4 * RG * pass;
-        const int r0 = base + g, r1 = base + 2 * RG - 1 - g, r2 = base + 2 * RG + g, r3 = base + 4 * RG - 1 - g;
+        const int base = NS * RG * pass;
         // rows are ascending; the ones beyond NB (inactive) form a suffix.  Slots are ordered by K extent, inactive
-        // slots (extent -1) first, so that "slots FIRST..3 active" holds in every segment.
-        const int na = (r0 < NB) + (r1 < NB) + (r2 < NB) + (r3 < NB);
-        int ext[4];
-        size_t abase[4];
-        double zs[4];              // z at this lane's row of each slot's block (0 for inactive slots)
+        // slots (extent -1) first, so that "slots FIRST..NS-1 active" holds in every segment.
+        int na = 0;
 #pragma unroll
-        for (int s = 0; s < 4; ++s) {
-            const int src = s - (4 - na);
-            const int r = src >= 0 ? pick4(r0, r1, r2, r3, src) : -1;
+        for (int i = 0; i < NS; ++i) na += warp_row<NS>(base, RG, g, i) < NB;
+        int ext[NS];
+        size_t abase[NS];
+        double zs[NS];             // z at this lane's row of each slot's block (0 for inactive slots)
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            const int src = s - (NS - na);
+            const int r = src >= 0 ? warp_row<NS>(base, RG, g, src) : -1;
             ext[s] = r;
             abase[s] = r >= 0 ? (size_t)r * (r + 1) / 2 * 32 : 0;
             zs[s] = r >= 0 ? __ldg(p.zvec + 8 * r + (lane >> 2)) : 0.0;
         }
-        double acc[4][BT][2];
+        double acc[NS][BT][2];
 #pragma unroll
-        for (int s = 0; s < 4; ++s)
+        for (int s = 0; s < NS; ++s)
 #pragma unroll
             for (int c = 0; c < BT; ++c) { acc[s][c][0] = 0.0; acc[s][c][1] = 0.0; }
-        double2 a[4];
+        double2 a[NS];
 #pragma unroll
-        for (int s = 0; s < 4; ++s) a[s] = __ldg(Afrag_lane + abase[s]);
-        mma_segment<BT, 0>(acc, a, Afrag_lane, abase, sB, TB, 0, ext[0]);
-        mma_segment<BT, 1>(acc, a, Afrag_lane, abase, sB, TB, ext[0] + 1, ext[1]);
-        mma_segment<BT, 2>(acc, a, Afrag_lane, abase, sB, TB, ext[1] + 1, ext[2]);
-        mma_segment<BT, 3>(acc, a, Afrag_lane, abase, sB, TB, ext[2] + 1, ext[3]);
+        for (int s = 0; s < NS; ++s) a[s] = __ldg(Afrag_lane + abase[s]);
+        SegmentChain<BT, NS, 0>::run(acc, a, Afrag_lane, abase, sB, TB, ext);
         // red[c*2+h] = sum of squares, red[2BT + c*2+h] = mean share, for column 8c + 2(lane%4) + h of this column group
         double red[4 * BT];
 #pragma unroll
@@ -260,7 +292,7 @@ __device__ __forceinline__ void contract_tile(const PostParams& p, const double2
             for (int hh = 0; hh < 2; ++hh) {
                 double q2 = 0.0, mz = 0.0;
 #pragma unroll
-                for (int s = 0; s < 4; ++s) {
+                for (int s = 0; s < NS; ++s) {
                     q2 = fma(acc[s][c][hh], acc[s][c][hh], q2);
                     mz = fma(acc[s][c][hh], zs[s], mz);
                 }

@@ -68,8 +68,12 @@ __host__ __device__ inline TmaSmem tma_smem(int kb_pad, int TB, int RG, int T) {
     return L;
 }
 
-template <int BT>
-__global__ void __launch_bounds__(kThreads, 1) k_posterior_tma(const __grid_constant__ TmaParams tp) {
+// WARPS = 8: four block rows per warp and pass (default); WARPS = 16: two (contract_tile<BT, 2>), i.e. four warps per
+// scheduler instead of two -- kept for A/B measurements (see tma_warps() in posterior.cu).
+template <int BT, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) k_posterior_tma(const __grid_constant__ TmaParams tp) {
+    constexpr int NS = WARPS == 16 ? 2 : 4;
+    constexpr int kCtaThreads = WARPS * 32;
     const PostParams& p = tp.p;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const TmaSmem L = tma_smem(tp.kb_pad, p.TB, p.RG, p.T);
@@ -119,14 +123,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_posterior_tma(const __grid_cons
         double* sSST = sSS + (size_t)b * RG * T;
         double* sMeanT = sMean + (size_t)b * RG * T;
 
+        const int64_t left = tp.fast_rows - (int64_t)j * T;
         mbar_wait(&full[b], ((unsigned)(it >> 1)) & 1u);
-        contract_tile<BT>(p, Afrag, sB, sSST, sMeanT, g, cg, lane);
+        // the last tile of a slow block is usually short: contract only the column tiles that hold rows
+        if (BT > 2 && p.CG == 1 && left <= 16) contract_tile<2, NS>(p, Afrag, sB, sSST, sMeanT, g, cg, lane);
+        else if (BT > 4 && p.CG == 1 && left <= 32) contract_tile<4, NS>(p, Afrag, sB, sSST, sMeanT, g, cg, lane);
+        else contract_tile<BT, NS>(p, Afrag, sB, sSST, sMeanT, g, cg, lane);
         __syncthreads();
 
         const int64_t tile_row0 = si * tp.fast_rows + (int64_t)j * T - p.row0;
-        const int64_t left = tp.fast_rows - (int64_t)j * T;
         const int valid_cols = left < T ? (int)left : T;
-        for (int t = threadIdx.x; t < T; t += kThreads) {
+        for (int t = threadIdx.x; t < T; t += kCtaThreads) {
             const int64_t row = tile_row0 + t;
             if (t < valid_cols && row >= 0 && row < p.M) finalize_row(p, sSST, sMeanT, t, row);
         }
