@@ -203,6 +203,63 @@ def test_grid_path_equals_rows_path(d, n, N):
     eng.close()
 
 
+def test_grid_tables_for_a_row_block_only():
+    """so_grid_prepare_rows: a rank builds the scaled-operand table for its own row block; rows inside give the bits of a
+    full preparation, rows outside are refused."""
+    from safeopt_b200.utilities import detect_grid
+    from safeopt_b200._lib import DeviceError
+    w = workloads.grid_workload("t", 4, [9, 14, 40, 11], 40)          # 3960 fast rows x 14 slow indices
+    grid = sb.linearly_spaced_combinations(w.bounds, [9, 14, 40, 11])
+    M = grid.shape[0]
+    eng = DeviceEngine(max_gps=1)
+    eng.fit(0, w.X, w.Y[:, 0], 0, w.lengthscale, w.variance, w.noise_var)
+    eng.define_grid(detect_grid(grid))
+    eng.prepare_grid(0)
+    full_m, full_v = eng.empty((M,)), eng.empty((M,))
+    eng.posterior_grid(0, 0, M, 2.0, 0.0, mean=full_m, var=full_v)
+    lo, hi = 2 * M // 5 + 3, 4 * M // 5 + 1
+    eng.prepare_grid(0, lo, hi - lo)
+    m, v = eng.empty((hi - lo,)), eng.empty((hi - lo,))
+    eng.posterior_grid(0, lo, hi - lo, 2.0, 0.0, mean=m, var=v)
+    assert torch.equal(m, full_m[lo:hi]) and torch.equal(v, full_v[lo:hi])
+    with pytest.raises(DeviceError):
+        eng.posterior_grid(0, 0, M, 2.0, 0.0, mean=full_m, var=full_v)
+    eng.close()
+
+
+def test_chained_set_passes_equal_host_chained():
+    """The *_chain entry points (scalars read from device records) give the records and masks of the host-scalar ones."""
+    from safeopt_b200.engine import MAX_REC_DTYPE, SAFE_REC_DTYPE
+    g = load_golden("expander_g2")
+    gps, grid, fmin = golden_problem(g, "gpu")
+    opt = sb.SafeOpt(gps, grid, fmin, beta=float(g["beta"]), threshold=float(g["threshold"]))
+    opt.update_confidence_intervals()
+    eng, G, M = opt._engine, len(gps), grid.shape[0]
+    rec_s, rec_m = eng.zeros((1, 64), "u8"), eng.zeros((1, 64), "u8")
+    eng.reduce_safe(opt._Q_d, G, 0, opt._S_d, rec_s)
+    safe = rec_s.cpu().numpy().view(SAFE_REC_DTYPE).reshape(-1)[0]
+    thr = np.full(G, float(g["threshold"]) * float(g["beta"]))
+    out = {}
+    for chained in (False, True):
+        Mm, key, row, cnt = eng.zeros((M,), "u8"), eng.empty((M,)), eng.empty((M,), "i64"), eng.zeros((1,), "i64")
+        if chained:
+            eng.maximizers_chain(opt._Q_d, G, 0, opt._S_d, rec_s, 1, opt.scaling, Mm, rec_m)
+        else:
+            eng.maximizers(opt._Q_d, G, 0, opt._S_d, float(safe["max_l0"]), opt.scaling, Mm, rec_m)
+        mx = rec_m.cpu().numpy().view(MAX_REC_DTYPE).reshape(-1)[0].copy()
+        if chained:
+            eng.candidates_chain(opt._Q_d, G, 0, opt._S_d, Mm, rec_m, 1, opt.scaling, thr, None, key, row, cnt)
+        else:
+            eng.candidates(opt._Q_d, G, 0, opt._S_d, Mm, float(mx["max_width0"]) / opt.scaling[0], opt.scaling, thr, None, key, row, cnt)
+        n = int(cnt.item())
+        order = torch.argsort(row[:n])
+        out[chained] = (mx, Mm.cpu().numpy(), row[:n][order].cpu().numpy(), key[:n][order].cpu().numpy())
+    assert out[False][0] == out[True][0] and int(out[True][0]["n_max"]) == int(unpack_mask(g["M"], M).sum())
+    for a, b in zip(out[False][1:], out[True][1:]):
+        assert np.array_equal(a, b)
+    assert out[True][2].size > 0
+
+
 def _check_argmax(row, row_ref, values_ref, mask_ref, tol):
     """`row` must be the reference's argmax row; if the reference's values tie within 100*tol, any tied row passes."""
     cand = np.flatnonzero(mask_ref)

@@ -60,6 +60,25 @@ def test_fails_loudly_without_gpu():
         sb.SafeOptSwarm(gp, 0.0, bounds=[(-1, 1)])
 
 
+def test_weak_scaling_workload_shapes():
+    """bench.py --scaling weak multiplies the points of axis 1 (the slowest axis of the reference row order) by the rank
+    count, so that contiguous row blocks of equal size are whole axis-1 slabs."""
+    from safeopt_b200 import workloads
+    from safeopt_b200.distributed import shard_bounds
+    from safeopt_b200.utilities import grid_row_strides
+    w = workloads.config("C4")
+    assert w.samples_per_axis == [50] * 4 and w.n_rows == 50 ** 4
+    per = w.samples_per_axis
+    per[1] *= 8
+    w.num_samples = per
+    assert w.n_rows == 8 * 50 ** 4
+    strides = grid_row_strides(w.samples_per_axis)
+    assert strides[1] == max(strides) == 50 ** 3
+    for r in range(8):
+        lo, hi = shard_bounds(w.n_rows, 8, r)
+        assert hi - lo == 50 ** 4 and lo % (50 * strides[1]) == 0
+
+
 def test_product_never_imports_oracle():
     """The oracle is test infrastructure; no module of the product may import it."""
     pkg = os.path.join(ROOT, "safeopt_b200")

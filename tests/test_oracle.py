@@ -84,6 +84,15 @@ def test_grid_order_matches_reference_description():
     assert g1.shape == (5, 1) and g1[-1, 0] == 1.0
 
 
+def test_grid_rows_equal_full_grid():
+    """port.grid_rows (used by the CPU baseline to take a sample without building a 50M-row grid) is bit-identical to
+    the rows of linearly_spaced_combinations."""
+    for bounds, n in [([(-5, 5)] * 4, [5, 10, 3, 4]), ([(-1, 2)], 7), ([(-5, 5), (0, 1)], [4, 6]), ([(-2, 2)] * 3, 5)]:
+        full = port.linearly_spaced_combinations(bounds, n)
+        rows = np.arange(full.shape[0])[::-1]
+        assert np.array_equal(port.grid_rows(bounds, n, rows), full[rows])
+
+
 def test_penalty_matches_reference_table():
     g = load_golden("swarm_fitness_3d")
     assert np.array_equal(port.penalty(g["penalty_in"]), g["penalty_out"])
