@@ -145,6 +145,25 @@ int so_posterior_grid(so_handle* h, int gp, int64_t row0, int64_t M, double beta
                       uint8_t* S_d, int safe_mode, void* stream);
 int so_posterior_rows_simple(so_handle* h, int gp, const double* Xstar_d, int64_t M,
                              double* mean_d, double* var_d, void* stream);
+/* GPs that share their inputs X, kernel (family, lengthscales, variance) and noise share K(X,X), its
+ * factor and the kernel rows k(x*, X): V = L^-1 k and the variance are common, only the mean
+ * V . (L^-1 y_g) differs.  The _multi variants evaluate n <= 4 such GPs with ONE contraction
+ * (the reference calls predict_noiseless once per GP, safeopt/gp_opt.py:468-476 and :969-973).
+ *   gps_h    : n GP indices (the first one provides the factorisation); the library checks size,
+ *              kernel and noise for equality -- equal X is the caller's responsibility
+ *   fmin_h, q_col_h : n entries; mean_dh / var_dh : host arrays of n device pointers (entries or
+ *              the arrays themselves may be NULL)
+ *   S_d      : combined per safe_mode with AND_g (l_g > fmin_g)
+ * Returns SO_ERR_CAPACITY when the shared-memory tile has no room for the extra partial sums; the
+ * caller then evaluates the GPs one by one. */
+int so_posterior_rows_multi(so_handle* h, int n, const int* gps_h, const double* Xstar_d, int64_t M,
+                            double beta, const double* fmin_h, double* const* mean_dh,
+                            double* const* var_dh, double* Q_d, int q_stride, const int* q_col_h,
+                            uint8_t* S_d, int safe_mode, void* stream);
+int so_posterior_grid_multi(so_handle* h, int n, const int* gps_h, int64_t row0, int64_t M,
+                            double beta, const double* fmin_h, double* const* mean_dh,
+                            double* const* var_dh, double* Q_d, int q_stride, const int* q_col_h,
+                            uint8_t* S_d, int safe_mode, void* stream);
 /* Materialise grid rows [row0, row0+M) as an (M x d) row-major array (tests, query point). */
 int so_grid_rows(so_handle* h, int64_t row0, int64_t M, double* X_d, void* stream);
 

@@ -20,8 +20,10 @@ namespace {
 template <int BT, int KIND, bool GRID>
 __global__ void __launch_bounds__(kThreads, 1) k_posterior(const __grid_constant__ PostParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const SmemLayout L = smem_layout(p.NB, p.T, p.d, p.RG, GRID);
+    const int n_extra = p.n_out - 1;
+    const SmemLayout L = smem_layout(p.NB, p.T, p.d, p.RG, GRID, n_extra);
     double2* sK = reinterpret_cast<double2*>(smem_raw);
+    double* sMeanX = reinterpret_cast<double*>(smem_raw + L.meanx_off);
     double* sXs = reinterpret_cast<double*>(smem_raw + L.xs_off);
     double* sXt = reinterpret_cast<double*>(smem_raw + L.xt_off);
     double* sSS = reinterpret_cast<double*>(smem_raw + L.ss_off);
@@ -43,6 +45,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_posterior(const __grid_constant
         const int64_t tile_local0 = tile * T;
         double* sSST = sSS + (size_t)par * RG * T;
         double* sMeanT = sMean + (size_t)par * RG * T;
+        double* sMeanXT = sMeanX + (size_t)par * n_extra * RG * T;
         if (GRID) gen_grid(p, sK, p.row0 + tile_local0, warp, lane);
         else gen_rows<KIND>(p, sK, sXs, sXt + (size_t)par * T * p.d, sExpT, warp, lane);
         __syncthreads();
@@ -51,11 +54,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_posterior(const __grid_constant
             const int64_t next = tile + gridDim.x;
             if (next < p.ntiles) load_tile_rows(p, sXt + (size_t)(par ^ 1) * T * p.d, next * T);
         }
-        contract_tile<BT>(p, p.Afrag + lane, sK + (size_t)(cg * BT) * 32 + lane, sSST, sMeanT, g, cg, lane);
+        contract_tile<BT>(p, p.Afrag + lane, sK + (size_t)(cg * BT) * 32 + lane, sSST, sMeanT, sMeanXT, g, cg, lane);
         __syncthreads();
         for (int t = threadIdx.x; t < T; t += kThreads) {
             const int64_t row = tile_local0 + t;
-            if (row < p.M) finalize_row(p, sSST, sMeanT, t, row);
+            if (row < p.M) finalize_row(p, sSST, sMeanT, sMeanXT, t, row);
         }
         // the partial-sum buffers alternate with `par`; sK is rewritten only after the barrier at the top of the next
         // iteration's contraction, which every thread reaches after its epilogue
@@ -154,12 +157,12 @@ void row_groups(int NB, int& RG, int& CG) {
     else { RG = 1; CG = 8; }
 }
 
-int plan_launch(so_handle* h, const GPState& g, int64_t M, bool grid, LaunchPlan& lp) {
+int plan_launch(so_handle* h, const GPState& g, int64_t M, bool grid, int n_extra, LaunchPlan& lp) {
     const int NB = g.NB;
     row_groups(NB, lp.RG, lp.CG);
     const size_t limit = (size_t)h->smem_optin;
     int BT = 8;
-    while (BT >= 2 && smem_layout(NB, 8 * BT * lp.CG, g.d, lp.RG, grid).total > limit) BT >>= 1;
+    while (BT >= 2 && smem_layout(NB, 8 * BT * lp.CG, g.d, lp.RG, grid, n_extra).total > limit) BT >>= 1;
     if (BT < 2) return so_fail(h, SO_ERR_CAPACITY, "posterior: N too large for the shared-memory tile (N <= ~1600)");
     // few tiles -> smaller tiles so that more SMs get work
     while (BT > 2 && (M + 8 * BT * lp.CG - 1) / (8 * BT * lp.CG) < 2 * (int64_t)h->num_sms) BT >>= 1;
@@ -167,9 +170,19 @@ int plan_launch(so_handle* h, const GPState& g, int64_t M, bool grid, LaunchPlan
     lp.T = 8 * BT * lp.CG;
     lp.TB = BT * lp.CG;
     lp.npass = (NB + 4 * lp.RG - 1) / (4 * lp.RG);
-    lp.smem = smem_layout(NB, lp.T, g.d, lp.RG, grid).total;
+    lp.smem = smem_layout(NB, lp.T, g.d, lp.RG, grid, n_extra).total;
     return SO_OK;
 }
+
+// Outputs 1..n-1 of a launch that evaluates several GPs sharing one factorisation (so_posterior_*_multi).
+struct ExtraOut {
+    int n = 0;
+    int gp[kMaxOut - 1];
+    double fmin[kMaxOut - 1];
+    double* mean[kMaxOut - 1];
+    double* var[kMaxOut - 1];
+    int q_col[kMaxOut - 1];
+};
 
 template <int BT, int KIND, bool GRID>
 int launch_one(so_handle* h, const PostParams& p, const LaunchPlan& lp, cudaStream_t stream) {
@@ -256,7 +269,7 @@ bool force_bulk() {
 
 int run_posterior(so_handle* h, int gp, const double* Xstar_d, bool grid, int64_t row0, int64_t M, double beta, double fmin,
                   double* mean_d, double* var_d, double* Q_d, int q_stride, int q_col, uint8_t* S_d, int safe_mode,
-                  void* stream_) {
+                  void* stream_, const ExtraOut* extra = nullptr) {
     if (!h) return SO_ERR_BAD_ARG;
     if (gp < 0 || gp >= h->max_gps) return so_fail(h, SO_ERR_BAD_ARG, "posterior: gp index out of range");
     GPState& g = h->gps[gp];
@@ -293,6 +306,24 @@ int run_posterior(so_handle* h, int gp, const double* Xstar_d, bool grid, int64_
     }
     p.beta = beta; p.fmin = fmin;
     p.mean = mean_d; p.var = var_d; p.Q = Q_d; p.q_stride = q_stride; p.q_col = q_col; p.S = S_d; p.safe_mode = safe_mode;
+    p.n_out = 1;
+    for (int o = 0; o < kMaxOut - 1; ++o) { p.zvec_x[o] = nullptr; p.fmin_x[o] = 0.0; p.mean_x[o] = nullptr; p.var_x[o] = nullptr; p.q_col_x[o] = 0; }
+    if (extra) {
+        for (int o = 0; o < extra->n; ++o) {
+            if (extra->gp[o] < 0 || extra->gp[o] >= h->max_gps) return so_fail(h, SO_ERR_BAD_ARG, "posterior_multi: gp index out of range");
+            const GPState& e = h->gps[extra->gp[o]];
+            if (!e.fitted) return so_fail(h, SO_ERR_NOT_FITTED, "posterior_multi: GP not fitted");
+            bool same = e.N == g.N && e.d == g.d && e.kind == g.kind && e.variance == g.variance && e.noise == g.noise;
+            for (int j = 0; j < g.d && same; ++j) same = e.inv_ls[j] == g.inv_ls[j];
+            if (!same) return so_fail(h, SO_ERR_BAD_ARG, "posterior_multi: the GPs do not share size, kernel and noise");
+            if (Q_d && (extra->q_col[o] < 0 || extra->q_col[o] + 2 > q_stride))
+                return so_fail(h, SO_ERR_BAD_ARG, "posterior_multi: Q column out of range");
+            p.zvec_x[o] = e.zvec; p.fmin_x[o] = extra->fmin[o]; p.mean_x[o] = extra->mean[o]; p.var_x[o] = extra->var[o];
+            p.q_col_x[o] = extra->q_col[o];
+        }
+        p.n_out = 1 + extra->n;
+    }
+    const int n_extra = p.n_out - 1;
 
     if (tma) {
         p.RG = g.tma_RG; p.CG = g.tma_CG; p.T = g.tma_T; p.TB = g.tma_BT * g.tma_CG;
@@ -308,11 +339,13 @@ int run_posterior(so_handle* h, int gp, const double* Xstar_d, bool grid, int64_
         const int64_t t1 = (last_row / F) * g.tma_tpb + (last_row % F) / p.T;
         tp.first_tile = t0;
         p.ntiles = t1 - t0 + 1;
-        const size_t smem = tma_smem(g.tma_kb_pad, p.TB, p.RG, p.T).total;
+        const size_t smem = tma_smem(g.tma_kb_pad, p.TB, p.RG, p.T, n_extra).total;
+        if (smem > (size_t)h->smem_optin)
+            return so_fail(h, SO_ERR_CAPACITY, "posterior_multi: the tile does not fit with that many outputs; evaluate the GPs one by one");
         return g.tma_warps == 16 ? launch_tma<16>(h, g.tma_BT, tp, smem, stream) : launch_tma<8>(h, g.tma_BT, tp, smem, stream);
     }
     LaunchPlan lp;
-    int rc = plan_launch(h, g, M, grid, lp);
+    int rc = plan_launch(h, g, M, grid, n_extra, lp);
     if (rc) return rc;
     p.RG = lp.RG; p.CG = lp.CG; p.T = lp.T; p.TB = lp.TB; p.npass = lp.npass;
     p.ntiles = (M + p.T - 1) / p.T;
@@ -336,6 +369,34 @@ extern "C" int so_posterior_grid(so_handle* h, int gp, int64_t row0, int64_t M, 
                                  double* var_d, double* Q_d, int q_stride, int q_col, uint8_t* S_d, int safe_mode,
                                  void* stream) {
     return run_posterior(h, gp, nullptr, true, row0, M, beta, fmin, mean_d, var_d, Q_d, q_stride, q_col, S_d, safe_mode, stream);
+}
+
+static int run_multi(so_handle* h, int n, const int* gps_h, const double* Xstar_d, bool grid, int64_t row0, int64_t M, double beta,
+                     const double* fmin_h, double* const* mean_dh, double* const* var_dh, double* Q_d, int q_stride,
+                     const int* q_col_h, uint8_t* S_d, int safe_mode, void* stream) {
+    if (!h || !gps_h || !fmin_h || !q_col_h) return SO_ERR_BAD_ARG;
+    if (n < 1 || n > kMaxOut) return so_fail(h, SO_ERR_BAD_ARG, "posterior_multi: 1 <= n <= 4");
+    ExtraOut ex;
+    ex.n = n - 1;
+    for (int o = 1; o < n; ++o) {
+        ex.gp[o - 1] = gps_h[o]; ex.fmin[o - 1] = fmin_h[o]; ex.q_col[o - 1] = q_col_h[o];
+        ex.mean[o - 1] = mean_dh ? mean_dh[o] : nullptr;
+        ex.var[o - 1] = var_dh ? var_dh[o] : nullptr;
+    }
+    return run_posterior(h, gps_h[0], Xstar_d, grid, row0, M, beta, fmin_h[0], mean_dh ? mean_dh[0] : nullptr,
+                         var_dh ? var_dh[0] : nullptr, Q_d, q_stride, q_col_h[0], S_d, safe_mode, stream, &ex);
+}
+
+extern "C" int so_posterior_rows_multi(so_handle* h, int n, const int* gps_h, const double* Xstar_d, int64_t M, double beta,
+                                       const double* fmin_h, double* const* mean_dh, double* const* var_dh, double* Q_d,
+                                       int q_stride, const int* q_col_h, uint8_t* S_d, int safe_mode, void* stream) {
+    return run_multi(h, n, gps_h, Xstar_d, false, 0, M, beta, fmin_h, mean_dh, var_dh, Q_d, q_stride, q_col_h, S_d, safe_mode, stream);
+}
+
+extern "C" int so_posterior_grid_multi(so_handle* h, int n, const int* gps_h, int64_t row0, int64_t M, double beta,
+                                       const double* fmin_h, double* const* mean_dh, double* const* var_dh, double* Q_d,
+                                       int q_stride, const int* q_col_h, uint8_t* S_d, int safe_mode, void* stream) {
+    return run_multi(h, n, gps_h, nullptr, true, row0, M, beta, fmin_h, mean_dh, var_dh, Q_d, q_stride, q_col_h, S_d, safe_mode, stream);
 }
 
 extern "C" int so_posterior_rows_simple(so_handle* h, int gp, const double* Xstar_d, int64_t M, double* mean_d,

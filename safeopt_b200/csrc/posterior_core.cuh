@@ -9,6 +9,7 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kWarps = 8;
 constexpr int kGridMaxDim = 6;   // grid fast path (larger d uses explicit rows)
+constexpr int kMaxOut = 4;       // GPs evaluated by one launch when they share the factorisation (so_posterior_*_multi)
 
 struct PostParams {
     int N, NB, d, RG, CG, T, TB, npass, kind;
@@ -31,14 +32,24 @@ struct PostParams {
     int q_stride, q_col;
     uint8_t* S;
     int safe_mode;
+    // Further GPs that share X, kernel and noise with this one (same L^-1, same kernel rows, same variance): only
+    // z_o = L^-1 y_o differs, so they cost one more V.z_o per row instead of one more contraction.  Output 0 is described
+    // by the fields above, outputs 1..n_out-1 by the arrays below.
+    int n_out;
+    const double* zvec_x[kMaxOut - 1];
+    double fmin_x[kMaxOut - 1];
+    double* mean_x[kMaxOut - 1];
+    double* var_x[kMaxOut - 1];
+    int q_col_x[kMaxOut - 1];
 };
 
 struct SmemLayout {
-    size_t k_bytes, xs_off, xt_off, ss_off, mean_off, exp_off, total;
+    size_t k_bytes, xs_off, xt_off, ss_off, mean_off, meanx_off, exp_off, total;
 };
 
-// [ Kx tile | scaled training inputs | two tiles of candidate rows | |V|^2 partials x2 | mean partials x2 | exp table ]
-__host__ __device__ inline SmemLayout smem_layout(int NB, int T, int d, int RG, bool grid) {
+// [ Kx tile | scaled training inputs | two tiles of candidate rows | |V|^2 partials x2 | mean partials x2 |
+//   mean partials of the further outputs x2 | exp table ]
+__host__ __device__ inline SmemLayout smem_layout(int NB, int T, int d, int RG, bool grid, int n_extra = 0) {
     SmemLayout L;
     const size_t Npad = 8 * (size_t)NB;
     L.k_bytes = Npad * T * sizeof(double);
@@ -46,7 +57,8 @@ __host__ __device__ inline SmemLayout smem_layout(int NB, int T, int d, int RG, 
     L.xt_off = L.xs_off + (grid ? 0 : Npad * d * sizeof(double));
     L.ss_off = L.xt_off + (grid ? 0 : 2 * (size_t)T * d * sizeof(double));
     L.mean_off = L.ss_off + 2 * (size_t)RG * T * sizeof(double);
-    L.exp_off = L.mean_off + 2 * (size_t)RG * T * sizeof(double);
+    L.meanx_off = L.mean_off + 2 * (size_t)RG * T * sizeof(double);
+    L.exp_off = L.meanx_off + 2 * (size_t)n_extra * RG * T * sizeof(double);
     L.total = L.exp_off + 64 * sizeof(double);
     return L;
 }
@@ -253,7 +265,7 @@ __device__ __forceinline__ void halving_reduce(double (&v)[K], int lane) {
 template <int BT, int NS = 4>
 __device__ __forceinline__ void contract_tile(const PostParams& p, const double2* __restrict__ Afrag_lane,
                                               const double2* __restrict__ sB, double* __restrict__ sSST,
-                                              double* __restrict__ sMeanT, int g, int cg, int lane) {
+                                              double* __restrict__ sMeanT, double* __restrict__ sMeanXT, int g, int cg, int lane) {
     static_assert(BT % 2 == 0, "BT must be even");
     static_assert(NS == 2 || NS == 4, "two or four block rows per warp and pass");
     const int RG = p.RG, NB = p.NB, TB = p.TB, T = p.T;
@@ -310,13 +322,50 @@ __device__ __forceinline__ void contract_tile(const PostParams& p, const double2
             double* dst = (is_mean ? sMeanT : sSST) + (size_t)g * T + (size_t)(cg * BT + (ch >> 1)) * 8 + 2 * (lane & 3) + (ch & 1);
             *dst = pass == 0 ? red[i] : *dst + red[i];
         }
+        // further outputs sharing this factorisation: V.z_o from the same accumulators, two outputs per reduction
+        // (plane o-1 of sMeanXT holds output o's partials, laid out like sMeanT)
+        for (int o = 1; o < p.n_out; o += 2) {
+            const bool two = o + 1 < p.n_out;
+            double za[NS], zb[NS];
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                const int r = ext[s];
+                za[s] = r >= 0 ? __ldg(p.zvec_x[o - 1] + 8 * r + (lane >> 2)) : 0.0;
+                zb[s] = (two && r >= 0) ? __ldg(p.zvec_x[o] + 8 * r + (lane >> 2)) : 0.0;
+            }
+            double red2[4 * BT];
+#pragma unroll
+            for (int c = 0; c < BT; ++c)
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    double ma = 0.0, mb = 0.0;
+#pragma unroll
+                    for (int s = 0; s < NS; ++s) {
+                        ma = fma(acc[s][c][hh], za[s], ma);
+                        mb = fma(acc[s][c][hh], zb[s], mb);
+                    }
+                    red2[c * 2 + hh] = ma;
+                    red2[2 * BT + c * 2 + hh] = mb;
+                }
+            halving_reduce<4 * BT>(red2, lane);
+#pragma unroll
+            for (int i = 0; i < BT / 2; ++i) {
+                const int idx = first + i;
+                const bool second = idx >= 2 * BT;
+                const int ch = second ? idx - 2 * BT : idx;
+                if (second && !two) continue;
+                double* dst = sMeanXT + (size_t)(o - 1 + (second ? 1 : 0)) * p.RG * T + (size_t)g * T +
+                              (size_t)(cg * BT + (ch >> 1)) * 8 + 2 * (lane & 3) + (ch & 1);
+                *dst = pass == 0 ? red2[i] : *dst + red2[i];
+            }
+        }
     }
 }
 
 // Finalise one row from the per-row-group partials: var = max(k** - |V|^2, 1e-15), l/u = mean -/+ beta sqrt(var) with
 // separate multiply and add roundings (NumPy does not contract, gp_opt.py:475-476), S bit (strict >, gp_opt.py:481).
 __device__ __forceinline__ void finalize_row(const PostParams& p, const double* __restrict__ sSST, const double* __restrict__ sMeanT,
-                                             int t, int64_t row) {
+                                             const double* __restrict__ sMeanXT, int t, int64_t row) {
     const int T = p.T, RG = p.RG;
     double sumsq = 0.0, mu = 0.0;
     for (int g = 0; g < RG; ++g) { sumsq += sSST[(size_t)g * T + t]; mu += sMeanT[(size_t)g * T + t]; }
@@ -332,10 +381,22 @@ __device__ __forceinline__ void finalize_row(const PostParams& p, const double* 
         if ((p.q_stride & 1) == 0 && (p.q_col & 1) == 0) *reinterpret_cast<double2*>(qp) = make_double2(lo, up);
         else { qp[0] = lo; qp[1] = up; }
     }
-    if (p.safe_mode != SO_SAFE_NONE && p.S) {
-        const uint8_t safe = lo > p.fmin ? 1 : 0;
-        p.S[row] = p.safe_mode == SO_SAFE_WRITE ? safe : (uint8_t)(p.S[row] & safe);
+    uint8_t safe = lo > p.fmin ? 1 : 0;
+    for (int o = 1; o < p.n_out; ++o) {                  // same variance, own mean / bounds / threshold
+        double mo = 0.0;
+        for (int g = 0; g < RG; ++g) mo += sMeanXT[((size_t)(o - 1) * RG + g) * T + t];
+        const double lo_o = __dsub_rn(mo, bs), up_o = __dadd_rn(mo, bs);
+        if (p.mean_x[o - 1]) p.mean_x[o - 1][row] = mo;
+        if (p.var_x[o - 1]) p.var_x[o - 1][row] = v;
+        if (p.Q) {
+            double* qp = p.Q + (size_t)row * p.q_stride + p.q_col_x[o - 1];
+            if ((p.q_stride & 1) == 0 && (p.q_col_x[o - 1] & 1) == 0) *reinterpret_cast<double2*>(qp) = make_double2(lo_o, up_o);
+            else { qp[0] = lo_o; qp[1] = up_o; }
+        }
+        safe &= lo_o > p.fmin_x[o - 1] ? 1 : 0;
     }
+    if (p.safe_mode != SO_SAFE_NONE && p.S)
+        p.S[row] = p.safe_mode == SO_SAFE_WRITE ? safe : (uint8_t)(p.S[row] & safe);
 }
 
 __device__ __forceinline__ void load_tile_rows(const PostParams& p, double* __restrict__ sXt, int64_t tile_local0) {

@@ -56,14 +56,15 @@ struct TmaParams {
     int kb_pad;                       // k-blocks per tile in the table (4 * ceil(NB / 4))
 };
 
-struct TmaSmem { size_t buf_bytes, ss_off, mean_off, bar_off, total; };
+struct TmaSmem { size_t buf_bytes, ss_off, mean_off, meanx_off, bar_off, total; };
 
-__host__ __device__ inline TmaSmem tma_smem(int kb_pad, int TB, int RG, int T) {
+__host__ __device__ inline TmaSmem tma_smem(int kb_pad, int TB, int RG, int T, int n_extra = 0) {
     TmaSmem L;
     L.buf_bytes = (size_t)kb_pad * TB * 512;
     L.ss_off = 2 * L.buf_bytes;
     L.mean_off = L.ss_off + 2 * (size_t)RG * T * sizeof(double);
-    L.bar_off = L.mean_off + 2 * (size_t)RG * T * sizeof(double);
+    L.meanx_off = L.mean_off + 2 * (size_t)RG * T * sizeof(double);
+    L.bar_off = L.meanx_off + 2 * (size_t)n_extra * RG * T * sizeof(double);
     L.total = L.bar_off + 64;
     return L;
 }
@@ -76,10 +77,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_posterior_tma(const __grid_co
     constexpr int kCtaThreads = WARPS * 32;
     const PostParams& p = tp.p;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const TmaSmem L = tma_smem(tp.kb_pad, p.TB, p.RG, p.T);
+    const int n_extra = p.n_out - 1;
+    const TmaSmem L = tma_smem(tp.kb_pad, p.TB, p.RG, p.T, n_extra);
     double2* sBuf = reinterpret_cast<double2*>(smem_raw);
     double* sSS = reinterpret_cast<double*>(smem_raw + L.ss_off);
     double* sMean = reinterpret_cast<double*>(smem_raw + L.mean_off);
+    double* sMeanX = reinterpret_cast<double*>(smem_raw + L.meanx_off);
     unsigned long long* full = reinterpret_cast<unsigned long long*>(smem_raw + L.bar_off);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int RG = p.RG, T = p.T, TB = p.TB;
@@ -122,20 +125,21 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_posterior_tma(const __grid_co
         const double2* sB = sBuf + (size_t)b * buf_elems + (size_t)(cg * BT) * 32 + lane;
         double* sSST = sSS + (size_t)b * RG * T;
         double* sMeanT = sMean + (size_t)b * RG * T;
+        double* sMeanXT = sMeanX + (size_t)b * n_extra * RG * T;
 
         const int64_t left = tp.fast_rows - (int64_t)j * T;
         mbar_wait(&full[b], ((unsigned)(it >> 1)) & 1u);
         // the last tile of a slow block is usually short: contract only the column tiles that hold rows
-        if (BT > 2 && p.CG == 1 && left <= 16) contract_tile<2, NS>(p, Afrag, sB, sSST, sMeanT, g, cg, lane);
-        else if (BT > 4 && p.CG == 1 && left <= 32) contract_tile<4, NS>(p, Afrag, sB, sSST, sMeanT, g, cg, lane);
-        else contract_tile<BT, NS>(p, Afrag, sB, sSST, sMeanT, g, cg, lane);
+        if (BT > 2 && p.CG == 1 && left <= 16) contract_tile<2, NS>(p, Afrag, sB, sSST, sMeanT, sMeanXT, g, cg, lane);
+        else if (BT > 4 && p.CG == 1 && left <= 32) contract_tile<4, NS>(p, Afrag, sB, sSST, sMeanT, sMeanXT, g, cg, lane);
+        else contract_tile<BT, NS>(p, Afrag, sB, sSST, sMeanT, sMeanXT, g, cg, lane);
         __syncthreads();
 
         const int64_t tile_row0 = si * tp.fast_rows + (int64_t)j * T - p.row0;
         const int valid_cols = left < T ? (int)left : T;
         for (int t = threadIdx.x; t < T; t += kCtaThreads) {
             const int64_t row = tile_row0 + t;
-            if (t < valid_cols && row >= 0 && row < p.M) finalize_row(p, sSST, sMeanT, t, row);
+            if (t < valid_cols && row >= 0 && row < p.M) finalize_row(p, sSST, sMeanT, sMeanXT, t, row);
         }
     }
 }

@@ -179,6 +179,30 @@ class DeviceEngine:
         self._check(rc, "so_posterior_grid")
         self.launches += 1 if M else 0
 
+    def posterior_multi(self, gps, Xstar, row0, M, beta, fmins, means=None, variances=None, Q=None, q_cols=None, S=None,
+                        safe_mode=_lib.SAFE_NONE) -> bool:
+        """Several GPs that share X, kernel and noise in ONE launch (one contraction, one V.z per GP).  ``Xstar`` = explicit
+        rows or ``None`` for the defined grid.  Returns False when the device has no room for the extra outputs (the caller
+        then evaluates the GPs one by one)."""
+        n = len(gps)
+        gi = (C.c_int * n)(*[int(g) for g in gps])
+        fm = _np_f64(fmins)
+        qc = (C.c_int * n)(*[int(c) for c in (q_cols if q_cols is not None else [0] * n)])
+        mp = (C.c_void_p * n)(*[0 if means is None or t is None else t.data_ptr() for t in (means or [None] * n)])
+        vp = (C.c_void_p * n)(*[0 if variances is None or t is None else t.data_ptr() for t in (variances or [None] * n)])
+        q_stride = 0 if Q is None else Q.shape[1]
+        if Xstar is None:
+            rc = self.lib.so_posterior_grid_multi(self.handle, n, gi, int(row0), int(M), float(beta), _hptr(fm), mp, vp, _ptr(Q),
+                                                  q_stride, qc, _ptr(S), safe_mode, self._stream())
+        else:
+            rc = self.lib.so_posterior_rows_multi(self.handle, n, gi, _ptr(Xstar), int(M), float(beta), _hptr(fm), mp, vp,
+                                                  _ptr(Q), q_stride, qc, _ptr(S), safe_mode, self._stream())
+        if rc == _lib.SO_ERR_CAPACITY:
+            return False
+        self._check(rc, "so_posterior_multi")
+        self.launches += 1 if M else 0
+        return True
+
     def posterior_rows_simple(self, gp, Xstar):
         M = Xstar.shape[0]
         mean, var = self.empty((M,)), self.empty((M,))

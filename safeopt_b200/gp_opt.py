@@ -168,6 +168,10 @@ class _DeviceFits:
         self.appends = 0
         self.removals = 0
         self.incremental = os.environ.get("SAFEOPT_B200_INCREMENTAL_FIT", "1") != "0"
+        # GPs with identical inputs, kernel and noise share K(X,X), its factor and every kernel row: they are evaluated by
+        # one launch (one contraction, one V.z per GP).  SAFEOPT_B200_SHARE_FITS=0 evaluates every GP on its own.
+        self.share = os.environ.get("SAFEOPT_B200_SHARE_FITS", "1") != "0"
+        self.groups = [[i] for i in range(len(gps))]
 
     def refresh(self, after_fit=None):
         for i, gp in enumerate(self.gps):
@@ -198,6 +202,23 @@ class _DeviceFits:
             self.hypers[i] = hyper
             if after_fit is not None:
                 after_fit(i, hyper)
+        self._regroup()
+
+    MAX_GROUP = 4       # kMaxOut of the kernels
+
+    def _regroup(self):
+        """Partition the GPs into groups that share (X, kernel, noise); order of first appearance, at most MAX_GROUP each."""
+        groups, index = [], {}
+        for i, data in enumerate(self._data):
+            key = None if (data is None or not self.share) else (data[0].shape, data[0].tobytes(), data[2])
+            slot = index.get(key) if key is not None else None
+            if slot is None or len(groups[slot]) >= self.MAX_GROUP:
+                if key is not None:
+                    index[key] = len(groups)
+                groups.append([i])
+            else:
+                groups[slot].append(i)
+        self.groups = groups
 
     def invalidate(self):
         """Forget the resident fits: the next refresh refits every GP from scratch."""
@@ -398,14 +419,27 @@ class SafeOpt(GaussianProcessOptimization):
         self._fits.refresh(self._after_fit)
         eng = self._engine
         m_local = self._row1 - self._row0
-        for i in range(len(self.gps)):
-            mode = _lib.SAFE_WRITE if i == 0 else _lib.SAFE_AND
-            if self._use_grid_kernel(i):
-                eng.posterior_grid(i, self._row0, m_local, beta, self.fmin[i], mean=self._mean_d[i], var=self._var_d[i],
-                                   Q=self._Q_d, q_col=2 * i, S=self._S_d, safe_mode=mode)
-            else:
-                eng.posterior_rows(i, self._ensure_rows_on_device(), beta, self.fmin[i], mean=self._mean_d[i],
-                                   var=self._var_d[i], Q=self._Q_d, q_col=2 * i, S=self._S_d, safe_mode=mode)
+        first = True
+        for group in self._fits.groups:
+            # GPs that share data, kernel and noise go through one launch; the S bit is the AND over all GPs (gp_opt.py:481)
+            rows_arg = None if self._use_grid_kernel(group[0]) else self._ensure_rows_on_device()
+            done = False
+            if len(group) > 1:
+                done = eng.posterior_multi(group, rows_arg, self._row0, m_local, beta, [self.fmin[i] for i in group],
+                                           means=[self._mean_d[i] for i in group], variances=[self._var_d[i] for i in group],
+                                           Q=self._Q_d, q_cols=[2 * i for i in group], S=self._S_d,
+                                           safe_mode=_lib.SAFE_WRITE if first else _lib.SAFE_AND)
+                first = first and not done
+            if not done:
+                for i in group:
+                    mode = _lib.SAFE_WRITE if first else _lib.SAFE_AND
+                    first = False
+                    if rows_arg is None:
+                        eng.posterior_grid(i, self._row0, m_local, beta, self.fmin[i], mean=self._mean_d[i], var=self._var_d[i],
+                                           Q=self._Q_d, q_col=2 * i, S=self._S_d, safe_mode=mode)
+                    else:
+                        eng.posterior_rows(i, rows_arg, beta, self.fmin[i], mean=self._mean_d[i], var=self._var_d[i],
+                                           Q=self._Q_d, q_col=2 * i, S=self._S_d, safe_mode=mode)
         self._ci_beta = beta
         self._ci_fmin = self.fmin.copy()
         self._safe_info = None
@@ -733,8 +767,13 @@ class SafeOptSwarm(GaussianProcessOptimization):
         G = len(self.gps)
         mean, var = eng.empty((G, P)), eng.empty((G, P))
         n_needed = 1 if swarm_type == "greedy" else G
-        for i in range(n_needed):
-            eng.posterior_rows(i, particles_d, beta, -np.inf, mean=mean[i], var=var[i])
+        for group in self._fits.groups:
+            group = [i for i in group if i < n_needed]
+            if len(group) > 1 and eng.posterior_multi(group, particles_d, 0, P, beta, [-np.inf] * len(group),
+                                                      means=[mean[i] for i in group], variances=[var[i] for i in group]):
+                continue
+            for i in group:
+                eng.posterior_rows(i, particles_d, beta, -np.inf, mean=mean[i], var=var[i])
         values, safe = eng.empty((P,)), eng.empty((P,), "u8")
         eng.swarm_fitness(_lib.SWARM_KINDS[swarm_type], G if n_needed == G else 1, P, mean, var, beta,
                           self.fmin[:n_needed] if n_needed == G else self.fmin[:1], self.scaling[:max(n_needed, 1)],

@@ -203,6 +203,51 @@ def test_grid_path_equals_rows_path(d, n, N):
     eng.close()
 
 
+@pytest.mark.parametrize("explicit", [False, True])
+def test_shared_factorisation_equals_separate_launches(explicit, monkeypatch):
+    """GPs with identical inputs, kernel and noise are evaluated by one launch (one contraction, one V.z per GP):
+    bit-identical to evaluating them one by one, on the grid path and on explicit rows."""
+    if explicit:
+        monkeypatch.setenv("SAFEOPT_B200_GRID_FAST_PATH", "0")
+    g = load_golden("config_C3_n80")                      # three GPs, same kernel, same X, different Y
+    res = {}
+    for share in ("1", "0"):
+        monkeypatch.setenv("SAFEOPT_B200_SHARE_FITS", share)
+        gps, grid, fmin = golden_problem(g, "gpu")
+        opt = sb.SafeOpt(gps, grid, fmin, beta=float(g["beta"]), threshold=float(g["threshold"]))
+        opt.optimize()
+        assert opt._fits.groups == ([[0, 1, 2]] if share == "1" else [[0], [1], [2]])
+        res[share] = (opt.Q.copy(), opt.S.copy(), opt.M.copy(), opt.last_query_row, opt._mean_d.cpu().numpy(), opt._var_d.cpu().numpy(),
+                      opt._engine.launches)
+    for a, b in zip(res["1"][:6], res["0"][:6]):
+        assert np.array_equal(a, b)
+    assert res["1"][6] < res["0"][6]
+    # a GP with its own kernel leaves the group
+    gps, grid, fmin = golden_problem(g, "gpu")
+    gps[1].kern.variance = np.array([1.7])
+    monkeypatch.setenv("SAFEOPT_B200_SHARE_FITS", "1")
+    opt = sb.SafeOpt(gps, grid, fmin, beta=float(g["beta"]), threshold=float(g["threshold"]))
+    opt.update_confidence_intervals()
+    assert opt._fits.groups == [[0, 2], [1]]
+
+
+def test_shared_factorisation_swarm_fitness(monkeypatch):
+    gl = load_golden("swarm_fitness_3d")
+    X, Y = gl["X"], gl["Y"]
+    d = X.shape[1]
+    out = {}
+    for share in ("1", "0"):
+        monkeypatch.setenv("SAFEOPT_B200_SHARE_FITS", share)
+        gps = [sb.GPRegression(X, Y[:, [i]], kernel=sb.RBF(d, variance=2.0, lengthscale=np.ones(d), ARD=True), noise_var=float(gl["noise_var"]))
+               for i in range(Y.shape[1])]
+        opt = sb.SafeOptSwarm(gps, list(gl["fmin"]), bounds=[(-1.0, 1.0)] * d, beta=float(gl["beta"]), swarm_size=20)
+        opt.best_lower_bound = float(gl["best_lower_bound"])
+        out[share] = [opt._compute_particle_fitness(kind, gl["particles"]) for kind in ["greedy", "maximizers", "expanders", "safe_set"]]
+        assert opt._fits.groups == ([[0, 1]] if share == "1" else [[0], [1]])
+    for (va, sa), (vb, sb_) in zip(out["1"], out["0"]):
+        assert np.array_equal(va, vb) and np.array_equal(sa, sb_)
+
+
 def test_grid_tables_for_a_row_block_only():
     """so_grid_prepare_rows: a rank builds the scaled-operand table for its own row block; rows inside give the bits of a
     full preparation, rows outside are refused."""
