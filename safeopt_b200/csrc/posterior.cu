@@ -410,7 +410,7 @@ extern "C" int so_posterior_rows_simple(so_handle* h, int gp, const double* Xsta
     double* inv_ls_d = nullptr;
     SO_CUDA(h, cudaMalloc(&inv_ls_d, sizeof(double) * SO_MAX_DIM));
     SO_CUDA(h, cudaMemcpyAsync(inv_ls_d, g.inv_ls, sizeof(double) * SO_MAX_DIM, cudaMemcpyHostToDevice, stream));
-    k_posterior_simple<<<(unsigned)M, 256, sizeof(double) * g.N, stream>>>(g.Linv, g.alpha, g.Xs, Xstar_d, g.N, g.ld, g.d,
+    k_posterior_simple<<<(unsigned)M, 256, sizeof(double) * (g.N + 2), stream>>>(g.Linv, g.alpha, g.Xs, Xstar_d, g.N, g.ld, g.d,
                                                                           g.kind, g.variance, inv_ls_d, M, mean_d, var_d);
     SO_CHECK_LAUNCH(h, "k_posterior_simple");
     SO_CUDA(h, cudaStreamSynchronize(stream));
