@@ -122,6 +122,10 @@ def combine_max_first(values: np.ndarray, rows: np.ndarray) -> Tuple[float, int]
 def reduce_safe_records(recs) -> dict:
     """Combine the per-rank records of so_sets_reduce_safe (structured array, one entry per rank) into the
     global one (gp_opt.py:504, :512, :634-636, :708-712); ties go to the lowest global row."""
+    if len(recs) == 1:          # single rank: nothing to combine (this runs once per optimize(), which is host-bound on small grids)
+        r = recs[0]
+        return dict(n_safe=int(r["n_safe"]), max_l0=float(r["max_l0"]), argmax_l0=int(r["argmax_l0"]), max_u0=float(r["max_u0"]),
+                    argmax_u0=int(r["argmax_u0"]))
     best_l, row_l = combine_max_first(recs["max_l0"], recs["argmax_l0"])
     best_u, row_u = combine_max_first(recs["max_u0"], recs["argmax_u0"])
     return dict(n_safe=int(np.sum(recs["n_safe"])), max_l0=best_l, argmax_l0=row_l, max_u0=best_u, argmax_u0=row_u)
@@ -129,6 +133,10 @@ def reduce_safe_records(recs) -> dict:
 
 def reduce_max_records(recs, scaling0) -> dict:
     """Combine the per-rank records of so_sets_maximizers (gp_opt.py:511-513, :642-644)."""
+    if len(recs) == 1:
+        r = recs[0]
+        return dict(n_max=int(r["n_max"]), max_var=float(r["max_width0"]) / scaling0, best_value=float(r["best_value"]),
+                    best_row=int(r["best_row"]))
     value, row = combine_max_first(recs["best_value"], recs["best_row"])
     return dict(n_max=int(np.sum(recs["n_max"])), max_var=float(np.max(recs["max_width0"])) / scaling0, best_value=value,
                 best_row=row)
