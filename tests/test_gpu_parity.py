@@ -159,6 +159,61 @@ def test_posterior_matches_oracle(N, d, kind, M):
     eng.close()
 
 
+def test_posterior_edge_shapes():
+    """Largest input dimension (16), no candidates, one candidate, and the largest fit (N = 2048) on the explicit-rows path."""
+    rs = np.random.RandomState(5)
+    d, N = 16, 33
+    X, Y, ls = rs.uniform(-1, 1, (N, d)), rs.randn(N), rs.uniform(1.0, 3.0, d)
+    eng = DeviceEngine(max_gps=1)
+    eng.fit(0, X, Y, 1, ls, 1.3, 0.01)
+    gp = gpy_lite.GPRegression(X, Y[:, None], kernel=oracle_kernel(1, d, 1.3, ls), noise_var=0.01)
+    for M in (0, 1, 777):
+        Xs = rs.uniform(-1, 1, (M, d))
+        mean, var = eng.empty((M,)), eng.empty((M,))
+        before = eng.launches
+        eng.posterior_rows(0, eng.to_device(Xs) if M else eng.empty((0, d)), 2.0, 0.0, mean=mean, var=var)
+        if M == 0:
+            assert eng.launches == before
+            continue
+        mo, vo = gp.predict_noiseless(Xs)
+        assert np.abs(mean.cpu().numpy() - mo[:, 0]).max() < 1e-11 * max(1.0, np.abs(Y).max())
+        assert np.abs(var.cpu().numpy() - vo[:, 0]).max() < 1e-10 * 1.3
+    N = 2048
+    X, Y, ls, _ = _problem(N, 4, 99)
+    eng.fit(0, X, Y, 0, ls, 2.0, 0.05 ** 2)
+    Xs = rs.uniform(-2, 2, (500, 4))
+    mean, var = eng.empty((500,)), eng.empty((500,))
+    try:
+        eng.posterior_rows(0, eng.to_device(Xs), 2.0, 0.0, mean=mean, var=var)
+    except sb.DeviceError as exc:               # the shared-memory tile caps the tensor-core kernel at N ~ 1600: refused, not wrong
+        assert exc.status == _lib.SO_ERR_CAPACITY
+    else:
+        gp = gpy_lite.GPRegression(X, Y[:, None], kernel=oracle_kernel(0, 4, 2.0, ls), noise_var=0.05 ** 2)
+        mo, vo = gp.predict_noiseless(Xs)
+        assert np.abs(mean.cpu().numpy() - mo[:, 0]).max() < 1e-9 * max(1.0, np.abs(Y).max())
+        assert np.abs(var.cpu().numpy() - vo[:, 0]).max() < 1e-9 * 2.0
+    eng.close()
+
+
+def test_safeopt_options_match_port():
+    """Callable beta, per-GP threshold array and an explicit scaling list (gp_opt.py:74-99, :536) against the port
+    (a plain list as threshold raises TypeError in the reference's `threshold * beta`; an array is what works there)."""
+    g = load_golden("expander_g2")
+    gps, grid, fmin = golden_problem(g, "gpu")
+    gos, _, _ = golden_problem(g, "cpu")
+    beta = lambda t: 1.5 + 0.01 * t
+    kw = dict(beta=beta, threshold=np.array([0.05, 0.2]), scaling=[1.2, 0.9])
+    opt = sb.SafeOpt(gps, grid, fmin, **kw)
+    ref = port.GridProblem.create(gos, grid, fmin, **kw)
+    x = opt.optimize()
+    x_ref, row_ref = ref.optimize()
+    assert np.abs(opt.Q - ref.Q).max() < 1e-9 * 2 * np.sqrt(2.0)
+    assert np.array_equal(opt.S, ref.S) and np.array_equal(opt.M, ref.M) and np.array_equal(opt.G, ref.G)
+    assert opt.last_query_row == row_ref and np.array_equal(x, x_ref)
+    with pytest.raises(ValueError):
+        sb.SafeOpt(gps, grid, fmin, scaling=[1.0])
+
+
 def test_posterior_safe_modes_and_columns():
     X, Y, ls, rs = _problem(30, 2, 3)
     Xs = rs.uniform(-4, 4, (999, 2))
