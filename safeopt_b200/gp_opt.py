@@ -708,10 +708,11 @@ class SafeOptSwarm(GaussianProcessOptimization):
         self._engine = DeviceEngine(device, max_gps=len(self.gps))
         self._comm = Comm(self._engine.device)
         self._fits = _DeviceFits(self._engine, self.gps)
+        self._fit_buffers = {}
         self.optimal_velocities = self.optimize_particle_velocity()
         swarm_types = ["greedy", "maximizers", "expanders"]
         if swarm_backend == "device":
-            self.swarms = {kind: DeviceSwarm(self._engine, self.optimal_velocities, partial(self._fitness_device, kind),
+            self.swarms = {kind: DeviceSwarm(self._engine, self.optimal_velocities, partial(self._swarm_fitness, kind),
                                              bounds=self.bounds, rng=rng, seed=seed + 1000 * k, comm=self._comm)
                            for k, kind in enumerate(swarm_types)}
         else:
@@ -758,14 +759,28 @@ class SafeOptSwarm(GaussianProcessOptimization):
         pen[big] = -300 * pen[big] ** 2
         return pen
 
-    def _fitness_device(self, swarm_type, particles_d):
-        """Fitness of device-resident particles; returns device tensors (values, safe)."""
+    def _fitness_buffers(self, P):
+        """Per-swarm-size scratch (posterior planes, values, flags), reused across the ~300 fitness passes of an optimize()."""
+        buf = self._fit_buffers.get(P)
+        if buf is None:
+            eng, G = self._engine, len(self.gps)
+            buf = (eng.empty((G, P)), eng.empty((G, P)), eng.empty((P,)), eng.empty((P,), "u8"))
+            if len(self._fit_buffers) > 4:
+                self._fit_buffers.clear()
+            self._fit_buffers[P] = buf
+        return buf
+
+    def _fitness_device(self, swarm_type, particles_d, fresh=True):
+        """Fitness of device-resident particles; returns device tensors (values, safe).  The returned tensors are scratch
+        that the next call with the same particle count overwrites (``DeviceSwarm`` consumes them at once).  Inside a swarm
+        run the GP objects cannot change, so ``fresh=False`` skips the fingerprint check of the device fits."""
         eng = self._engine
-        self._fits.refresh()
+        if fresh:
+            self._fits.refresh()
         beta = self.beta(self.t)
         P = particles_d.shape[0]
         G = len(self.gps)
-        mean, var = eng.empty((G, P)), eng.empty((G, P))
+        mean, var, values, safe = self._fitness_buffers(P)
         n_needed = 1 if swarm_type == "greedy" else G
         for group in self._fits.groups:
             group = [i for i in group if i < n_needed]
@@ -774,11 +789,14 @@ class SafeOptSwarm(GaussianProcessOptimization):
                 continue
             for i in group:
                 eng.posterior_rows(i, particles_d, beta, -np.inf, mean=mean[i], var=var[i])
-        values, safe = eng.empty((P,)), eng.empty((P,), "u8")
         eng.swarm_fitness(_lib.SWARM_KINDS[swarm_type], G if n_needed == G else 1, P, mean, var, beta,
                           self.fmin[:n_needed] if n_needed == G else self.fmin[:1], self.scaling[:max(n_needed, 1)],
                           self.best_lower_bound, values, safe)
         return values, safe
+
+    def _swarm_fitness(self, swarm_type, particles_d):
+        """Fitness callback of the device swarms: the fits were refreshed by get_new_query_point before the run."""
+        return self._fitness_device(swarm_type, particles_d, fresh=False)
 
     def _compute_particle_fitness(self, swarm_type, particles):
         """Fitness value and safety flag of every particle (reference: gp_opt.py:901-1013).
@@ -788,7 +806,7 @@ class SafeOptSwarm(GaussianProcessOptimization):
             raise AssertionError("Invalid swarm type")
         particles = np.ascontiguousarray(np.atleast_2d(np.asarray(particles, dtype=float)))
         values, safe = self._fitness_device(swarm_type, self._engine.to_device(particles))
-        return values.cpu().numpy(), safe.cpu().numpy().astype(bool)
+        return values.cpu().numpy(), safe.cpu().numpy().astype(bool)      # .cpu() copies: the scratch may be reused
 
     def get_new_query_point(self, swarm_type):
         """Run one swarm and return (point, value / std-devs) (reference: gp_opt.py:1015-1134)."""

@@ -50,7 +50,8 @@ def main():
     opt = sb.SafeOptSwarm(gps, [0.0, 0.2], bounds=w.bounds, beta=w.beta, swarm_size=args.particles)
     opt.best_lower_bound = 0.5
     kind = "maximizers"
-    swarm = sb.DeviceSwarm(opt._engine, opt.optimal_velocities, lambda p: opt._fitness_device(kind, p), bounds=w.bounds, rng="device")
+    opt._fits.refresh()
+    swarm = sb.DeviceSwarm(opt._engine, opt.optimal_velocities, lambda p: opt._swarm_fitness(kind, p), bounds=w.bounds, rng="device")
     swarm.init_swarm(w.particles.copy())
     swarm.run_swarm(3)
     sync()
@@ -64,7 +65,7 @@ def main():
     pos = swarm.positions
     e0.record()
     for _ in range(args.iters):
-        opt._fitness_device(kind, pos)
+        opt._swarm_fitness(kind, pos)
     e1.record()
     sync()
     ms_fit = max_ranks(e0.elapsed_time(e1))
