@@ -251,7 +251,7 @@ def run_b200(args, w, rank, world, local_rank):
     X_pin = torch.from_numpy(np.ascontiguousarray(w.X)).pin_memory()
     Y_pin = torch.from_numpy(np.ascontiguousarray(w.Y)).pin_memory()
     h2d = X_pin.numel() * 8 + Y_pin.numel() * 8 + (w.d + 2) * 8 * w.n_gps
-    d2h = 2 * 64 + 8 + w.n_gps * 4     # two records, candidate count, fit status words
+    d2h = 136 * world + w.n_gps * 4    # every rank's two 64-byte records + candidate count (one copy), fit status words
 
     def e2e_step():
         Xh, Yh = X_pin.numpy(), Y_pin.numpy()
@@ -303,6 +303,9 @@ def run_b200(args, w, rank, world, local_rank):
                 "kernel_share_of_step": k2_ms * (len(k2_events) / args.steps) / (dev_ms / args.steps),
                 "fp64_dmma_microbench_tflops": 37.1, "algorithmic_hbm_gbs": bytes_per_eval(w.d, w.n_gps, grid_path) * local_rows / (k2_ms * 1e-3) / 1e9,
                 "hbm_peak_gbs_measured": hbm_peak,
+                "traffic_note": "684 MB of the measured DRAM traffic is the precomputed scaled-operand table A'(s) (2500 x 270 KB), "
+                                "read exactly once per launch; it replaces 1.6e9 fp64 exp per launch on the FP64 pipe the "
+                                "contraction saturates. Outputs: 33 B/row = 206 MB",
                 "note": "fp64 path: MEASURED_PEAKS.json has no fp64 number, so the denominator is cuBLAS DGEMM measured in this session"}
     cpu = None
     if not args.no_cpu_baseline and world == 1:
