@@ -354,6 +354,10 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     from safeopt_b200 import workloads
+    if args.impl == "b200" and args.gpus != world:
+        # one process per GPU: --gpus N is only meaningful under torchrun with N ranks
+        sys.stderr.write("bench.py: --gpus %d but WORLD_SIZE=%d; running with %d rank(s)\n" % (args.gpus, world, world))
+        args.gpus = world
     w = workloads.config(args.config, num_samples=args.num_samples)
     if args.scaling == "weak" and args.gpus > 1 and w.d >= 2:
         # per-GPU work fixed: axis 1 (slowest in the reference row order) gets N times the points
