@@ -271,7 +271,7 @@ extern "C" int so_expander_check(so_handle* h, int gp, const double* Xstar_d, in
     }
     p.beta = beta; p.fmin = fmin;
     p.mean = const_cast<double*>(mean_d); p.var = const_cast<double*>(var_d); p.Q = nullptr; p.q_stride = 0; p.q_col = 0;
-    p.S = const_cast<uint8_t*>(S_d); p.safe_mode = SO_SAFE_NONE; p.n_out = 1;
+    p.S = const_cast<uint8_t*>(S_d); p.safe_mode = SO_SAFE_NONE; p.n_out = 1; p.use_row_table = 0;
     ep.Zfrag = reinterpret_cast<const double2*>(Zfrag);
     ep.cinfo = cinfo; ep.xcs = xcs; ep.axis = h->grid.axis; ep.B = B; ep.flags = flags_d;
     const size_t smem = smem_layout(NB, T, d, 1, grid).total;

@@ -13,6 +13,7 @@
 // Algorithmic work per row and GP: N^2/2 FMA (contraction) + N kernel evaluations; algorithmic HBM bytes: d*8 in (0 on
 // the grid path) + 32 out (mean, var, l, u) + 1 (S).  See DESIGN.md section 3.
 #include "posterior_tma.cuh"
+#include <algorithm>
 #include <cstdlib>
 
 namespace {
@@ -174,6 +175,27 @@ int plan_launch(so_handle* h, const GPState& g, int64_t M, bool grid, int n_extr
     return SO_OK;
 }
 
+// Block rows of the eight warps for an arbitrary NB (see PostParams::row_table): longest row first to the least loaded warp,
+// every warp at most 4 * npass rows; each warp's rows ascending, four per pass.
+int plan_rows(int NB, signed char (&table)[kMaxPass][8][4]) {
+    const int per_warp = (NB + 7) / 8;
+    const int npass = (per_warp + 3) / 4;
+    int load[8] = {0, 0, 0, 0, 0, 0, 0, 0}, count[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int mine[8][4 * kMaxPass];
+    for (int i = NB - 1; i >= 0; --i) {
+        int best = -1;
+        for (int w = 0; w < 8; ++w)
+            if (count[w] < 4 * npass && (best < 0 || load[w] < load[best])) best = w;
+        mine[best][count[best]++] = i;
+        load[best] += i + 1;
+    }
+    for (int w = 0; w < 8; ++w) {
+        std::sort(mine[w], mine[w] + count[w]);
+        for (int q = 0; q < 4 * npass; ++q) table[q / 4][w][q % 4] = (signed char)(q < count[w] ? mine[w][q] : -1);
+    }
+    return npass;
+}
+
 // Outputs 1..n-1 of a launch that evaluates several GPs sharing one factorisation (so_posterior_*_multi).
 struct ExtraOut {
     int n = 0;
@@ -219,7 +241,7 @@ int tma_warps() {
 
 int plan_tma(so_handle* h, const GPState& g, TmaPlan& tp) {
     const int NB = g.NB;
-    tp.kb_pad = kChunkK * ((NB + kChunkK - 1) / kChunkK);
+    tp.kb_pad = NB;       // no padding to whole bulk-copy chunks: at NB = 33..35 that padding alone pushed the tile from 48 to 32 rows
     const int options[3] = {6, 4, 2};
     for (int warps = tma_warps(); warps >= 8; warps -= 8) {
         const int ns = warps == 16 ? 2 : 4;
@@ -324,11 +346,18 @@ int run_posterior(so_handle* h, int gp, const double* Xstar_d, bool grid, int64_
         p.n_out = 1 + extra->n;
     }
     const int n_extra = p.n_out - 1;
+    p.use_row_table = 0;
+    int table_npass = 0;
+    if (g.NB >= 32 && g.NB % 32 != 0 && g.NB <= 8 * 4 * kMaxPass) {       // RG == 8 and the closed-form pairing is unbalanced
+        table_npass = plan_rows(g.NB, p.row_table);
+        p.use_row_table = 1;
+    }
 
     if (tma) {
         p.RG = g.tma_RG; p.CG = g.tma_CG; p.T = g.tma_T; p.TB = g.tma_BT * g.tma_CG;
         const int ns = g.tma_warps == 16 ? 2 : 4;
         p.npass = (g.NB + ns * p.RG - 1) / (ns * p.RG);
+        if (ns == 4 && p.RG == 8 && p.use_row_table) p.npass = table_npass; else p.use_row_table = 0;
         tp.PfFrag = g.PfFrag; tp.Aprime = g.Aprime; tp.a_stride = g.a_stride; tp.s0 = g.ap_s0;
         if (row0 / h->grid.fast_rows < g.ap_s0 || (row0 + M - 1) / h->grid.fast_rows >= g.ap_s1)
             return so_fail(h, SO_ERR_NOT_FITTED, "posterior_grid: rows outside the range given to so_grid_prepare_rows");
@@ -348,6 +377,7 @@ int run_posterior(so_handle* h, int gp, const double* Xstar_d, bool grid, int64_
     int rc = plan_launch(h, g, M, grid, n_extra, lp);
     if (rc) return rc;
     p.RG = lp.RG; p.CG = lp.CG; p.T = lp.T; p.TB = lp.TB; p.npass = lp.npass;
+    if (p.RG == 8 && p.use_row_table) p.npass = table_npass; else p.use_row_table = 0;
     p.ntiles = (M + p.T - 1) / p.T;
     if (grid) return launch_bt<SO_KERNEL_RBF, true>(h, p, lp, stream);
     switch (g.kind) {

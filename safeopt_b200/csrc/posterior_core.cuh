@@ -10,6 +10,7 @@ constexpr int kThreads = 256;
 constexpr int kWarps = 8;
 constexpr int kGridMaxDim = 6;   // grid fast path (larger d uses explicit rows)
 constexpr int kMaxOut = 4;       // GPs evaluated by one launch when they share the factorisation (so_posterior_*_multi)
+constexpr int kMaxPass = 8;      // passes of four block rows per warp: 8 warps x 8 x 4 = 256 block rows (N = 2048)
 
 struct PostParams {
     int N, NB, d, RG, CG, T, TB, npass, kind;
@@ -41,6 +42,12 @@ struct PostParams {
     double* mean_x[kMaxOut - 1];
     double* var_x[kMaxOut - 1];
     int q_col_x[kMaxOut - 1];
+    // Block rows of every warp per pass when the eight warps split the rows (RG == 8): for NB a multiple of 32 the closed-form
+    // pairing {g, 15-g, 16+g, 31-g} balances the triangular work exactly; for any other NB (a BO loop adds one observation
+    // per iteration) the host assigns the rows longest-first to the least loaded warp (plan_rows) -- with the closed form,
+    // NB = 33 put the whole extra block row on one warp in a second pass and a tile took 1.7x as long.
+    int use_row_table;
+    signed char row_table[kMaxPass][8][4];      // ascending per pass, -1 = unused slot (suffix)
 };
 
 struct SmemLayout {
@@ -273,16 +280,24 @@ __device__ __forceinline__ void contract_tile(const PostParams& p, const double2
         const int base = NS * RG * pass;
         // rows are ascending; the ones beyond NB (inactive) form a suffix.  Slots are ordered by K extent, inactive
         // slots (extent -1) first, so that "slots FIRST..NS-1 active" holds in every segment.
+        int rows[NS];
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+            int r = (NS == 4 && p.use_row_table) ? (int)p.row_table[pass][g][i & 3] : warp_row<NS>(base, RG, g, i);
+            rows[i] = r < NB ? r : -1;
+        }
         int na = 0;
 #pragma unroll
-        for (int i = 0; i < NS; ++i) na += warp_row<NS>(base, RG, g, i) < NB;
+        for (int i = 0; i < NS; ++i) na += rows[i] >= 0;
         int ext[NS];
         size_t abase[NS];
         double zs[NS];             // z at this lane's row of each slot's block (0 for inactive slots)
 #pragma unroll
         for (int s = 0; s < NS; ++s) {
             const int src = s - (NS - na);
-            const int r = src >= 0 ? warp_row<NS>(base, RG, g, src) : -1;
+            int r = -1;
+#pragma unroll
+            for (int i = 0; i < NS; ++i) r = (i == src) ? rows[i] : r;
             ext[s] = r;
             abase[s] = r >= 0 ? (size_t)r * (r + 1) / 2 * 32 : 0;
             zs[s] = r >= 0 ? __ldg(p.zvec + 8 * r + (lane >> 2)) : 0.0;

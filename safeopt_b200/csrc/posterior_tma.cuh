@@ -53,7 +53,7 @@ struct TmaParams {
     int64_t fast_rows;
     int64_t first_tile;
     int tpb;                          // tiles per slow block
-    int kb_pad;                       // k-blocks per tile in the table (4 * ceil(NB / 4))
+    int kb_pad;                       // k-blocks per tile in the table (= NB: the last bulk copy of a tile may be short)
 };
 
 struct TmaSmem { size_t buf_bytes, ss_off, mean_off, meanx_off, bar_off, total; };
@@ -89,7 +89,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_posterior_tma(const __grid_co
     const int g = warp % RG, cg = warp / RG;
     const size_t buf_elems = L.buf_bytes / sizeof(double2);
     const unsigned chunk_bytes = (unsigned)(kChunkK * TB * 512);
-    const int nchunks = tp.kb_pad / kChunkK;
+    const int nchunks = (tp.kb_pad + kChunkK - 1) / kChunkK;
+    const unsigned last_bytes = (unsigned)((tp.kb_pad - (nchunks - 1) * kChunkK) * TB * 512);
 
     if (threadIdx.x == 0) {
         mbar_init(&full[0], 1);
@@ -105,7 +106,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_posterior_tma(const __grid_co
         double2* dst = sBuf + (size_t)b * buf_elems;
         mbar_expect_tx(&full[b], (unsigned)L.buf_bytes);
         for (int c = 0; c < nchunks; ++c)
-            tma_bulk_g2s(dst + (size_t)c * (chunk_bytes / 16), src + (size_t)c * (chunk_bytes / 16), chunk_bytes, &full[b]);
+            tma_bulk_g2s(dst + (size_t)c * (chunk_bytes / 16), src + (size_t)c * (chunk_bytes / 16),
+                         c + 1 < nchunks ? chunk_bytes : last_bytes, &full[b]);
     };
 
     if (threadIdx.x == 0 && (int64_t)blockIdx.x < p.ntiles) issue(blockIdx.x, 0);
