@@ -13,6 +13,7 @@
 // Algorithmic work per row and GP: N^2/2 FMA (contraction) + N kernel evaluations; algorithmic HBM bytes: d*8 in (0 on
 // the grid path) + 32 out (mean, var, l, u) + 1 (S).  See DESIGN.md section 3.
 #include "posterior_tma.cuh"
+#include "posterior_ring.cuh"
 #include <algorithm>
 #include <cstdlib>
 
@@ -55,7 +56,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_posterior(const __grid_constant
             const int64_t next = tile + gridDim.x;
             if (next < p.ntiles) load_tile_rows(p, sXt + (size_t)(par ^ 1) * T * p.d, next * T);
         }
-        contract_tile<BT>(p, p.Afrag + lane, sK + (size_t)(cg * BT) * 32 + lane, sSST, sMeanT, sMeanXT, g, cg, lane);
+        PlainB bsrc{sK + (size_t)(cg * BT) * 32 + lane, p.TB};
+        contract_tile<BT>(p, p.Afrag + lane, bsrc, sSST, sMeanT, sMeanXT, g, cg, lane);
         __syncthreads();
         for (int t = threadIdx.x; t < T; t += kThreads) {
             const int64_t row = tile_local0 + t;
@@ -229,7 +231,18 @@ int launch_bt(so_handle* h, const PostParams& p, const LaunchPlan& lp, cudaStrea
 }
 
 // ---- TMA double-buffer kernel (grid path default) ----------------------------------------------------------------
-struct TmaPlan { int BT, RG, CG, T, TB, npass, kb_pad, warps; size_t smem; };
+struct TmaPlan { int BT, RG, CG, T, TB, npass, kb_pad, warps; size_t smem; bool ring; };
+
+// SO_K2_RING=0 keeps the resident double buffer (smaller tiles) for every N, SO_K2_RING=all streams as soon as the 48-row
+// tile does not fit twice (A/B measurements); default: stream when the 32-row tile does not fit twice either.
+bool ring_allowed() {
+    const char* v = std::getenv("SO_K2_RING");
+    return !(v && std::string(v) == "0");
+}
+int ring_after_option() {
+    const char* v = std::getenv("SO_K2_RING");
+    return v && std::string(v) == "all" ? 0 : 1;
+}
 
 // 8 warps per CTA (four block rows per warp) by default; SO_K2_WARPS=16 selects the 16-warp variant (two block rows per
 // warp, four warps per scheduler) for A/B measurements -- measured 13.55 vs 13.40 ms at config 4, pipe 84.7 % vs 85.5 %
@@ -243,6 +256,7 @@ int plan_tma(so_handle* h, const GPState& g, TmaPlan& tp) {
     const int NB = g.NB;
     tp.kb_pad = NB;       // no padding to whole bulk-copy chunks: at NB = 33..35 that padding alone pushed the tile from 48 to 32 rows
     const int options[3] = {6, 4, 2};
+    tp.ring = false;
     for (int warps = tma_warps(); warps >= 8; warps -= 8) {
         const int ns = warps == 16 ? 2 : 4;
         int rg = 1;
@@ -254,6 +268,14 @@ int plan_tma(so_handle* h, const GPState& g, TmaPlan& tp) {
             const TmaSmem L = tma_smem(tp.kb_pad, bt * tp.CG, tp.RG, 8 * bt * tp.CG);
             if (L.total <= (size_t)h->smem_optin) {
                 tp.BT = bt; tp.TB = bt * tp.CG; tp.T = 8 * bt * tp.CG; tp.smem = L.total;
+                return SO_OK;
+            }
+            // neither a 48- nor a 32-row tile fits twice (N > 416): stream B through the k-chunk ring and keep the tile 48 rows
+            // wide.  Measured at config 4's grid: N = 512 64.8 ms (ring) vs 69.8 (16-row double buffer); for N = 281..416 the
+            // 32-row double buffer is faster than the ring (21.2 vs 28.7 ms at N = 288), so it stays.
+            if (k == ring_after_option() && warps == 8 && rg == 8 && ring_allowed() &&
+                ring_smem(6, 8, 48, kMaxOut - 1, (size_t)h->smem_optin).stages >= 4) {
+                tp.BT = 6; tp.TB = 6; tp.T = 48; tp.smem = 0; tp.ring = true;
                 return SO_OK;
             }
         }
@@ -368,6 +390,18 @@ int run_posterior(so_handle* h, int gp, const double* Xstar_d, bool grid, int64_
         const int64_t t1 = (last_row / F) * g.tma_tpb + (last_row % F) / p.T;
         tp.first_tile = t0;
         p.ntiles = t1 - t0 + 1;
+        if (g.tma_ring) {
+            const RingSmem rs = ring_smem(p.TB, p.RG, p.T, n_extra, (size_t)h->smem_optin);
+            static int ring_configured_for = -1;
+            if (ring_configured_for != h->device) {
+                SO_CUDA(h, cudaFuncSetAttribute(k_posterior_ring<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
+                ring_configured_for = h->device;
+            }
+            const int nblk = (int)(p.ntiles < (int64_t)h->num_sms ? p.ntiles : (int64_t)h->num_sms);
+            k_posterior_ring<6><<<nblk, kThreads, rs.total, stream>>>(tp, rs.stages);
+            SO_CHECK_LAUNCH(h, "k_posterior_ring");
+            return SO_OK;
+        }
         const size_t smem = tma_smem(g.tma_kb_pad, p.TB, p.RG, p.T, n_extra).total;
         if (smem > (size_t)h->smem_optin)
             return so_fail(h, SO_ERR_CAPACITY, "posterior_multi: the tile does not fit with that many outputs; evaluate the GPs one by one");
@@ -605,7 +639,7 @@ extern "C" int so_grid_prepare_rows(so_handle* h, int gp, int64_t row0, int64_t 
         SO_CUDA(h, cudaMemsetAsync(g.Aprime + (size_t)n_slow * a_stride, 0, sizeof(double2) * 128, stream));
         g.ap_s0 = s_lo; g.ap_s1 = s_hi;
         g.a_stride = a_stride; g.tma_T = pl.T; g.tma_tpb = tpb; g.tma_BT = pl.BT; g.tma_RG = pl.RG; g.tma_CG = pl.CG;
-        g.tma_kb_pad = pl.kb_pad; g.tma_warps = pl.warps; g.tma_ready = true;
+        g.tma_kb_pad = pl.kb_pad; g.tma_warps = pl.warps; g.tma_ring = pl.ring; g.tma_ready = true;
     }
     g.grid_ready = true;
     return SO_OK;

@@ -180,47 +180,79 @@ __device__ __forceinline__ void gen_grid(const PostParams& p, double2* __restric
 #ifndef SO_K2_A_PF_L1
 #define SO_K2_A_PF_L1 2
 #endif
+// Where the B fragments of a k-block come from.  PlainB: the whole tile is resident in shared memory (bulk kernel, TMA
+// double-buffer kernel).  The ring kernel (posterior_ring.cuh) streams k-block chunks and synchronises in acquire/release.
+// A source hands out B in spans of consecutive k-blocks that need no synchronisation inside (kSpan = whole range for PlainB,
+// one ring stage for RingB): the k-block loop is split into an outer loop over spans (acquire / release, possibly blocking)
+// and a plain inner loop that ptxas can software-pipeline.
+struct PlainB {
+    static constexpr bool kStreaming = false;
+    static constexpr int kSpan = 1 << 20;
+    const double2* sB;      // tile base + this warp's column group + lane
+    int TB;
+    __device__ __forceinline__ void enter(int) const {}                      // first k-block of a span is about to be read
+    __device__ __forceinline__ const double2* at(int kb) const { return sB + (size_t)kb * TB * 32; }
+    __device__ __forceinline__ void leave(int) const {}                      // last k-block of a span has been read
+    __device__ __forceinline__ void drain(int) const {}
+};
+
+// One k-block of a segment: prefetch the next block's A fragments (registers one block ahead, L1 two blocks ahead), then
+// 2 * BT * (NS - FIRST) DMMAs on the current one.
 template <int BT, int NS, int FIRST>
-__device__ __forceinline__ void mma_segment(double (&acc)[NS][BT][2], double2 (&a)[NS], const double2* __restrict__ Afrag,
-                                            const size_t (&abase)[NS], const double2* __restrict__ sB, int TB,
-                                            int kb_lo, int kb_hi) {
-    for (int kb = kb_lo; kb <= kb_hi; ++kb) {
-        double2 an[NS];
+__device__ __forceinline__ void mma_kblock(double (&acc)[NS][BT][2], double2 (&a)[NS], const double2* __restrict__ Afrag,
+                                           const size_t (&abase)[NS], const double2* __restrict__ bp, int kb) {
+    double2 an[NS];
 #pragma unroll
-        for (int s = FIRST; s < NS; ++s) an[s] = __ldg(Afrag + abase[s] + (size_t)(kb + 1) * 32);
+    for (int s = FIRST; s < NS; ++s) an[s] = __ldg(Afrag + abase[s] + (size_t)(kb + 1) * 32);
 #if SO_K2_A_PF_L1 > 0
 #pragma unroll
-        for (int s = FIRST; s < NS; ++s)
-            asm volatile("prefetch.global.L1 [%0];\n" ::"l"(Afrag + abase[s] + (size_t)(kb + SO_K2_A_PF_L1) * 32));
+    for (int s = FIRST; s < NS; ++s)
+        asm volatile("prefetch.global.L1 [%0];\n" ::"l"(Afrag + abase[s] + (size_t)(kb + SO_K2_A_PF_L1) * 32));
 #endif
-        const double2* bp = sB + (size_t)kb * TB * 32;
 #pragma unroll
-        for (int c = 0; c < BT; ++c) {
-            const double2 b = bp[c * 32];
+    for (int c = 0; c < BT; ++c) {
+        const double2 b = bp[c * 32];
 #pragma unroll
-            for (int s = FIRST; s < NS; ++s) {
-                dmma884(acc[s][c][0], acc[s][c][1], a[s].x, b.x);
-                dmma884(acc[s][c][0], acc[s][c][1], a[s].y, b.y);
-            }
+        for (int s = FIRST; s < NS; ++s) {
+            dmma884(acc[s][c][0], acc[s][c][1], a[s].x, b.x);
+            dmma884(acc[s][c][0], acc[s][c][1], a[s].y, b.y);
         }
+    }
 #pragma unroll
-        for (int s = FIRST; s < NS; ++s) a[s] = an[s];
+    for (int s = FIRST; s < NS; ++s) a[s] = an[s];
+}
+
+template <int BT, int NS, int FIRST, typename BS>
+__device__ __forceinline__ void mma_segment(double (&acc)[NS][BT][2], double2 (&a)[NS], const double2* __restrict__ Afrag,
+                                            const size_t (&abase)[NS], BS& bs, int kb_lo, int kb_hi) {
+    if (!BS::kStreaming) {
+        // resident tile: one plain loop (ptxas software-pipelines the B loads across k-blocks)
+        for (int kb = kb_lo; kb <= kb_hi; ++kb) mma_kblock<BT, NS, FIRST>(acc, a, Afrag, abase, bs.at(kb), kb);
+        return;
+    }
+    // streamed B: outer loop over the spans of k-blocks inside one ring stage (enter / leave may block), plain inner loop
+    for (int kb0 = kb_lo; kb0 <= kb_hi;) {
+        const int span_end = (kb0 / BS::kSpan) * BS::kSpan + BS::kSpan - 1;
+        const int kb1 = span_end < kb_hi ? span_end : kb_hi;
+        if (kb0 % BS::kSpan == 0) bs.enter(kb0);
+        for (int kb = kb0; kb <= kb1; ++kb) mma_kblock<BT, NS, FIRST>(acc, a, Afrag, abase, bs.at(kb), kb);
+        bs.leave(kb1);
+        kb0 = kb1 + 1;
     }
 }
 
-template <int BT, int NS, int FIRST>
+template <int BT, int NS, int FIRST, typename BS>
 struct SegmentChain {       // segments FIRST..NS-1 in order; segment s covers k-blocks ext[s-1]+1 .. ext[s]
     static __device__ __forceinline__ void run(double (&acc)[NS][BT][2], double2 (&a)[NS], const double2* __restrict__ Afrag,
-                                               const size_t (&abase)[NS], const double2* __restrict__ sB, int TB,
-                                               const int (&ext)[NS]) {
-        mma_segment<BT, NS, FIRST>(acc, a, Afrag, abase, sB, TB, FIRST == 0 ? 0 : ext[FIRST > 0 ? FIRST - 1 : 0] + 1, ext[FIRST]);
-        SegmentChain<BT, NS, FIRST + 1>::run(acc, a, Afrag, abase, sB, TB, ext);
+                                               const size_t (&abase)[NS], BS& bs, const int (&ext)[NS]) {
+        mma_segment<BT, NS, FIRST, BS>(acc, a, Afrag, abase, bs, FIRST == 0 ? 0 : ext[FIRST > 0 ? FIRST - 1 : 0] + 1, ext[FIRST]);
+        SegmentChain<BT, NS, FIRST + 1, BS>::run(acc, a, Afrag, abase, bs, ext);
     }
 };
-template <int BT, int NS>
-struct SegmentChain<BT, NS, NS> {
+template <int BT, int NS, typename BS>
+struct SegmentChain<BT, NS, NS, BS> {
     static __device__ __forceinline__ void run(double (&)[NS][BT][2], double2 (&)[NS], const double2* __restrict__,
-                                               const size_t (&)[NS], const double2* __restrict__, int, const int (&)[NS]) {}
+                                               const size_t (&)[NS], BS&, const int (&)[NS]) {}
 };
 
 // Block rows of a warp in one pass, ascending: {g, 2RG-1-g} (NS = 2) or {g, 2RG-1-g, 2RG+g, 4RG-1-g} (NS = 4) above
@@ -269,13 +301,13 @@ __device__ __forceinline__ void halving_reduce(double (&v)[K], int lane) {
 // taken from the accumulators in one pass, reduced over the 8 row lanes by recursive halving and left in this row
 // group's slot of sSS / sMean (fixed order everywhere => bit-reproducible).  NS = 4 with 8 warps per CTA, NS = 2 with 16
 // (half the accumulators per warp, twice the warps per scheduler to cover each other's waits).
-template <int BT, int NS = 4>
-__device__ __forceinline__ void contract_tile(const PostParams& p, const double2* __restrict__ Afrag_lane,
-                                              const double2* __restrict__ sB, double* __restrict__ sSST,
-                                              double* __restrict__ sMeanT, double* __restrict__ sMeanXT, int g, int cg, int lane) {
+template <int BT, int NS = 4, typename BS = PlainB>
+__device__ __forceinline__ void contract_tile(const PostParams& p, const double2* __restrict__ Afrag_lane, BS& bs,
+                                              double* __restrict__ sSST, double* __restrict__ sMeanT,
+                                              double* __restrict__ sMeanXT, int g, int cg, int lane) {
     static_assert(BT % 2 == 0, "BT must be even");
     static_assert(NS == 2 || NS == 4, "two or four block rows per warp and pass");
-    const int RG = p.RG, NB = p.NB, TB = p.TB, T = p.T;
+    const int RG = p.RG, NB = p.NB, T = p.T;
     for (int pass = 0; pass < p.npass; ++pass) {
         const int base = NS * RG * pass;
         // rows are ascending; the ones beyond NB (inactive) form a suffix.  Slots are ordered by K extent, inactive
@@ -310,7 +342,8 @@ __device__ __forceinline__ void contract_tile(const PostParams& p, const double2
         double2 a[NS];
 #pragma unroll
         for (int s = 0; s < NS; ++s) a[s] = __ldg(Afrag_lane + abase[s]);
-        SegmentChain<BT, NS, 0>::run(acc, a, Afrag_lane, abase, sB, TB, ext);
+        SegmentChain<BT, NS, 0, BS>::run(acc, a, Afrag_lane, abase, bs, ext);
+        bs.drain(ext[NS - 1] + 1);      // streamed B: the k-blocks this warp has no rows for are still handed back
         // red[c*2+h] = sum of squares, red[2BT + c*2+h] = mean share, for column 8c + 2(lane%4) + h of this column group
         double red[4 * BT];
 #pragma unroll

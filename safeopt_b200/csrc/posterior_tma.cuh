@@ -132,9 +132,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_posterior_tma(const __grid_co
         const int64_t left = tp.fast_rows - (int64_t)j * T;
         mbar_wait(&full[b], ((unsigned)(it >> 1)) & 1u);
         // the last tile of a slow block is usually short: contract only the column tiles that hold rows
-        if (BT > 2 && p.CG == 1 && left <= 16) contract_tile<2, NS>(p, Afrag, sB, sSST, sMeanT, sMeanXT, g, cg, lane);
-        else if (BT > 4 && p.CG == 1 && left <= 32) contract_tile<4, NS>(p, Afrag, sB, sSST, sMeanT, sMeanXT, g, cg, lane);
-        else contract_tile<BT, NS>(p, Afrag, sB, sSST, sMeanT, sMeanXT, g, cg, lane);
+        PlainB bsrc{sB, TB};
+        if (BT > 2 && p.CG == 1 && left <= 16) contract_tile<2, NS>(p, Afrag, bsrc, sSST, sMeanT, sMeanXT, g, cg, lane);
+        else if (BT > 4 && p.CG == 1 && left <= 32) contract_tile<4, NS>(p, Afrag, bsrc, sSST, sMeanT, sMeanXT, g, cg, lane);
+        else contract_tile<BT, NS>(p, Afrag, bsrc, sSST, sMeanT, sMeanXT, g, cg, lane);
         __syncthreads();
 
         const int64_t tile_row0 = si * tp.fast_rows + (int64_t)j * T - p.row0;
