@@ -174,6 +174,7 @@ class _DeviceFits:
         self.groups = [[i] for i in range(len(gps))]
 
     def refresh(self, after_fit=None):
+        changed = False
         for i, gp in enumerate(self.gps):
             hyper = extract_hyper(gp)
             fp = fingerprint(gp, hyper)
@@ -197,12 +198,14 @@ class _DeviceFits:
             if not done:
                 self.engine.fit(i, X, Y, hyper.kind, hyper.lengthscale, hyper.variance, hyper.noise_var)
                 self.refits += 1
+            changed = True
             self._fp[i] = fp
             self._data[i] = (X.copy(), Y.copy(), key)
             self.hypers[i] = hyper
             if after_fit is not None:
                 after_fit(i, hyper)
-        self._regroup()
+        if changed:
+            self._regroup()
 
     MAX_GROUP = 4       # kMaxOut of the kernels
 

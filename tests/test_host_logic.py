@@ -60,6 +60,70 @@ def test_fails_loudly_without_gpu():
         sb.SafeOptSwarm(gp, 0.0, bounds=[(-1, 1)])
 
 
+class _RecordingEngine:
+    """Stands in for DeviceEngine in the host-logic test of _DeviceFits: records which fit entry point would be called."""
+
+    def __init__(self, append_ok=True):
+        self.calls = []
+        self.append_ok = append_ok
+
+    def fit(self, i, X, Y, kind, ls, variance, noise):
+        self.calls.append(("fit", i, X.shape[0]))
+
+    def fit_append(self, i, x, y):
+        self.calls.append(("append", i, float(y)))
+        return self.append_ok
+
+    def fit_remove_last(self, i):
+        self.calls.append(("remove", i))
+
+
+def test_device_fits_choose_the_cheapest_update(monkeypatch):
+    """_DeviceFits.refresh: nothing changed -> no call; one row appended -> so_fit_append (falling back to so_fit when the
+    device refuses); last row removed -> so_fit_remove_last; anything else -> so_fit.  GPs that share inputs, kernel and
+    noise form one group (one launch), a GP with its own kernel its own."""
+    from safeopt_b200.gp_opt import _DeviceFits
+    monkeypatch.delenv("SAFEOPT_B200_INCREMENTAL_FIT", raising=False)
+    monkeypatch.delenv("SAFEOPT_B200_SHARE_FITS", raising=False)
+    rs = np.random.RandomState(0)
+    X, Y = rs.rand(5, 2), rs.rand(5, 3)
+    mk = lambda i, var=2.0: sb.GPRegression(X, Y[:, [i]], kernel=sb.RBF(2, variance=var, lengthscale=np.ones(2), ARD=True), noise_var=0.01)
+    gps = [mk(0), mk(1), mk(2, var=1.5)]
+    eng = _RecordingEngine()
+    fits = _DeviceFits(eng, gps)
+    seen = []
+    fits.refresh(lambda i, hyper: seen.append(i))
+    assert eng.calls == [("fit", 0, 5), ("fit", 1, 5), ("fit", 2, 5)] and seen == [0, 1, 2]
+    assert fits.groups == [[0, 1], [2]]
+    eng.calls.clear()
+    fits.refresh()
+    assert eng.calls == []
+    x_new, y_new = rs.rand(1, 2), rs.rand(1, 3)
+    for i, gp in enumerate(gps):
+        gp.set_XY(np.vstack([gp.X, x_new]), np.vstack([gp.Y, y_new[:, [i]]]))
+    fits.refresh()
+    assert eng.calls == [("append", i, float(y_new[0, i])) for i in range(3)] and fits.appends == 3
+    assert fits.groups == [[0, 1], [2]]
+    eng.calls.clear()
+    gps[0].set_XY(gps[0].X[:-1], gps[0].Y[:-1])
+    fits.refresh()
+    assert eng.calls == [("remove", 0)] and fits.groups == [[0], [1], [2]]          # GP 0 now has different data
+    eng.calls.clear()
+    gps[1].kern.lengthscale = np.array([0.5, 2.0])                                  # hyper-parameter change
+    Xm = gps[2].X.copy()
+    Xm[0, 0] += 1e-9                                                                # a row in the middle changed
+    gps[2].set_XY(Xm, gps[2].Y)
+    fits.refresh()
+    assert eng.calls == [("fit", 1, 6), ("fit", 2, 6)]
+    eng.calls.clear()
+    eng.append_ok = False                                                           # device buffers full
+    gps[1].set_XY(np.vstack([gps[1].X, x_new]), np.vstack([gps[1].Y, y_new[:, [1]]]))
+    fits.refresh()
+    assert eng.calls == [("append", 1, float(y_new[0, 1])), ("fit", 1, 7)]
+    monkeypatch.setenv("SAFEOPT_B200_SHARE_FITS", "0")
+    assert _DeviceFits(_RecordingEngine(), [mk(0), mk(1)]).share is False
+
+
 def test_weak_scaling_workload_shapes():
     """bench.py --scaling weak multiplies the points of axis 1 (the slowest axis of the reference row order) by the rank
     count, so that contiguous row blocks of equal size are whole axis-1 slabs."""
