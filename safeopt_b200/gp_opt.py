@@ -809,7 +809,9 @@ class SafeOptSwarm(GaussianProcessOptimization):
             raise AssertionError("Invalid swarm type")
         particles = np.ascontiguousarray(np.atleast_2d(np.asarray(particles, dtype=float)))
         values, safe = self._fitness_device(swarm_type, self._engine.to_device(particles))
-        return values.cpu().numpy(), safe.cpu().numpy().astype(bool)      # .cpu() copies: the scratch may be reused
+        # fresh host arrays: the device tensors are scratch that the next fitness pass overwrites, and SwarmOptimization keeps
+        # the returned values as its best_values (swarm.py:80)
+        return np.array(values.cpu().numpy(), copy=True), safe.cpu().numpy().astype(bool)
 
     def get_new_query_point(self, swarm_type):
         """Run one swarm and return (point, value / std-devs) (reference: gp_opt.py:1015-1134)."""

@@ -9,7 +9,7 @@ The product never imports this module.
 import numpy as np
 import torch
 
-from oracle import gpy_lite
+from oracle import gpy_lite, safeopt_port as port
 from safeopt_b200 import _lib
 from safeopt_b200.engine import MAX_REC_DTYPE, SAFE_REC_DTYPE
 from safeopt_b200.utilities import grid_rows_from_index
@@ -185,3 +185,54 @@ class FakeEngine:
             if Xu.shape[0] and np.any(float(u_c.numpy()[b]) - lipschitz * dist >= fmin):
                 flags.numpy()[b] |= 1
         self.launches += 1
+
+    # ---- swarm fitness epilogue and safe-set maintenance (host-backend SafeOptSwarm)
+    def swarm_fitness(self, kind, n_gps, P, mean, var, beta, fmin, scaling, best_lower_bound, values, safe):
+        from scipy.special import expit
+        from scipy.stats import norm
+        name = {v: k for k, v in _lib.SWARM_KINDS.items()}[kind]
+        m, v = mean.numpy()[:, :P], var.numpy()[:, :P]
+        sd = np.sqrt(v[0])
+        lower, upper = m[0] - beta * sd, m[0] + beta * sd
+        if name == "greedy":
+            values.numpy()[:] = lower
+            safe.numpy()[:] = 1
+            return
+        vals = sd / scaling[0]
+        interest = {"safe_set": None, "expanders": n_gps * np.ones(P),
+                    "maximizers": expit(10 * (upper - best_lower_bound) / scaling[0])}[name]
+        ok, pen = np.ones(P, dtype=bool), np.zeros(P)
+        for i in range(n_gps):
+            if i > 0:
+                sd = np.sqrt(v[i])
+                lower = m[i] - beta * sd
+                vals = np.maximum(vals, sd / scaling[i])
+            if fmin[i] == -np.inf:
+                continue
+            slack = lower - fmin[i]
+            ok &= slack >= 0
+            if name == "safe_set":
+                continue
+            slack = slack / scaling[i]
+            pen += port.penalty(slack)
+            if name == "expanders":
+                interest = interest * norm.pdf(slack, scale=0.2)
+        values.numpy()[:] = lower if name == "safe_set" else (vals + pen) * interest
+        safe.numpy()[:] = ok
+        self.launches += 1
+
+    def safeset_filter(self, gp, cand, ref, scale2, thresh, keep):
+        g = self.gps[gp]
+        c = cand.numpy()
+        keep.numpy()[:] = np.all(g.kern.K(c, ref.numpy()) / scale2 <= thresh, axis=1) if ref.shape[0] else 1
+
+    def safeset_insert(self, gp, cand, keep, scale2, thresh, accept, accepted_pos, n_accept):
+        g = self.gps[gp]
+        c, k = cand.numpy(), keep.numpy().astype(bool)
+        acc = np.zeros(c.shape[0], dtype=bool)
+        for j in np.flatnonzero(k):
+            if not acc.any() or np.all(g.kern.K(c[[j]], c[acc])[0] / scale2 <= thresh):
+                acc[j] = True
+        accept.numpy()[:] = acc
+        accepted_pos.numpy()[:acc.sum()] = c[acc]
+        n_accept.numpy()[0] = acc.sum()

@@ -100,3 +100,28 @@ def test_contexts(name, fake_device):
         assert np.array_equal(x, g["x%d" % k]) and x.shape == (1,)
     opt.add_new_data_point(x, np.array([[0.5]]), context=ctx)
     assert opt.x.shape == (13, 2) and opt.x[-1, 1] == ctx[0]
+
+
+@pytest.mark.parametrize("name", ["swarm_query_2d", "swarm_query_2d_mat32"])
+def test_safeoptswarm_trajectory(name, fake_device):
+    """SafeOptSwarm with the host swarm back end over the stand-in engine follows the reference's seeded trajectory:
+    safe-set re-check, particle sampling, PSO, correlation-filtered growth of the safe set, greedy-point bookkeeping."""
+    g = load_golden(name)
+    X, Y = g["X"], g["Y"]
+    d = X.shape[1]
+    cls = {0: sb.RBF, 1: sb.Matern32, 2: sb.Matern52}[int(g["kind"])]
+    gps = [sb.GPRegression(X, Y[:, [i]], kernel=cls(d, variance=float(g["variance"]), lengthscale=g["lengthscale"], ARD=True),
+                           noise_var=float(g["noise_var"])) for i in range(Y.shape[1])]
+    opt = sb.SafeOptSwarm(gps, list(g["fmin"]), bounds=[tuple(b) for b in g["bounds"]], beta=float(g["beta"]),
+                          swarm_size=int(g["swarm_size"]), swarm_backend="host")
+    opt.max_iters = int(g["max_iters"])
+    assert np.allclose(opt.optimal_velocities, np.asarray(opt.optimal_velocities)) and opt.swarm_backend == "host"
+    np.random.seed(int(g["seed"]))
+    for stage in ["greedy", "maximizers", "expanders"]:
+        assert np.array_equal(opt.S, g[stage + "_S_before"]), stage
+        x, v = opt.get_new_query_point(stage)
+        if stage == "greedy":
+            opt.greedy, opt.best_lower_bound = x, v
+        assert np.abs(opt.swarms[stage].best_positions - g[stage + "_best_positions"]).max() < 1e-9, stage
+        assert np.abs(np.asarray(x) - g[stage + "_x"]).max() < 1e-9 and np.abs(np.asarray(v) - g[stage + "_v"]).max() < 1e-9, stage
+        assert opt.S.shape == g[stage + "_S_after"].shape and np.abs(opt.S - g[stage + "_S_after"]).max() < 1e-9, stage
