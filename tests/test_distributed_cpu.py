@@ -160,6 +160,44 @@ def test_sharded_swarm_host_logic_gloo(tmp_path):
     assert all(os.path.exists(os.path.join(str(tmp_path), "ok_%d" % r)) for r in range(world))
 
 
+def _orchestration_worker(rank, world, port, fixture, out_dir):
+    """The whole sharded optimize() of the product's host code on CPU: every rank drives the NumPy stand-in engine
+    (tests/fake_engine.py) on its row block, records and flags cross the ranks over gloo."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from conftest import golden_lipschitz, golden_problem, load_golden, unpack_mask
+        from fake_engine import FakeEngine
+        import safeopt_b200 as sb
+        from safeopt_b200 import gp_opt
+        gp_opt.DeviceEngine = FakeEngine
+        g = load_golden(fixture)
+        gps, grid, fmin = golden_problem(g, "gpu")
+        n_rows = int(g["n_rows"])
+        opt = sb.SafeOpt(gps if len(gps) > 1 else gps[0], grid, fmin if len(gps) > 1 else fmin[0], lipschitz=golden_lipschitz(g),
+                         beta=float(g["beta"]), threshold=float(g["threshold"]))
+        assert opt._comm.world == world and opt._row1 - opt._row0 < n_rows
+        x = opt.optimize()
+        ok = opt.last_query_row == int(g["row_next"]) and np.array_equal(x, g["x_next"])
+        ok = ok and np.abs(opt.Q - g["Q"]).max() < 1e-9
+        ok = ok and np.array_equal(opt.S, unpack_mask(g["S"], n_rows)) and np.array_equal(opt.M, unpack_mask(g["M"], n_rows))
+        ok = ok and np.array_equal(opt.G, unpack_mask(g["G"], n_rows))
+        mx = opt.get_maximum()
+        ok = ok and np.array_equal(mx[0], g["max_x"]) and abs(mx[1] - float(g["max_val"])) < 1e-9
+        open(os.path.join(out_dir, "ok_%d" % rank), "w").write("1" if ok else "0")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("fixture,world", [("expander_g2", 2), ("expander_tight", 3), ("lipschitz_g2", 2), ("matern32_3d", 2)])
+def test_sharded_optimize_host_orchestration_gloo(fixture, world, tmp_path):
+    mp.spawn(_orchestration_worker, args=(world, _free_port(), fixture, str(tmp_path)), nprocs=world, join=True)
+    assert all(open(os.path.join(str(tmp_path), "ok_%d" % r)).read() == "1" for r in range(world))
+
+
 def test_single_rank_comm_is_identity():
     from safeopt_b200 import distributed as D
     comm = D.Comm()
