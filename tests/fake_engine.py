@@ -236,3 +236,44 @@ class FakeEngine:
         accept.numpy()[:] = acc
         accepted_pos.numpy()[:acc.sum()] = c[acc]
         n_accept.numpy()[0] = acc.sum()
+
+    # ---- device swarm (K6): update rule of safeopt/swarm.py:98-146 on the stand-in tensors
+    def swarm_step(self, pos, vel, best_pos, global_best, r, inertia, velocity_scale, bounds):
+        P = pos.shape[0]
+        x, v, bp, gb, rr = pos.numpy(), vel.numpy(), best_pos.numpy(), global_best.numpy(), r.numpy()
+        vs = np.asarray(velocity_scale, dtype=float)
+        v *= inertia
+        v += (rr[:P] * (bp - x) + rr[P:] * (gb - x)) / vs
+        np.clip(v, -10 * vs, 10 * vs, out=v)
+        x += v
+        if bounds is not None:
+            b = np.asarray(bounds, dtype=float)
+            np.clip(x, b[:, 0], b[:, 1], out=x)
+        self.launches += 1
+
+    def swarm_update_best(self, pos, values, safe, best_pos, best_values, best_idx, p0=0, rec=None):
+        x, val, ok = pos.numpy(), values.numpy(), safe.numpy().astype(bool)
+        bp, bv = best_pos.numpy(), best_values.numpy()
+        better = (val > bv) & ok
+        bv[better] = val[better]
+        bp[better] = x[better]
+        k = int(np.argmax(bv))
+        best_idx.numpy()[0] = k
+        if rec is not None:
+            out = rec.numpy()
+            out[0], out[1] = bv[k], float(p0 + k)
+            out[2:2 + x.shape[1]] = bp[k]
+        self.launches += 1
+
+    def swarm_combine_best(self, recs, d, global_best, global_rec=None):
+        r = recs.numpy()
+        best = None
+        for row in r:
+            if row[1] < 0:
+                continue
+            if best is None or row[0] > best[0] or (row[0] == best[0] and row[1] < best[1]):
+                best = row
+        global_best.numpy()[:] = best[2:2 + d]
+        if global_rec is not None:
+            global_rec.numpy()[:2] = best[:2]
+        self.launches += 1

@@ -198,6 +198,48 @@ def test_sharded_optimize_host_orchestration_gloo(fixture, world, tmp_path):
     assert all(open(os.path.join(str(tmp_path), "ok_%d" % r)).read() == "1" for r in range(world))
 
 
+def _swarm_orchestration_worker(rank, world, port, fixture, out_dir):
+    """SafeOptSwarm with the device swarm back end sharded over the ranks (stand-in engine, gloo): particle blocks, the
+    per-iteration best-record exchange and the gathered safe-set insertion must follow the reference's trajectory."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from conftest import load_golden
+        from fake_engine import FakeEngine
+        import safeopt_b200 as sb
+        from safeopt_b200 import gp_opt
+        from safeopt_b200 import distributed as D
+        gp_opt.DeviceEngine = FakeEngine
+        g = load_golden(fixture)
+        X, Y = g["X"], g["Y"]
+        d = X.shape[1]
+        cls = {0: sb.RBF, 1: sb.Matern32, 2: sb.Matern52}[int(g["kind"])]
+        gps = [sb.GPRegression(X, Y[:, [i]], kernel=cls(d, variance=float(g["variance"]), lengthscale=g["lengthscale"], ARD=True),
+                               noise_var=float(g["noise_var"])) for i in range(Y.shape[1])]
+        opt = sb.SafeOptSwarm(gps, list(g["fmin"]), bounds=[tuple(b) for b in g["bounds"]], beta=float(g["beta"]),
+                              swarm_size=int(g["swarm_size"]), swarm_backend="device", rng="host")
+        opt.max_iters = int(g["max_iters"])
+        np.random.seed(int(g["seed"]))
+        x = opt.optimize()
+        sw = opt.swarms["expanders"]
+        ok = sw.comm.world == world and sw.p1 - sw.p0 < int(g["swarm_size"])
+        ok = ok and np.abs(x - g["x_next"]).max() < 1e-9 and opt.S.shape == g["S_final"].shape and np.abs(opt.S - g["S_final"]).max() < 1e-9
+        full = D.gather_padded_rows(sw.comm, sw.best_positions, int(g["swarm_size"])).numpy()
+        ok = ok and np.abs(full - g["expanders_best_positions"]).max() < 1e-9
+        open(os.path.join(out_dir, "ok_%d" % rank), "w").write("1" if ok else "0")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("fixture,world", [("swarm_query_2d", 2), ("swarm_query_2d_mat32", 3)])
+def test_sharded_swarm_host_orchestration_gloo(fixture, world, tmp_path):
+    mp.spawn(_swarm_orchestration_worker, args=(world, _free_port(), fixture, str(tmp_path)), nprocs=world, join=True)
+    assert all(open(os.path.join(str(tmp_path), "ok_%d" % r)).read() == "1" for r in range(world))
+
+
 def test_single_rank_comm_is_identity():
     from safeopt_b200 import distributed as D
     comm = D.Comm()
