@@ -164,6 +164,10 @@ int so_posterior_grid_multi(so_handle* h, int n, const int* gps_h, int64_t row0,
                             double beta, const double* fmin_h, double* const* mean_dh,
                             double* const* var_dh, double* Q_d, int q_stride, const int* q_col_h,
                             uint8_t* S_d, int safe_mode, void* stream);
+/* Diagnostic, host only (no device work): the assignment of the NB block rows of L^-1 to the eight warps of
+ * the contraction for a fit with NB = ceil(N/8) block rows, as the posterior kernels use it when NB is not a
+ * multiple of 32.  table_h: 8 passes x 8 warps x 4 slots (int16, ascending per pass, -1 = unused). */
+int so_debug_row_plan(int NB, int16_t* table_h, int* npass_h);
 /* Materialise grid rows [row0, row0+M) as an (M x d) row-major array (tests, query point). */
 int so_grid_rows(so_handle* h, int64_t row0, int64_t M, double* X_d, void* stream);
 

@@ -179,7 +179,7 @@ int plan_launch(so_handle* h, const GPState& g, int64_t M, bool grid, int n_extr
 
 // Block rows of the eight warps for an arbitrary NB (see PostParams::row_table): longest row first to the least loaded warp,
 // every warp at most 4 * npass rows; each warp's rows ascending, four per pass.
-int plan_rows(int NB, signed char (&table)[kMaxPass][8][4]) {
+int plan_rows(int NB, short (&table)[kMaxPass][8][4]) {
     const int per_warp = (NB + 7) / 8;
     const int npass = (per_warp + 3) / 4;
     int load[8] = {0, 0, 0, 0, 0, 0, 0, 0}, count[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -193,7 +193,7 @@ int plan_rows(int NB, signed char (&table)[kMaxPass][8][4]) {
     }
     for (int w = 0; w < 8; ++w) {
         std::sort(mine[w], mine[w] + count[w]);
-        for (int q = 0; q < 4 * npass; ++q) table[q / 4][w][q % 4] = (signed char)(q < count[w] ? mine[w][q] : -1);
+        for (int q = 0; q < 4 * npass; ++q) table[q / 4][w][q % 4] = (short)(q < count[w] ? mine[w][q] : -1);
     }
     return npass;
 }
@@ -461,6 +461,19 @@ extern "C" int so_posterior_grid_multi(so_handle* h, int n, const int* gps_h, in
                                        const double* fmin_h, double* const* mean_dh, double* const* var_dh, double* Q_d,
                                        int q_stride, const int* q_col_h, uint8_t* S_d, int safe_mode, void* stream) {
     return run_multi(h, n, gps_h, nullptr, true, row0, M, beta, fmin_h, mean_dh, var_dh, Q_d, q_stride, q_col_h, S_d, safe_mode, stream);
+}
+
+extern "C" int so_debug_row_plan(int NB, int16_t* table_h, int* npass_h) {
+    if (!table_h || !npass_h || NB < 1 || NB > 8 * 4 * kMaxPass) return SO_ERR_BAD_ARG;
+    short table[kMaxPass][8][4];
+    for (int p = 0; p < kMaxPass; ++p)
+        for (int w = 0; w < 8; ++w)
+            for (int s = 0; s < 4; ++s) table[p][w][s] = -1;
+    *npass_h = plan_rows(NB, table);
+    for (int p = 0; p < kMaxPass; ++p)
+        for (int w = 0; w < 8; ++w)
+            for (int s = 0; s < 4; ++s) table_h[(p * 8 + w) * 4 + s] = (int16_t)table[p][w][s];
+    return SO_OK;
 }
 
 extern "C" int so_posterior_rows_simple(so_handle* h, int gp, const double* Xstar_d, int64_t M, double* mean_d,

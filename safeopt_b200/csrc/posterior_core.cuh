@@ -47,7 +47,7 @@ struct PostParams {
     // per iteration) the host assigns the rows longest-first to the least loaded warp (plan_rows) -- with the closed form,
     // NB = 33 put the whole extra block row on one warp in a second pass and a tile took 1.7x as long.
     int use_row_table;
-    signed char row_table[kMaxPass][8][4];      // ascending per pass, -1 = unused slot (suffix)
+    short row_table[kMaxPass][8][4];            // ascending per pass, -1 = unused slot (suffix); NB <= 256
 };
 
 struct SmemLayout {

@@ -39,6 +39,31 @@ def test_library_exports_every_declared_symbol():
     assert _lib.status_string(_lib.SO_ERR_NOT_PD) == "covariance matrix not positive definite"
 
 
+@pytest.mark.parametrize("NB", [1, 7, 32, 33, 35, 36, 40, 52, 63, 64, 65, 100, 129, 256])
+def test_block_row_plan_is_a_balanced_partition(NB):
+    """plan_rows (host side of the contraction kernels): every block row is owned by exactly one warp, rows ascend inside a
+    pass, unused slots trail, and the triangular work (row i costs i + 1 k-blocks) is balanced over the eight warps."""
+    import ctypes
+    lib = _lib.load()
+    table = np.full(8 * 8 * 4, -2, dtype=np.int16)
+    npass = ctypes.c_int(0)
+    assert lib.so_debug_row_plan(NB, table.ctypes.data, ctypes.byref(npass)) == 0
+    t = table.reshape(8, 8, 4)
+    n = npass.value
+    assert n == -(-(-(-NB // 8)) // 4) and np.all(t[n:] == -1)
+    rows = t[:n][t[:n] >= 0]
+    assert sorted(rows.tolist()) == list(range(NB))
+    for p in range(n):
+        for w in range(8):
+            slot = t[p, w]
+            used = slot[slot >= 0]
+            assert np.all(np.diff(used) > 0) and np.all(slot[len(used):] == -1)
+    load = np.array([sum(int(r) + 1 for r in t[:n, w].ravel() if r >= 0) for w in range(8)])
+    ideal = NB * (NB + 1) / 2 / 8
+    assert load.max() <= ideal + NB          # longest-first greedy: within one (longest) row of the ideal share
+    assert lib.so_debug_row_plan(0, table.ctypes.data, ctypes.byref(npass)) == _lib.SO_ERR_BAD_ARG
+
+
 def test_record_layouts_match_header():
     import ctypes
     from safeopt_b200.engine import MAX_REC_DTYPE, SAFE_REC_DTYPE
