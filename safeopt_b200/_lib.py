@@ -78,6 +78,7 @@ SIGNATURES = {
     "so_posterior_rows_multi": (_i, [_P, _i, _P, _P, _i64, _dbl, _P, _P, _P, _P, _i, _P, _P, _i, _P]),
     "so_posterior_grid_multi": (_i, [_P, _i, _P, _i64, _i64, _dbl, _P, _P, _P, _P, _i, _P, _P, _i, _P]),
     "so_debug_row_plan": (_i, [_i, _P, _P]),
+    "so_debug_tile_plans": (_i, [_i, _i, _i64, _i, _i64, _i, _P]),
     "so_posterior_rows_simple": (_i, [_P, _i, _P, _i64, _P, _P, _P]),
     "so_grid_rows": (_i, [_P, _i64, _i64, _P, _P]),
     "so_sets_reduce_safe": (_i, [_P, _P, _i, _i64, _i64, _P, _P, _P]),

@@ -463,6 +463,47 @@ extern "C" int so_posterior_grid_multi(so_handle* h, int n, const int* gps_h, in
     return run_multi(h, n, gps_h, nullptr, true, row0, M, beta, fmin_h, mean_dh, var_dh, Q_d, q_stride, q_col_h, S_d, safe_mode, stream);
 }
 
+// Diagnostic, host only: the tile plans of the posterior kernels for a fit with NB block rows on a device with
+// `smem_limit` bytes of opt-in shared memory and `num_sms` SMs, without touching a device.
+//   out_h[0..9] = grid (TMA) kernel: status, BT, RG, CG, T, npass, ring (0/1), ring stages, shared-memory bytes, warps
+//   out_h[10..17] = explicit-rows kernel (M candidates, dimension d): status, BT, RG, CG, T, npass, shared-memory bytes, 0
+extern "C" int so_debug_tile_plans(int NB, int d, int64_t M, int n_extra, int64_t smem_limit, int num_sms, int64_t* out_h) {
+    if (!out_h || NB < 1 || NB > 256 || d < 1 || d > SO_MAX_DIM || n_extra < 0 || n_extra >= kMaxOut || smem_limit < 0 || num_sms < 1)
+        return SO_ERR_BAD_ARG;
+    so_handle h;
+    h.smem_optin = (int)smem_limit;
+    h.num_sms = num_sms;
+    GPState g;
+    g.NB = NB; g.N = 8 * NB; g.d = d;
+    for (int i = 0; i < 18; ++i) out_h[i] = 0;
+    TmaPlan tp;
+    const int rc = plan_tma(&h, g, tp);
+    out_h[0] = rc;
+    if (rc == SO_OK) {
+        const int ns = tp.warps == 16 ? 2 : 4;
+        int npass = (NB + ns * tp.RG - 1) / (ns * tp.RG);
+        if (NB >= 32 && NB % 32 != 0 && tp.RG == 8 && ns == 4) {
+            short table[kMaxPass][8][4];
+            npass = plan_rows(NB, table);
+        }
+        out_h[1] = tp.BT; out_h[2] = tp.RG; out_h[3] = tp.CG; out_h[4] = tp.T; out_h[5] = npass; out_h[6] = tp.ring ? 1 : 0;
+        if (tp.ring) {
+            const RingSmem rs = ring_smem(tp.TB, tp.RG, tp.T, n_extra, (size_t)smem_limit);
+            out_h[7] = rs.stages; out_h[8] = (int64_t)rs.total;
+        } else {
+            out_h[8] = (int64_t)tma_smem(tp.kb_pad, tp.TB, tp.RG, tp.T, n_extra).total;
+        }
+        out_h[9] = tp.warps;
+    }
+    LaunchPlan lp;
+    const int rc2 = plan_launch(&h, g, M, false, n_extra, lp);
+    out_h[10] = rc2;
+    if (rc2 == SO_OK) {
+        out_h[11] = lp.BT; out_h[12] = lp.RG; out_h[13] = lp.CG; out_h[14] = lp.T; out_h[15] = lp.npass; out_h[16] = (int64_t)lp.smem;
+    }
+    return SO_OK;
+}
+
 extern "C" int so_debug_row_plan(int NB, int16_t* table_h, int* npass_h) {
     if (!table_h || !npass_h || NB < 1 || NB > 8 * 4 * kMaxPass) return SO_ERR_BAD_ARG;
     short table[kMaxPass][8][4];

@@ -64,6 +64,42 @@ def test_block_row_plan_is_a_balanced_partition(NB):
     assert lib.so_debug_row_plan(0, table.ctypes.data, ctypes.byref(npass)) == _lib.SO_ERR_BAD_ARG
 
 
+def test_tile_plans_fit_the_device_for_every_size():
+    """Host-side planning of the posterior kernels for every NB (N = 8 .. 2048) and 0..3 further outputs, on a B200's
+    227 KB of opt-in shared memory: whatever is planned fits, tiles are whole 8-row blocks, the eight warps are split
+    RG x CG, the passes cover all block rows, and the grid kernel keeps 48-row tiles wherever the ring is used."""
+    lib = _lib.load()
+    limit, sms = 232448, 148
+    out = np.zeros(18, dtype=np.int64)
+    seen_ring = seen_db48 = 0
+    for nb in range(1, 257):
+        for n_extra in range(4):
+            assert lib.so_debug_tile_plans(nb, 4, 6_250_000, n_extra, limit, sms, out.ctypes.data) == 0
+            st, bt, rg, cg, T, npass, ring, stages, smem, warps = out[:10]
+            if st == 0:
+                # the tile is planned for one output; with further outputs a launch that no longer fits is refused with
+                # SO_ERR_CAPACITY and the host evaluates the GPs one by one (the ring re-sizes itself and always fits)
+                assert (smem <= limit or (n_extra > 0 and not ring)) and bt in (2, 4, 6) and rg * cg == warps == 8 and T == 8 * bt * cg
+                assert 4 * rg * npass >= nb
+                if ring:
+                    assert stages >= 4 and T == 48 and rg == 8
+                    seen_ring += 1
+                elif T == 48 and cg == 1:
+                    seen_db48 += 1
+            else:
+                assert st == _lib.SO_ERR_CAPACITY
+            st2, bt2, rg2, cg2, T2, npass2, smem2 = out[10:17]
+            if st2 == 0:
+                assert smem2 <= limit and bt2 in (2, 4, 8) and rg2 * cg2 == 8 and T2 == 8 * bt2 * cg2 and 4 * rg2 * npass2 >= nb
+            else:
+                assert st2 == _lib.SO_ERR_CAPACITY and nb > 150           # the resident K tile caps the explicit-rows kernel
+    assert seen_ring > 0 and seen_db48 > 0
+    # config 4: N = 256 -> 48-row double buffer; N = 257..280 keep it; N = 512 streams
+    for nb, want_T, want_ring in [(32, 48, 0), (33, 48, 0), (35, 48, 0), (36, 32, 0), (52, 32, 0), (64, 48, 1)]:
+        lib.so_debug_tile_plans(nb, 4, 6_250_000, 0, limit, sms, out.ctypes.data)
+        assert (out[4], out[6]) == (want_T, want_ring), nb
+
+
 def test_record_layouts_match_header():
     import ctypes
     from safeopt_b200.engine import MAX_REC_DTYPE, SAFE_REC_DTYPE
