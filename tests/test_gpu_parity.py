@@ -694,6 +694,60 @@ def test_config_c3_three_gps_properties():
     assert np.abs(Q[rows] - port.confidence_intervals(gos, grid[rows], w.beta)).max() < 1e-9 * 2 * np.sqrt(w.variance)
 
 
+# ---------------------------------------------------------------- the CPU stand-in engine honours the same contracts
+def test_stand_in_engine_agrees_with_the_device():
+    """tests/fake_engine.py (NumPy, used by the CPU orchestration tests) and the real engine give the same answers to the
+    same calls: posterior + bounds + safe bits, the three chained set passes, both expander tests."""
+    from fake_engine import FakeEngine
+    from safeopt_b200.engine import MAX_REC_DTYPE, SAFE_REC_DTYPE
+    from safeopt_b200.utilities import detect_grid
+    g = load_golden("expander_g2")
+    X, Y = g["X"], g["Y"]
+    grid = port.linearly_spaced_combinations([tuple(b) for b in g["bounds"]], [int(v) for v in np.atleast_1d(g["num_samples"])])
+    M, G, beta = grid.shape[0], Y.shape[1], float(g["beta"])
+    fmin = [float(v) for v in g["fmin"]]
+    scaling = np.full(G, np.sqrt(float(g["variance"])))
+    thr = np.full(G, float(g["threshold"]) * beta)
+    out = {}
+    for name, eng in (("dev", DeviceEngine(max_gps=G)), ("fake", FakeEngine(max_gps=G))):
+        eng.define_grid(detect_grid(grid))
+        for i in range(G):
+            eng.fit(i, X, Y[:, i], int(g["kind"]), g["lengthscale"], float(g["variance"]), float(g["noise_var"]))
+            eng.prepare_grid(i)
+        Q, S, Mm = eng.empty((M, 2 * G)), eng.zeros((M,), "u8"), eng.zeros((M,), "u8")
+        mean, var = eng.empty((G, M)), eng.empty((G, M))
+        for i in range(G):
+            eng.posterior_grid(i, 0, M, beta, fmin[i], mean=mean[i], var=var[i], Q=Q, q_col=2 * i, S=S,
+                               safe_mode=_lib.SAFE_WRITE if i == 0 else _lib.SAFE_AND)
+        rs, rm = eng.zeros((1, 64), "u8"), eng.zeros((1, 64), "u8")
+        key, row, cnt = eng.empty((M,)), eng.empty((M,), "i64"), eng.zeros((1,), "i64")
+        eng.reduce_safe(Q, G, 0, S, rs)
+        eng.maximizers_chain(Q, G, 0, S, rs, 1, scaling, Mm, rm)
+        eng.candidates_chain(Q, G, 0, S, Mm, rm, 1, scaling, thr, None, key, row, cnt)
+        n = int(cnt.cpu().numpy()[0])
+        rows = np.sort(row.cpu().numpy()[:n])
+        # expander tests on the four widest candidates
+        Qh, meanh, varh = Q.cpu().numpy(), mean.cpu().numpy(), var.cpu().numpy()
+        cand = rows[np.argsort(-(Qh[rows, 1] - Qh[rows, 0]))[:4]]
+        xc = eng.to_device(grid[cand])
+        flags_gp, flags_lip = eng.zeros((32,), "u8"), eng.zeros((32,), "u8")
+        eng.expander_check(0, None, 0, M, S, mean[0], var[0], xc, eng.to_device(meanh[0, cand]), eng.to_device(varh[0, cand]),
+                           eng.to_device(Qh[cand, 1]), beta, fmin[0], flags_gp)
+        eng.expander_lipschitz(None, 2, 0, M, S, xc, eng.to_device(Qh[cand, 1]), 2.0, fmin[0], flags_lip)
+        out[name] = dict(Q=Qh, S=S.cpu().numpy(), M=Mm.cpu().numpy(), safe=rs.cpu().numpy().view(SAFE_REC_DTYPE).reshape(-1)[0],
+                         mx=rm.cpu().numpy().view(MAX_REC_DTYPE).reshape(-1)[0], rows=rows, cand=cand,
+                         fgp=flags_gp.cpu().numpy()[:4].copy(), flip=flags_lip.cpu().numpy()[:4].copy())
+        eng.close()
+    d, f = out["dev"], out["fake"]
+    assert np.abs(d["Q"] - f["Q"]).max() < 1e-9 * 2 * np.sqrt(2.0)
+    assert np.array_equal(d["S"], f["S"]) and np.array_equal(d["M"], f["M"]) and np.array_equal(d["rows"], f["rows"])
+    assert np.array_equal(d["cand"], f["cand"]) and np.array_equal(d["fgp"], f["fgp"]) and np.array_equal(d["flip"], f["flip"])
+    for k in ("n_safe", "argmax_l0", "argmax_u0"):
+        assert d["safe"][k] == f["safe"][k]
+    assert abs(d["safe"]["max_l0"] - f["safe"]["max_l0"]) < 1e-9 and d["mx"]["n_max"] == f["mx"]["n_max"]
+    assert d["mx"]["best_row"] == f["mx"]["best_row"] and abs(d["mx"]["max_width0"] - f["mx"]["max_width0"]) < 1e-9
+
+
 # ---------------------------------------------------------------- multi-GPU (runs when the box has >= 2 GPUs)
 def _nccl_worker(rank, world, port_no, out):
     import os
