@@ -32,7 +32,7 @@ struct GPState {
     // grid tables (grid fast path): per axis j, E_j[i][n], i < n_j, n < Npad
     double* E = nullptr;
     size_t capE = 0;
-    // two-level product tables (warp-specialised kernel): fast_rows + slow_rows rows of Npad doubles
+    // two-level product tables of the grid path: fast_rows + slow_rows rows of Npad doubles (Pfast, Pslow)
     double* P2 = nullptr;
     size_t capP2 = 0;
     // tables of the TMA kernel: fragment-ordered fast table, scaled operands A'(s) (see posterior_tma.cuh)
