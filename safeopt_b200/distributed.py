@@ -16,6 +16,11 @@ from typing import Tuple
 import numpy as np
 
 
+def torch_empty_like(t):
+    import torch
+    return torch.empty_like(t)
+
+
 def shard_bounds(n_rows: int, world: int, rank: int) -> Tuple[int, int]:
     """Contiguous row block of ``rank``: blocks of ceil(M/R) rows, the last ones possibly short/empty."""
     per = -(-int(n_rows) // int(world))
@@ -31,12 +36,14 @@ class Comm:
         self.rank, self.world = 0, 1
         self._dist = None
         self._device = device
+        self._flat_gather = False
         try:
             import torch.distributed as dist
             if dist.is_available() and dist.is_initialized():
                 self._dist = dist
                 self.rank = dist.get_rank()
                 self.world = dist.get_world_size()
+                self._flat_gather = hasattr(dist, "all_gather_into_tensor")
         except ImportError:  # pragma: no cover
             pass
 
@@ -71,12 +78,7 @@ class Comm:
             return t.cpu().numpy()[None, ...]
         import torch
         out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
-        try:
-            self._dist.all_gather_into_tensor(out, t.contiguous())
-        except (RuntimeError, AttributeError, NotImplementedError):
-            parts = [torch.empty_like(t) for _ in range(self.world)]
-            self._dist.all_gather(parts, t.contiguous())
-            out = torch.stack(parts, dim=0)
+        self.all_gather_into(out, t)
         return out.cpu().numpy()
 
     def all_gather_into(self, out, t):
@@ -84,11 +86,16 @@ class Comm:
         if not self.active:
             out[0].copy_(t)
             return out
-        try:
-            self._dist.all_gather_into_tensor(out, t.contiguous())
-        except (RuntimeError, AttributeError, NotImplementedError):
-            parts = [out[r] for r in range(self.world)]
+        # the variant is chosen ONCE by capability, never by catching an error of a live collective (a retry with a
+        # different collective after a genuine failure would desynchronise the ranks)
+        if self._flat_gather and out.is_contiguous():
+            # flattened views: gloo accepts only the concatenated 1-D form, NCCL accepts both
+            self._dist.all_gather_into_tensor(out.view(-1), t.contiguous().view(-1))
+        else:
+            parts = [torch_empty_like(t) for _ in range(self.world)]
             self._dist.all_gather(parts, t.contiguous())
+            for r in range(self.world):
+                out[r].copy_(parts[r])
         return out
 
     def gather_records(self, rec_u8, dtype: np.dtype) -> np.ndarray:
@@ -187,8 +194,9 @@ def shard_stacked_blocks(full: np.ndarray, blocks: int, total: int, lo: int, hi:
 
 
 def order_candidates(comm: Comm, rows_sorted: np.ndarray, keys_sorted: np.ndarray) -> np.ndarray:
-    """Global visiting order of expander candidates: key descending, ties by ascending row."""
+    """Global visiting order of expander candidates: key descending, ties by DESCENDING row -- what the
+    reference's ``argsort()[::-1]`` (gp_opt.py:545-552) yields wherever NumPy's sort is stable."""
     if not comm.active:
         return rows_sorted
     allr, allk = gather_ragged(comm, rows_sorted), gather_ragged(comm, keys_sorted)
-    return allr[np.lexsort((allr, -allk))]
+    return allr[np.lexsort((-allr, -allk))]

@@ -52,7 +52,11 @@ class GaussianProcessOptimization(object):
         self.fmin = fmin
         if not isinstance(self.fmin, list):
             self.fmin = [self.fmin] * len(self.gps)
+        # None = unconstrained, like -inf (np.asarray would turn None into NaN, and every comparison with NaN is False)
+        self.fmin = [(-np.inf if f is None else f) for f in self.fmin]
         self.fmin = np.atleast_1d(np.asarray(self.fmin, dtype=float).squeeze())
+        if np.isnan(self.fmin).any():
+            raise ValueError("fmin must not contain NaN (use -np.inf or None for an unconstrained GP)")
 
         self.beta = beta if callable(beta) else (lambda t: beta)
 
@@ -276,8 +280,8 @@ class SafeOpt(GaussianProcessOptimization):
         self._use_lipschitz = lipschitz is not None
 
         # ---- device state
-        self._comm = Comm()
         self._engine = DeviceEngine(device, max_gps=len(self.gps))
+        self._comm = Comm(self._engine.device)       # NCCL staging tensors live on the engine's device, not the current one
         self._fits = _DeviceFits(self._engine, self.gps)
         n_rows = self.inputs.shape[0]
         self._row0, self._row1 = shard_bounds(n_rows, self._comm.world, self._comm.rank)
@@ -365,19 +369,31 @@ class SafeOpt(GaussianProcessOptimization):
             self._host_cache[key] = arr.astype(bool) if as_bool else arr
         return self._host_cache[key]
 
+    def local_block(self, name):
+        """Rank-local shard of ``'Q'``, ``'S'`` or ``'M'`` as a host array together with its global row range
+        ``(row0, row1)``.  Never communicates -- the accessor to use from ONE rank (logging, plotting) in a multi-GPU run,
+        where the properties ``Q`` / ``S`` / ``M`` are collectives."""
+        t = {"Q": self._Q_d, "S": self._S_d, "M": self._M_d}[name]
+        arr = t.cpu().numpy()
+        return (arr if name == "Q" else arr.astype(bool)), (self._row0, self._row1)
+
     @property
     def Q(self):
-        """Confidence intervals, ``(M, 2G)`` float64: columns ``l0, u0, l1, u1, ...`` (copied from the device on access)."""
+        """Confidence intervals, ``(M, 2G)`` float64: columns ``l0, u0, l1, u1, ...`` (copied from the device on access).
+
+        With ``torch.distributed`` initialised, ``Q``, ``S`` and ``M`` reassemble the row-sharded arrays with an
+        all-gather: they are COLLECTIVES that every rank must read (the result is cached until the next device pass);
+        reading one on a single rank only deadlocks the job -- use :meth:`local_block` there."""
         return self._host("Q", self._Q_d)
 
     @property
     def S(self):
-        """Safe set mask ``(M,)`` bool."""
+        """Safe set mask ``(M,)`` bool (multi-rank: a collective, see :attr:`Q`)."""
         return self._host("S", self._S_d, as_bool=True)
 
     @property
     def M(self):
-        """Maximiser mask ``(M,)`` bool."""
+        """Maximiser mask ``(M,)`` bool (multi-rank: a collective, see :attr:`Q`)."""
         return self._host("M", self._M_d, as_bool=True)
 
     @property
@@ -542,14 +558,20 @@ class SafeOpt(GaussianProcessOptimization):
 
     # ---- expander search ------------------------------------------------------------------
     def _ordered_candidates(self, rows_local, keys_local):
-        """Global visiting order: widest (unscaled) interval first, ties by row (gp_opt.py:551-552)."""
+        """Global visiting order: widest (unscaled) interval first (gp_opt.py:551-552).
+
+        Ties: the reference visits ``keys.argsort()[::-1]``.  NumPy's default argsort is not stable, so its order among
+        exactly equal keys is implementation-defined; where it is defined (up to 16 candidates NumPy runs an insertion
+        sort, which is stable) the reversal puts the HIGHER row first.  That is the convention used here for any size:
+        key descending, then row descending (``order_candidates``)."""
         t = self._engine.torch
         if keys_local is None:
             rows = rows_local.cpu().numpy()
             allr = self._gather_var(rows)
             return np.sort(allr)
-        # deterministic local order first (the append order of the candidate kernel is not)
-        order = t.argsort(rows_local)
+        # deterministic local order first (the append order of the candidate kernel is not): rows descending, then a
+        # stable sort by key keeps the higher row first among equal keys
+        order = t.argsort(rows_local, descending=True)
         rows_local, keys_local = rows_local[order], keys_local[order]
         order = t.argsort(keys_local, descending=True, stable=True)
         rows = rows_local[order].cpu().numpy()

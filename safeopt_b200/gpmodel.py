@@ -183,12 +183,24 @@ def extract_hyper(gp) -> Hyper:
         noise = _scalar(gp.likelihood.variance)
     except AttributeError as exc:
         raise UnsupportedModelError("model has no Gaussian likelihood.variance") from exc
+    # GPy's GP applies `mean_function` and `normalizer` inside predict_noiseless; the device posterior has neither, so a
+    # model that uses them would silently get different bounds.  Refuse it (GPy's normalizer=False/None means "off").
+    if getattr(gp, "mean_function", None) is not None:
+        raise UnsupportedModelError("models with a mean_function are not supported by the device path")
+    if getattr(gp, "normalizer", None) not in (None, False):
+        raise UnsupportedModelError("models with an output normalizer are not supported by the device path")
     parts = getattr(k, "parts", None)
     if parts is None or _kind_of(k) is not None:
         kind, ls, var = _stationary_part(k, d)
         if np.isnan(ls).any():
             raise UnsupportedModelError("kernel does not cover all %d input dimensions" % d)
         return Hyper(kind, ls, var, noise)
+    # composite kernel: only a PRODUCT is separable (GPy: class Prod, name 'mul'); a sum (class Add, name 'sum') or any
+    # other combination has a different covariance and must not be folded into one ARD kernel
+    if not (type(k).__name__ in ("Prod", "ProductKernel") or getattr(k, "name", None) == "mul"):
+        raise UnsupportedModelError(
+            "composite kernel %r (name %r) is not supported by the device path: only products of RBF kernels on disjoint "
+            "active_dims are (there is no CPU fallback)" % (type(k).__name__, getattr(k, "name", None)))
     # product kernel: RBF x RBF on disjoint dims == one ARD RBF with the variances multiplied
     ls = np.full(d, np.nan)
     var = 1.0

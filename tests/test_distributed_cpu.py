@@ -82,18 +82,18 @@ def _worker(rank, world, port, fixture, out_dir):
         assert np.array_equal(D.gather_row_blocks(comm, Sl.astype(np.uint8), n_rows).astype(bool), S_ref)
         assert np.array_equal(D.gather_row_blocks(comm, Ml.astype(np.uint8), n_rows).astype(bool), M_ref)
         assert np.array_equal(D.gather_row_blocks(comm, Ql, n_rows), Q)
-        # candidates: s = S & ~M & wide enough; global order = key desc, row asc
+        # candidates: s = S & ~M & wide enough; global order = key desc, row desc on ties (stable argsort reversed)
         beta, thr = float(g["beta"]), float(g["threshold"])
         w = Ql[:, 1::2] - Ql[:, ::2]
         s = Sl & ~Ml & (np.max(w / scaling, axis=1) > mx["max_var"]) & np.any(w > thr * beta, axis=1)
         rows = np.flatnonzero(s) + r0
         keys = np.max(w[s], axis=1)
-        o = np.lexsort((rows, -keys))
+        o = np.lexsort((-rows, -keys))
         order = D.order_candidates(comm, rows[o], keys[o])
         wf = Q[:, 1::2] - Q[:, ::2]
         sf = S_ref & ~M_ref & (np.max(wf / scaling, axis=1) > mx["max_var"]) & np.any(wf > thr * beta, axis=1)
         rf, kf = np.flatnonzero(sf), np.max(wf[sf], axis=1)
-        assert np.array_equal(order, rf[np.lexsort((rf, -kf))])
+        assert np.array_equal(order, rf[np.argsort(kf, kind="stable")[::-1]])
         # the no-expander query point: best scaled width over M, first row on ties
         G_ref = unpack_mask(g["G"], n_rows)
         if not G_ref.any():

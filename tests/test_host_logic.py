@@ -271,6 +271,41 @@ def test_combine_max_first_is_numpy_argmax():
     assert combine_max_first([1.0, -np.inf], [4, -1]) == (1.0, 4)
 
 
+def test_candidate_order_on_ties_follows_the_reference():
+    """gp_opt.py:545-552 visits ``keys.argsort()[::-1]``: on exactly equal keys (where NumPy's sort is stable, i.e. the
+    insertion sort it runs up to 16 elements) the HIGHER row comes first."""
+    from safeopt_b200.distributed import Comm, order_candidates
+    keys = np.array([1.0, 2.0, 2.0, 1.0, 3.0, 2.0])
+    rows = np.array([10, 11, 12, 13, 14, 15])
+    ref = rows[keys.argsort()[::-1]]
+    assert list(ref) == [14, 15, 12, 11, 13, 10]
+    # single rank: the caller pre-sorts (rows descending, then stable by key descending) exactly like SafeOpt._ordered_candidates
+    import torch
+    r, k = torch.from_numpy(rows), torch.from_numpy(keys)
+    o = torch.argsort(r, descending=True)
+    r, k = r[o], k[o]
+    o = torch.argsort(k, descending=True, stable=True)
+    assert np.array_equal(order_candidates(Comm(), r[o].numpy(), k[o].numpy()), ref)
+
+
+def test_fmin_none_means_unconstrained():
+    """The docstring promises None == -inf; np.asarray(None, float) would be NaN and make every row unsafe."""
+    from safeopt_b200.gp_opt import GaussianProcessOptimization
+
+    class K:
+        def Kdiag(self, x):
+            return np.ones(len(x))
+
+    class GP:
+        X, Y, input_dim, kern = np.zeros((1, 1)), np.zeros((1, 1)), 1, K()
+
+    opt = GaussianProcessOptimization([GP(), GP()], fmin=[None, 0.5])
+    assert np.array_equal(opt.fmin, [-np.inf, 0.5])
+    assert np.array_equal(GaussianProcessOptimization(GP(), fmin=None).fmin, [-np.inf])
+    with pytest.raises(ValueError):
+        GaussianProcessOptimization(GP(), fmin=float("nan"))
+
+
 # ---------------------------------------------------------------- hyper-parameter adapter
 def test_extract_hyper_from_product_and_oracle_models():
     from oracle import gpy_lite
@@ -299,6 +334,37 @@ def test_extract_hyper_from_product_and_oracle_models():
     gp.kern = Weird()
     with pytest.raises(gpmodel.UnsupportedModelError):
         gpmodel.extract_hyper(gp)
+
+
+def test_extract_hyper_refuses_sums_mean_functions_and_normalizers():
+    """A GPy Add kernel (name 'sum') also has ``.parts``; folding it into one ARD RBF would silently change the posterior
+    of a safety-critical optimiser.  Same for models whose predict applies a mean function or an output normaliser."""
+    from oracle import gpy_lite
+    X = np.random.RandomState(0).rand(5, 2)
+    Y = np.zeros((5, 1))
+
+    class Add:                      # test double with GPy's Add surface
+        name = "sum"
+        input_dim = 2
+
+        def __init__(self, parts):
+            self.parts = parts
+
+    gp = gpy_lite.GPRegression(X, Y, kernel=gpy_lite.RBF(2), noise_var=0.1)
+    gp.kern = Add([gpy_lite.RBF(1, variance=1.0, active_dims=[0]), gpy_lite.RBF(1, variance=2.0, active_dims=[1])])
+    with pytest.raises(gpmodel.UnsupportedModelError, match="composite"):
+        gpmodel.extract_hyper(gp)
+    gp = gpy_lite.GPRegression(X, Y, kernel=gpy_lite.RBF(2), noise_var=0.1)
+    assert gpmodel.extract_hyper(gp).kind == _lib.KERNEL_RBF
+    gp.mean_function = lambda x: x
+    with pytest.raises(gpmodel.UnsupportedModelError, match="mean_function"):
+        gpmodel.extract_hyper(gp)
+    gp.mean_function = None
+    gp.normalizer = object()
+    with pytest.raises(gpmodel.UnsupportedModelError, match="normalizer"):
+        gpmodel.extract_hyper(gp)
+    gp.normalizer = False           # GPy's "off"
+    assert gpmodel.extract_hyper(gp).variance == 1.0
 
 
 def test_host_kernels_match_oracle():
