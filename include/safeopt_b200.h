@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SO_ABI_VERSION 2
+#define SO_ABI_VERSION 3
 
 /* status codes */
 #define SO_OK                  0
@@ -35,6 +35,7 @@ extern "C" {
 #define SO_ERR_NOT_FITTED     -5
 #define SO_ERR_CAPACITY       -6
 #define SO_ERR_NO_DEVICE      -7
+#define SO_ERR_TIMEOUT        -8   /* a peer rank never published its record (cross-rank exchange) */
 
 /* stationary kernel families (GPy class names RBF / Matern32 / Matern52) */
 #define SO_KERNEL_RBF          0
@@ -211,6 +212,36 @@ int so_sets_candidates_chain(so_handle* h, const double* Q_d, int n_gps, int64_t
                              uint8_t* cand_mask_d, double* cand_key_d, int64_t* cand_row_d,
                              int64_t cap, int64_t* n_cand_d, void* stream);
 
+/* Fused variant: the three passes above AND the cross-rank exchange of their records in ONE cooperative launch
+ * (compute_sets, safeopt/gp_opt.py:483-536; query-point records of :634-644).  Between the passes every rank's
+ * record is written straight into every rank's exchange buffer over NVLink (so_xchg_*), so no collective and no host
+ * round trip separates them; with one rank the same kernel runs against the local buffer.
+ *   with_candidates = 0 skips the candidate pass (full_sets: every safe row is a candidate, gp_opt.py:527-528).
+ *   result_h: NULL, or a host buffer of SO_SETS_RESULT_BYTES(world) bytes; if given, the call copies the combined
+ *   records there and synchronises `stream` before returning:
+ *       [world x so_safe_record][world x so_max_record][world x int64 candidate count][int64 status][int64 epoch]
+ *   (records in rank order).  With result_h == NULL the launch stays asynchronous (e.g. inside a CUDA graph) and
+ *   so_sets_fused_result fetches the records later.  Returns SO_ERR_TIMEOUT when a peer never published. */
+#define SO_SETS_RESULT_BYTES(world) ((size_t)(world) * 136 + 16)
+int so_sets_fused(so_handle* h, const double* Q_d, int n_gps, int64_t M, int64_t row0, const uint8_t* S_d,
+                  const double* scaling_h, const double* thr_h, int with_candidates, uint8_t* Mmask_d,
+                  double* cand_key_d, int64_t* cand_row_d, int64_t cap, void* result_h, void* stream);
+int so_sets_fused_result(so_handle* h, void* result_h, void* stream);
+
+/* ------------------------------------------------------------------ cross-rank record exchange (multi-GPU, one process per GPU)
+ * the candidate rows are sharded, and the only data that crosses GPUs are the 64..144-byte records of
+ * the reductions (safe set, maximisers, candidate count, swarm best).  They travel through peer-mapped device
+ * memory written from inside the kernels, not through a collective between kernels:
+ *   so_xchg_export  : allocates this rank's exchange buffer (once) and returns its CUDA IPC handle (64 bytes);
+ *   so_xchg_connect : given the handles of all `world` ranks in rank order (exchanged by the host runtime, e.g. one
+ *                     torch.distributed all_gather at construction), maps the peers' buffers.  Collective in the sense
+ *                     that every rank must call it before the first fused kernel runs; the caller places a host barrier
+ *                     after it.  Without a connect the handle behaves as world = 1. */
+#define SO_XCHG_HANDLE_BYTES 64
+int so_xchg_export(so_handle* h, void* ipc_handle_h);
+int so_xchg_connect(so_handle* h, int world, int rank, const void* ipc_handles_h);
+int so_xchg_world(const so_handle* h);
+
 /* ------------------------------------------------------------------ K4: batched expander test
  * Stands in for the refit/predict/refit loop of safeopt/gp_opt.py:579-606 for B
  * candidates at once, through the rank-1 identity:
@@ -264,6 +295,27 @@ int so_swarm_update_best(so_handle* h, int64_t P, int d, const double* pos_d, co
  * {value, index}.  Stream-ordered, no host involvement: a PSO iteration has no host sync. */
 int so_swarm_combine_best(so_handle* h, const double* recs_d, int n_ranks, int d,
                           double* global_best_d, double* global_rec_d, void* stream);
+
+/* Graph-replayable PSO iteration (device-resident swarms, BASELINE config 5): nothing in these launches changes between
+ * iterations, so randoms -> update -> posterior -> fitness -> bests -> global best can be captured once and replayed.
+ *   state_d : 4 doubles in device memory: [0] inertia, [1] inertia increment per iteration (swarm.py:94-96, :117),
+ *             [2] iteration number (selects the random block), [3] reserved.  so_swarm_update_best_x advances [0] and [2].
+ *   so_swarm_rand     : out_d[(p, j)] = U[0,1) of Philox4x32-10 keyed by `seed` at (counter, global particle p0 + p, j);
+ *                       the value depends on the GLOBAL particle index only, so a sharded swarm draws what one GPU would.
+ *   so_swarm_step_dev : so_swarm_step with the two random blocks of swarm.py:105 drawn in the kernel (same generator,
+ *                       counter = state_d[2]) and the inertia read from state_d[0].
+ *   so_swarm_update_best_x : so_swarm_update_best + the cross-rank exchange + so_swarm_combine_best in ONE launch: the
+ *                       last block writes this rank's {value, global index, position} into every rank's exchange buffer
+ *                       (so_xchg_*; peer-mapped stores, no collective), waits for the `world` records of this iteration
+ *                       and leaves the global best in global_best_d (d) / global_rec_d = {value, index, status}.
+ *                       state_d may be NULL (host-driven inertia). */
+int so_swarm_rand(so_handle* h, int64_t P, int d, int64_t p0, uint64_t seed, uint64_t counter, double* out_d, void* stream);
+int so_swarm_step_dev(so_handle* h, int64_t P, int d, int64_t p0, double* pos_d, double* vel_d, const double* best_pos_d,
+                      const double* global_best_d, const double* state_d, uint64_t seed, const double* velocity_scale_h,
+                      const double* bounds_h, void* stream);
+int so_swarm_update_best_x(so_handle* h, int64_t P, int d, const double* pos_d, const double* values_d,
+                           const uint8_t* safe_d, double* best_pos_d, double* best_values_d, int64_t* best_idx_d,
+                           int64_t p0, double* global_best_d, double* global_rec_d, double* state_d, void* stream);
 
 /* ------------------------------------------------------------------ f1: swarm safe-set maintenance
  * Stands in for the dense correlation test of safeopt/gp_opt.py:1088-1110

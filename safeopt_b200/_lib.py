@@ -21,6 +21,7 @@ SO_ERR_CUDA = -4
 SO_ERR_NOT_FITTED = -5
 SO_ERR_CAPACITY = -6
 SO_ERR_NO_DEVICE = -7
+SO_ERR_TIMEOUT = -8
 
 KERNEL_RBF, KERNEL_MATERN32, KERNEL_MATERN52 = 0, 1, 2
 SAFE_NONE, SAFE_WRITE, SAFE_AND = 0, 1, 2
@@ -28,8 +29,15 @@ SWARM_GREEDY, SWARM_MAXIMIZERS, SWARM_EXPANDERS, SWARM_SAFE_SET = 0, 1, 2, 3
 SWARM_KINDS = {"greedy": SWARM_GREEDY, "maximizers": SWARM_MAXIMIZERS, "expanders": SWARM_EXPANDERS,
                "safe_set": SWARM_SAFE_SET}
 EXPANDER_MAX_BATCH = 32
-ABI_VERSION = 2
+ABI_VERSION = 3
 SWARM_REC_DOUBLES = 18
+XCHG_HANDLE_BYTES = 64
+XCHG_MAX_WORLD = 16
+
+
+def sets_result_bytes(world: int) -> int:
+    """SO_SETS_RESULT_BYTES of the header."""
+    return world * 136 + 16
 
 
 class NativeLibraryError(RuntimeError):
@@ -56,7 +64,7 @@ class MaxRecord(C.Structure):
 
 
 _P = C.c_void_p
-_i, _i64, _dbl = C.c_int, C.c_int64, C.c_double
+_i, _i64, _dbl, _u64 = C.c_int, C.c_int64, C.c_double, C.c_uint64
 
 # name -> (restype, argtypes); exactly the declarations of include/safeopt_b200.h
 SIGNATURES = {
@@ -86,12 +94,20 @@ SIGNATURES = {
     "so_sets_candidates": (_i, [_P, _P, _i, _i64, _i64, _P, _P, _dbl, _P, _P, _P, _P, _P, _i64, _P, _P]),
     "so_sets_maximizers_chain": (_i, [_P, _P, _i, _i64, _i64, _P, _P, _i, _P, _P, _P, _P]),
     "so_sets_candidates_chain": (_i, [_P, _P, _i, _i64, _i64, _P, _P, _P, _i, _P, _P, _P, _P, _P, _i64, _P, _P]),
+    "so_sets_fused": (_i, [_P, _P, _i, _i64, _i64, _P, _P, _P, _i, _P, _P, _P, _i64, _P, _P]),
+    "so_sets_fused_result": (_i, [_P, _P, _P]),
+    "so_xchg_export": (_i, [_P, _P]),
+    "so_xchg_connect": (_i, [_P, _i, _i, _P]),
+    "so_xchg_world": (_i, [_P]),
     "so_expander_check": (_i, [_P, _i, _P, _i64, _i64, _P, _P, _P, _P, _P, _P, _P, _i, _dbl, _dbl, _P, _P]),
     "so_expander_lipschitz": (_i, [_P, _P, _i, _i64, _i64, _P, _P, _P, _i, _dbl, _dbl, _P, _P]),
     "so_swarm_fitness": (_i, [_P, _i, _i, _i64, _P, _P, _dbl, _P, _P, _dbl, _P, _P, _P]),
     "so_swarm_step": (_i, [_P, _i64, _i, _P, _P, _P, _P, _P, _dbl, _P, _P, _P]),
     "so_swarm_update_best": (_i, [_P, _i64, _i, _P, _P, _P, _P, _P, _P, _i64, _P, _P]),
     "so_swarm_combine_best": (_i, [_P, _P, _i, _i, _P, _P, _P]),
+    "so_swarm_rand": (_i, [_P, _i64, _i, _i64, _u64, _u64, _P, _P]),
+    "so_swarm_step_dev": (_i, [_P, _i64, _i, _i64, _P, _P, _P, _P, _P, _u64, _P, _P, _P]),
+    "so_swarm_update_best_x": (_i, [_P, _i64, _i, _P, _P, _P, _P, _P, _P, _i64, _P, _P, _P, _P]),
     "so_safeset_filter": (_i, [_P, _i, _P, _i64, _P, _i64, _dbl, _dbl, _P, _P]),
     "so_safeset_insert": (_i, [_P, _i, _P, _i64, _P, _dbl, _dbl, _P, _P, _P, _P]),
 }

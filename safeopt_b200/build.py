@@ -14,7 +14,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libsafeopt_b200.so")
-SOURCES = ["api.cu", "fit.cu", "posterior.cu", "sets.cu", "expander.cu", "lipschitz.cu", "swarm.cu", "safeset.cu"]
+SOURCES = ["api.cu", "fit.cu", "posterior.cu", "sets.cu", "expander.cu", "lipschitz.cu", "swarm.cu", "safeset.cu", "xchg.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

@@ -1,6 +1,8 @@
 // Handle lifetime and error reporting for the C ABI (include/safeopt_b200.h).
 #include "common.cuh"
 
+void xchg_destroy(so_handle* h);
+
 extern "C" {
 
 int so_abi_version(void) { return SO_ABI_VERSION; }
@@ -15,6 +17,7 @@ const char* so_status_string(int status) {
         case SO_ERR_NOT_FITTED: return "GP not fitted";
         case SO_ERR_CAPACITY: return "capacity exceeded";
         case SO_ERR_NO_DEVICE: return "no CUDA device";
+        case SO_ERR_TIMEOUT: return "cross-rank exchange timed out";
         default: return "unknown status";
     }
 }
@@ -62,6 +65,9 @@ int so_destroy(so_handle* h) {
     cudaFree(h->ws_partials);
     cudaFree(h->ws_counter);
     cudaFree(h->ws_z);
+    xchg_destroy(h);
+    cudaFree(h->fused_bar); cudaFree(h->fused_part); cudaFree(h->fused_ncand); cudaFree(h->fused_result_d);
+    cudaFreeHost(h->fused_result_h);
     delete h;
     return SO_OK;
 }

@@ -62,6 +62,8 @@ struct GridSpec {
     int64_t fast_rows = 1, slow_rows = 1;
 };
 
+struct XchgBuf;                  // xchg.cuh: per-rank exchange buffer of the cross-rank record protocols
+
 struct so_handle {
     int device = 0;
     int max_gps = 0;
@@ -75,6 +77,21 @@ struct so_handle {
     unsigned int* ws_counter = nullptr;  // last-block-done ticket, self-resetting
     double* ws_z = nullptr;      // expander batch workspace (expander.cu)
     size_t ws_z_cap = 0;
+    // cross-rank record exchange (xchg.cu): this rank's buffer and the peers' buffers as mapped here (peer[rank] = local)
+    XchgBuf* xchg_local = nullptr;
+    XchgBuf* xchg_peer[16] = {};
+    bool xchg_opened[16] = {};
+    int xchg_world = 1, xchg_rank = 0;
+    unsigned long long* xchg_epochs = nullptr;   // device: [0] set-pass epoch, [1] swarm epoch, [2] swarm iteration counter
+    // fused set pass (sets.cu: k_sets_fused): grid barrier {count, generation}, two partial arrays, candidate counter,
+    // pinned host mirror of the combined records
+    unsigned int* fused_bar = nullptr;
+    void* fused_part = nullptr;
+    unsigned long long* fused_ncand = nullptr;
+    int* fused_status = nullptr;
+    void* fused_result_d = nullptr;  // world x 136 bytes + status + epoch, device
+    void* fused_result_h = nullptr;  // pinned host copy target
+    int fused_grid = 0;
     std::string err;
 };
 

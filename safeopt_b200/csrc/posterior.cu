@@ -15,6 +15,7 @@
 #include "posterior_tma.cuh"
 #include "posterior_ring.cuh"
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 
 namespace {
@@ -638,8 +639,24 @@ extern "C" int so_grid_prepare_rows(so_handle* h, int gp, int64_t row0, int64_t 
     const int64_t s_hi = M > 0 ? (row0 + M - 1) / gs.fast_rows + 1 : 0;
     const int64_t n_slow = s_hi - s_lo;
     const size_t ap_elems = (size_t)n_slow * a_stride + 128;   // the A prefetch runs up to 3 blocks past a row
-    const bool fits = plan_tma(h, g, pl) == SO_OK && trows <= 2147483647 && n_slow <= 65535 &&
-                      (size_t)trows * Npad * sizeof(double) <= ((size_t)4 << 30) && ap_elems * sizeof(double2) <= ((size_t)8 << 30);
+    // The scaled-operand table costs n_slow x ~N^2/2 x 8 bytes (676 MB at config 4, 4x that at N = 512): above the limit
+    // (8 GB by default, SO_APRIME_LIMIT_MB overrides it) the grid path drops to the per-axis table kernel (k_posterior<GRID>,
+    // slower: it spends fp64 multiplies on generating kernel rows) -- and says so, once.
+    size_t ap_limit = (size_t)8 << 30;
+    if (const char* v = std::getenv("SO_APRIME_LIMIT_MB")) ap_limit = (size_t)std::strtoull(v, nullptr, 10) << 20;
+    const bool planned = plan_tma(h, g, pl) == SO_OK && trows <= 2147483647 && n_slow <= 65535 &&
+                         (size_t)trows * Npad * sizeof(double) <= ((size_t)4 << 30);
+    const bool fits = planned && ap_elems * sizeof(double2) <= ap_limit;
+    if (!fits) {
+        static bool said = false;
+        if (!said) {
+            said = true;
+            fprintf(stderr, "safeopt_b200: grid path without the scaled-operand table (needs %.1f MB for %lld slow indices at N = %d, "
+                            "limit %.1f MB%s): using the per-axis table kernel\n",
+                    ap_elems * sizeof(double2) / 1048576.0, (long long)n_slow, g.N, ap_limit / 1048576.0,
+                    planned ? "" : "; tile plan or table size out of range");
+        }
+    }
     if (fits) {
         const size_t need2 = (size_t)trows * Npad;
         if (need2 > g.capP2) {

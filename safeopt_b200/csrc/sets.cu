@@ -10,7 +10,11 @@
 // The *_chain variants take the scalar that links two passes (max l0[S]; max width over M) from the
 // records of the previous pass in device memory -- one record per rank, as all-gathered -- so the three
 // passes run back to back on the stream and the host reads all results with a single copy.
-#include "common.cuh"
+#include "xchg.cuh"
+#include <cstring>
+
+int xchg_ensure_local(so_handle* h);
+XchgView xchg_view(const so_handle* h);
 
 namespace {
 
@@ -129,11 +133,10 @@ __device__ __forceinline__ void store_mask16(uint8_t* __restrict__ m, int64_t r0
     }
 }
 
-__global__ void __launch_bounds__(kThreads) k_reduce_safe(const double* __restrict__ Q, int q_stride, int64_t M, int64_t row0,
-                                                         const uint8_t* __restrict__ S, SafePartial* __restrict__ part,
-                                                         unsigned int* __restrict__ counter, so_safe_record* __restrict__ out) {
-    const SafePartial identity = {0, -INFINITY, -1, -INFINITY, -1};
-    SafePartial acc = identity;
+// The three streaming scans, shared by the one-pass kernels and the fused kernel.
+__device__ __forceinline__ SafePartial scan_safe(const double* __restrict__ Q, int q_stride, int64_t M, int64_t row0,
+                                                 const uint8_t* __restrict__ S) {
+    SafePartial acc = {0, -INFINITY, -1, -INFINITY, -1};
     const bool aligned = (reinterpret_cast<uintptr_t>(S) & 15) == 0;
     const int64_t nchunks = (M + kRows - 1) / kRows;
     for (int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x; c < nchunks; c += (int64_t)gridDim.x * kThreads) {
@@ -151,23 +154,13 @@ __global__ void __launch_bounds__(kThreads) k_reduce_safe(const double* __restri
             take_max_first(acc.max_u, acc.arg_u, lu.y, row0 + r);
         }
     }
-    if (grid_reduce(acc, part, counter, identity)) {
-        out->n_safe = acc.n; out->max_l0 = acc.max_l; out->argmax_l0 = acc.arg_l; out->max_u0 = acc.max_u; out->argmax_u0 = acc.arg_u;
-        out->reserved[0] = out->reserved[1] = out->reserved[2] = 0;
-    }
+    return acc;
 }
 
-__global__ void __launch_bounds__(kThreads) k_maximizers(const double* __restrict__ Q, int G, int64_t M, int64_t row0,
-                                                        const uint8_t* __restrict__ S, double max_l0,
-                                                        const so_safe_record* __restrict__ safe_recs, int n_recs, Scal scaling,
-                                                        uint8_t* __restrict__ Mmask, MaxPartial* __restrict__ part,
-                                                        unsigned int* __restrict__ counter, so_max_record* __restrict__ out) {
-    if (safe_recs) {                            // chained: max over the ranks' records of max l0[S] (-inf where a rank has none)
-        max_l0 = -INFINITY;
-        for (int r = 0; r < n_recs; ++r) max_l0 = safe_recs[r].max_l0 > max_l0 ? safe_recs[r].max_l0 : max_l0;
-    }
-    const MaxPartial identity = {0, -INFINITY, -INFINITY, -1};
-    MaxPartial acc = identity;
+__device__ __forceinline__ MaxPartial scan_maximizers(const double* __restrict__ Q, int G, int64_t M, int64_t row0,
+                                                      const uint8_t* __restrict__ S, double max_l0, const Scal& scaling,
+                                                      uint8_t* __restrict__ Mmask) {
+    MaxPartial acc = {0, -INFINITY, -INFINITY, -1};
     const int qs = 2 * G;
     const bool aligned = ((reinterpret_cast<uintptr_t>(S) | reinterpret_cast<uintptr_t>(Mmask)) & 15) == 0;
     const int64_t nchunks = (M + kRows - 1) / kRows;
@@ -200,23 +193,14 @@ __global__ void __launch_bounds__(kThreads) k_maximizers(const double* __restric
         }
         store_mask16(Mmask, r0, M, aligned, m);
     }
-    if (grid_reduce(acc, part, counter, identity)) {
-        out->n_max = acc.n; out->max_width0 = acc.max_w0; out->best_value = acc.best; out->best_row = acc.best_row;
-        out->reserved[0] = out->reserved[1] = out->reserved[2] = out->reserved[3] = 0;
-    }
+    return acc;
 }
 
-__global__ void __launch_bounds__(kThreads) k_candidates(const double* __restrict__ Q, int G, int64_t M, int64_t row0,
-                                                        const uint8_t* __restrict__ S, const uint8_t* __restrict__ Mmask,
-                                                        double max_var, const so_max_record* __restrict__ max_recs, int n_recs,
-                                                        Scal scaling, Scal thr, uint8_t* __restrict__ cmask,
-                                                        double* __restrict__ ckey, int64_t* __restrict__ crow, int64_t cap,
-                                                        unsigned long long* __restrict__ n_cand) {
-    if (max_recs) {                             // chained: gp_opt.py:513 from the ranks' maximiser records
-        double w = -INFINITY;
-        for (int r = 0; r < n_recs; ++r) w = max_recs[r].max_width0 > w ? max_recs[r].max_width0 : w;
-        max_var = w / scaling.v[0];
-    }
+__device__ __forceinline__ void scan_candidates(const double* __restrict__ Q, int G, int64_t M, int64_t row0,
+                                                const uint8_t* __restrict__ S, const uint8_t* __restrict__ Mmask, double max_var,
+                                                const Scal& scaling, const Scal& thr, uint8_t* __restrict__ cmask,
+                                                double* __restrict__ ckey, int64_t* __restrict__ crow, int64_t cap,
+                                                unsigned long long* __restrict__ n_cand) {
     const int qs = 2 * G;
     const bool aligned = ((reinterpret_cast<uintptr_t>(S) | reinterpret_cast<uintptr_t>(Mmask) | reinterpret_cast<uintptr_t>(cmask)) & 15) == 0;
     const int64_t nchunks = (M + kRows - 1) / kRows;
@@ -279,6 +263,195 @@ __global__ void __launch_bounds__(kThreads) k_candidates(const double* __restric
             }
             ++slot;
         }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_reduce_safe(const double* __restrict__ Q, int q_stride, int64_t M, int64_t row0,
+                                                         const uint8_t* __restrict__ S, SafePartial* __restrict__ part,
+                                                         unsigned int* __restrict__ counter, so_safe_record* __restrict__ out) {
+    const SafePartial identity = {0, -INFINITY, -1, -INFINITY, -1};
+    SafePartial acc = scan_safe(Q, q_stride, M, row0, S);
+    if (grid_reduce(acc, part, counter, identity)) {
+        out->n_safe = acc.n; out->max_l0 = acc.max_l; out->argmax_l0 = acc.arg_l; out->max_u0 = acc.max_u; out->argmax_u0 = acc.arg_u;
+        out->reserved[0] = out->reserved[1] = out->reserved[2] = 0;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_maximizers(const double* __restrict__ Q, int G, int64_t M, int64_t row0,
+                                                        const uint8_t* __restrict__ S, double max_l0,
+                                                        const so_safe_record* __restrict__ safe_recs, int n_recs, Scal scaling,
+                                                        uint8_t* __restrict__ Mmask, MaxPartial* __restrict__ part,
+                                                        unsigned int* __restrict__ counter, so_max_record* __restrict__ out) {
+    if (safe_recs) {                            // chained: max over the ranks' records of max l0[S] (-inf where a rank has none)
+        max_l0 = -INFINITY;
+        for (int r = 0; r < n_recs; ++r) max_l0 = safe_recs[r].max_l0 > max_l0 ? safe_recs[r].max_l0 : max_l0;
+    }
+    const MaxPartial identity = {0, -INFINITY, -INFINITY, -1};
+    MaxPartial acc = scan_maximizers(Q, G, M, row0, S, max_l0, scaling, Mmask);
+    if (grid_reduce(acc, part, counter, identity)) {
+        out->n_max = acc.n; out->max_width0 = acc.max_w0; out->best_value = acc.best; out->best_row = acc.best_row;
+        out->reserved[0] = out->reserved[1] = out->reserved[2] = out->reserved[3] = 0;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_candidates(const double* __restrict__ Q, int G, int64_t M, int64_t row0,
+                                                        const uint8_t* __restrict__ S, const uint8_t* __restrict__ Mmask,
+                                                        double max_var, const so_max_record* __restrict__ max_recs, int n_recs,
+                                                        Scal scaling, Scal thr, uint8_t* __restrict__ cmask,
+                                                        double* __restrict__ ckey, int64_t* __restrict__ crow, int64_t cap,
+                                                        unsigned long long* __restrict__ n_cand) {
+    if (max_recs) {                             // chained: gp_opt.py:513 from the ranks' maximiser records
+        double w = -INFINITY;
+        for (int r = 0; r < n_recs; ++r) w = max_recs[r].max_width0 > w ? max_recs[r].max_width0 : w;
+        max_var = w / scaling.v[0];
+    }
+    scan_candidates(Q, G, M, row0, S, Mmask, max_var, scaling, thr, cmask, ckey, crow, cap, n_cand);
+}
+
+// ---------------------------------------------------------------- fused: the three passes and their cross-rank exchanges in ONE launch
+// compute_sets needs max l0[S] before M and max width(M) before the candidates -- two true data dependencies, each a
+// reduction over every rank's rows.  Chained as separate kernels with an NCCL all-gather of the 64-byte record after each
+// (round 1) the chain cost 0.35 ms of a 2 ms step on eight GPUs.  Here one cooperative kernel does all of it: scan -> grid
+// barrier -> block 0 combines the partials and publishes this rank's record into every rank's exchange buffer over NVLink
+// (xchg.cuh) -> every block waits for the `world` stamps of the phase -> next scan.  When the kernel ends, the records of
+// all ranks for all three phases sit in `result` (device) in the layout the host parses with one copy.
+struct FusedParams {
+    const double* Q;
+    int G;
+    int with_candidates;
+    int64_t M, row0;
+    const uint8_t* S;
+    uint8_t* Mmask;
+    Scal scaling, thr;
+    double* ckey;
+    int64_t* crow;
+    int64_t cap;
+    SafePartial* partA;
+    MaxPartial* partB;
+    unsigned int* bar;                   // {arrivals, generation}
+    unsigned long long* ncand;
+    unsigned long long* epoch;
+    XchgView x;
+    unsigned char* result;               // [world x safe record][world x max record][world x count][status][epoch]
+};
+
+// Self-resetting grid barrier (all blocks are co-resident: cooperative launch).  The generation is read BEFORE arriving, so it
+// cannot advance until this block has arrived too.
+__device__ __forceinline__ void grid_barrier(unsigned int* bar) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        volatile unsigned int* vgen = bar + 1;
+        const unsigned int gen = *vgen;
+        __threadfence();
+        if (atomicAdd(bar, 1u) == gridDim.x - 1) {
+            bar[0] = 0;
+            __threadfence();
+            atomicAdd(bar + 1, 1u);
+        } else {
+            while (*vgen == gen) { }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// All `world` stamps of a phase carry `epoch`?  (block-wide; returns the same answer in every thread)
+__device__ __forceinline__ bool wait_phase(const unsigned long long* flags, int world, unsigned long long epoch) {
+    int ok = 1;
+    if ((int)threadIdx.x < world) ok = xchg_wait(flags, threadIdx.x, epoch) ? 1 : 0;
+    return __syncthreads_and(ok) != 0;
+}
+
+__global__ void __launch_bounds__(kThreads) k_sets_fused(const __grid_constant__ FusedParams p) {
+    __shared__ SafePartial smA[kThreads / 32];
+    __shared__ MaxPartial smB[kThreads / 32];
+    const unsigned long long epoch = *p.epoch + 1;          // bumped by block 0 after the last grid barrier
+    const int par = (int)(epoch & 1), world = p.x.world, rank = p.x.rank;
+    XchgSets* mine = &p.x.local->sets[par];
+    int status = SO_OK;
+
+    // ---- phase A: safe-set record
+    if (blockIdx.x == 0 && threadIdx.x == 0) *p.ncand = 0;  // first touched after the second grid barrier
+    {
+        SafePartial acc = block_reduce(scan_safe(p.Q, 2 * p.G, p.M, p.row0, p.S), smA);
+        if (threadIdx.x == 0) p.partA[blockIdx.x] = acc;
+    }
+    grid_barrier(p.bar);
+    if (blockIdx.x == 0) {
+        SafePartial t = {0, -INFINITY, -1, -INFINITY, -1};
+        for (unsigned b = threadIdx.x; b < gridDim.x; b += kThreads) merge(t, p.partA[b]);
+        t = block_reduce(t, smA);
+        if (threadIdx.x == 0) {
+            so_safe_record rec;
+            rec.n_safe = t.n; rec.max_l0 = t.max_l; rec.argmax_l0 = t.arg_l; rec.max_u0 = t.max_u; rec.argmax_u0 = t.arg_u;
+            rec.reserved[0] = rec.reserved[1] = rec.reserved[2] = 0;
+            for (int r = 0; r < world; ++r) p.x.peer[r]->sets[par].safe[rank] = rec;
+            __threadfence_system();
+            for (int r = 0; r < world; ++r) st_release_sys(&p.x.peer[r]->sets[par].flag[0][rank], epoch);
+        }
+    }
+    if (!wait_phase(mine->flag[0], world, epoch)) status = SO_ERR_TIMEOUT;
+    double max_l0 = -INFINITY;
+    for (int r = 0; r < world; ++r) {
+        const double v = __ldcg(&mine->safe[r].max_l0);
+        max_l0 = v > max_l0 ? v : max_l0;
+    }
+
+    // ---- phase B: maximisers
+    {
+        MaxPartial acc = block_reduce(scan_maximizers(p.Q, p.G, p.M, p.row0, p.S, max_l0, p.scaling, p.Mmask), smB);
+        if (threadIdx.x == 0) p.partB[blockIdx.x] = acc;
+    }
+    grid_barrier(p.bar);
+    if (blockIdx.x == 0) {
+        MaxPartial t = {0, -INFINITY, -INFINITY, -1};
+        for (unsigned b = threadIdx.x; b < gridDim.x; b += kThreads) merge(t, p.partB[b]);
+        t = block_reduce(t, smB);
+        if (threadIdx.x == 0) {
+            so_max_record rec;
+            rec.n_max = t.n; rec.max_width0 = t.max_w0; rec.best_value = t.best; rec.best_row = t.best_row;
+            rec.reserved[0] = rec.reserved[1] = rec.reserved[2] = rec.reserved[3] = 0;
+            for (int r = 0; r < world; ++r) p.x.peer[r]->sets[par].max[rank] = rec;
+            __threadfence_system();
+            for (int r = 0; r < world; ++r) st_release_sys(&p.x.peer[r]->sets[par].flag[1][rank], epoch);
+        }
+    }
+    if (!wait_phase(mine->flag[1], world, epoch)) status = SO_ERR_TIMEOUT;
+
+    // ---- phase C: expander candidates (skipped for full_sets: every safe row is a candidate there)
+    if (p.with_candidates) {
+        double w = -INFINITY;
+        for (int r = 0; r < world; ++r) {
+            const double v = __ldcg(&mine->max[r].max_width0);
+            w = v > w ? v : w;
+        }
+        scan_candidates(p.Q, p.G, p.M, p.row0, p.S, p.Mmask, w / p.scaling.v[0], p.scaling, p.thr, nullptr, p.ckey, p.crow, p.cap,
+                        p.ncand);
+    }
+    grid_barrier(p.bar);
+    if (blockIdx.x != 0) return;
+    if (threadIdx.x == 0) {
+        const long long n = p.with_candidates ? (long long)*reinterpret_cast<volatile unsigned long long*>(p.ncand) : 0;
+        for (int r = 0; r < world; ++r) p.x.peer[r]->sets[par].ncand[rank] = n;
+        __threadfence_system();
+        for (int r = 0; r < world; ++r) st_release_sys(&p.x.peer[r]->sets[par].flag[2][rank], epoch);
+    }
+    // the kernel may only end once every rank's phase-C record has landed here: the host reads `result` next
+    if (!wait_phase(mine->flag[2], world, epoch)) status = SO_ERR_TIMEOUT;
+    unsigned long long* res = reinterpret_cast<unsigned long long*>(p.result);
+    const unsigned long long* src_safe = reinterpret_cast<const unsigned long long*>(mine->safe);
+    const unsigned long long* src_max = reinterpret_cast<const unsigned long long*>(mine->max);
+    for (int i = threadIdx.x; i < world * 8; i += kThreads) {
+        res[i] = __ldcg(src_safe + i);
+        res[world * 8 + i] = __ldcg(src_max + i);
+    }
+    for (int r = threadIdx.x; r < world; r += kThreads)
+        res[world * 16 + r] = (unsigned long long)__ldcg(reinterpret_cast<const unsigned long long*>(mine->ncand) + r);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        res[world * 17] = (unsigned long long)(long long)status;
+        res[world * 17 + 1] = epoch;
+        *p.epoch = epoch;
     }
 }
 
@@ -362,4 +535,66 @@ extern "C" int so_sets_candidates_chain(so_handle* h, const double* Q_d, int n_g
     if (!max_recs_d || n_recs < 1) return SO_ERR_BAD_ARG;
     return run_candidates(h, Q_d, n_gps, M, row0, S_d, Mmask_d, 0.0, max_recs_d, n_recs, scaling_h, thr_h, cand_mask_d, cand_key_d,
                           cand_row_d, cap, n_cand_d, stream);
+}
+
+// ---------------------------------------------------------------- fused entry points
+static int fused_setup(so_handle* h) {
+    if (h->fused_part) return SO_OK;
+    int rc = xchg_ensure_local(h);
+    if (rc) return rc;
+    SO_CUDA(h, cudaMalloc(&h->fused_part, (size_t)2 * SO_WS_MAX_BLOCKS * 64));
+    SO_CUDA(h, cudaMalloc(&h->fused_bar, 2 * sizeof(unsigned int)));
+    SO_CUDA(h, cudaMemset(h->fused_bar, 0, 2 * sizeof(unsigned int)));
+    SO_CUDA(h, cudaMalloc(&h->fused_ncand, sizeof(unsigned long long)));
+    SO_CUDA(h, cudaMalloc(&h->fused_result_d, SO_SETS_RESULT_BYTES(kXchgMaxWorld)));
+    SO_CUDA(h, cudaMemset(h->fused_result_d, 0, SO_SETS_RESULT_BYTES(kXchgMaxWorld)));
+    SO_CUDA(h, cudaMallocHost(&h->fused_result_h, SO_SETS_RESULT_BYTES(kXchgMaxWorld)));
+    int per_sm = 0;
+    SO_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sets_fused, kThreads, 0));
+    if (per_sm < 1) return so_fail(h, SO_ERR_CUDA, "so_sets_fused: the fused kernel does not fit on an SM");
+    if (per_sm > 4) per_sm = 4;          // a few resident CTAs per SM saturate HBM; more only lengthens the grid barrier
+    h->fused_grid = per_sm * h->num_sms;
+    if (h->fused_grid > SO_WS_MAX_BLOCKS) h->fused_grid = SO_WS_MAX_BLOCKS;
+    return SO_OK;
+}
+
+extern "C" int so_sets_fused_result(so_handle* h, void* result_h, void* stream_) {
+    if (!h || !result_h) return SO_ERR_BAD_ARG;
+    if (!h->fused_part) return so_fail(h, SO_ERR_BAD_ARG, "so_sets_fused_result: so_sets_fused has not run");
+    DeviceGuard guard(h->device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const size_t bytes = SO_SETS_RESULT_BYTES(h->xchg_world);
+    SO_CUDA(h, cudaMemcpyAsync(h->fused_result_h, h->fused_result_d, bytes, cudaMemcpyDeviceToHost, stream));
+    SO_CUDA(h, cudaStreamSynchronize(stream));
+    memcpy(result_h, h->fused_result_h, bytes);
+    const long long status = reinterpret_cast<const long long*>(h->fused_result_h)[17 * h->xchg_world];
+    if (status == SO_ERR_TIMEOUT)
+        return so_fail(h, SO_ERR_TIMEOUT, "so_sets_fused: a rank never published its record (peer exchange timed out)");
+    return SO_OK;
+}
+
+extern "C" int so_sets_fused(so_handle* h, const double* Q_d, int n_gps, int64_t M, int64_t row0, const uint8_t* S_d,
+                             const double* scaling_h, const double* thr_h, int with_candidates, uint8_t* Mmask_d,
+                             double* cand_key_d, int64_t* cand_row_d, int64_t cap, void* result_h, void* stream_) {
+    if (!h || !Q_d || !S_d || !scaling_h || !thr_h || !Mmask_d || n_gps < 1 || n_gps > 64 || M < 0 || cap < 0) return SO_ERR_BAD_ARG;
+    if (with_candidates && cap > 0 && (!cand_key_d || !cand_row_d)) return SO_ERR_BAD_ARG;
+    DeviceGuard guard(h->device);
+    int rc = fused_setup(h);
+    if (rc) return rc;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    FusedParams p;
+    p.Q = Q_d; p.G = n_gps; p.with_candidates = with_candidates ? 1 : 0; p.M = M; p.row0 = row0; p.S = S_d; p.Mmask = Mmask_d;
+    for (int i = 0; i < 64; ++i) { p.scaling.v[i] = i < n_gps ? scaling_h[i] : 1.0; p.thr.v[i] = i < n_gps ? thr_h[i] : 0.0; }
+    p.ckey = cand_key_d; p.crow = cand_row_d; p.cap = cap;
+    p.partA = static_cast<SafePartial*>(h->fused_part);
+    p.partB = reinterpret_cast<MaxPartial*>(static_cast<unsigned char*>(h->fused_part) + (size_t)SO_WS_MAX_BLOCKS * 64);
+    p.bar = h->fused_bar; p.ncand = h->fused_ncand; p.epoch = h->xchg_epochs;
+    p.x = xchg_view(h);
+    p.result = static_cast<unsigned char*>(h->fused_result_d);
+    int grid = grid_for(h, M);
+    if (grid > h->fused_grid) grid = h->fused_grid;
+    void* args[] = {&p};
+    SO_CUDA(h, cudaLaunchCooperativeKernel((const void*)k_sets_fused, dim3(grid), dim3(kThreads), args, 0, stream));
+    if (result_h) return so_sets_fused_result(h, result_h, stream_);
+    return SO_OK;
 }

@@ -7,7 +7,10 @@
 //   so_swarm_update_best : personal / global best (safeopt/swarm.py:132-146).
 // All three are elementwise, HBM-streaming kernels (tens of bytes per particle); operations are
 // written with explicit roundings where the reference's NumPy expression would not contract.
-#include "common.cuh"
+#include "xchg.cuh"
+
+int xchg_ensure_local(so_handle* h);
+XchgView xchg_view(const so_handle* h);
 
 namespace {
 
@@ -99,13 +102,77 @@ __global__ void __launch_bounds__(kThreads) k_swarm_step(int64_t P, int d, doubl
     pos[e] = xn;
 }
 
+// ---- counter-based uniform randoms (Philox4x32-10): element (global particle, dimension) of iteration `it` gets the same two
+// doubles whatever the sharding, so a swarm split over R ranks follows the single-GPU trajectory bit for bit.
+__device__ __forceinline__ void philox4x32_10(unsigned (&c)[4], unsigned k0, unsigned k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        const unsigned hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        const unsigned n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+        c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+__device__ __forceinline__ double u53(unsigned hi, unsigned lo) {          // uniform in [0, 1), 53 random bits
+    const unsigned long long u = (((unsigned long long)hi << 32) | lo) >> 11;
+    return (double)u * (1.0 / 9007199254740992.0);
+}
+__device__ __forceinline__ void swarm_rand2(unsigned long long seed, unsigned long long it, unsigned long long elem, double& r1, double& r2) {
+    unsigned c[4] = {(unsigned)elem, (unsigned)(elem >> 32), (unsigned)it, (unsigned)(it >> 32)};
+    philox4x32_10(c, (unsigned)seed, (unsigned)(seed >> 32));
+    r1 = u53(c[0], c[1]);
+    r2 = u53(c[2], c[3]);
+}
+
+__global__ void __launch_bounds__(kThreads) k_swarm_rand(int64_t P, int d, int64_t p0, unsigned long long seed, unsigned long long it,
+                                                        double* __restrict__ out) {
+    const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (e >= P * d) return;
+    double r1, r2;
+    swarm_rand2(seed, it, (unsigned long long)(p0 * d + e), r1, r2);
+    out[e] = r1;
+}
+
+// k_swarm_step with the randoms drawn in the kernel and the inertia / iteration number read from device memory
+// (state[0] = inertia, state[1] = inertia increment per iteration, state[2] = iteration number; advanced by
+// k_swarm_update_best at the end of the iteration) -- nothing in the launch changes from one iteration to the next, so the
+// whole PSO iteration can be replayed from a CUDA graph.
+__global__ void __launch_bounds__(kThreads) k_swarm_step_dev(int64_t P, int d, int64_t p0, double* __restrict__ pos,
+                                                            double* __restrict__ vel, const double* __restrict__ best_pos,
+                                                            const double* __restrict__ gbest, const double* __restrict__ state,
+                                                            unsigned long long seed, Vec16 vscale, Vec16 lo, Vec16 hi, int has_bounds) {
+    const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (e >= P * d) return;
+    const int j = (int)(e % d);
+    const double inertia = state[0];
+    const unsigned long long it = (unsigned long long)state[2];
+    double r1, r2;
+    swarm_rand2(seed, it, (unsigned long long)(p0 * d + e), r1, r2);
+    const double x = pos[e];
+    const double d_self = __dsub_rn(best_pos[e], x);
+    const double d_glob = __dsub_rn(gbest[j], x);
+    double v = __dmul_rn(vel[e], inertia);
+    const double pull = __ddiv_rn(__dadd_rn(__dmul_rn(r1, d_self), __dmul_rn(r2, d_glob)), vscale.v[j]);
+    v = __dadd_rn(v, pull);
+    const double vmax = 10.0 * vscale.v[j];
+    v = v < -vmax ? -vmax : (v > vmax ? vmax : v);
+    double xn = __dadd_rn(x, v);
+    if (has_bounds) xn = xn < lo.v[j] ? lo.v[j] : (xn > hi.v[j] ? hi.v[j] : xn);
+    vel[e] = v;
+    pos[e] = xn;
+}
+
 struct BestPartial { double v; long long idx; };
 
 __global__ void __launch_bounds__(kThreads) k_swarm_update_best(int64_t P, int d, const double* __restrict__ pos,
                                                                const double* __restrict__ values, const uint8_t* __restrict__ safe,
                                                                double* __restrict__ best_pos, double* __restrict__ best_values,
                                                                BestPartial* __restrict__ part, unsigned int* __restrict__ counter,
-                                                               int64_t* __restrict__ best_idx, int64_t p0, double* __restrict__ rec) {
+                                                               int64_t* __restrict__ best_idx, int64_t p0, double* __restrict__ rec,
+                                                               XchgView x, unsigned long long* __restrict__ epoch_p,
+                                                               double* __restrict__ gbest, double* __restrict__ grec,
+                                                               double* __restrict__ state) {
     BestPartial acc = {-INFINITY, -1};
     for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < P; i += (int64_t)gridDim.x * kThreads) {
         double bv = best_values[i];
@@ -153,6 +220,37 @@ __global__ void __launch_bounds__(kThreads) k_swarm_update_best(int64_t P, int d
             rec[0] = t.v;
             rec[1] = (double)(p0 + t.idx);
             for (int j = 0; j < d; ++j) rec[2 + j] = best_pos[(size_t)t.idx * d + j];
+        }
+        if (state) { state[0] += state[1]; state[2] += 1.0; }      // `inertia += step` of swarm.py:117, next iteration's randoms
+        if (gbest) {
+            // exchange in the kernel: this rank's record goes into every rank's buffer (NVLink stores + a release stamp), then
+            // the `world` stamps of this epoch are awaited and the global best is combined -- largest value, ties to the
+            // lowest global particle index (np.argmax over the unsharded swarm, swarm.py:146)
+            const unsigned long long epoch = *epoch_p + 1;
+            const int par = (int)(epoch & 1);
+            for (int r = 0; r < x.world; ++r) {
+                double* dst = x.peer[r]->swarm[par].rec[x.rank];
+                dst[0] = t.v;
+                dst[1] = (double)(p0 + t.idx);
+                for (int j = 0; j < d; ++j) dst[2 + j] = best_pos[(size_t)t.idx * d + j];
+            }
+            __threadfence_system();
+            for (int r = 0; r < x.world; ++r) st_release_sys(&x.peer[r]->swarm[par].flag[x.rank], epoch);
+            const XchgSwarm* mine = &x.local->swarm[par];
+            bool ok = true;
+            for (int r = 0; r < x.world; ++r) ok = xchg_wait(mine->flag, r, epoch) && ok;
+            int best = -1;
+            double bv = 0.0, bi = 0.0;
+            for (int r = 0; r < x.world; ++r) {
+                const double v = __ldcg(&mine->rec[r][0]), i = __ldcg(&mine->rec[r][1]);
+                if (i < 0.0) continue;
+                if (best < 0 || v > bv || (v == bv && i < bi)) { best = r; bv = v; bi = i; }
+            }
+            if (best >= 0) {
+                for (int j = 0; j < d; ++j) gbest[j] = __ldcg(&mine->rec[best][2 + j]);
+                if (grec) { grec[0] = bv; grec[1] = bi; grec[2] = ok ? 0.0 : (double)SO_ERR_TIMEOUT; }
+            }
+            *epoch_p = epoch;
         }
     }
 }
@@ -220,9 +318,60 @@ extern "C" int so_swarm_update_best(so_handle* h, int64_t P, int d, const double
     DeviceGuard guard(h->device);
     int64_t blocks = (P + kThreads - 1) / kThreads;
     if (blocks > SO_WS_MAX_BLOCKS) blocks = SO_WS_MAX_BLOCKS;
+    XchgView none;
+    none.local = nullptr; none.world = 0; none.rank = 0;
+    for (int r = 0; r < kXchgMaxWorld; ++r) none.peer[r] = nullptr;
     k_swarm_update_best<<<(unsigned)blocks, kThreads, 0, (cudaStream_t)stream>>>(
-        P, d, pos_d, values_d, safe_d, best_pos_d, best_values_d, (BestPartial*)h->ws_partials, h->ws_counter, best_idx_d, p0, rec_d);
+        P, d, pos_d, values_d, safe_d, best_pos_d, best_values_d, (BestPartial*)h->ws_partials, h->ws_counter, best_idx_d, p0, rec_d,
+        none, nullptr, nullptr, nullptr, nullptr);
     SO_CHECK_LAUNCH(h, "k_swarm_update_best");
+    return SO_OK;
+}
+
+extern "C" int so_swarm_update_best_x(so_handle* h, int64_t P, int d, const double* pos_d, const double* values_d,
+                                      const uint8_t* safe_d, double* best_pos_d, double* best_values_d, int64_t* best_idx_d,
+                                      int64_t p0, double* global_best_d, double* global_rec_d, double* state_d, void* stream) {
+    if (!h || !pos_d || !values_d || !safe_d || !best_pos_d || !best_values_d || !best_idx_d || !global_best_d || P < 1)
+        return SO_ERR_BAD_ARG;
+    if (d < 1 || d > SO_MAX_DIM) return so_fail(h, SO_ERR_UNSUPPORTED, "swarm_update_best_x: 1 <= d <= 16");
+    DeviceGuard guard(h->device);
+    int rc = xchg_ensure_local(h);
+    if (rc) return rc;
+    int64_t blocks = (P + kThreads - 1) / kThreads;
+    if (blocks > SO_WS_MAX_BLOCKS) blocks = SO_WS_MAX_BLOCKS;
+    k_swarm_update_best<<<(unsigned)blocks, kThreads, 0, (cudaStream_t)stream>>>(
+        P, d, pos_d, values_d, safe_d, best_pos_d, best_values_d, (BestPartial*)h->ws_partials, h->ws_counter, best_idx_d, p0, nullptr,
+        xchg_view(h), h->xchg_epochs + 1, global_best_d, global_rec_d, state_d);
+    SO_CHECK_LAUNCH(h, "k_swarm_update_best_x");
+    return SO_OK;
+}
+
+extern "C" int so_swarm_rand(so_handle* h, int64_t P, int d, int64_t p0, uint64_t seed, uint64_t counter, double* out_d, void* stream) {
+    if (!h || !out_d || P < 0 || p0 < 0) return SO_ERR_BAD_ARG;
+    if (d < 1 || d > SO_MAX_DIM) return so_fail(h, SO_ERR_UNSUPPORTED, "swarm_rand: 1 <= d <= 16");
+    if (P == 0) return SO_OK;
+    DeviceGuard guard(h->device);
+    k_swarm_rand<<<(unsigned)((P * d + kThreads - 1) / kThreads), kThreads, 0, (cudaStream_t)stream>>>(P, d, p0, seed, counter, out_d);
+    SO_CHECK_LAUNCH(h, "k_swarm_rand");
+    return SO_OK;
+}
+
+extern "C" int so_swarm_step_dev(so_handle* h, int64_t P, int d, int64_t p0, double* pos_d, double* vel_d, const double* best_pos_d,
+                                 const double* global_best_d, const double* state_d, uint64_t seed, const double* velocity_scale_h,
+                                 const double* bounds_h, void* stream) {
+    if (!h || !pos_d || !vel_d || !best_pos_d || !global_best_d || !state_d || !velocity_scale_h || P < 0 || p0 < 0) return SO_ERR_BAD_ARG;
+    if (d < 1 || d > SO_MAX_DIM) return so_fail(h, SO_ERR_UNSUPPORTED, "swarm_step_dev: 1 <= d <= 16");
+    if (P == 0) return SO_OK;
+    DeviceGuard guard(h->device);
+    Vec16 vs, lo, hi;
+    for (int j = 0; j < SO_MAX_DIM; ++j) {
+        vs.v[j] = j < d ? velocity_scale_h[j] : 1.0;
+        lo.v[j] = (bounds_h && j < d) ? bounds_h[2 * j] : 0.0;
+        hi.v[j] = (bounds_h && j < d) ? bounds_h[2 * j + 1] : 0.0;
+    }
+    k_swarm_step_dev<<<(unsigned)((P * d + kThreads - 1) / kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+        P, d, p0, pos_d, vel_d, best_pos_d, global_best_d, state_d, seed, vs, lo, hi, bounds_h ? 1 : 0);
+    SO_CHECK_LAUNCH(h, "k_swarm_step_dev");
     return SO_OK;
 }
 

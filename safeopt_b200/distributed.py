@@ -32,11 +32,13 @@ def shard_bounds(n_rows: int, world: int, rank: int) -> Tuple[int, int]:
 class Comm:
     """Thin wrapper over torch.distributed that degrades to a single rank."""
 
-    def __init__(self, device=None):
+    def __init__(self, device=None, enabled=True):
         self.rank, self.world = 0, 1
         self._dist = None
         self._device = device
         self._flat_gather = False
+        if not enabled:                 # a deliberately rank-local object inside a multi-rank job
+            return
         try:
             import torch.distributed as dist
             if dist.is_available() and dist.is_initialized():

@@ -63,6 +63,8 @@ class DeviceEngine:
         self.launches = 0          # kernels launched through this engine (bench bookkeeping)
         self._raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
         self._grid_axes = None
+        self.xchg_world = 1
+        self._sets_result = np.zeros(_lib.sets_result_bytes(1), dtype=np.uint8)
 
     # ------------------------------------------------------------------ helpers
     def close(self):
@@ -252,6 +254,56 @@ class DeviceEngine:
                     "so_sets_candidates_chain")
         self.launches += 1
 
+    def sets_fused(self, Q, n_gps, row0, S, scaling, thr, with_candidates, Mmask, cand_key, cand_row, fetch=True):
+        """The three set passes and their cross-rank record exchange in one launch (so_sets_fused).  With ``fetch`` the
+        call waits for the kernel and returns the combined records of all ranks as a uint8 array laid out
+        [world x safe record][world x max record][world x int64 count]; otherwise use :meth:`sets_fused_result`."""
+        sc, th = _np_f64(scaling), _np_f64(thr)
+        cap = 0 if cand_key is None else cand_key.shape[0]
+        out = self._sets_result if fetch else None
+        rc = self.lib.so_sets_fused(self.handle, _ptr(Q), int(n_gps), Q.shape[0], int(row0), _ptr(S), _hptr(sc), _hptr(th),
+                                    1 if with_candidates else 0, _ptr(Mmask), _ptr(cand_key), _ptr(cand_row), cap,
+                                    _hptr(out), self._stream())
+        self._check(rc, "so_sets_fused")
+        self.launches += 1
+        return out[:136 * self.xchg_world] if fetch else None
+
+    def sets_fused_result(self):
+        out = self._sets_result
+        self._check(self.lib.so_sets_fused_result(self.handle, _hptr(out), self._stream()), "so_sets_fused_result")
+        return out[:136 * self.xchg_world]
+
+    # ------------------------------------------------------------------ cross-rank exchange
+    def connect_exchange(self, comm) -> bool:
+        """Map the peers' exchange buffers (CUDA IPC) so that the fused kernels exchange their records over NVLink
+        themselves.  Collective over ``comm`` (every rank constructs the same objects in the same order).  Returns False --
+        after saying so once on stderr -- when IPC mapping is unavailable; the callers then keep the NCCL all-gather path."""
+        if not comm.active:
+            return True
+        import os
+        import sys
+        if os.environ.get("SAFEOPT_B200_PEER_EXCHANGE", "1") == "0":
+            return False
+        mine = np.zeros(_lib.XCHG_HANDLE_BYTES, dtype=np.uint8)
+        rc = self.lib.so_xchg_export(self.handle, _hptr(mine))
+        ok = np.array([1 if rc == 0 else 0], dtype=np.int64)
+        handles = comm.all_gather(mine)                           # (world, 64) uint8, rank order
+        if comm.all_gather(ok).min() == 1:
+            rc = self.lib.so_xchg_connect(self.handle, comm.world, comm.rank, _hptr(np.ascontiguousarray(handles)))
+            ok[0] = 1 if rc == 0 else 0
+        good = bool(comm.all_gather(ok).min() == 1)               # all ranks take the same path
+        if not good:
+            if rc == 0:                                           # a peer failed: fall back to a single-rank view here too
+                self.lib.so_xchg_connect(self.handle, 1, 0, _hptr(mine))
+            if comm.rank == 0:
+                sys.stderr.write("safeopt_b200: CUDA IPC peer mapping unavailable (%s); cross-rank records go through "
+                                 "torch.distributed all-gathers instead\n" % self.lib.so_last_error(self.handle).decode(errors="replace"))
+            return False
+        self.xchg_world = comm.world
+        self._sets_result = np.zeros(_lib.sets_result_bytes(comm.world), dtype=np.uint8)
+        comm.barrier()                                            # nobody launches a fused kernel before everyone is mapped
+        return True
+
     # ------------------------------------------------------------------ K4
     def expander_check(self, gp, Xstar, row0, M, S, mean, var, xc, mean_c, var_c, u_c, beta, fmin, flags):
         B = xc.shape[0]
@@ -289,6 +341,28 @@ class DeviceEngine:
         rc = self.lib.so_swarm_update_best(self.handle, P, d, _ptr(pos), _ptr(values), _ptr(safe), _ptr(best_pos),
                                            _ptr(best_values), _ptr(best_idx), int(p0), _ptr(rec), self._stream())
         self._check(rc, "so_swarm_update_best")
+        self.launches += 1
+
+    def swarm_rand(self, P, d, p0, seed, counter, out):
+        self._check(self.lib.so_swarm_rand(self.handle, int(P), int(d), int(p0), int(seed), int(counter), _ptr(out), self._stream()),
+                    "so_swarm_rand")
+        self.launches += 1
+
+    def swarm_step_dev(self, pos, vel, best_pos, global_best, state, seed, p0, velocity_scale, bounds):
+        P, d = pos.shape
+        vs = _np_f64(velocity_scale)
+        bd = None if bounds is None else _np_f64(bounds)
+        rc = self.lib.so_swarm_step_dev(self.handle, P, d, int(p0), _ptr(pos), _ptr(vel), _ptr(best_pos), _ptr(global_best),
+                                        _ptr(state), int(seed), _hptr(vs), _hptr(bd), self._stream())
+        self._check(rc, "so_swarm_step_dev")
+        self.launches += 1
+
+    def swarm_update_best_x(self, pos, values, safe, best_pos, best_values, best_idx, p0, global_best, global_rec, state=None):
+        P, d = pos.shape
+        rc = self.lib.so_swarm_update_best_x(self.handle, P, d, _ptr(pos), _ptr(values), _ptr(safe), _ptr(best_pos),
+                                             _ptr(best_values), _ptr(best_idx), int(p0), _ptr(global_best), _ptr(global_rec),
+                                             _ptr(state), self._stream())
+        self._check(rc, "so_swarm_update_best_x")
         self.launches += 1
 
     def swarm_combine_best(self, recs, d, global_best, global_rec=None):

@@ -237,7 +237,9 @@ class SafeOpt(GaussianProcessOptimization):
     """Safe Bayesian optimisation over a finite parameter set (reference: gp_opt.py:281-712).
 
     Parameters are the reference's (``gp, parameter_set, fmin, lipschitz=None, beta=2,
-    num_contexts=0, threshold=0, scaling='auto'``) plus ``device`` (CUDA device, default current).
+    num_contexts=0, threshold=0, scaling='auto'``) plus ``device`` (CUDA device, default current) and
+    ``distributed`` (default True: shard the rows over the ranks of ``torch.distributed`` when it is
+    initialised; False: this object evaluates every row on its own GPU).
 
     Examples
     --------
@@ -251,7 +253,7 @@ class SafeOpt(GaussianProcessOptimization):
     """
 
     def __init__(self, gp, parameter_set, fmin, lipschitz=None, beta=2, num_contexts=0, threshold=0,
-                 scaling="auto", device=None):
+                 scaling="auto", device=None, distributed=True):
         super(SafeOpt, self).__init__(gp, fmin=fmin, beta=beta, num_contexts=num_contexts, threshold=threshold,
                                       scaling=scaling)
         parameter_set = np.asarray(parameter_set, dtype=float)
@@ -281,8 +283,15 @@ class SafeOpt(GaussianProcessOptimization):
 
         # ---- device state
         self._engine = DeviceEngine(device, max_gps=len(self.gps))
-        self._comm = Comm(self._engine.device)       # NCCL staging tensors live on the engine's device, not the current one
+        # NCCL staging tensors live on the engine's device, not the current one; distributed=False keeps this object
+        # rank-local although torch.distributed is initialised (it then evaluates ALL rows on this GPU)
+        self._comm = Comm(self._engine.device, enabled=distributed)
         self._fits = _DeviceFits(self._engine, self.gps)
+        # cross-rank records through peer-mapped memory written by the kernels themselves (so_xchg_*); where IPC mapping is
+        # not available -- and in the CPU tests' stand-in engine -- records go through all-gathers between chained kernels
+        self._peer = bool(hasattr(self._engine, "connect_exchange") and self._engine.connect_exchange(self._comm))
+        self._fused = (hasattr(self._engine, "sets_fused") and (self._peer or not self._comm.active)
+                       and os.environ.get("SAFEOPT_B200_FUSED_SETS", "1") != "0")
         n_rows = self.inputs.shape[0]
         self._row0, self._row1 = shard_bounds(n_rows, self._comm.world, self._comm.rank)
         m_local = self._row1 - self._row0
@@ -522,19 +531,25 @@ class SafeOpt(GaussianProcessOptimization):
         m_local = self._row1 - self._row0
         thr = np.broadcast_to(np.asarray(self.threshold, dtype=float), (G,)) * beta
 
-        eng.reduce_safe(self._Q_d, G, self._row0, self._S_d, self._rec_safe_l)
-        self._share(self._safe_all_d, self._rec_safe_l)
-        eng.maximizers_chain(self._Q_d, G, self._row0, self._S_d, self._safe_all_d, world, self.scaling, self._M_d,
-                             self._rec_max_l)
-        self._share(self._max_all_d, self._rec_max_l)
-        if not full_sets:
-            if self._cand_key_d is None:
-                self._cand_key_d = eng.empty((max(m_local, 1),))
-                self._cand_row_d = eng.empty((max(m_local, 1),), "i64")
-            eng.candidates_chain(self._Q_d, G, self._row0, self._S_d, self._M_d, self._max_all_d, world, self.scaling, thr,
-                                 None, self._cand_key_d, self._cand_row_d, self._n_cand_l)
-            self._share(self._ncand_all_d, self._n_cand_l)
-        host = recs.cpu().numpy()                                   # the one host wait of compute_sets
+        if not full_sets and self._cand_key_d is None:
+            self._cand_key_d = eng.empty((max(m_local, 1),))
+            self._cand_row_d = eng.empty((max(m_local, 1),), "i64")
+        if self._fused:
+            # one cooperative launch: the three passes, and between them every rank's record written straight into every
+            # rank's exchange buffer over NVLink (no collective, no host round trip); one copy + one wait for all records
+            host = eng.sets_fused(self._Q_d, G, self._row0, self._S_d, self.scaling, thr, not full_sets, self._M_d,
+                                  None if full_sets else self._cand_key_d, None if full_sets else self._cand_row_d)
+        else:
+            eng.reduce_safe(self._Q_d, G, self._row0, self._S_d, self._rec_safe_l)
+            self._share(self._safe_all_d, self._rec_safe_l)
+            eng.maximizers_chain(self._Q_d, G, self._row0, self._S_d, self._safe_all_d, world, self.scaling, self._M_d,
+                                 self._rec_max_l)
+            self._share(self._max_all_d, self._rec_max_l)
+            if not full_sets:
+                eng.candidates_chain(self._Q_d, G, self._row0, self._S_d, self._M_d, self._max_all_d, world, self.scaling, thr,
+                                     None, self._cand_key_d, self._cand_row_d, self._n_cand_l)
+                self._share(self._ncand_all_d, self._n_cand_l)
+            host = recs.cpu().numpy()                               # the one host wait of compute_sets
         self._safe_info = reduce_safe_records(host[:world * 64].view(SAFE_REC_DTYPE).reshape(-1))
         if self._safe_info["n_safe"] == 0:                          # gp_opt.py:504-507 (M is already all-False: M is a subset of S)
             return
@@ -715,7 +730,7 @@ class SafeOptSwarm(GaussianProcessOptimization):
     CORRELATION_LIMIT = 0.95        # gp_opt.py:1105
 
     def __init__(self, gp, fmin, bounds, beta=2, scaling="auto", threshold=0, swarm_size=20, device=None,
-                 swarm_backend="auto", rng="host", seed=0):
+                 swarm_backend="auto", rng="host", seed=0, distributed=True):
         super(SafeOptSwarm, self).__init__(gp, fmin=fmin, beta=beta, num_contexts=0, threshold=threshold,
                                            scaling=scaling)
         self.S = np.asarray(self.gps[0].X)
@@ -731,15 +746,18 @@ class SafeOptSwarm(GaussianProcessOptimization):
             swarm_backend = "device" if swarm_size >= self.DEVICE_SWARM_MIN else "host"
         self.swarm_backend = swarm_backend
         self._engine = DeviceEngine(device, max_gps=len(self.gps))
-        self._comm = Comm(self._engine.device)
+        self._comm = Comm(self._engine.device, enabled=distributed)
         self._fits = _DeviceFits(self._engine, self.gps)
         self._fit_buffers = {}
         self.optimal_velocities = self.optimize_particle_velocity()
         swarm_types = ["greedy", "maximizers", "expanders"]
         if swarm_backend == "device":
+            self._peer = bool(hasattr(self._engine, "connect_exchange") and self._engine.connect_exchange(self._comm))
             self.swarms = {kind: DeviceSwarm(self._engine, self.optimal_velocities, partial(self._swarm_fitness, kind),
-                                             bounds=self.bounds, rng=rng, seed=seed + 1000 * k, comm=self._comm)
+                                             bounds=self.bounds, rng=rng, seed=seed + 1000 * k, comm=self._comm, peer=self._peer)
                            for k, kind in enumerate(swarm_types)}
+            for sw in self.swarms.values():
+                sw.fitness_key = self._fitness_key
         else:
             self.swarms = {kind: SwarmOptimization(swarm_size, self.optimal_velocities,
                                                    partial(self._compute_particle_fitness, kind), bounds=self.bounds)
@@ -818,6 +836,13 @@ class SafeOptSwarm(GaussianProcessOptimization):
                           self.fmin[:n_needed] if n_needed == G else self.fmin[:1], self.scaling[:max(n_needed, 1)],
                           self.best_lower_bound, values, safe)
         return values, safe
+
+    def _fitness_key(self):
+        """Everything ``_fitness_device`` passes to its launches by value: a captured PSO iteration is valid while this is
+        unchanged (a new observation, new thresholds or a new greedy bound re-capture it)."""
+        f = self._fits
+        return (float(self.beta(self.t)), float(self.best_lower_bound), self.fmin.tobytes(), np.asarray(self.scaling).tobytes(),
+                f.refits, f.appends, f.removals, tuple(tuple(g) for g in f.groups), self.t)
 
     def _swarm_fitness(self, swarm_type, particles_d):
         """Fitness callback of the device swarms: the fits were refreshed by get_new_query_point before the run."""

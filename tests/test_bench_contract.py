@@ -43,8 +43,27 @@ def test_reference_arm_other_ranks_are_silent():
     assert r.returncode == 0 and r.stdout.strip() == ""
 
 
+def test_strong_scaling_is_the_default_and_keeps_the_named_grid():
+    """BASELINE config 4 is "50^4 ... sharded 8xB200": with N ranks the FIXED grid is split, per-GPU rows shrink."""
+    r = _run(["--impl", "reference", "--gpus", "8", "--steps", "1", "--warmup", "0", "--cpu-sample-rows", "5000"],
+             env={"RANK": "0", "WORLD_SIZE": "8", "LOCAL_RANK": "0", "OPENBLAS_NUM_THREADS": "2"})
+    assert r.returncode == 0, r.stderr[-2000:]
+    j = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][0])
+    assert j["scaling"] == "strong" and j["config"]["rows"] == 50 ** 4 and j["config"]["rows_per_gpu"] == 50 ** 4 // 8
+    assert "50x50x50x50" in j["config"]["workload"] and j["n_gpus"] == 8
+
+
+def test_reference_arm_config5_line():
+    r = _run(["--impl", "reference", "--config", "C5", "--steps", "1", "--warmup", "0", "--particles", "3000"],
+             env={"OPENBLAS_NUM_THREADS": "2"})
+    assert r.returncode == 0, r.stderr[-2000:]
+    j = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][0])
+    assert j["impl"] == "reference" and "C5" in j["config"]["workload"] and j["config"]["n_train"] == 512 and j["config"]["n_gps"] == 2
+    assert j["value"] > 0 and j["cpu_baseline"]["kind"] == "port" and j["e2e"]["value"] == j["value"]
+
+
 def test_weak_scaling_names_the_larger_grid():
-    r = _run(["--impl", "reference", "--gpus", "4", "--steps", "1", "--warmup", "0", "--cpu-sample-rows", "5000"],
+    r = _run(["--impl", "reference", "--gpus", "4", "--steps", "1", "--warmup", "0", "--cpu-sample-rows", "5000", "--scaling", "weak"],
              env={"RANK": "0", "WORLD_SIZE": "4", "LOCAL_RANK": "0", "OPENBLAS_NUM_THREADS": "2"})
     assert r.returncode == 0, r.stderr[-2000:]
     j = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][0])

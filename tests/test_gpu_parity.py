@@ -155,6 +155,11 @@ def test_posterior_matches_oracle(N, d, kind, M):
     assert np.array_equal(S.astype(bool), Q[:, 0] > 0.0)
     clear = np.abs(Qo[:, 0]) > 1e-8
     assert np.array_equal(S.astype(bool)[clear], (Qo[:, 0] > 0.0)[clear])
+    # report the margin (a seeded problem drifting onto a knife edge would otherwise pass silently through the band):
+    # at most a handful of rows may sit inside the band, and the closest one is printed with -s
+    print("posterior N=%d d=%d kind=%d M=%d: min |l - fmin| = %.3e, rows inside the 1e-8 band: %d" % (
+        N, d, kind, M, np.abs(Qo[:, 0]).min(), int((~clear).sum())))
+    assert (~clear).sum() <= max(1, M // 10000)
     assert np.array_equal(Q[:, 0], mean - 2.0 * np.sqrt(var)) and np.array_equal(Q[:, 1], mean + 2.0 * np.sqrt(var))
     eng.close()
 
@@ -661,11 +666,22 @@ def test_config_c4_full_size_properties():
     width = (Q[:, 1] - Q[:, 0]) / opt.scaling[0]
     assert opt.last_query_row == np.flatnonzero(MG)[np.argmax(width[MG])]
     assert np.array_equal(x, grid[opt.last_query_row])
-    # random rows against the oracle
-    rows = np.random.RandomState(0).choice(grid.shape[0], 20000, replace=False)
+    # EVERY row against the oracle port (6.25e6 rows in 250k-row chunks, ~30 s of host time): Q within tolerance, the masks
+    # S / M / G and the query row bit-exact -- BASELINE's "safe-set masks bit-exact vs reference" at d=4, N=256, full size
     go = gpy_lite.GPRegression(w.X, w.Y, kernel=gpy_lite.RBF(w.d, variance=w.variance, lengthscale=w.lengthscale, ARD=True), noise_var=w.noise_var)
-    Qo = port.confidence_intervals([go], grid[rows], w.beta)
-    assert np.abs(Q[rows] - Qo).max() < 1e-9 * 2 * np.sqrt(w.variance)
+    Qo = port.confidence_intervals([go], grid, w.beta, chunk=250_000)
+    assert np.abs(Q - Qo).max() < 1e-9 * 2 * np.sqrt(w.variance)
+    fm = np.array([0.0])
+    trace = {}
+    So, Mo, Go = port.compute_sets([go], grid, Qo, fm, w.beta, opt.scaling, w.threshold, trace=trace)
+    margin_S = np.abs(Qo[:, 0] - 0.0).min()
+    margin_M = np.abs(Qo[So, 1] - Qo[So, 0].max()).min()
+    print("C4 full size: |dQ| = %.2e, min margin S = %.3e, M = %.3e, |S| = %d, |M| = %d, |G| = %d, candidates = %d" % (
+        np.abs(Q - Qo).max(), margin_S, margin_M, So.sum(), Mo.sum(), Go.sum(), trace.get("n_candidates", 0)))
+    assert margin_S > 1e-8 and margin_M > 1e-8, "workload sits on a knife edge: masks would not be comparable"
+    assert np.array_equal(S, So) and np.array_equal(M, Mo) and np.array_equal(G, Go)
+    _, row_o = port.new_query_point(grid, Qo, So, Mo, Go, opt.scaling)
+    assert opt.last_query_row == row_o
     # sharding invariance: the second half computed as its own shard is bit-identical
     eng = opt._engine
     h = grid.shape[0] // 2
@@ -688,10 +704,18 @@ def test_config_c3_three_gps_properties():
     assert Q.shape == (250000, 6)
     assert np.array_equal(S, np.all(Q[:, ::2] > 0.0, axis=1))
     assert np.array_equal(M, S & (Q[:, 1] >= Q[S, 0].max()))
-    rows = np.random.RandomState(1).choice(grid.shape[0], 5000, replace=False)
+    # every row and every GP against the oracle port (250k rows x 3 GPs): Q within tolerance, masks and query row bit-exact
     gos = [gpy_lite.GPRegression(w.X, w.Y[:, [i]], kernel=gpy_lite.RBF(w.d, variance=w.variance, lengthscale=w.lengthscale, ARD=True),
                                  noise_var=w.noise_var) for i in range(3)]
-    assert np.abs(Q[rows] - port.confidence_intervals(gos, grid[rows], w.beta)).max() < 1e-9 * 2 * np.sqrt(w.variance)
+    Qo = port.confidence_intervals(gos, grid, w.beta, chunk=125_000)
+    assert np.abs(Q - Qo).max() < 1e-9 * 2 * np.sqrt(w.variance)
+    So, Mo, Go = port.compute_sets(gos, grid, Qo, np.asarray(w.fmin, dtype=float), w.beta, opt.scaling, w.threshold)
+    margin_S = np.abs(Qo[:, ::2] - 0.0).min()
+    margin_M = np.abs(Qo[So, 1] - Qo[So, 0].max()).min()
+    print("C3 full size: |dQ| = %.2e, min margin S = %.3e, M = %.3e" % (np.abs(Q - Qo).max(), margin_S, margin_M))
+    assert margin_S > 1e-8 and margin_M > 1e-8
+    assert np.array_equal(S, So) and np.array_equal(M, Mo) and np.array_equal(opt.G, Go)
+    assert opt.last_query_row == port.new_query_point(grid, Qo, So, Mo, Go, opt.scaling)[1]
 
 
 # ---------------------------------------------------------------- the CPU stand-in engine honours the same contracts
@@ -748,6 +772,182 @@ def test_stand_in_engine_agrees_with_the_device():
     assert d["mx"]["best_row"] == f["mx"]["best_row"] and abs(d["mx"]["max_width0"] - f["mx"]["max_width0"]) < 1e-9
 
 
+# ---------------------------------------------------------------- fused set pass, in-kernel exchange, graph replay
+@pytest.mark.parametrize("name", ["doctest_1d", "config_C2", "expander_g1", "expander_g2", "expander_tight", "full_sets_g1", "lipschitz_g2"])
+def test_fused_set_pass_equals_chained_passes(name, monkeypatch):
+    """so_sets_fused (one cooperative launch, records exchanged through the peer buffers) against the three chained kernels."""
+    g = load_golden(name)
+    n_rows = int(g["n_rows"])
+    full = bool(g["full_sets"]) if "full_sets" in g.files else False
+    got = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("SAFEOPT_B200_FUSED_SETS", mode)
+        gps, grid, fmin = golden_problem(g, "gpu")
+        opt = sb.SafeOpt(gps if len(gps) > 1 else gps[0], grid, fmin if len(gps) > 1 else fmin[0], lipschitz=golden_lipschitz(g),
+                         beta=float(g["beta"]), threshold=float(g["threshold"]))
+        assert opt._fused == (mode == "1")
+        for rep in range(3):                                  # epochs alternate the parity slots of the exchange buffer
+            opt.update_confidence_intervals()
+            opt.compute_sets(full_sets=full)
+            got[(mode, rep)] = (opt.S.copy(), opt.M.copy(), opt.G.copy(), dict(opt._safe_info), dict(opt._max_info or {}),
+                                opt.last_trace.get("n_candidates"), None if full else opt.get_new_query_point().copy())
+    for rep in range(3):
+        a, b = got[("1", rep)], got[("0", rep)]
+        assert all(np.array_equal(a[k], b[k]) for k in range(3)) and a[3] == b[3] and a[4] == b[4] and a[5] == b[5]
+        assert full or np.array_equal(a[6], b[6])
+    assert np.array_equal(got[("1", 2)][0], unpack_mask(g["S"], n_rows)) and np.array_equal(got[("1", 2)][1], unpack_mask(g["M"], n_rows))
+    assert np.array_equal(got[("1", 2)][2], unpack_mask(g["G"], n_rows))
+
+
+def test_fused_set_pass_with_no_safe_rows_and_ragged_sizes():
+    """Edge cases of the fused kernel: nothing safe, a single row, sizes that are not multiples of the 16-row chunks."""
+    eng = DeviceEngine(max_gps=1)
+    rs = np.random.RandomState(5)
+    for M in [1, 15, 16, 17, 1000, 70001]:
+        Qh = np.sort(rs.randn(M, 2), axis=1)
+        for frac in [0.0, 0.3, 1.0]:
+            Sh = (rs.rand(M) < frac).astype(np.uint8)
+            Q, S, Mm = eng.to_device(Qh), eng.to_device(Sh), eng.zeros((M,), "u8")
+            key, row = eng.empty((M,)), eng.empty((M,), "i64")
+            host = eng.sets_fused(Q, 1, 1000, S, [1.0], [0.1], True, Mm, key, row)
+            from safeopt_b200.engine import MAX_REC_DTYPE, SAFE_REC_DTYPE
+            sr = host[:64].view(SAFE_REC_DTYPE)[0]
+            mr = host[64:128].view(MAX_REC_DTYPE)[0]
+            n_c = int(host[128:136].view(np.int64)[0])
+            sb_ = Sh.astype(bool)
+            assert sr["n_safe"] == sb_.sum()
+            if not sb_.any():
+                assert sr["argmax_l0"] == -1 and mr["n_max"] == 0 and n_c == 0 and not Mm.cpu().numpy().any()
+                continue
+            rows = np.flatnonzero(sb_)
+            assert sr["max_l0"] == Qh[sb_, 0].max() and sr["argmax_l0"] == 1000 + rows[np.argmax(Qh[sb_, 0])]
+            assert sr["argmax_u0"] == 1000 + rows[np.argmax(Qh[sb_, 1])]
+            Mo = sb_ & (Qh[:, 1] >= Qh[sb_, 0].max())
+            assert np.array_equal(Mm.cpu().numpy().astype(bool), Mo) and mr["n_max"] == Mo.sum()
+            w = Qh[:, 1] - Qh[:, 0]
+            assert mr["max_width0"] == w[Mo].max() and mr["best_row"] == 1000 + np.flatnonzero(Mo)[np.argmax(w[Mo])]
+            c = sb_ & ~Mo & (w > w[Mo].max()) & (w > 0.1)
+            assert n_c == c.sum() and np.array_equal(np.sort(row.cpu().numpy()[:n_c]), 1000 + np.flatnonzero(c))
+    eng.close()
+
+
+def test_swarm_randoms_do_not_depend_on_the_sharding():
+    """so_swarm_rand / so_swarm_step_dev key their randoms by the GLOBAL particle index: any shard draws what one GPU would."""
+    eng = DeviceEngine(max_gps=1)
+    P, d = 1000, 6
+    full = eng.empty((P, d))
+    eng.swarm_rand(P, d, 0, 12345, 7, full)
+    part = eng.empty((300, d))
+    eng.swarm_rand(300, d, 450, 12345, 7, part)
+    assert torch.equal(part, full[450:750])
+    f = full.cpu().numpy()
+    assert 0.0 <= f.min() and f.max() < 1.0 and abs(f.mean() - 0.5) < 0.02 and abs(f.var() - 1 / 12) < 0.01
+    other = eng.empty((P, d))
+    eng.swarm_rand(P, d, 0, 12345, 8, other)
+    assert not torch.equal(other, full) and abs(np.corrcoef(f.ravel(), other.cpu().numpy().ravel())[0, 1]) < 0.05
+    eng.close()
+
+
+def test_device_swarm_graph_replay_equals_kernel_by_kernel(monkeypatch):
+    """rng='device': a PSO run replayed from the captured CUDA graph is bit-identical to launching kernel by kernel, and a
+    second optimise() (new greedy bound => re-capture) still is."""
+    g = load_golden("swarm_query_2d")
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("SAFEOPT_B200_SWARM_GRAPH", mode)
+        opt = _swarm_query_problem(g, swarm_backend="device", rng="device", seed=3)
+        opt.swarm_size = 4000
+        np.random.seed(11)
+        xs = [opt.optimize().copy() for _ in range(2)]
+        sw = opt.swarms["expanders"]
+        assert sw.use_graph == (mode == "1") and sw.in_kernel_exchange
+        out[mode] = (xs, sw.best_positions.cpu().numpy().copy(), sw.best_values.cpu().numpy().copy(), opt.S.copy())
+    for a, b in zip(out["1"][0], out["0"][0]):
+        assert np.array_equal(a, b)
+    assert np.array_equal(out["1"][1], out["0"][1]) and np.array_equal(out["1"][2], out["0"][2]) and np.array_equal(out["1"][3], out["0"][3])
+
+
+# ---------------------------------------------------------------- the boundary: foreign GPy-protocol models, the INTEGRATION.md stub
+def test_foreign_gpy_protocol_models_go_straight_in():
+    """"GPy model in, same methods out" (gp_opt.py:58-67, :347): objects that are NOT ours -- oracle.gpy_lite models with GPy's
+    attribute surface, incl. a non-ARD kernel and a Prod of RBFs -- are handed to sb.SafeOpt / sb.SafeOptSwarm unchanged."""
+    g = load_golden("expander_g2")
+    gps, grid, fmin = golden_problem(g, "cpu")                      # gpy_lite.GPRegression objects
+    assert not isinstance(gps[0], sb.GPRegression)
+    opt = sb.SafeOpt(gps, grid, fmin, beta=float(g["beta"]), threshold=float(g["threshold"]))
+    x = opt.optimize()
+    n_rows = int(g["n_rows"])
+    assert opt.last_query_row == int(g["row_next"]) and np.array_equal(x, g["x_next"]) and np.abs(opt.Q - g["Q"]).max() < 1e-9 * 2 * np.sqrt(2.0)
+    assert np.array_equal(opt.S, unpack_mask(g["S"], n_rows)) and np.array_equal(opt.M, unpack_mask(g["M"], n_rows))
+    assert np.array_equal(opt.G, unpack_mask(g["G"], n_rows))
+    opt.add_new_data_point(x, np.array([[1.0, 1.0]]))               # set_XY on the foreign objects, incremental device update
+    assert gps[0].X.shape[0] == g["X"].shape[0] + 1 and opt.optimize() is not None and opt._fits.appends == len(gps)
+    # contexts with a foreign Prod kernel
+    c = load_golden("context_1p1c")
+    kern = gpy_lite.RBF(1, variance=float(c["var0"]), lengthscale=float(c["ls0"]), active_dims=[0]) * \
+        gpy_lite.RBF(1, variance=float(c["var1"]), lengthscale=float(c["ls1"]), active_dims=[1])
+    assert type(kern).__name__ == "Prod"
+    gp = gpy_lite.GPRegression(c["X"], c["Y"], kernel=kern, noise_var=float(c["noise_var"]))
+    opt = sb.SafeOpt(gp, c["pset"], float(c["fmin"]), num_contexts=1, beta=float(c["beta"]), threshold=float(c["threshold"]))
+    ctx = np.array([float(c["ctx0"])])
+    xq = opt.optimize(context=ctx)
+    n = int(c["n_rows"])
+    assert np.abs(opt.Q - c["Q0"]).max() < 1e-9 * 2 * np.sqrt(3.0) and np.array_equal(xq, c["x0"])
+    assert np.array_equal(opt.S, unpack_mask(c["S0"], n)) and np.array_equal(opt.M, unpack_mask(c["M0"], n))
+    # a non-ARD kernel (one lengthscale for all dimensions) through the swarm optimiser
+    rs = np.random.RandomState(2)
+    X = rs.uniform(-0.5, 0.5, (12, 3))
+    Y = (1 - 0.3 * np.sum(X * X, 1))[:, None]
+    fgp = gpy_lite.GPRegression(X, Y, kernel=gpy_lite.RBF(3, variance=1.5, lengthscale=0.8), noise_var=1e-3)
+    sw = sb.SafeOptSwarm(fgp, 0.0, bounds=[(-1, 1)] * 3, swarm_size=40)
+    pts = rs.uniform(-1, 1, (50, 3))
+    vd, sd = sw._compute_particle_fitness("expanders", pts)
+    vo, so = port.particle_fitness([fgp], np.array([0.0]), 2.0, sw.scaling, "expanders", pts)
+    assert np.abs(vd - vo).max() < 1e-9 and np.array_equal(sd, so)
+
+
+def test_integration_md_stub_runs_against_the_port():
+    """The ctypes stub INTEGRATION.md section 2 shows a maintainer (class B200Posterior) is executed verbatim against the
+    port's GridProblem (the reference's SafeOpt attribute surface): same Q, same S as the port's own NumPy path."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    block = re.search(r"## 2\..*?```python\n(.*?)```", text, re.S).group(1)
+    assert "class B200Posterior" in block
+    block = block.replace('C.CDLL("libsafeopt_b200.so")', 'C.CDLL(%r)' % _lib.LIB_PATH)
+    ns = {}
+    exec(compile(block, "INTEGRATION.md#stub", "exec"), ns)
+    g = load_golden("expander_g2")
+    gps, grid, fmin = golden_problem(g, "cpu")
+    prob = port.GridProblem.create(gps, grid, fmin, beta=float(g["beta"]), threshold=float(g["threshold"]))
+    prob.Q = np.zeros((grid.shape[0], 2 * len(gps)))
+    prob.S = np.zeros(grid.shape[0], dtype=bool)
+    ns["B200Posterior"](prob, device=torch.cuda.current_device()).update(prob, float(g["beta"]))
+    assert np.abs(prob.Q - g["Q"]).max() < 1e-9 * 2 * np.sqrt(2.0)
+    assert np.array_equal(prob.S, unpack_mask(g["S"], int(g["n_rows"])))
+
+
+def test_scaled_operand_table_fallback_is_logged_and_equal(monkeypatch, capfd):
+    """Above SO_APRIME_LIMIT_MB the grid path drops from the scaled-operand (A') kernel to the per-axis table kernel: it
+    says so once on stderr and the answers do not change."""
+    g = load_golden("config_C2")
+    res = {}
+    for limit in (None, "0"):
+        if limit is None:
+            monkeypatch.delenv("SO_APRIME_LIMIT_MB", raising=False)
+        else:
+            monkeypatch.setenv("SO_APRIME_LIMIT_MB", limit)
+        gps, grid, fmin = golden_problem(g, "gpu")
+        opt = sb.SafeOpt(gps[0], grid, fmin[0], beta=float(g["beta"]), threshold=float(g["threshold"]))
+        opt.optimize()
+        res[limit] = (opt.Q.copy(), opt.S.copy(), opt.M.copy(), opt.last_query_row)
+    err = capfd.readouterr().err
+    assert "scaled-operand table" in err
+    a, b = res[None], res["0"]
+    assert np.abs(a[0] - b[0]).max() < 1e-10 and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and a[3] == b[3]
+
+
 # ---------------------------------------------------------------- multi-GPU (runs when the box has >= 2 GPUs)
 def _nccl_worker(rank, world, port_no, out):
     import os
@@ -793,6 +993,47 @@ def _nccl_swarm_worker(rank, world, port_no, out):
         open(os.path.join(out, "ok_%d" % rank), "w").write("1" if ok else "0")
     finally:
         dist.destroy_process_group()
+
+
+def _nccl_device_rng_worker(rank, world, port_no, out):
+    """rng='device' draws by global particle index: the sharded swarm must follow the single-GPU trajectory bit for bit
+    (graph replay + in-kernel record exchange on both sides)."""
+    import os
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port_no)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        g = load_golden("swarm_query_2d")
+        res = []
+        for distributed in (True, False):
+            opt = _swarm_query_problem(g, swarm_backend="device", rng="device", seed=5, device=torch.device("cuda", rank),
+                                       distributed=distributed)
+            opt.swarm_size = 3001
+            np.random.seed(4)
+            x = opt.optimize()
+            sw = opt.swarms["expanders"]
+            full = D.gather_padded_rows(sw.comm, sw.best_positions, 3001).cpu().numpy()
+            res.append((x.copy(), full, opt.S.copy(), sw.comm.world, sw.in_kernel_exchange))
+        ok = res[0][3] == world and res[1][3] == 1 and res[0][4] and res[1][4]
+        ok = ok and np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1]) and np.array_equal(res[0][2], res[1][2])
+        open(os.path.join(out, "ok_%d" % rank), "w").write("1" if ok else "0")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_device_rng_swarm_equals_single_gpu(tmp_path):
+    import os
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port_no = s.getsockname()[1]
+    s.close()
+    mp.spawn(_nccl_device_rng_worker, args=(2, port_no, str(tmp_path)), nprocs=2, join=True)
+    assert all(open(os.path.join(str(tmp_path), "ok_%d" % r)).read() == "1" for r in range(2))
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
