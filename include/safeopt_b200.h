@@ -165,6 +165,17 @@ int so_posterior_grid_multi(so_handle* h, int n, const int* gps_h, int64_t row0,
                             double beta, const double* fmin_h, double* const* mean_dh,
                             double* const* var_dh, double* Q_d, int q_stride, const int* q_col_h,
                             uint8_t* S_d, int safe_mode, void* stream);
+/* fp32 arithmetic mode of the grid path (BASELINE config 3: "fp32", posterior within 1e-4 relative): the same
+ * contraction on the 5th-generation tensor cores (tcgen05.mma kind::tf32, error-compensated 3xTF32 split, fp32
+ * accumulators in TMEM); fit, epilogue (bounds, safe bit) and everything downstream stay fp64.  N <= 256, RBF, grid.
+ *   so_grid_prepare_f32   : packs the TF32 hi/lo operand planes for grid rows [row0, row0+M); call after so_grid_prepare(_rows)
+ *                           of the same GP (again after every fit / one-point update).
+ *   so_posterior_grid_f32 : so_posterior_grid_multi in that mode (n <= 4 GPs sharing X, kernel and noise; the first one
+ *                           provides the operands). */
+int so_grid_prepare_f32(so_handle* h, int gp, int64_t row0, int64_t M, void* stream);
+int so_posterior_grid_f32(so_handle* h, int n, const int* gps_h, int64_t row0, int64_t M, double beta,
+                          const double* fmin_h, double* const* mean_dh, double* const* var_dh, double* Q_d,
+                          int q_stride, const int* q_col_h, uint8_t* S_d, int safe_mode, void* stream);
 /* Diagnostic, host only (no device work): the assignment of the NB block rows of L^-1 to the eight warps of
  * the contraction for a fit with NB = ceil(N/8) block rows, as the posterior kernels use it when NB is not a
  * multiple of 32.  table_h: 8 passes x 8 warps x 4 slots (int16, ascending per pass, -1 = unused). */
@@ -227,6 +238,9 @@ int so_sets_fused(so_handle* h, const double* Q_d, int n_gps, int64_t M, int64_t
                   const double* scaling_h, const double* thr_h, int with_candidates, uint8_t* Mmask_d,
                   double* cand_key_d, int64_t* cand_row_d, int64_t cap, void* result_h, void* stream);
 int so_sets_fused_result(so_handle* h, void* result_h, void* stream);
+/* Diagnostic: SM-clock stamps (block 0) at the phase boundaries of the last so_sets_fused; needs SO_FUSED_DEBUG_TIMES=1 in the
+ * environment.  out_h: 16 int64 (scan A, barrier, publish, wait, scan B, ..., end). */
+int so_debug_fused_times(so_handle* h, int64_t* out_h);
 
 /* ------------------------------------------------------------------ cross-rank record exchange (multi-GPU, one process per GPU)
  * the candidate rows are sharded, and the only data that crosses GPUs are the 64..144-byte records of

@@ -85,6 +85,8 @@ SIGNATURES = {
     "so_posterior_grid": (_i, [_P, _i, _i64, _i64, _dbl, _dbl, _P, _P, _P, _i, _i, _P, _i, _P]),
     "so_posterior_rows_multi": (_i, [_P, _i, _P, _P, _i64, _dbl, _P, _P, _P, _P, _i, _P, _P, _i, _P]),
     "so_posterior_grid_multi": (_i, [_P, _i, _P, _i64, _i64, _dbl, _P, _P, _P, _P, _i, _P, _P, _i, _P]),
+    "so_grid_prepare_f32": (_i, [_P, _i, _i64, _i64, _P]),
+    "so_posterior_grid_f32": (_i, [_P, _i, _P, _i64, _i64, _dbl, _P, _P, _P, _P, _i, _P, _P, _i, _P]),
     "so_debug_row_plan": (_i, [_i, _P, _P]),
     "so_debug_tile_plans": (_i, [_i, _i, _i64, _i, _i64, _i, _P]),
     "so_posterior_rows_simple": (_i, [_P, _i, _P, _i64, _P, _P, _P]),
@@ -96,6 +98,7 @@ SIGNATURES = {
     "so_sets_candidates_chain": (_i, [_P, _P, _i, _i64, _i64, _P, _P, _P, _i, _P, _P, _P, _P, _P, _i64, _P, _P]),
     "so_sets_fused": (_i, [_P, _P, _i, _i64, _i64, _P, _P, _P, _i, _P, _P, _P, _i64, _P, _P]),
     "so_sets_fused_result": (_i, [_P, _P, _P]),
+    "so_debug_fused_times": (_i, [_P, _P]),
     "so_xchg_export": (_i, [_P, _P]),
     "so_xchg_connect": (_i, [_P, _i, _i, _P]),
     "so_xchg_world": (_i, [_P]),

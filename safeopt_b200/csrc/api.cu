@@ -51,7 +51,7 @@ int so_create(int device, int max_gps, so_handle** out) {
 
 static void free_gp(GPState& g) {
     cudaFree(g.X); cudaFree(g.Xs); cudaFree(g.Y); cudaFree(g.K); cudaFree(g.Linv);
-    cudaFree(g.alpha); cudaFree(g.zvec); cudaFree(g.Afrag); cudaFree(g.E); cudaFree(g.P2); cudaFree(g.PfFrag); cudaFree(g.Aprime);
+    cudaFree(g.alpha); cudaFree(g.zvec); cudaFree(g.Afrag); cudaFree(g.E); cudaFree(g.P2); cudaFree(g.PfFrag); cudaFree(g.Aprime); cudaFree(g.f32_A); cudaFree(g.f32_B); cudaFree(g.f32_PfT);
     g = GPState();
 }
 
@@ -65,8 +65,9 @@ int so_destroy(so_handle* h) {
     cudaFree(h->ws_partials);
     cudaFree(h->ws_counter);
     cudaFree(h->ws_z);
+    cudaFree(h->f32_mean_scratch);
     xchg_destroy(h);
-    cudaFree(h->fused_bar); cudaFree(h->fused_part); cudaFree(h->fused_ncand); cudaFree(h->fused_result_d);
+    cudaFree(h->fused_bar); cudaFree(h->fused_part); cudaFree(h->fused_ncand); cudaFree(h->fused_result_d); cudaFree(h->fused_dbg);
     cudaFreeHost(h->fused_result_h);
     delete h;
     return SO_OK;

@@ -46,6 +46,17 @@ struct GPState {
     bool tma_ready = false;
     bool tma_ring = false;       // B streams through the k-chunk ring (posterior_ring.cuh) instead of a resident double buffer
     bool grid_ready = false;
+    // fp32 arithmetic mode (posterior_f32.cuh): TF32 hi/lo operand planes in UMMA canonical layout
+    float* f32_A = nullptr;      // fast-table tiles
+    size_t capF32A = 0;
+    float* f32_B = nullptr;      // scaled operands A'(s) for the slow indices [f32_s0, f32_s1)
+    size_t capF32B = 0;
+    double* f32_PfT = nullptr;   // transposed fp64 fast table of the mean kernel
+    size_t capF32PfT = 0;
+    int64_t f32_Fpad = 0;
+    int f32_Np = 0, f32_tpb = 0;
+    int64_t f32_s0 = 0, f32_s1 = 0;
+    bool f32_ready = false;
 };
 
 struct GridSpec {
@@ -89,6 +100,9 @@ struct so_handle {
     void* fused_part = nullptr;
     unsigned long long* fused_ncand = nullptr;
     int* fused_status = nullptr;
+    long long* fused_dbg = nullptr;
+    double* f32_mean_scratch = nullptr;   // fp64 means of the fp32 mode when the caller wants none (G x M)
+    size_t f32_mean_cap = 0;
     void* fused_result_d = nullptr;  // world x 136 bytes + status + epoch, device
     void* fused_result_h = nullptr;  // pinned host copy target
     int fused_grid = 0;

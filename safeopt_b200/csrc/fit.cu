@@ -291,6 +291,7 @@ extern "C" int so_fit(so_handle* h, int gp, const double* X_h, const double* Y_h
     const int ld = g.ld;
     g.fitted = false;
     g.grid_ready = false;
+    g.f32_ready = false;
     g.N = N; g.d = d; g.kind = kernel_kind; g.NB = NB;
     g.variance = variance; g.noise = noise_var;
     InvLs il;
@@ -458,6 +459,7 @@ extern "C" int so_fit_append(so_handle* h, int gp, const double* x_new_h, double
     const int ld = g.ld;
     g.fitted = false;
     g.grid_ready = false;
+    g.f32_ready = false;
     g.tma_ready = false;
     if (NB1 != g.NB) {
         // a new block of 8 rows starts: its 7 other rows are padding (finite zeros), its fragment blocks start empty
@@ -502,6 +504,7 @@ extern "C" int so_fit_remove_last(so_handle* h, int gp, void* stream_) {
     const int N1 = g.N - 1, d = g.d, ld = g.ld;
     const int NB1 = (N1 + 7) / 8, Npad1 = 8 * NB1;
     g.grid_ready = false;
+    g.f32_ready = false;
     g.tma_ready = false;
     // row N1 becomes padding; alpha / z are rebuilt from the leading block of L^-1 (exactly what a refit would use)
     k_clear_rows<<<(d + 3 + 127) / 128, 128, 0, stream>>>(g.Xs, g.Y, g.alpha, g.zvec, N1, N1 + 1, d);

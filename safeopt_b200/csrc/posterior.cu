@@ -14,6 +14,7 @@
 // the grid path) + 32 out (mean, var, l, u) + 1 (S).  See DESIGN.md section 3.
 #include "posterior_tma.cuh"
 #include "posterior_ring.cuh"
+#include "posterior_f32.cuh"
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -592,7 +593,36 @@ extern "C" int so_grid_define(so_handle* h, int d, const int32_t* n_h, const dou
         gs.slow_rows = rows / fr;
     }
     gs.d = d; gs.total = total; gs.rows = rows; gs.defined = true;
-    for (auto& g : h->gps) g.grid_ready = false;
+    for (auto& g : h->gps) { g.grid_ready = false; g.f32_ready = false; }
+    return SO_OK;
+}
+
+// Two-level product tables of the grid path (Pfast: fast_rows x Npad, Pslow: slow_rows x Npad, back to back in g.P2).
+static int build_product_tables(so_handle* h, GPState& g, const double* inv_ls_d, cudaStream_t stream) {
+    GridSpec& gs = h->grid;
+    const int Npad = 8 * g.NB;
+    const int64_t trows = gs.fast_rows + gs.slow_rows;
+    const size_t need2 = (size_t)trows * Npad;
+    if (need2 > g.capP2) {
+        SO_CUDA(h, cudaStreamSynchronize(stream));
+        if (g.P2) cudaFree(g.P2);
+        g.P2 = nullptr;
+        const size_t cap2 = (size_t)trows * g.capN;
+        SO_CUDA(h, cudaMalloc(&g.P2, sizeof(double) * cap2));
+        g.capP2 = cap2;
+    }
+    TableSpec ts;
+    ts.d = gs.d;
+    for (int j = 0; j < kGridMaxDim; ++j) {
+        ts.n[j] = j < gs.d ? gs.n[j] : 1;
+        ts.off[j] = j < gs.d ? gs.off[j] : 0;
+        ts.stride[j] = j < gs.d ? gs.stride[j] : 1;
+        ts.in_fast[j] = j < gs.d ? gs.in_fast[j] : 0;
+    }
+    ts.fast_rows = gs.fast_rows; ts.slow_rows = gs.slow_rows;
+    k_grid_tables2<<<(unsigned)trows, 128, 0, stream>>>(ts, gs.axis, g.Xs, g.P2, g.P2 + (size_t)gs.fast_rows * Npad, g.N, Npad, g.d,
+                                                        g.variance, inv_ls_d);
+    SO_CHECK_LAUNCH(h, "k_grid_tables2");
     return SO_OK;
 }
 
@@ -658,28 +688,10 @@ extern "C" int so_grid_prepare_rows(so_handle* h, int gp, int64_t row0, int64_t 
         }
     }
     if (fits) {
-        const size_t need2 = (size_t)trows * Npad;
-        if (need2 > g.capP2) {
-            SO_CUDA(h, cudaStreamSynchronize(stream));
-            if (g.P2) cudaFree(g.P2);
-            g.P2 = nullptr;
-            const size_t cap2 = (size_t)trows * g.capN;
-            SO_CUDA(h, cudaMalloc(&g.P2, sizeof(double) * cap2));
-            g.capP2 = cap2;
-        }
-        TableSpec ts;
-        ts.d = gs.d;
-        for (int j = 0; j < kGridMaxDim; ++j) {
-            ts.n[j] = j < gs.d ? gs.n[j] : 1;
-            ts.off[j] = j < gs.d ? gs.off[j] : 0;
-            ts.stride[j] = j < gs.d ? gs.stride[j] : 1;
-            ts.in_fast[j] = j < gs.d ? gs.in_fast[j] : 0;
-        }
-        ts.fast_rows = gs.fast_rows; ts.slow_rows = gs.slow_rows;
+        int rc2 = build_product_tables(h, g, inv_ls_d, stream);
+        if (rc2) return rc2;
         double* Pfast = g.P2;
         double* Pslow = g.P2 + (size_t)gs.fast_rows * Npad;
-        k_grid_tables2<<<(unsigned)trows, 128, 0, stream>>>(ts, gs.axis, g.Xs, Pfast, Pslow, g.N, Npad, g.d, g.variance, inv_ls_d);
-        SO_CHECK_LAUNCH(h, "k_grid_tables2");
 
         const int tpb = (int)((gs.fast_rows + pl.T - 1) / pl.T);
         const size_t pf_elems = (size_t)tpb * pl.kb_pad * pl.TB * 32;
@@ -732,5 +744,168 @@ extern "C" int so_grid_rows(so_handle* h, int64_t row0, int64_t M, double* X_d, 
     }
     k_grid_rows<<<(unsigned)((M + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(gd, gs.axis, row0, M, X_d);
     SO_CHECK_LAUNCH(h, "k_grid_rows");
+    return SO_OK;
+}
+
+// ---------------------------------------------------------------- fp32 arithmetic mode (tcgen05 / TMEM), grid path
+extern "C" int so_grid_prepare_f32(so_handle* h, int gp, int64_t row0, int64_t M, void* stream_) {
+    if (!h || gp < 0 || gp >= h->max_gps) return SO_ERR_BAD_ARG;
+    GPState& g = h->gps[gp];
+    GridSpec& gs = h->grid;
+    if (!gs.defined) return so_fail(h, SO_ERR_BAD_ARG, "so_grid_prepare_f32: no grid defined");
+    if (row0 < 0 || M < 0 || row0 + M > gs.rows) return so_fail(h, SO_ERR_BAD_ARG, "so_grid_prepare_f32: rows outside the grid");
+    if (!g.fitted) return so_fail(h, SO_ERR_NOT_FITTED, "so_grid_prepare_f32: GP not fitted");
+    if (g.kind != SO_KERNEL_RBF) return so_fail(h, SO_ERR_UNSUPPORTED, "so_grid_prepare_f32: separable tables need an RBF kernel");
+    if (g.d != gs.d) return so_fail(h, SO_ERR_BAD_ARG, "so_grid_prepare_f32: grid dimension differs from the GP input dimension");
+    const int nslab = f32_nslab(g.N), Np = nslab * kF32SlabK;
+    if (Np > kF32MaxNp) return so_fail(h, SO_ERR_CAPACITY, "so_grid_prepare_f32: the fp32 tensor-core path holds N <= 256 (TMEM accumulator columns)");
+    if (!g.E) return so_fail(h, SO_ERR_NOT_FITTED, "so_grid_prepare_f32: call so_grid_prepare(_rows) first (per-axis tables, hyper-parameters)");
+    DeviceGuard guard(h->device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int Npad = 8 * g.NB;
+    const double* inv_ls_d = g.E + (size_t)gs.total * g.capN;     // left there by so_grid_prepare_rows
+    int rc = build_product_tables(h, g, inv_ls_d, stream);
+    if (rc) return rc;
+    const int tpb = (int)((gs.fast_rows + kF32TileRows - 1) / kF32TileRows);
+    const int64_t s_lo = M > 0 ? row0 / gs.fast_rows : 0;
+    const int64_t s_hi = M > 0 ? (row0 + M - 1) / gs.fast_rows + 1 : 0;
+    const int64_t n_slow = s_hi - s_lo;
+    if (n_slow > 65535) return so_fail(h, SO_ERR_CAPACITY, "so_grid_prepare_f32: more than 65535 slow indices in one row block");
+    const size_t a_floats = (size_t)tpb * nslab * (kF32ASlabBytes / 4);
+    const size_t b_stride = f32_b_bytes(Np);
+    const size_t b_floats = (size_t)(n_slow > 0 ? n_slow : 1) * (b_stride / 4);
+    if (b_floats * 4 > ((size_t)16 << 30)) return so_fail(h, SO_ERR_CAPACITY, "so_grid_prepare_f32: operand table above 16 GB");
+    if (a_floats > g.capF32A) {
+        SO_CUDA(h, cudaStreamSynchronize(stream));
+        if (g.f32_A) cudaFree(g.f32_A);
+        g.f32_A = nullptr;
+        SO_CUDA(h, cudaMalloc(&g.f32_A, a_floats * 4 * 2));
+        g.capF32A = a_floats * 2;
+    }
+    if (b_floats > g.capF32B) {
+        SO_CUDA(h, cudaStreamSynchronize(stream));
+        if (g.f32_B) cudaFree(g.f32_B);
+        g.f32_B = nullptr;
+        const size_t cap = b_floats + b_floats / 4;
+        SO_CUDA(h, cudaMalloc(&g.f32_B, cap * 4));
+        g.capF32B = cap;
+    }
+    const size_t a_blocks = (a_floats / 2 + 255) / 256;
+    k_f32_pack_a<<<(unsigned)(a_blocks < 2048 ? a_blocks : 2048), 256, 0, stream>>>(g.P2, g.f32_A, gs.fast_rows, g.N, Npad, nslab, tpb);
+    SO_CHECK_LAUNCH(h, "k_f32_pack_a");
+    if (n_slow > 0) {
+        const size_t plane0 = (size_t)8 * Np * 4;
+        dim3 grd((unsigned)((plane0 + 255) / 256), (unsigned)n_slow);
+        k_f32_pack_b<<<grd, 256, 0, stream>>>(g.Linv, g.ld, g.P2 + (size_t)gs.fast_rows * Npad, Npad, g.f32_B, b_stride / 4, s_lo, g.N, Np);
+        SO_CHECK_LAUNCH(h, "k_f32_pack_b");
+    }
+    // transposed fp64 fast table of the mean kernel
+    const int64_t Fpad = (gs.fast_rows + 127) / 128 * 128;
+    const size_t pt = (size_t)Fpad * Npad;
+    if (pt > g.capF32PfT) {
+        SO_CUDA(h, cudaStreamSynchronize(stream));
+        if (g.f32_PfT) cudaFree(g.f32_PfT);
+        g.f32_PfT = nullptr;
+        SO_CUDA(h, cudaMalloc(&g.f32_PfT, sizeof(double) * (size_t)Fpad * g.capN));
+        g.capF32PfT = (size_t)Fpad * g.capN;
+    }
+    k_transpose_pfast<<<dim3((unsigned)(Fpad / 32), (unsigned)((g.N + 31) / 32)), dim3(32, 8), 0, stream>>>(g.P2, g.f32_PfT, gs.fast_rows, Fpad,
+                                                                                                        g.N, Npad);
+    SO_CHECK_LAUNCH(h, "k_transpose_pfast");
+    g.f32_Fpad = Fpad;
+    g.f32_Np = Np; g.f32_tpb = tpb; g.f32_s0 = s_lo; g.f32_s1 = s_hi; g.f32_ready = true;
+    return SO_OK;
+}
+
+extern "C" int so_posterior_grid_f32(so_handle* h, int n, const int* gps_h, int64_t row0, int64_t M, double beta,
+                                     const double* fmin_h, double* const* mean_dh, double* const* var_dh, double* Q_d,
+                                     int q_stride, const int* q_col_h, uint8_t* S_d, int safe_mode, void* stream_) {
+    if (!h || !gps_h || !fmin_h || !q_col_h) return SO_ERR_BAD_ARG;
+    if (n < 1 || n > kMaxOut) return so_fail(h, SO_ERR_BAD_ARG, "posterior_grid_f32: 1 <= n <= 4");
+    if (gps_h[0] < 0 || gps_h[0] >= h->max_gps) return so_fail(h, SO_ERR_BAD_ARG, "posterior_grid_f32: gp index out of range");
+    GPState& g = h->gps[gps_h[0]];
+    if (!g.fitted || !g.f32_ready) return so_fail(h, SO_ERR_NOT_FITTED, "posterior_grid_f32: so_grid_prepare_f32 not called after the fit");
+    if (M < 0 || row0 < 0 || row0 + M > h->grid.rows) return so_fail(h, SO_ERR_BAD_ARG, "posterior_grid_f32: rows outside the grid");
+    if (M == 0) return SO_OK;
+    if (safe_mode < SO_SAFE_NONE || safe_mode > SO_SAFE_AND) return so_fail(h, SO_ERR_BAD_ARG, "posterior_grid_f32: bad safe_mode");
+    const int64_t F = h->grid.fast_rows;
+    if (row0 / F < g.f32_s0 || (row0 + M - 1) / F >= g.f32_s1)
+        return so_fail(h, SO_ERR_NOT_FITTED, "posterior_grid_f32: rows outside the range given to so_grid_prepare_f32");
+    F32Params fp;
+    PostParams& p = fp.p;
+    p.N = g.N; p.NB = g.NB; p.d = g.d; p.kind = g.kind; p.zvec = g.zvec; p.variance = g.variance;
+    p.M = M; p.row0 = row0; p.beta = beta; p.Q = Q_d; p.q_stride = q_stride; p.S = S_d; p.safe_mode = safe_mode;
+    p.n_out = n;
+    p.fmin = fmin_h[0]; p.q_col = q_col_h[0];
+    p.mean = mean_dh ? mean_dh[0] : nullptr; p.var = var_dh ? var_dh[0] : nullptr;
+    for (int o = 0; o < kMaxOut - 1; ++o) { p.zvec_x[o] = nullptr; p.fmin_x[o] = 0.0; p.mean_x[o] = nullptr; p.var_x[o] = nullptr; p.q_col_x[o] = 0; }
+    for (int o = 1; o < n; ++o) {
+        if (gps_h[o] < 0 || gps_h[o] >= h->max_gps) return so_fail(h, SO_ERR_BAD_ARG, "posterior_grid_f32: gp index out of range");
+        const GPState& e = h->gps[gps_h[o]];
+        if (!e.fitted) return so_fail(h, SO_ERR_NOT_FITTED, "posterior_grid_f32: GP not fitted");
+        bool same = e.N == g.N && e.d == g.d && e.kind == g.kind && e.variance == g.variance && e.noise == g.noise;
+        for (int j = 0; j < g.d && same; ++j) same = e.inv_ls[j] == g.inv_ls[j];
+        if (!same) return so_fail(h, SO_ERR_BAD_ARG, "posterior_grid_f32: the GPs do not share size, kernel and noise");
+        p.zvec_x[o - 1] = e.zvec; p.fmin_x[o - 1] = fmin_h[o]; p.q_col_x[o - 1] = q_col_h[o];
+        p.mean_x[o - 1] = mean_dh ? mean_dh[o] : nullptr; p.var_x[o - 1] = var_dh ? var_dh[o] : nullptr;
+    }
+    for (int o = 0; o < n; ++o)
+        if (Q_d && (q_col_h[o] < 0 || q_col_h[o] + 2 > q_stride)) return so_fail(h, SO_ERR_BAD_ARG, "posterior_grid_f32: Q column out of range");
+    fp.Aop = reinterpret_cast<const unsigned char*>(g.f32_A);
+    fp.Bop = reinterpret_cast<const unsigned char*>(g.f32_B);
+    fp.Np = g.f32_Np; fp.nslab = g.f32_Np / kF32SlabK; fp.b_stride = f32_b_bytes(g.f32_Np);
+    fp.s0 = g.f32_s0; fp.fast_rows = F; fp.tpb = g.f32_tpb;
+    const int64_t last_row = row0 + M - 1;
+    const int64_t t0 = (row0 / F) * fp.tpb + (row0 % F) / kF32TileRows;
+    const int64_t t1 = (last_row / F) * fp.tpb + (last_row % F) / kF32TileRows;
+    fp.first_tile = t0;
+    p.ntiles = t1 - t0 + 1;
+    int stages = 4;
+    while (stages > 1 && f32_smem(fp.Np, stages, n).total > (size_t)h->smem_optin) --stages;
+    if (f32_smem(fp.Np, stages, n).total > (size_t)h->smem_optin) return so_fail(h, SO_ERR_CAPACITY, "posterior_grid_f32: shared memory");
+    fp.stages = stages;
+    DeviceGuard guard(h->device);
+    static int configured_for = -1;
+    if (configured_for != h->device) {
+        SO_CUDA(h, cudaFuncSetAttribute(k_posterior_f32, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
+        configured_for = h->device;
+    }
+    // ---- the means in fp64 first (k_mean_grid), into the caller's planes or a scratch plane
+    MeanParams mq;
+    {
+        size_t need = 0;
+        for (int o = 0; o < n; ++o)
+            if (!(mean_dh && mean_dh[o])) need += (size_t)M;
+        if (need > h->f32_mean_cap) {
+            SO_CUDA(h, cudaStreamSynchronize((cudaStream_t)stream_));
+            if (h->f32_mean_scratch) cudaFree(h->f32_mean_scratch);
+            h->f32_mean_scratch = nullptr;
+            SO_CUDA(h, cudaMalloc(&h->f32_mean_scratch, sizeof(double) * need));
+            h->f32_mean_cap = need;
+        }
+        double* scratch = h->f32_mean_scratch;
+        for (int o = 0; o < kMaxOut; ++o) { mq.alpha[o] = nullptr; mq.mean[o] = nullptr; fp.mean_in[o] = nullptr; }
+        for (int o = 0; o < n; ++o) {
+            double* dst = (mean_dh && mean_dh[o]) ? mean_dh[o] : scratch;
+            if (!(mean_dh && mean_dh[o])) scratch += M;
+            mq.mean[o] = dst;
+            fp.mean_in[o] = dst;
+            mq.alpha[o] = h->gps[gps_h[o]].alpha;
+        }
+        const int Npad = 8 * g.NB;
+        mq.PfastT = g.f32_PfT; mq.Pslow = g.P2 + (size_t)F * Npad; mq.n_out = n; mq.N = g.N; mq.ldp = Npad;
+        mq.TR = Npad <= 128 ? 128 : 64; mq.split = 128 / mq.TR;
+        mq.Fpad = g.f32_Fpad; mq.fast_rows = F; mq.row0 = row0; mq.M = M;
+        mq.s_lo = row0 / F; mq.s_hi = (row0 + M - 1) / F + 1;
+        const int64_t gx = (F + mq.TR - 1) / mq.TR;
+        int64_t gy = ((int64_t)h->num_sms + gx - 1) / gx;                 // about one CTA per SM: each keeps its slice in L1
+        if (gy > mq.s_hi - mq.s_lo) gy = mq.s_hi - mq.s_lo;
+        if (gy > 65535) gy = 65535;
+        k_mean_grid<<<dim3((unsigned)gx, (unsigned)gy), 128, 0, (cudaStream_t)stream_>>>(mq);
+        SO_CHECK_LAUNCH(h, "k_mean_grid");
+    }
+    const int grid = (int)(p.ntiles < (int64_t)h->num_sms ? p.ntiles : (int64_t)h->num_sms);
+    k_posterior_f32<<<grid, kF32Threads, f32_smem(fp.Np, stages, n).total, (cudaStream_t)stream_>>>(fp);
+    SO_CHECK_LAUNCH(h, "k_posterior_f32");
     return SO_OK;
 }

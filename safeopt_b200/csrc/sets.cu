@@ -11,6 +11,7 @@
 // records of the previous pass in device memory -- one record per rank, as all-gathered -- so the three
 // passes run back to back on the stream and the host reads all results with a single copy.
 #include "xchg.cuh"
+#include <cstdlib>
 #include <cstring>
 
 int xchg_ensure_local(so_handle* h);
@@ -333,7 +334,10 @@ struct FusedParams {
     unsigned long long* epoch;
     XchgView x;
     unsigned char* result;               // [world x safe record][world x max record][world x count][status][epoch]
+    long long* dbg;                      // optional: SM-clock stamps of block 0 at the phase boundaries (so_debug_fused_times)
 };
+
+#define SO_FUSED_STAMP(i) do { if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) p.dbg[i] = clock64(); } while (0)
 
 // Self-resetting grid barrier (all blocks are co-resident: cooperative launch).  The generation is read BEFORE arriving, so it
 // cannot advance until this block has arrived too.
@@ -358,8 +362,15 @@ __device__ __forceinline__ void grid_barrier(unsigned int* bar) {
 // All `world` stamps of a phase carry `epoch`?  (block-wide; returns the same answer in every thread)
 __device__ __forceinline__ bool wait_phase(const unsigned long long* flags, int world, unsigned long long epoch) {
     int ok = 1;
-    if ((int)threadIdx.x < world) ok = xchg_wait(flags, threadIdx.x, epoch) ? 1 : 0;
+    if ((int)threadIdx.x < world) ok = xchg_wait(flags, threadIdx.x, epoch, world > 1) ? 1 : 0;
     return __syncthreads_and(ok) != 0;
+}
+
+// Block 0, thread 0: stamp `epoch` into flag[rank] of every rank's buffer.  The record stores before it were issued by the same
+// thread, so the release orders them (system scope across GPUs, device scope when this GPU is alone).
+__device__ __forceinline__ void publish_flags(const XchgView& x, int par, int phase, unsigned long long epoch) {
+    if (x.world == 1) { st_release_gpu(&x.local->sets[par].flag[phase][0], epoch); return; }
+    for (int r = 0; r < x.world; ++r) st_release_sys(&x.peer[r]->sets[par].flag[phase][x.rank], epoch);
 }
 
 __global__ void __launch_bounds__(kThreads) k_sets_fused(const __grid_constant__ FusedParams p) {
@@ -370,13 +381,16 @@ __global__ void __launch_bounds__(kThreads) k_sets_fused(const __grid_constant__
     XchgSets* mine = &p.x.local->sets[par];
     int status = SO_OK;
 
+    SO_FUSED_STAMP(0);
     // ---- phase A: safe-set record
     if (blockIdx.x == 0 && threadIdx.x == 0) *p.ncand = 0;  // first touched after the second grid barrier
     {
         SafePartial acc = block_reduce(scan_safe(p.Q, 2 * p.G, p.M, p.row0, p.S), smA);
         if (threadIdx.x == 0) p.partA[blockIdx.x] = acc;
     }
+    SO_FUSED_STAMP(1);
     grid_barrier(p.bar);
+    SO_FUSED_STAMP(2);
     if (blockIdx.x == 0) {
         SafePartial t = {0, -INFINITY, -1, -INFINITY, -1};
         for (unsigned b = threadIdx.x; b < gridDim.x; b += kThreads) merge(t, p.partA[b]);
@@ -386,11 +400,12 @@ __global__ void __launch_bounds__(kThreads) k_sets_fused(const __grid_constant__
             rec.n_safe = t.n; rec.max_l0 = t.max_l; rec.argmax_l0 = t.arg_l; rec.max_u0 = t.max_u; rec.argmax_u0 = t.arg_u;
             rec.reserved[0] = rec.reserved[1] = rec.reserved[2] = 0;
             for (int r = 0; r < world; ++r) p.x.peer[r]->sets[par].safe[rank] = rec;
-            __threadfence_system();
-            for (int r = 0; r < world; ++r) st_release_sys(&p.x.peer[r]->sets[par].flag[0][rank], epoch);
+            publish_flags(p.x, par, 0, epoch);
         }
     }
+    SO_FUSED_STAMP(3);
     if (!wait_phase(mine->flag[0], world, epoch)) status = SO_ERR_TIMEOUT;
+    SO_FUSED_STAMP(4);
     double max_l0 = -INFINITY;
     for (int r = 0; r < world; ++r) {
         const double v = __ldcg(&mine->safe[r].max_l0);
@@ -402,7 +417,9 @@ __global__ void __launch_bounds__(kThreads) k_sets_fused(const __grid_constant__
         MaxPartial acc = block_reduce(scan_maximizers(p.Q, p.G, p.M, p.row0, p.S, max_l0, p.scaling, p.Mmask), smB);
         if (threadIdx.x == 0) p.partB[blockIdx.x] = acc;
     }
+    SO_FUSED_STAMP(5);
     grid_barrier(p.bar);
+    SO_FUSED_STAMP(6);
     if (blockIdx.x == 0) {
         MaxPartial t = {0, -INFINITY, -INFINITY, -1};
         for (unsigned b = threadIdx.x; b < gridDim.x; b += kThreads) merge(t, p.partB[b]);
@@ -412,11 +429,12 @@ __global__ void __launch_bounds__(kThreads) k_sets_fused(const __grid_constant__
             rec.n_max = t.n; rec.max_width0 = t.max_w0; rec.best_value = t.best; rec.best_row = t.best_row;
             rec.reserved[0] = rec.reserved[1] = rec.reserved[2] = rec.reserved[3] = 0;
             for (int r = 0; r < world; ++r) p.x.peer[r]->sets[par].max[rank] = rec;
-            __threadfence_system();
-            for (int r = 0; r < world; ++r) st_release_sys(&p.x.peer[r]->sets[par].flag[1][rank], epoch);
+            publish_flags(p.x, par, 1, epoch);
         }
     }
+    SO_FUSED_STAMP(7);
     if (!wait_phase(mine->flag[1], world, epoch)) status = SO_ERR_TIMEOUT;
+    SO_FUSED_STAMP(8);
 
     // ---- phase C: expander candidates (skipped for full_sets: every safe row is a candidate there)
     if (p.with_candidates) {
@@ -428,16 +446,18 @@ __global__ void __launch_bounds__(kThreads) k_sets_fused(const __grid_constant__
         scan_candidates(p.Q, p.G, p.M, p.row0, p.S, p.Mmask, w / p.scaling.v[0], p.scaling, p.thr, nullptr, p.ckey, p.crow, p.cap,
                         p.ncand);
     }
+    SO_FUSED_STAMP(9);
     grid_barrier(p.bar);
+    SO_FUSED_STAMP(10);
     if (blockIdx.x != 0) return;
     if (threadIdx.x == 0) {
         const long long n = p.with_candidates ? (long long)*reinterpret_cast<volatile unsigned long long*>(p.ncand) : 0;
         for (int r = 0; r < world; ++r) p.x.peer[r]->sets[par].ncand[rank] = n;
-        __threadfence_system();
-        for (int r = 0; r < world; ++r) st_release_sys(&p.x.peer[r]->sets[par].flag[2][rank], epoch);
+        publish_flags(p.x, par, 2, epoch);
     }
     // the kernel may only end once every rank's phase-C record has landed here: the host reads `result` next
     if (!wait_phase(mine->flag[2], world, epoch)) status = SO_ERR_TIMEOUT;
+    SO_FUSED_STAMP(11);
     unsigned long long* res = reinterpret_cast<unsigned long long*>(p.result);
     const unsigned long long* src_safe = reinterpret_cast<const unsigned long long*>(mine->safe);
     const unsigned long long* src_max = reinterpret_cast<const unsigned long long*>(mine->max);
@@ -453,6 +473,7 @@ __global__ void __launch_bounds__(kThreads) k_sets_fused(const __grid_constant__
         res[world * 17 + 1] = epoch;
         *p.epoch = epoch;
     }
+    SO_FUSED_STAMP(12);
 }
 
 int grid_for(const so_handle* h, int64_t M) {
@@ -549,6 +570,10 @@ static int fused_setup(so_handle* h) {
     SO_CUDA(h, cudaMalloc(&h->fused_result_d, SO_SETS_RESULT_BYTES(kXchgMaxWorld)));
     SO_CUDA(h, cudaMemset(h->fused_result_d, 0, SO_SETS_RESULT_BYTES(kXchgMaxWorld)));
     SO_CUDA(h, cudaMallocHost(&h->fused_result_h, SO_SETS_RESULT_BYTES(kXchgMaxWorld)));
+    if (std::getenv("SO_FUSED_DEBUG_TIMES")) {
+        SO_CUDA(h, cudaMalloc(&h->fused_dbg, 16 * sizeof(long long)));
+        SO_CUDA(h, cudaMemset(h->fused_dbg, 0, 16 * sizeof(long long)));
+    }
     int per_sm = 0;
     SO_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sets_fused, kThreads, 0));
     if (per_sm < 1) return so_fail(h, SO_ERR_CUDA, "so_sets_fused: the fused kernel does not fit on an SM");
@@ -591,10 +616,22 @@ extern "C" int so_sets_fused(so_handle* h, const double* Q_d, int n_gps, int64_t
     p.bar = h->fused_bar; p.ncand = h->fused_ncand; p.epoch = h->xchg_epochs;
     p.x = xchg_view(h);
     p.result = static_cast<unsigned char*>(h->fused_result_d);
+    p.dbg = h->fused_dbg;
     int grid = grid_for(h, M);
     if (grid > h->fused_grid) grid = h->fused_grid;
     void* args[] = {&p};
     SO_CUDA(h, cudaLaunchCooperativeKernel((const void*)k_sets_fused, dim3(grid), dim3(kThreads), args, 0, stream));
     if (result_h) return so_sets_fused_result(h, result_h, stream_);
+    return SO_OK;
+}
+
+// Diagnostic: SM-clock stamps of block 0 at the phase boundaries of the last so_sets_fused (needs SO_FUSED_DEBUG_TIMES=1 in the
+// environment when the handle first runs the fused kernel).  out_h: 16 int64.
+extern "C" int so_debug_fused_times(so_handle* h, int64_t* out_h) {
+    if (!h || !out_h) return SO_ERR_BAD_ARG;
+    if (!h->fused_dbg) return so_fail(h, SO_ERR_BAD_ARG, "so_debug_fused_times: start the process with SO_FUSED_DEBUG_TIMES=1");
+    DeviceGuard guard(h->device);
+    SO_CUDA(h, cudaDeviceSynchronize());
+    SO_CUDA(h, cudaMemcpy(out_h, h->fused_dbg, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
     return SO_OK;
 }

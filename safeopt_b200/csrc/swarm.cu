@@ -234,20 +234,21 @@ __global__ void __launch_bounds__(kThreads) k_swarm_update_best(int64_t P, int d
                 dst[1] = (double)(p0 + t.idx);
                 for (int j = 0; j < d; ++j) dst[2 + j] = best_pos[(size_t)t.idx * d + j];
             }
-            __threadfence_system();
-            for (int r = 0; r < x.world; ++r) st_release_sys(&x.peer[r]->swarm[par].flag[x.rank], epoch);
             const XchgSwarm* mine = &x.local->swarm[par];
             bool ok = true;
-            for (int r = 0; r < x.world; ++r) ok = xchg_wait(mine->flag, r, epoch) && ok;
+            if (x.world > 1) {          // alone, the record just written is the whole exchange
+                for (int r = 0; r < x.world; ++r) st_release_sys(&x.peer[r]->swarm[par].flag[x.rank], epoch);
+                for (int r = 0; r < x.world; ++r) ok = xchg_wait(mine->flag, r, epoch, true) && ok;
+            }
             int best = -1;
             double bv = 0.0, bi = 0.0;
             for (int r = 0; r < x.world; ++r) {
-                const double v = __ldcg(&mine->rec[r][0]), i = __ldcg(&mine->rec[r][1]);
+                const double v = x.world > 1 ? __ldcg(&mine->rec[r][0]) : mine->rec[r][0], i = x.world > 1 ? __ldcg(&mine->rec[r][1]) : mine->rec[r][1];
                 if (i < 0.0) continue;
                 if (best < 0 || v > bv || (v == bv && i < bi)) { best = r; bv = v; bi = i; }
             }
             if (best >= 0) {
-                for (int j = 0; j < d; ++j) gbest[j] = __ldcg(&mine->rec[best][2 + j]);
+                for (int j = 0; j < d; ++j) gbest[j] = x.world > 1 ? __ldcg(&mine->rec[best][2 + j]) : mine->rec[best][2 + j];
                 if (grec) { grec[0] = bv; grec[1] = bi; grec[2] = ok ? 0.0 : (double)SO_ERR_TIMEOUT; }
             }
             *epoch_p = epoch;

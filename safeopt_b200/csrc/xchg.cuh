@@ -45,21 +45,28 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
-    return t;
+__device__ __forceinline__ void st_release_gpu(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+    return v;
 }
 
-// Spin until flag[r] >= epoch for every r < world (threads r < world poll one flag each; the caller synchronises the block
-// afterwards).  A peer that never arrives (crashed rank) must not hang the GPU: after kXchgTimeoutNs the wait gives up and
-// returns false; the kernel then stamps an error into its status word and the host raises.
-constexpr unsigned long long kXchgTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
-__device__ __forceinline__ bool xchg_wait(const unsigned long long* flags, int r, unsigned long long epoch) {
-    const unsigned long long t0 = globaltimer_ns();
+// Spin until flag[r] >= epoch (threads r < world poll one flag each; the caller synchronises the block afterwards).  With one
+// rank the flag was written by this GPU: device scope suffices.  A peer that never arrives (crashed rank) must not hang the
+// GPU: after ~kXchgTimeoutCycles of this SM's clock the wait gives up and returns false; the kernel then stamps an error into
+// its status word and the host raises.  (The SM cycle counter is used, not %globaltimer, whose reads cost microseconds.)
+constexpr long long kXchgTimeoutCycles = 40ll * 1000ll * 1000ll * 1000ll;       // ~20 s at 2 GHz
+__device__ __forceinline__ bool xchg_wait(const unsigned long long* flags, int r, unsigned long long epoch, bool multi_gpu) {
+    long long t0 = 0;
     unsigned spins = 0;
-    while (ld_acquire_sys(flags + r) < epoch) {
-        if ((++spins & 0x3ffu) == 0 && globaltimer_ns() - t0 > kXchgTimeoutNs) return false;
+    while ((multi_gpu ? ld_acquire_sys(flags + r) : ld_acquire_gpu(flags + r)) < epoch) {
+        if ((++spins & 0xfffu) == 0) {
+            if (t0 == 0) t0 = clock64();
+            else if (clock64() - t0 > kXchgTimeoutCycles) return false;
+        }
     }
     return true;
 }

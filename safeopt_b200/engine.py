@@ -211,6 +211,27 @@ class DeviceEngine:
         self.launches += 1 if M else 0
         return True
 
+    def prepare_grid_f32(self, gp: int, row0: int, n_rows: int):
+        """TF32 hi/lo operand planes of the fp32 tensor-core grid kernel for GP ``gp`` and this row block."""
+        self._check(self.lib.so_grid_prepare_f32(self.handle, gp, int(row0), int(n_rows), self._stream()), "so_grid_prepare_f32")
+        self.launches += 3
+
+    def posterior_grid_f32(self, gps, row0, M, beta, fmins, means=None, variances=None, Q=None, q_cols=None, S=None,
+                           safe_mode=_lib.SAFE_NONE):
+        """posterior_multi on the defined grid in fp32 arithmetic (tcgen05 3xTF32, TMEM accumulators); one GP or several that
+        share the factorisation."""
+        n = len(gps)
+        gi = (C.c_int * n)(*[int(g) for g in gps])
+        fm = _np_f64(fmins)
+        qc = (C.c_int * n)(*[int(c) for c in (q_cols if q_cols is not None else [0] * n)])
+        mp = (C.c_void_p * n)(*[0 if means is None or t is None else t.data_ptr() for t in (means or [None] * n)])
+        vp = (C.c_void_p * n)(*[0 if variances is None or t is None else t.data_ptr() for t in (variances or [None] * n)])
+        q_stride = 0 if Q is None else Q.shape[1]
+        rc = self.lib.so_posterior_grid_f32(self.handle, n, gi, int(row0), int(M), float(beta), _hptr(fm), mp, vp, _ptr(Q), q_stride,
+                                            qc, _ptr(S), safe_mode, self._stream())
+        self._check(rc, "so_posterior_grid_f32")
+        self.launches += 2 if M else 0            # k_mean_grid (fp64 means) + k_posterior_f32
+
     def posterior_rows_simple(self, gp, Xstar):
         M = Xstar.shape[0]
         mean, var = self.empty((M,)), self.empty((M,))

@@ -30,6 +30,10 @@ from .utilities import detect_grid, grid_rows_from_index, linearly_spaced_combin
 
 __all__ = ["SafeOpt", "SafeOptSwarm", "GaussianProcessOptimization"]
 
+import struct as _struct
+_SAFE_STRUCT = _struct.Struct("<qdqdq")       # so_safe_record: n_safe, max_l0, argmax_l0, max_u0, argmax_u0
+_MAX_STRUCT = _struct.Struct("<qddq")         # so_max_record: n_max, max_width0, best_value, best_row
+
 
 class GaussianProcessOptimization(object):
     """Common bookkeeping of the optimisers (reference: gp_opt.py:30-278).
@@ -166,6 +170,7 @@ class _DeviceFits:
         self.engine = engine
         self.gps = gps
         self._fp = [None] * len(gps)
+        self._ident = [None] * len(gps)       # (X object, Y object, scalar hyper-parameters) seen at the last refresh
         self._data = [None] * len(gps)        # (X, Y, hyper key) the device fit was built from
         self.hypers = [None] * len(gps)
         self.refits = 0
@@ -181,8 +186,16 @@ class _DeviceFits:
         changed = False
         for i, gp in enumerate(self.gps):
             hyper = extract_hyper(gp)
+            # GPy's own posterior cache is keyed on set_XY / parameter updates, not on the array contents: the same X / Y
+            # OBJECTS under the same hyper-parameters mean nothing changed (skips hashing the data on every optimize())
+            ident = (gp.X, gp.Y, hyper.kind, hyper.variance, hyper.noise_var)
+            last = self._ident[i]
+            if (last is not None and last[0] is ident[0] and last[1] is ident[1] and last[2:] == ident[2:]
+                    and self.hypers[i] is not None and np.array_equal(hyper.lengthscale, self.hypers[i].lengthscale)):
+                continue
             fp = fingerprint(gp, hyper)
             if fp == self._fp[i]:
+                self._ident[i] = ident
                 continue
             X = np.ascontiguousarray(np.asarray(gp.X, dtype=float))
             Y = np.ascontiguousarray(np.asarray(gp.Y, dtype=float)[:, 0])
@@ -204,6 +217,7 @@ class _DeviceFits:
                 self.refits += 1
             changed = True
             self._fp[i] = fp
+            self._ident[i] = ident
             self._data[i] = (X.copy(), Y.copy(), key)
             self.hypers[i] = hyper
             if after_fit is not None:
@@ -230,6 +244,7 @@ class _DeviceFits:
     def invalidate(self):
         """Forget the resident fits: the next refresh refits every GP from scratch."""
         self._fp = [None] * len(self.gps)
+        self._ident = [None] * len(self.gps)
         self._data = [None] * len(self.gps)
 
 
@@ -237,9 +252,13 @@ class SafeOpt(GaussianProcessOptimization):
     """Safe Bayesian optimisation over a finite parameter set (reference: gp_opt.py:281-712).
 
     Parameters are the reference's (``gp, parameter_set, fmin, lipschitz=None, beta=2,
-    num_contexts=0, threshold=0, scaling='auto'``) plus ``device`` (CUDA device, default current) and
+    num_contexts=0, threshold=0, scaling='auto'``) plus ``device`` (CUDA device, default current),
     ``distributed`` (default True: shard the rows over the ranks of ``torch.distributed`` when it is
-    initialised; False: this object evaluates every row on its own GPU).
+    initialised; False: this object evaluates every row on its own GPU) and ``precision``: ``'fp64'``
+    (default, the reference's arithmetic: bounds within 1e-9, masks bit-exact) or ``'fp32'`` -- the
+    posterior contraction on the tcgen05 tensor cores in error-compensated TF32 (posterior within 1e-4
+    relative, masks exact outside that band around the thresholds; product grids with RBF kernels and
+    N <= 256, anything else keeps the fp64 kernels and says so once); fit and set logic stay fp64.
 
     Examples
     --------
@@ -252,10 +271,17 @@ class SafeOpt(GaussianProcessOptimization):
     >>> opt.add_new_data_point(next_parameters, np.array([[1.]]))          # doctest: +SKIP
     """
 
+    F32_MAX_N = 256          # the fp32 tensor-core kernel keeps N <= 256 (TMEM accumulator columns)
+    precision = "fp64"       # arithmetic of the posterior contraction (constructor keyword)
+
     def __init__(self, gp, parameter_set, fmin, lipschitz=None, beta=2, num_contexts=0, threshold=0,
-                 scaling="auto", device=None, distributed=True):
+                 scaling="auto", device=None, distributed=True, precision="fp64"):
         super(SafeOpt, self).__init__(gp, fmin=fmin, beta=beta, num_contexts=num_contexts, threshold=threshold,
                                       scaling=scaling)
+        if precision not in ("fp64", "fp32"):
+            raise ValueError("precision must be 'fp64' or 'fp32'")
+        self.precision = precision
+        self._f32_warned = False
         parameter_set = np.asarray(parameter_set, dtype=float)
         # SAFEOPT_B200_GRID_FAST_PATH=0 forces the explicit-rows kernels (tests / A-B measurements)
         axes = None
@@ -313,6 +339,9 @@ class SafeOpt(GaussianProcessOptimization):
         self._n_cand_d = eng.zeros((1,), "i64")
         self._cand_key_d = None
         self._cand_row_d = None
+        self._grid_state = {}                 # GP index -> which grid tables are current (see _ensure_grid_tables)
+        self._grid_strides = None
+        self._thr_cache = None
         self._G_rows: List[int] = []          # global rows currently in the expander set
         self._host_cache = {}
         self._safe_info = None                # combined record of the last compute_safe_set
@@ -417,6 +446,15 @@ class SafeOpt(GaussianProcessOptimization):
         for k in (keys or list(self._host_cache)):
             self._host_cache.pop(k, None)
 
+    def _row_point(self, row: int) -> np.ndarray:
+        """Parameters (and contexts) of one global row -- scalar arithmetic, this runs once per optimize()."""
+        if self._grid_axes is not None:
+            if self._grid_strides is None:
+                from .utilities import grid_row_strides
+                self._grid_strides = grid_row_strides([len(a) for a in self._grid_axes])
+            return np.array([a[(row // st) % len(a)] for a, st in zip(self._grid_axes, self._grid_strides)], dtype=float)
+        return np.asarray(self.inputs[row], dtype=float)
+
     def _row_coordinates(self, rows) -> np.ndarray:
         rows = np.atleast_1d(np.asarray(rows, dtype=np.int64))
         if self._grid_axes is not None:
@@ -425,11 +463,38 @@ class SafeOpt(GaussianProcessOptimization):
 
     # ------------------------------------------------------------------ hot path
     def _after_fit(self, i, hyper):
-        if self._grid_axes is not None and hyper.kind == _lib.KERNEL_RBF:
-            self._engine.prepare_grid(i, self._row0, self._row1 - self._row0)
+        # the grid tables of GP i are rebuilt lazily, by whoever needs them next (_ensure_grid_tables): only the GP that
+        # provides a group's factorisation needs the large operand tables, the others only the small per-axis tables and
+        # only if an expander search runs
+        self._grid_state[i] = None
 
     def _use_grid_kernel(self, i) -> bool:
         return self._grid_axes is not None and self._fits.hypers[i].kind == _lib.KERNEL_RBF
+
+    def _use_f32(self, i) -> bool:
+        if self.precision != "fp32":
+            return False
+        ok = self._use_grid_kernel(i) and self.gps[i].X.shape[0] <= self.F32_MAX_N and hasattr(self._engine, "posterior_grid_f32")
+        if not ok and not self._f32_warned:
+            self._f32_warned = True
+            logging.warning("precision='fp32' needs a product grid, an RBF kernel and N <= %d: using the fp64 kernels" % self.F32_MAX_N)
+        return ok
+
+    def _ensure_grid_tables(self, i, level):
+        """Grid tables of GP ``i`` after its last (re)fit.  level 'axes': per-axis tables only (expander kernel);
+        'fp64': + the scaled-operand table of this rank's rows (fp64 grid kernel); 'fp32': + the TF32 operand planes."""
+        have = self._grid_state.get(i) or set()
+        eng, m_local = self._engine, self._row1 - self._row0
+        if level == "fp64" and "fp64" not in have:
+            eng.prepare_grid(i, self._row0, m_local)
+            have |= {"axes", "fp64"}
+        elif "axes" not in have:
+            eng.prepare_grid(i, self._row0, 0)          # per-axis and product tables, no scaled-operand table
+            have.add("axes")
+        if level == "fp32" and "fp32" not in have:
+            eng.prepare_grid_f32(i, self._row0, m_local)
+            have.add("fp32")
+        self._grid_state[i] = have
 
     def _ensure_rows_on_device(self):
         """Explicit rows are needed when some GP cannot use the separable grid tables."""
@@ -451,6 +516,17 @@ class SafeOpt(GaussianProcessOptimization):
         for group in self._fits.groups:
             # GPs that share data, kernel and noise go through one launch; the S bit is the AND over all GPs (gp_opt.py:481)
             rows_arg = None if self._use_grid_kernel(group[0]) else self._ensure_rows_on_device()
+            if rows_arg is None and self._use_f32(group[0]):
+                # fp32 arithmetic mode: tcgen05 tensor cores (3xTF32), TMEM accumulators; fp64 epilogue
+                self._ensure_grid_tables(group[0], "fp32")
+                eng.posterior_grid_f32(group, self._row0, m_local, beta, [self.fmin[i] for i in group],
+                                       means=[self._mean_d[i] for i in group], variances=[self._var_d[i] for i in group],
+                                       Q=self._Q_d, q_cols=[2 * i for i in group], S=self._S_d,
+                                       safe_mode=_lib.SAFE_WRITE if first else _lib.SAFE_AND)
+                first = False
+                continue
+            if rows_arg is None:
+                self._ensure_grid_tables(group[0], "fp64")
             done = False
             if len(group) > 1:
                 done = eng.posterior_multi(group, rows_arg, self._row0, m_local, beta, [self.fmin[i] for i in group],
@@ -463,6 +539,7 @@ class SafeOpt(GaussianProcessOptimization):
                     mode = _lib.SAFE_WRITE if first else _lib.SAFE_AND
                     first = False
                     if rows_arg is None:
+                        self._ensure_grid_tables(i, "fp64")
                         eng.posterior_grid(i, self._row0, m_local, beta, self.fmin[i], mean=self._mean_d[i], var=self._var_d[i],
                                            Q=self._Q_d, q_col=2 * i, S=self._S_d, safe_mode=mode)
                     else:
@@ -529,7 +606,12 @@ class SafeOpt(GaussianProcessOptimization):
         self._invalidate_host("S", "M")
         recs = self._record_buffers()
         m_local = self._row1 - self._row0
-        thr = np.broadcast_to(np.asarray(self.threshold, dtype=float), (G,)) * beta
+        tkey = (id(self.threshold), beta) if np.isscalar(self.threshold) else None
+        if tkey is not None and self._thr_cache is not None and self._thr_cache[0] == tkey and self._thr_cache[1] == self.threshold:
+            thr = self._thr_cache[2]
+        else:
+            thr = np.ascontiguousarray(np.broadcast_to(np.asarray(self.threshold, dtype=float), (G,)) * beta)
+            self._thr_cache = (tkey, self.threshold, thr) if tkey is not None else None
 
         if not full_sets and self._cand_key_d is None:
             self._cand_key_d = eng.empty((max(m_local, 1),))
@@ -550,10 +632,20 @@ class SafeOpt(GaussianProcessOptimization):
                                      None, self._cand_key_d, self._cand_row_d, self._n_cand_l)
                 self._share(self._ncand_all_d, self._n_cand_l)
             host = recs.cpu().numpy()                               # the one host wait of compute_sets
-        self._safe_info = reduce_safe_records(host[:world * 64].view(SAFE_REC_DTYPE).reshape(-1))
-        if self._safe_info["n_safe"] == 0:                          # gp_opt.py:504-507 (M is already all-False: M is a subset of S)
-            return
-        self._max_info = reduce_max_records(host[world * 64:world * 128].view(MAX_REC_DTYPE).reshape(-1), self.scaling[0])
+        if world == 1:
+            # one rank: nothing to combine -- unpack the two records directly (this runs once per optimize(), which is
+            # host-bound on small grids)
+            n_safe, max_l0, arg_l0, max_u0, arg_u0 = _SAFE_STRUCT.unpack_from(host, 0)
+            self._safe_info = dict(n_safe=n_safe, max_l0=max_l0, argmax_l0=arg_l0, max_u0=max_u0, argmax_u0=arg_u0)
+            if n_safe == 0:
+                return
+            n_max, max_w0, best_value, best_row = _MAX_STRUCT.unpack_from(host, 64)
+            self._max_info = dict(n_max=n_max, max_var=max_w0 / float(self.scaling[0]), best_value=best_value, best_row=best_row)
+        else:
+            self._safe_info = reduce_safe_records(host[:world * 64].view(SAFE_REC_DTYPE).reshape(-1))
+            if self._safe_info["n_safe"] == 0:                      # gp_opt.py:504-507 (M is already all-False: M is a subset of S)
+                return
+            self._max_info = reduce_max_records(host[world * 64:world * 128].view(MAX_REC_DTYPE).reshape(-1), self.scaling[0])
         max_var = self._max_info["max_var"]
         if full_sets:
             # every safe point is a candidate, natural order (gp_opt.py:527-528, :555)
@@ -646,6 +738,8 @@ class SafeOpt(GaussianProcessOptimization):
                         break
                     continue
                 rows_arg = None if self._use_grid_kernel(i) else self._ensure_rows_on_device()
+                if rows_arg is None:
+                    self._ensure_grid_tables(i, "axes")
                 eng.expander_check(i, rows_arg, self._row0, m_local, self._S_d, self._mean_d[i], self._var_d[i], xc_d,
                                    eng.to_device(mean[i]), eng.to_device(var[i]), eng.to_device(q[:, 2 * i + 1]),
                                    beta, self.fmin[i], flags)
@@ -686,7 +780,7 @@ class SafeOpt(GaussianProcessOptimization):
                 rows = np.concatenate(([row], self._G_rows)).astype(np.int64)
                 value, row = combine_max_first(vals, rows)
         self.last_query_row = int(row)
-        x = self._row_coordinates([row])[0] if not self.num_contexts else np.asarray(self.inputs[row], dtype=float)
+        x = self._row_point(int(row)) if not self.num_contexts else np.asarray(self.inputs[row], dtype=float)
         return x[:-self.num_contexts] if self.num_contexts else x
 
     def optimize(self, context=None, ucb=False):

@@ -867,6 +867,96 @@ def test_device_swarm_graph_replay_equals_kernel_by_kernel(monkeypatch):
     assert np.array_equal(out["1"][1], out["0"][1]) and np.array_equal(out["1"][2], out["0"][2]) and np.array_equal(out["1"][3], out["0"][3])
 
 
+# ---------------------------------------------------------------- fp32 arithmetic mode (tcgen05 3xTF32, TMEM accumulators)
+F32_TOL = 1e-4          # north star: "posterior mean/var within ... 1e-4 rel fp32" -- relative to the prior scale (sigma_f^2, max|y|)
+
+
+@pytest.mark.parametrize("N,d,n,G", [(5, 1, 300, 1), (31, 2, 40, 1), (64, 2, 200, 1), (100, 2, 90, 2), (128, 2, 500, 3), (129, 2, 130, 1),
+                                     (200, 3, 30, 1), (256, 4, 14, 2)])
+def test_fp32_grid_kernel_matches_fp64_oracle(N, d, n, G):
+    """so_posterior_grid_f32 against the fp64 oracle: |d mean| <= 1e-4 max(1, |y|), |d var| <= 1e-4 sigma_f^2, bounds within
+    1e-4 * 2 sqrt(sigma_f^2); the safe bit is exactly the device's own l > fmin and equals the oracle's outside the band."""
+    rs = np.random.RandomState(N + d)
+    X = rs.uniform(-1.5, 1.5, (N, d))
+    Y = np.stack([2 * np.exp(-np.sum(X * X, 1) / 8) + 0.05 * rs.randn(N) for _ in range(G)], axis=1)
+    ls = rs.uniform(0.8, 1.4, d)
+    var, noise, beta = 2.0, 0.05 ** 2, 2.0
+    grid = sb.linearly_spaced_combinations([(-5, 5)] * d, n)
+    M = grid.shape[0]
+    from safeopt_b200.utilities import detect_grid
+    eng = DeviceEngine(max_gps=G)
+    eng.define_grid(detect_grid(grid))
+    for i in range(G):
+        eng.fit(i, X, Y[:, i], 0, ls, var, noise)
+    eng.prepare_grid(0, 0, 0)
+    eng.prepare_grid_f32(0, 0, M)
+    Q, S = eng.empty((M, 2 * G)), eng.zeros((M,), "u8")
+    mean, varr = eng.empty((G, M)), eng.empty((G, M))
+    fmins = [0.1 * i for i in range(G)]
+    eng.posterior_grid_f32(list(range(G)), 0, M, beta, fmins, means=[mean[i] for i in range(G)], variances=[varr[i] for i in range(G)],
+                           Q=Q, q_cols=[2 * i for i in range(G)], S=S, safe_mode=_lib.SAFE_WRITE)
+    Qh, Sh, mh, vh = Q.cpu().numpy(), S.cpu().numpy().astype(bool), mean.cpu().numpy(), varr.cpu().numpy()
+    safe_o = np.ones(M, dtype=bool)
+    clear = np.ones(M, dtype=bool)
+    worst = [0.0, 0.0, 0.0]
+    for i in range(G):
+        go = gpy_lite.GPRegression(X, Y[:, [i]], kernel=gpy_lite.RBF(d, variance=var, lengthscale=ls, ARD=True), noise_var=noise)
+        mo, vo = go.predict_noiseless(grid)
+        mo, vo = mo[:, 0], vo[:, 0]
+        lo, up = mo - beta * np.sqrt(vo), mo + beta * np.sqrt(vo)
+        worst = [max(worst[0], np.abs(mh[i] - mo).max()), max(worst[1], np.abs(vh[i] - vo).max()), max(worst[2], np.abs(Qh[:, 2 * i] - lo).max())]
+        assert np.abs(mh[i] - mo).max() <= F32_TOL * max(1.0, np.abs(Y).max())
+        assert np.abs(vh[i] - vo).max() <= F32_TOL * var
+        # near the variance floor sqrt amplifies: d sd = d var / (2 sd), so the bound on l/u is taken where sd is not tiny
+        big = vo > 1e-3 * var
+        assert np.abs(Qh[big, 2 * i] - lo[big]).max() <= F32_TOL * 2 * np.sqrt(var) * 3
+        assert np.abs(Qh[big, 2 * i + 1] - up[big]).max() <= F32_TOL * 2 * np.sqrt(var) * 3
+        assert np.array_equal(Qh[:, 2 * i], mh[i] - beta * np.sqrt(vh[i]))
+        safe_o &= lo > fmins[i]
+        clear &= np.abs(lo - fmins[i]) > F32_TOL * 2 * np.sqrt(var) * 3
+    assert np.array_equal(Sh, np.all(Qh[:, ::2] > np.asarray(fmins), axis=1))
+    assert np.array_equal(Sh[clear], safe_o[clear])
+    print("fp32 N=%d d=%d M=%d G=%d: |d mean| %.2e |d var| %.2e |d l| %.2e, rows inside the band %d" % (N, d, M, G, *worst, int((~clear).sum())))
+    # a shard of the rows gives the same bits as the whole grid
+    if M > 300:
+        r0, m = M // 3, M // 2
+        eng.prepare_grid_f32(0, r0, m)
+        Q2 = eng.empty((m, 2 * G))
+        eng.posterior_grid_f32(list(range(G)), r0, m, beta, fmins, Q=Q2, q_cols=[2 * i for i in range(G)])
+        assert torch.equal(Q2, Q[r0:r0 + m])
+    eng.close()
+
+
+def test_fp32_mode_of_safeopt_on_config3():
+    """SafeOpt(precision='fp32') on BASELINE config 3 (2-D, 3 GPs, 500x500, N=128): bounds within the fp32 tolerance of the
+    fp64 run, masks and query row identical outside the tolerance band, same class surface; a BO step keeps working (N = 129)."""
+    w = workloads.config("C3")
+    grid = sb.linearly_spaced_combinations(w.bounds, w.num_samples)
+    out = {}
+    for prec in ("fp64", "fp32"):
+        gps = [sb.GPRegression(w.X, w.Y[:, [i]], kernel=sb.RBF(w.d, variance=w.variance, lengthscale=w.lengthscale, ARD=True), noise_var=w.noise_var)
+               for i in range(3)]
+        opt = sb.SafeOpt(gps, grid, w.fmin, beta=w.beta, threshold=w.threshold, precision=prec)
+        x = opt.optimize()
+        out[prec] = (opt.Q.copy(), opt.S.copy(), opt.M.copy(), opt.last_query_row, x.copy(), opt)
+    Q64, S64, M64 = out["fp64"][:3]
+    Q32, S32, M32 = out["fp32"][:3]
+    tol = F32_TOL * 2 * np.sqrt(w.variance) * 3
+    big = np.all((Q64[:, 1::2] - Q64[:, ::2]) > 4 * np.sqrt(1e-3 * w.variance), axis=1)
+    assert np.abs(Q32 - Q64)[big].max() <= tol
+    band = np.all(np.abs(Q64[:, ::2] - 0.0) > tol, axis=1)
+    assert np.array_equal(S32[band], S64[band])
+    best = Q64[S64, 0].max()
+    band_m = band & (np.abs(Q64[:, 1] - best) > 2 * tol)
+    assert np.array_equal(M32[band_m], M64[band_m])
+    print("C3 fp32 vs fp64: |dQ| %.2e (tol %.1e), S differs on %d rows, M on %d rows (all inside the band), query rows %d / %d" % (
+        np.abs(Q32 - Q64)[big].max(), tol, int((S32 != S64).sum()), int((M32 != M64).sum()), out["fp32"][3], out["fp64"][3]))
+    opt = out["fp32"][5]
+    assert any("fp32" in st for st in opt._grid_state.values())
+    opt.add_new_data_point(out["fp32"][4], np.array([[1.0, 1.0, 1.0]]))
+    assert opt.optimize() is not None and opt.t == 129
+
+
 # ---------------------------------------------------------------- the boundary: foreign GPy-protocol models, the INTEGRATION.md stub
 def test_foreign_gpy_protocol_models_go_straight_in():
     """"GPy model in, same methods out" (gp_opt.py:58-67, :347): objects that are NOT ours -- oracle.gpy_lite models with GPy's
