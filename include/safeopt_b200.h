@@ -107,6 +107,10 @@ int so_fit(so_handle* h, int gp, const double* X_h, const double* Y_h, int N, in
  * After either call so_grid_prepare must run again (like after so_fit). */
 int so_fit_append(so_handle* h, int gp, const double* x_new_h, double y_new, void* stream);
 int so_fit_remove_last(so_handle* h, int gp, void* stream);
+/* Fit of a GP that shares inputs, kernel and noise with the already fitted `src_gp` (SafeOpt's GPs share their inputs,
+ * safeopt/gp_opt.py:121-130): K, L and L^-1 are copied device-to-device, only alpha = Ky^-1 Y is computed.  Equal X and
+ * hyper-parameters are the caller's responsibility.  Y_h: the N targets of `gp`. */
+int so_fit_like(so_handle* h, int gp, int src_gp, const double* Y_h, void* stream);
 /* Test/diagnostic read-back (synchronous): any of the outputs may be NULL.
  *   L_h, Linv_h: N x N row-major; alpha_h: N. */
 int so_fit_export(so_handle* h, int gp, double* L_h, double* Linv_h, double* alpha_h);

@@ -67,7 +67,7 @@ int so_destroy(so_handle* h) {
     cudaFree(h->ws_z);
     cudaFree(h->f32_mean_scratch);
     xchg_destroy(h);
-    cudaFree(h->fused_bar); cudaFree(h->fused_part); cudaFree(h->fused_ncand); cudaFree(h->fused_result_d); cudaFree(h->fused_dbg);
+    cudaFree(h->fused_bar); cudaFree(h->fused_part); cudaFree(h->fused_ncand); cudaFree(h->fused_dbg);
     cudaFreeHost(h->fused_result_h);
     delete h;
     return SO_OK;

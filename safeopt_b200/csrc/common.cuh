@@ -103,9 +103,10 @@ struct so_handle {
     long long* fused_dbg = nullptr;
     double* f32_mean_scratch = nullptr;   // fp64 means of the fp32 mode when the caller wants none (G x M)
     size_t f32_mean_cap = 0;
-    void* fused_result_d = nullptr;  // world x 136 bytes + status + epoch, device
-    void* fused_result_h = nullptr;  // pinned host copy target
+    void* fused_result_h = nullptr;  // world x 136 bytes + status + epoch stamp: mapped pinned host memory
+    void* fused_result_d = nullptr;  // its device-side address (zero copy)
     int fused_grid = 0;
+    int fused_inflight = 0;          // so_sets_fused launches without a fetch since the last synchronising fetch
     std::string err;
 };
 

@@ -5,7 +5,9 @@
 // full inverse) is what the posterior contraction consumes: var = k** - |L^-1 k|^2 costs
 // N^2/2 FMAs per candidate instead of N^2 and is the better-conditioned form (SURVEY.md
 // section 7, hard part 1).
-#include "common.cuh"
+#include "fit_cluster.cuh"
+#include <cstdio>
+#include <cstdlib>
 
 namespace {
 
@@ -250,6 +252,42 @@ int grow(so_handle* h, T*& ptr, size_t count) {
     return SO_OK;
 }
 
+// Cluster size for the one-launch fit of N points (0 = use the kernel-per-panel path): 16 CTAs where the device can co-schedule
+// such a cluster (non-portable size), else 8.
+int fit_cluster_size(so_handle* h, int N) {
+    if (N > kFcMaxN) return 0;
+    const char* v = std::getenv("SO_FIT_CLUSTER");
+    if (v && std::string(v) == "0") return 0;
+    static int cached_dev = -1, cached = 0;
+    if (cached_dev == h->device) return cached;
+    cached_dev = h->device;
+    cached = 0;
+    int want = 16;
+    if (v && std::atoi(v) > 0) want = std::atoi(v);
+    if (cudaFuncSetAttribute(k_fit_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFcDynSmem) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    for (int cs = want; cs >= 2; cs /= 2) {
+        if (cs > 8 && cudaFuncSetAttribute(k_fit_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+            cudaGetLastError();
+            continue;
+        }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(cs); cfg.blockDim = dim3(kFcThreads); cfg.dynamicSmemBytes = kFcDynSmem;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, k_fit_cluster, &cfg) == cudaSuccess && n >= 1) { cached = cs; break; }
+        cudaGetLastError();
+    }
+    if (std::getenv("SO_FIT_VERBOSE"))
+        fprintf(stderr, "safeopt_b200: one-launch fit uses a cluster of %d CTAs%s\n", cached, cached ? "" : " (unavailable: kernel-per-panel fit)");
+    return cached;
+}
+
 }  // namespace
 
 extern "C" int so_fit(so_handle* h, int gp, const double* X_h, const double* Y_h, int N, int d, int kernel_kind,
@@ -299,6 +337,31 @@ extern "C" int so_fit(so_handle* h, int gp, const double* X_h, const double* Y_h
 
     SO_CUDA(h, cudaMemcpyAsync(g.X, X_h, sizeof(double) * N * d, cudaMemcpyHostToDevice, stream));
     SO_CUDA(h, cudaMemcpyAsync(g.Y, Y_h, sizeof(double) * N, cudaMemcpyHostToDevice, stream));
+    // N <= 512: the whole fit in one launch of one thread-block cluster (fit_cluster.cuh); SO_FIT_CLUSTER=0 keeps the
+    // kernel-per-panel version below (also used for larger N)
+    const int csize = fit_cluster_size(h, N);
+    if (csize > 0) {
+        FitClusterParams fp;
+        fp.X = g.X; fp.Y = g.Y; fp.Xs = g.Xs; fp.K = g.K; fp.W = g.Linv; fp.alpha = g.alpha; fp.zvec = g.zvec; fp.Afrag = g.Afrag;
+        fp.N = N; fp.Npad = Npad; fp.NP = (Npad + kFcB - 1) / kFcB * kFcB; fp.ld = ld; fp.d = d; fp.kind = kernel_kind; fp.NB = NB;
+        fp.variance = variance; fp.diag_add = noise_var + SO_JITTER;
+        for (int j = 0; j < SO_MAX_DIM; ++j) fp.inv_ls[j] = il.v[j];
+        fp.status = h->d_status;
+        SO_CUDA(h, cudaMemsetAsync(h->d_status, 0, sizeof(int), stream));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(csize); cfg.blockDim = dim3(kFcThreads); cfg.dynamicSmemBytes = kFcDynSmem; cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        SO_CUDA(h, cudaLaunchKernelEx(&cfg, k_fit_cluster, fp));
+        SO_CUDA(h, cudaMemcpyAsync(h->h_status, h->d_status, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        SO_CUDA(h, cudaStreamSynchronize(stream));
+        if (*h->h_status != SO_OK)
+            return so_fail(h, SO_ERR_NOT_PD, "so_fit: K + (noise + 1e-8) I is not positive definite");
+        g.fitted = true;
+        return SO_OK;
+    }
     k_scale_x<<<(Npad * d + 255) / 256, 256, 0, stream>>>(g.X, g.Xs, N, Npad, d, il);
     dim3 blk(16, 16), grd((Npad + 15) / 16, (Npad + 15) / 16);
     k_build_ky<<<grd, blk, 0, stream>>>(g.Xs, g.K, N, Npad, ld, d, kernel_kind, variance, noise_var + SO_JITTER);
@@ -323,6 +386,51 @@ extern "C" int so_fit(so_handle* h, int gp, const double* X_h, const double* Y_h
     SO_CUDA(h, cudaStreamSynchronize(stream));
     if (*h->h_status != SO_OK)
         return so_fail(h, SO_ERR_NOT_PD, "so_fit: K + (noise + 1e-8) I is not positive definite");
+    g.fitted = true;
+    return SO_OK;
+}
+
+// GPs that share inputs, kernel and noise (SafeOpt's constraint GPs usually do, gp_opt.py:121-130) share K, L and L^-1: the
+// factorisation of `src_gp` is copied device-to-device and only z = L^-1 y, alpha = L^-T z are computed for the new targets.
+extern "C" int so_fit_like(so_handle* h, int gp, int src_gp, const double* Y_h, void* stream_) {
+    if (!h || !Y_h) return SO_ERR_BAD_ARG;
+    if (gp < 0 || gp >= h->max_gps || src_gp < 0 || src_gp >= h->max_gps || gp == src_gp)
+        return so_fail(h, SO_ERR_BAD_ARG, "so_fit_like: gp index out of range");
+    GPState& s = h->gps[src_gp];
+    GPState& g = h->gps[gp];
+    if (!s.fitted) return so_fail(h, SO_ERR_NOT_FITTED, "so_fit_like: source GP not fitted");
+    DeviceGuard guard(h->device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int N = s.N, d = s.d, NB = s.NB, Npad = 8 * NB;
+    if (Npad > g.capN || d != g.d) {
+        const int cap = s.capN, capNB = cap / 8;
+        SO_CUDA(h, cudaStreamSynchronize(stream));
+        int rc;
+        if ((rc = grow(h, g.X, (size_t)cap * d))) return rc;
+        if ((rc = grow(h, g.Xs, (size_t)cap * d))) return rc;
+        if ((rc = grow(h, g.Y, (size_t)cap))) return rc;
+        if ((rc = grow(h, g.K, (size_t)cap * cap))) return rc;
+        if ((rc = grow(h, g.Linv, (size_t)cap * cap))) return rc;
+        if ((rc = grow(h, g.alpha, (size_t)cap))) return rc;
+        if ((rc = grow(h, g.zvec, (size_t)cap))) return rc;
+        if ((rc = grow(h, g.Afrag, (tri_blocks(capNB) + 4) * 32))) return rc;
+        g.capN = cap;
+        g.ld = cap;
+    }
+    g.fitted = false;
+    g.grid_ready = false;
+    g.f32_ready = false;
+    g.tma_ready = false;
+    g.N = N; g.d = d; g.kind = s.kind; g.NB = NB; g.variance = s.variance; g.noise = s.noise;
+    for (int j = 0; j < SO_MAX_DIM; ++j) g.inv_ls[j] = s.inv_ls[j];
+    SO_CUDA(h, cudaMemcpyAsync(g.X, s.X, sizeof(double) * N * d, cudaMemcpyDeviceToDevice, stream));
+    SO_CUDA(h, cudaMemcpyAsync(g.Xs, s.Xs, sizeof(double) * Npad * d, cudaMemcpyDeviceToDevice, stream));
+    SO_CUDA(h, cudaMemcpy2DAsync(g.K, sizeof(double) * g.ld, s.K, sizeof(double) * s.ld, sizeof(double) * Npad, Npad, cudaMemcpyDeviceToDevice, stream));
+    SO_CUDA(h, cudaMemcpy2DAsync(g.Linv, sizeof(double) * g.ld, s.Linv, sizeof(double) * s.ld, sizeof(double) * Npad, Npad, cudaMemcpyDeviceToDevice, stream));
+    SO_CUDA(h, cudaMemcpyAsync(g.Afrag, s.Afrag, sizeof(double2) * (tri_blocks(NB) + 4) * 32, cudaMemcpyDeviceToDevice, stream));
+    SO_CUDA(h, cudaMemcpyAsync(g.Y, Y_h, sizeof(double) * N, cudaMemcpyHostToDevice, stream));
+    k_alpha<<<1, 1024, sizeof(double) * Npad, stream>>>(g.Linv, g.Y, g.alpha, g.zvec, N, Npad, g.ld);
+    SO_CHECK_LAUNCH(h, "so_fit_like kernels");
     g.fitted = true;
     return SO_OK;
 }

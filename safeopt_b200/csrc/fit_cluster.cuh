@@ -1,0 +1,324 @@
+// K1 in ONE launch (N <= 512): the whole training-side fit -- scaled inputs, Ky = K(X,X) + (noise + 1e-8) I, blocked
+// right-looking Cholesky, the triangular inverse W = L^-1 (forward substitution on the identity, done right-looking
+// alongside the factorisation), z = W y, alpha = W^T z and the DMMA fragment packing -- by one thread-block CLUSTER whose
+// CTAs synchronise with the hardware cluster barrier (~0.2 us) instead of kernel boundaries (the multi-kernel version below
+// spends 2 launches per 32-wide panel; at N = 256 that was 21 launches and 0.44 ms, almost all of it launch latency and
+// instruction fetch of fully unrolled single-use code).
+//
+// Per panel P (32 columns at p0), with R = the rows below it:
+//   1. every CTA factors the 32x32 diagonal block in its own shared memory (256 threads, one barrier per column: the
+//      trailing update uses a_ik -= a_ij a_kj / d_jj on the unscaled column, the scaled column goes to a separate array) and
+//      inverts it (32 forward substitutions) -- redundantly, which saves a broadcast and a cluster barrier;
+//   2. 32x32 tiles, round-robin over the CTAs, each a DMMA (mma.sync m8n8k4 f64) product from shared memory:
+//         L[R,P]      = A[R,P] inv(L_PP)^T          (the panel solve as a product with the explicit 32x32 inverse)
+//         W[P,0:p0]   = inv(L_PP) W[P,0:p0]
+//      cluster barrier
+//   3. trailing tiles:   A[R,R] -= L[R,P] L[R,P]^T (lower tiles)   and   W[R,0:p0+32] -= L[R,P] W[P,0:p0+32]
+//      cluster barrier
+// The matrices stay in global memory (<= 2 MB each: L2-resident); cross-CTA data is read with ld.global.cg.
+#pragma once
+#include "common.cuh"
+
+namespace {
+
+constexpr int kFcThreads = 256;
+constexpr int kFcB = 32;                 // panel width = tile size
+constexpr int kFcLd = kFcB + 1;
+constexpr int kFcMaxN = 512;
+constexpr size_t kFcDynSmem = (size_t)(kFcThreads / 32) * 2 * kFcB * kFcLd * sizeof(double);     // 8 warps x two 32x33 tiles = 135 KB
+
+struct FitClusterParams {
+    const double* X;         // N x d raw inputs (device)
+    const double* Y;         // N
+    double* Xs;              // Npad x d scaled inputs out
+    double* K;               // work / L, leading dimension ld
+    double* W;               // L^-1, leading dimension ld
+    double* alpha;
+    double* zvec;
+    double2* Afrag;
+    int N, Npad, NP, ld, d, kind, NB;
+    double variance, diag_add;
+    double inv_ls[SO_MAX_DIM];
+    int* status;
+};
+
+__device__ __forceinline__ unsigned fc_cluster_rank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned fc_cluster_size() { unsigned r; asm volatile("mov.u32 %0, %%cluster_nctarank;\n" : "=r"(r)); return r; }
+__device__ __forceinline__ void fc_cluster_sync() {
+    __threadfence();
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+
+__device__ __forceinline__ double fc_kernel(int kind, double r2, double variance) {
+    switch (kind) {
+        case SO_KERNEL_RBF: return kernel_of_r2<SO_KERNEL_RBF>(r2, variance);
+        case SO_KERNEL_MATERN32: return kernel_of_r2<SO_KERNEL_MATERN32>(r2, variance);
+        default: return kernel_of_r2<SO_KERNEL_MATERN52>(r2, variance);
+    }
+}
+
+// Tiles are processed by single WARPS (each with its own pair of shared-memory tiles), so a CTA has eight tiles in flight and a
+// 16-CTA cluster 128 -- at N = 256 every phase is one round, and no block-level barrier sits between a tile's load and its use.
+// 32x32 tile <- global (rows r0.., cols c0.., leading dimension ld); optional transpose.  Lane l loads column l of each row.
+__device__ __forceinline__ void fc_load_tile(double (*s)[kFcLd], const double* __restrict__ G, int ld, int r0, int c0, bool transpose) {
+    const int lane = threadIdx.x & 31;
+    double v[kFcB];
+#pragma unroll
+    for (int i = 0; i < kFcB; ++i) v[i] = __ldcg(G + (size_t)(r0 + i) * ld + c0 + lane);
+#pragma unroll
+    for (int i = 0; i < kFcB; ++i) {
+        if (transpose) s[lane][i] = v[i]; else s[i][lane] = v[i];
+    }
+}
+
+// C(32x32) = A(32x32, [i][k]) . B(32x32, [k][j]) on the fp64 tensor pipe, by ONE warp: sixteen 8x8 blocks, lane l ends with
+// C[8 bi + l/4][8 bj + 2 (l%4) + {0,1}] in c[bi][bj][0..1].
+__device__ __forceinline__ void fc_tile_mma(const double (*sA)[kFcLd], const double (*sB)[kFcLd], double (&c)[4][4][2]) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int bi = 0; bi < 4; ++bi)
+#pragma unroll
+        for (int bj = 0; bj < 4; ++bj) c[bi][bj][0] = c[bi][bj][1] = 0.0;
+#pragma unroll
+    for (int ks = 0; ks < kFcB / 4; ++ks) {
+        double a[4], b[4];
+#pragma unroll
+        for (int bi = 0; bi < 4; ++bi) a[bi] = sA[8 * bi + (lane >> 2)][4 * ks + (lane & 3)];
+#pragma unroll
+        for (int bj = 0; bj < 4; ++bj) b[bj] = sB[4 * ks + (lane & 3)][8 * bj + (lane >> 2)];
+#pragma unroll
+        for (int bi = 0; bi < 4; ++bi)
+#pragma unroll
+            for (int bj = 0; bj < 4; ++bj) dmma884(c[bi][bj][0], c[bi][bj][1], a[bi], b[bj]);
+    }
+}
+
+// dst tile (global): mode 0 = C, 1 = -C (first touch: starts from zero), 2 = dst - C
+__device__ __forceinline__ void fc_store_tile(double* __restrict__ G, int ld, int r0, int c0, const double (&c)[4][4][2], int mode) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int bi = 0; bi < 4; ++bi)
+#pragma unroll
+        for (int bj = 0; bj < 4; ++bj) {
+            double2* p = reinterpret_cast<double2*>(G + (size_t)(r0 + 8 * bi + (lane >> 2)) * ld + c0 + 8 * bj + 2 * (lane & 3));
+            double2 v = make_double2(c[bi][bj][0], c[bi][bj][1]);
+            if (mode == 1) { v.x = -v.x; v.y = -v.y; }
+            else if (mode == 2) { const double2 o = __ldcg(p); v.x = o.x - v.x; v.y = o.y - v.y; }
+            *p = v;
+        }
+}
+
+__global__ void __launch_bounds__(kFcThreads, 1) k_fit_cluster(const __grid_constant__ FitClusterParams fp) {
+    extern __shared__ __align__(16) unsigned char fc_dyn[];      // per warp: two 32x33 tiles
+    __shared__ double sL[kFcB][kFcLd];      // L_PP
+    __shared__ double sI[kFcB][kFcLd];      // inv(L_PP), lower
+    __shared__ double sIT[kFcB][kFcLd];     // its transpose
+    __shared__ double sCol[2][kFcB];        // unscaled column j of the block being factored (double buffered over j)
+    __shared__ double sRinv[kFcB];          // 1 / L_jj
+    __shared__ int sBad;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned rank = fc_cluster_rank(), csize = fc_cluster_size();
+    const int N = fp.N, NP = fp.NP, ld = fp.ld, d = fp.d;
+    const int gtid = rank * kFcThreads + tid, gthreads = csize * kFcThreads;
+    const int gwarp = rank * (kFcThreads / 32) + warp, gwarps = csize * (kFcThreads / 32);
+    const int nblk = NP / kFcB;
+    double (*wA)[kFcLd] = reinterpret_cast<double (*)[kFcLd]>(fc_dyn + (size_t)warp * 2 * kFcB * kFcLd * sizeof(double));
+    double (*wB)[kFcLd] = wA + kFcB;
+
+    // the (up to three) elements of the 32x32 lower triangle this thread keeps in registers while a diagonal block is factored
+    int ei[3], ek[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        const int e = tid + q * kFcThreads;
+        int ii = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+        while ((ii + 1) * (ii + 2) / 2 <= e) ++ii;
+        while (ii * (ii + 1) / 2 > e) --ii;
+        ei[q] = e < kFcB * (kFcB + 1) / 2 ? ii : -1;
+        ek[q] = e - ii * (ii + 1) / 2;
+    }
+
+    // ---- phase 0: scaled inputs, Ky (identity in the padding), W = 0
+    for (int e = gtid; e < fp.Npad * d; e += gthreads) {
+        const int n = e / d, j = e - n * d;
+        fp.Xs[e] = n < N ? fp.X[e] * fp.inv_ls[j] : 0.0;
+    }
+    for (int e = gtid; e < NP * NP; e += gthreads) {
+        const int i = e / NP, j = e - i * NP;
+        double v;
+        if (i < N && j < N) {
+            double r2 = 0.0;
+            for (int c = 0; c < d; ++c) {
+                const double t = fp.X[i * d + c] * fp.inv_ls[c] - fp.X[j * d + c] * fp.inv_ls[c];
+                r2 = fma(t, t, r2);
+            }
+            v = fc_kernel(fp.kind, r2, fp.variance);
+            if (i == j) v += fp.diag_add;
+        } else {
+            v = i == j ? 1.0 : 0.0;
+        }
+        fp.K[(size_t)i * ld + j] = v;
+        fp.W[(size_t)i * ld + j] = 0.0;
+    }
+    if (tid == 0) sBad = 0;
+    fc_cluster_sync();
+
+    for (int pi = 0; pi < nblk; ++pi) {
+        const int p0 = pi * kFcB;
+        // ---- 1. diagonal block: factor and invert (every CTA, redundantly).  The trailing elements live in registers; per
+        //         column j the owners of a_ij (k == j) put the unscaled column into shared memory, one barrier, and every
+        //         remaining element takes a_ik -= a_ij a_kj / d_jj.  1 / L_jj = rsqrt(d_jj), no division, no sqrt.
+        double a[3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) a[q] = ei[q] >= 0 ? __ldcg(fp.K + (size_t)(p0 + ei[q]) * ld + p0 + ek[q]) : 0.0;
+        for (int j = 0; j < kFcB; ++j) {
+            double* col = sCol[j & 1];
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+                if (ei[q] >= 0 && ek[q] == j) col[ei[q]] = a[q];
+            __syncthreads();
+            const double djj = col[j];
+            const bool ok = djj > 0.0 && !isinf(djj);
+            const double dd = ok ? djj : 1.0;
+            if (!ok && tid == 0) sBad = 1;
+            const double inv_s = rsqrt(dd), inv_d = inv_s * inv_s;
+            if (tid < kFcB) {
+                sL[tid][j] = tid > j ? col[tid] * inv_s : (tid == j ? dd * inv_s : 0.0);
+                if (tid == j) sRinv[j] = inv_s;
+            }
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+                if (ei[q] >= 0 && ek[q] > j) a[q] = fma(-col[ei[q]] * inv_d, col[ek[q]], a[q]);
+            // the other half of sCol is written next: its last readers passed this iteration's barrier already
+        }
+        __syncthreads();
+        // inv(L_PP): column c by thread c (forward substitution on e_c), two accumulators, reciprocals from the factorisation
+        if (tid < kFcB) {
+            const int c = tid;
+            for (int i = 0; i < kFcB; ++i) {
+                double s0 = i == c ? 1.0 : 0.0, s1 = 0.0;
+                int k = c;
+                for (; k + 1 < i; k += 2) {
+                    s0 = fma(-sL[i][k], sI[k][c], s0);
+                    s1 = fma(-sL[i][k + 1], sI[k + 1][c], s1);
+                }
+                if (k < i) s0 = fma(-sL[i][k], sI[k][c], s0);
+                const double x = i >= c ? (s0 + s1) * sRinv[i] : 0.0;
+                sI[i][c] = x;
+                sIT[c][i] = x;
+            }
+        }
+        __syncthreads();
+        if (rank == 0) {                                // L_PP into K, inv(L_PP) into W[P,P]
+            for (int e = tid; e < kFcB * kFcB; e += kFcThreads) {
+                const int i = e >> 5, j = e & 31;
+                if (j <= i) {
+                    fp.K[(size_t)(p0 + i) * ld + p0 + j] = sL[i][j];
+                    fp.W[(size_t)(p0 + i) * ld + p0 + j] = sI[i][j];
+                }
+            }
+        }
+        // ---- 2. panel solve and W[P, 0:p0]: 32x32 tiles, one per warp, round-robin over the cluster's warps
+        {
+            const int n_rows = nblk - 1 - pi, n_cols = pi;
+            for (int t = gwarp; t < n_rows + n_cols; t += gwarps) {
+                double c[4][4][2];
+                if (t < n_rows) {
+                    // L[rb,P] = A[rb,P] inv(L_PP)^T : A tile [i][k], B[k][j] = inv[j][k]
+                    const int r0 = (pi + 1 + t) * kFcB;
+                    fc_load_tile(wA, fp.K, ld, r0, p0, false);
+                    __syncwarp();
+                    fc_tile_mma(wA, sIT, c);
+                    fc_store_tile(fp.K, ld, r0, p0, c, 0);
+                } else {
+                    // W[P,cb] = inv(L_PP) W[P,cb]
+                    const int c0 = (t - n_rows) * kFcB;
+                    fc_load_tile(wB, fp.W, ld, p0, c0, false);
+                    __syncwarp();
+                    fc_tile_mma(sI, wB, c);
+                    fc_store_tile(fp.W, ld, p0, c0, c, 0);
+                }
+                __syncwarp();
+            }
+        }
+        fc_cluster_sync();
+        // ---- 3. trailing update: A[rb,cb] -= L[rb,P] L[cb,P]^T (pi < cb <= rb) and W[rb,cb] -= L[rb,P] W[P,cb] (cb <= pi)
+        {
+            const int m = nblk - 1 - pi;                // row blocks below the panel
+            const int per_row = pi + 1;                 // W tiles per row block
+            const int n_a = m * (m + 1) / 2, n_w = m * per_row;
+            for (int t = gwarp; t < n_a + n_w; t += gwarps) {
+                double c[4][4][2];
+                if (t < n_a) {
+                    int ii = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+                    while ((ii + 1) * (ii + 2) / 2 <= t) ++ii;
+                    while (ii * (ii + 1) / 2 > t) --ii;
+                    const int kk = t - ii * (ii + 1) / 2;
+                    const int r0 = (pi + 1 + ii) * kFcB, c0 = (pi + 1 + kk) * kFcB;
+                    fc_load_tile(wA, fp.K, ld, r0, p0, false);
+                    fc_load_tile(wB, fp.K, ld, c0, p0, true);             // B[k][j] = L[c0 + j][p0 + k]
+                    __syncwarp();
+                    fc_tile_mma(wA, wB, c);
+                    fc_store_tile(fp.K, ld, r0, c0, c, 2);
+                } else {
+                    const int u = t - n_a;
+                    const int rb = u / per_row, cb = u - rb * per_row;
+                    const int r0 = (pi + 1 + rb) * kFcB, c0 = cb * kFcB;
+                    fc_load_tile(wA, fp.K, ld, r0, p0, false);
+                    fc_load_tile(wB, fp.W, ld, p0, c0, false);
+                    __syncwarp();
+                    fc_tile_mma(wA, wB, c);
+                    fc_store_tile(fp.W, ld, r0, c0, c, cb == pi ? 1 : 2);  // W[R,P] starts from zero
+                }
+                __syncwarp();
+            }
+        }
+        fc_cluster_sync();
+    }
+
+    // ---- z = W y (one warp per row), alpha = W^T z (one thread per column), fragment packing
+    for (int i = rank * (kFcThreads / 32) + warp; i < fp.Npad; i += csize * (kFcThreads / 32)) {
+        double part = 0.0;
+        if (i < N)
+            for (int k = lane; k <= i; k += 32) part = fma(__ldcg(fp.W + (size_t)i * ld + k), fp.Y[k], part);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if (lane == 0) fp.zvec[i] = i < N ? part : 0.0;
+    }
+    fc_cluster_sync();
+    for (int c = gtid; c < fp.Npad; c += gthreads) {
+        double s0 = 0.0, s1 = 0.0;
+        if (c < N) {
+            int i = c;
+            for (; i + 1 < N; i += 2) {
+                s0 = fma(__ldcg(fp.W + (size_t)i * ld + c), __ldcg(fp.zvec + i), s0);
+                s1 = fma(__ldcg(fp.W + (size_t)(i + 1) * ld + c), __ldcg(fp.zvec + i + 1), s1);
+            }
+            if (i < N) s0 = fma(__ldcg(fp.W + (size_t)i * ld + c), __ldcg(fp.zvec + i), s0);
+        }
+        fp.alpha[c] = s0 + s1;
+    }
+    {
+        const size_t nfrag = tri_blocks(fp.NB) * 32;
+        for (size_t e = gtid; e < nfrag + 4 * 32; e += gthreads) {
+            double2 v = make_double2(0.0, 0.0);
+            if (e < nfrag) {
+                const size_t blk = e >> 5;
+                const int l = (int)(e & 31);
+                int i = (int)((sqrt(8.0 * (double)blk + 1.0) - 1.0) * 0.5);
+                while ((size_t)(i + 1) * (i + 2) / 2 <= blk) ++i;
+                while ((size_t)i * (i + 1) / 2 > blk) --i;
+                const int kb = (int)(blk - (size_t)i * (i + 1) / 2);
+                const int r = 8 * i + (l >> 2), c0 = 8 * kb + 2 * (l & 3);
+                if (r < N) {
+                    if (c0 < N && c0 <= r) v.x = __ldcg(fp.W + (size_t)r * ld + c0);
+                    if (c0 + 1 < N && c0 + 1 <= r) v.y = __ldcg(fp.W + (size_t)r * ld + c0 + 1);
+                }
+            }
+            fp.Afrag[e] = v;
+        }
+    }
+    if (rank == 0 && tid == 0 && sBad) *fp.status = SO_ERR_NOT_PD;
+}
+
+}  // namespace

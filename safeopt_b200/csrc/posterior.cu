@@ -855,15 +855,19 @@ extern "C" int so_posterior_grid_f32(so_handle* h, int n, const int* gps_h, int6
     fp.Bop = reinterpret_cast<const unsigned char*>(g.f32_B);
     fp.Np = g.f32_Np; fp.nslab = g.f32_Np / kF32SlabK; fp.b_stride = f32_b_bytes(g.f32_Np);
     fp.s0 = g.f32_s0; fp.fast_rows = F; fp.tpb = g.f32_tpb;
-    const int64_t last_row = row0 + M - 1;
-    const int64_t t0 = (row0 / F) * fp.tpb + (row0 % F) / kF32TileRows;
-    const int64_t t1 = (last_row / F) * fp.tpb + (last_row % F) / kF32TileRows;
-    fp.first_tile = t0;
-    p.ntiles = t1 - t0 + 1;
+    fp.s_lo = row0 / F; fp.s_hi = (row0 + M - 1) / F + 1;
+    // one fast tile per CTA, `lanes` CTAs per fast tile walking the slow indices; A resident when two B stages still fit beside it
+    int lanes = h->num_sms / fp.tpb;
+    if (lanes < 1) lanes = 1;
+    if ((int64_t)lanes > fp.s_hi - fp.s_lo) lanes = (int)(fp.s_hi - fp.s_lo);
+    fp.lanes = lanes;
+    const char* res_env = std::getenv("SO_F32_A_RESIDENT");           // "0": always stream A (A/B measurements)
+    fp.a_resident = !(res_env && res_env[0] == '0') && f32_smem(fp.Np, 2, true).total <= (size_t)h->smem_optin ? 1 : 0;
     int stages = 4;
-    while (stages > 1 && f32_smem(fp.Np, stages, n).total > (size_t)h->smem_optin) --stages;
-    if (f32_smem(fp.Np, stages, n).total > (size_t)h->smem_optin) return so_fail(h, SO_ERR_CAPACITY, "posterior_grid_f32: shared memory");
+    while (stages > 1 && f32_smem(fp.Np, stages, fp.a_resident != 0).total > (size_t)h->smem_optin) --stages;
+    if (f32_smem(fp.Np, stages, fp.a_resident != 0).total > (size_t)h->smem_optin) return so_fail(h, SO_ERR_CAPACITY, "posterior_grid_f32: shared memory");
     fp.stages = stages;
+    p.ntiles = (int64_t)fp.tpb * (fp.s_hi - fp.s_lo);
     DeviceGuard guard(h->device);
     static int configured_for = -1;
     if (configured_for != h->device) {
@@ -904,8 +908,7 @@ extern "C" int so_posterior_grid_f32(so_handle* h, int n, const int* gps_h, int6
         k_mean_grid<<<dim3((unsigned)gx, (unsigned)gy), 128, 0, (cudaStream_t)stream_>>>(mq);
         SO_CHECK_LAUNCH(h, "k_mean_grid");
     }
-    const int grid = (int)(p.ntiles < (int64_t)h->num_sms ? p.ntiles : (int64_t)h->num_sms);
-    k_posterior_f32<<<grid, kF32Threads, f32_smem(fp.Np, stages, n).total, (cudaStream_t)stream_>>>(fp);
+    k_posterior_f32<<<fp.tpb * fp.lanes, kF32Threads, f32_smem(fp.Np, fp.stages, fp.a_resident != 0).total, (cudaStream_t)stream_>>>(fp);
     SO_CHECK_LAUNCH(h, "k_posterior_f32");
     return SO_OK;
 }

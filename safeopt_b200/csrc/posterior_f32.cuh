@@ -19,6 +19,9 @@
 // square at N = 128).  Both operands are pre-packed (k_f32_pack_a / k_f32_pack_b) in the no-swizzle K-major canonical layout
 // of the UMMA shared-memory descriptor, [K chunk of 16 bytes][row][4 floats]: a slab is one contiguous bulk copy per operand.
 //
+// Work split: CTA b owns ONE fast tile j = b % tpb (128 candidate rows of every slow block) and walks the slow indices
+// s_lo + b / tpb, + lanes, ...: its A operand never changes, so when it fits (N <= 128: 128 KB for hi + lo) it is loaded once and
+// stays in shared memory, and only the B slabs of A'(s) stream through the ring (80 KB per 128 rows at N = 128).
 // Roles (192 threads): warp 0 lane 0 = TMA producer (ring of kStages slabs, full/empty mbarriers), warp 1 lane 0 = MMA issuer
 // (tcgen05.commit releases a slab / publishes an accumulator), warps 2..5 = epilogue, one thread per candidate row = TMEM
 // lane.  Two accumulators of up to 256 columns: the MMAs of tile t+1 run under the epilogue of tile t.
@@ -46,8 +49,11 @@ struct F32Params {
     const unsigned char* Aop;       // [tile in slow block][slab][plane][chunk][row][4 floats]
     const unsigned char* Bop;       // [slow index - s0][slab (trimmed rows)][plane][chunk][row][4 floats]
     size_t b_stride;                // bytes per slow index
-    int64_t s0, fast_rows, first_tile;
+    int64_t s0, fast_rows;
+    int64_t s_lo, s_hi;             // slow indices this launch covers
     int tpb, Np, nslab, stages;
+    int lanes;                      // CTA b owns the fast tile j = b % tpb for the slow indices s_lo + b / tpb, + lanes, + 2 lanes, ...
+    int a_resident;                 // the CTA's A operand (its fast tile, all slabs, hi + lo) stays in shared memory for the whole launch
     const double* mean_in[kMaxOut]; // per output: the fp64 means of these rows (written by k_mean_grid just before)
 };
 
@@ -103,12 +109,12 @@ __device__ __forceinline__ void mbar_arrive_plain(unsigned long long* bar) {
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(smem_u32(bar)) : "memory");
 }
 
-struct F32Smem { size_t stage_bytes, z_off, bar_off, total; };
-__host__ __device__ inline F32Smem f32_smem(int Np, int stages, int n_out) {
+struct F32Smem { size_t a_bytes, stage_bytes, bar_off, total; };
+__host__ __device__ inline F32Smem f32_smem(int Np, int stages, bool a_resident) {
     F32Smem L;
-    L.stage_bytes = (size_t)kF32ASlabBytes + f32_b_slab_bytes(Np, 0);
-    L.z_off = (size_t)stages * L.stage_bytes;
-    L.bar_off = L.z_off;
+    L.a_bytes = a_resident ? (size_t)(Np / kF32SlabK) * kF32ASlabBytes : 0;
+    L.stage_bytes = (a_resident ? 0 : (size_t)kF32ASlabBytes) + f32_b_slab_bytes(Np, 0);
+    L.bar_off = L.a_bytes + (size_t)stages * L.stage_bytes;
     L.total = L.bar_off + 16 * sizeof(unsigned long long) + 16;
     return L;
 }
@@ -117,17 +123,23 @@ __global__ void __launch_bounds__(kF32Threads, 1) k_posterior_f32(const __grid_c
     const PostParams& p = fp.p;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int Np = fp.Np, nslab = fp.nslab, stages = fp.stages, n_out = p.n_out;
-    const F32Smem L = f32_smem(Np, stages, n_out);
+    const bool resident = fp.a_resident != 0;
+    const F32Smem L = f32_smem(Np, stages, resident);
+    unsigned char* sStage = smem_raw + L.a_bytes;
     unsigned long long* full = reinterpret_cast<unsigned long long*>(smem_raw + L.bar_off);      // [stages] (<= 4)
     unsigned long long* empty = full + 4;
     unsigned long long* acc_full = full + 8;                                                      // [2]
     unsigned long long* acc_empty = full + 10;                                                    // [2]
+    unsigned long long* a_full = full + 12;
     unsigned* tmem_slot = reinterpret_cast<unsigned*>(full + 16);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int j = blockIdx.x % fp.tpb;                   // this CTA's fast tile
+    const int64_t s_first = fp.s_lo + blockIdx.x / fp.tpb;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
+        mbar_init(a_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (warp == 1) tmem_alloc_512(tmem_slot);
@@ -135,26 +147,30 @@ __global__ void __launch_bounds__(kF32Threads, 1) k_posterior_f32(const __grid_c
     __syncthreads();
     tc_fence_after();
     const unsigned tmem_base = *tmem_slot;
+    const unsigned char* a_src = fp.Aop + (size_t)j * nslab * kF32ASlabBytes;
 
-    const int64_t ntiles = p.ntiles;
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
+            if (resident && s_first < fp.s_hi) {
+                mbar_expect_tx(a_full, (unsigned)L.a_bytes);
+                for (int k = 0; k < nslab; ++k)
+                    tma_bulk_g2s(smem_raw + (size_t)k * kF32ASlabBytes, a_src + (size_t)k * kF32ASlabBytes, (unsigned)kF32ASlabBytes, a_full);
+            }
             int st = 0;
             unsigned ph = 0;
-            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                const int64_t gt = fp.first_tile + tile;
-                const int64_t si = gt / fp.tpb;
-                const int j = (int)(gt - si * fp.tpb);
-                const unsigned char* a_src = fp.Aop + (size_t)j * nslab * kF32ASlabBytes;
+            for (int64_t si = s_first; si < fp.s_hi; si += fp.lanes) {
                 const unsigned char* b_src = fp.Bop + (size_t)(si - fp.s0) * fp.b_stride;
                 for (int k = 0; k < nslab; ++k) {
                     mbar_wait(&empty[st], ph ^ 1u);
-                    unsigned char* dst = smem_raw + (size_t)st * L.stage_bytes;
+                    unsigned char* dst = sStage + (size_t)st * L.stage_bytes;
                     const unsigned bbytes = (unsigned)f32_b_slab_bytes(Np, k);
-                    mbar_expect_tx(&full[st], (unsigned)kF32ASlabBytes + bbytes);
-                    tma_bulk_g2s(dst, a_src + (size_t)k * kF32ASlabBytes, (unsigned)kF32ASlabBytes, &full[st]);
-                    tma_bulk_g2s(dst + kF32ASlabBytes, b_src + f32_b_slab_offset(Np, k), bbytes, &full[st]);
+                    mbar_expect_tx(&full[st], (resident ? 0u : (unsigned)kF32ASlabBytes) + bbytes);
+                    if (!resident) {
+                        tma_bulk_g2s(dst, a_src + (size_t)k * kF32ASlabBytes, (unsigned)kF32ASlabBytes, &full[st]);
+                        dst += kF32ASlabBytes;
+                    }
+                    tma_bulk_g2s(dst, b_src + f32_b_slab_offset(Np, k), bbytes, &full[st]);
                     if (++st == stages) { st = 0; ph ^= 1u; }
                 }
             }
@@ -165,7 +181,8 @@ __global__ void __launch_bounds__(kF32Threads, 1) k_posterior_f32(const __grid_c
             int st = 0;
             unsigned ph = 0;
             int it = 0;
-            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            if (resident && s_first < fp.s_hi) { mbar_wait(a_full, 0); tc_fence_after(); }
+            for (int64_t si = s_first; si < fp.s_hi; si += fp.lanes, ++it) {
                 const int acc = it & 1;
                 mbar_wait(&acc_empty[acc], (((unsigned)it >> 1) & 1u) ^ 1u);      // the epilogue has drained this accumulator
                 tc_fence_after();
@@ -173,8 +190,9 @@ __global__ void __launch_bounds__(kF32Threads, 1) k_posterior_f32(const __grid_c
                     mbar_wait(&full[st], ph);
                     tc_fence_after();
                     const int Nk = Np - kF32SlabK * k;
-                    const unsigned a_base = smem_u32(smem_raw + (size_t)st * L.stage_bytes);
-                    const unsigned b_base = a_base + kF32ASlabBytes;
+                    const unsigned stage_base = smem_u32(sStage + (size_t)st * L.stage_bytes);
+                    const unsigned a_base = resident ? smem_u32(smem_raw + (size_t)k * kF32ASlabBytes) : stage_base;
+                    const unsigned b_base = resident ? stage_base : stage_base + kF32ASlabBytes;
                     const unsigned a_lbo = kF32TileRows * 16, b_lbo = (unsigned)Nk * 16;
                     const unsigned a_plane = 8 * a_lbo, b_plane = 8 * b_lbo;
                     const unsigned idesc = umma_idesc_tf32(Nk);
@@ -200,8 +218,9 @@ __global__ void __launch_bounds__(kF32Threads, 1) k_posterior_f32(const __grid_c
         // ===== epilogue: one thread per candidate row (TMEM lane); a warp reaches the lane quarter warp % 4 =====
         const int q = warp & 3;
         const int trow = 32 * q + lane;
+        const int64_t frow = (int64_t)j * kF32TileRows + trow;                     // row inside the slow block
         int it = 0;
-        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        for (int64_t si = s_first; si < fp.s_hi; si += fp.lanes, ++it) {
             const int acc = it & 1;
             mbar_wait(&acc_full[acc], ((unsigned)it >> 1) & 1u);
             tc_fence_after();
@@ -223,10 +242,6 @@ __global__ void __launch_bounds__(kF32Threads, 1) k_posterior_f32(const __grid_c
             __syncwarp();
             if (lane == 0) mbar_arrive_plain(&acc_empty[acc]);
 
-            const int64_t gt = fp.first_tile + tile;
-            const int64_t si = gt / fp.tpb;
-            const int j = (int)(gt - si * fp.tpb);
-            const int64_t frow = (int64_t)j * kF32TileRows + trow;                 // row inside the slow block
             const int64_t row = si * fp.fast_rows + frow - p.row0;                  // local output row
             if (frow < fp.fast_rows && row >= 0 && row < p.M) {
                 double v = p.variance - sumsq;
@@ -236,8 +251,7 @@ __global__ void __launch_bounds__(kF32Threads, 1) k_posterior_f32(const __grid_c
 #pragma unroll
                 for (int o = 0; o < kMaxOut; ++o) {
                     if (o >= n_out) break;
-                    const double* mp_in = fp.mean_in[o];
-                    const double mu = mp_in[row];           // fp64 mean of k_mean_grid (same stream, launched before)
+                    const double mu = fp.mean_in[o][row];     // fp64 mean of k_mean_grid (same stream, launched before)
                     const double lo = __dsub_rn(mu, bs), up = __dadd_rn(mu, bs);
                     double* vp = o == 0 ? p.var : p.var_x[o - 1];
                     const int qc = o == 0 ? p.q_col : p.q_col_x[o - 1];

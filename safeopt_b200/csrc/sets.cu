@@ -69,11 +69,11 @@ __device__ __forceinline__ P block_reduce(P acc, P* sm) {
     if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
     __syncthreads();
     if (threadIdx.x < 32) {
-        P t = sm[threadIdx.x < kThreads / 32 ? threadIdx.x : 0];
-        if (threadIdx.x >= kThreads / 32) t = sm[0];          // duplicates of entry 0 do not change max / are not summed:
-        if (threadIdx.x >= kThreads / 32) t.n = 0;            // only their counts must not be added twice
+        const unsigned nw = blockDim.x >> 5;                  // 8 warps (one-pass kernels, fused) or 32 (single-block fused)
+        P t = sm[threadIdx.x < nw ? threadIdx.x : 0];
+        if (threadIdx.x >= nw) t.n = 0;                       // duplicates of entry 0 do not change a max; their counts must not be added twice
 #pragma unroll
-        for (int o = 4; o > 0; o >>= 1) merge(t, shfl_xor(t, o));
+        for (int o = 16; o > 0; o >>= 1) merge(t, shfl_xor(t, o));
         acc = t;
     }
     __syncthreads();
@@ -84,7 +84,7 @@ __device__ __forceinline__ P block_reduce(P acc, P* sm) {
 // in thread 0 with the total in `acc`.
 template <typename P>
 __device__ __forceinline__ bool grid_reduce(P& acc, P* __restrict__ part, unsigned int* __restrict__ counter, P identity) {
-    __shared__ P sm[kThreads / 32];
+    __shared__ P sm[32];
     __shared__ bool last;
     acc = block_reduce(acc, sm);
     if (threadIdx.x == 0) {
@@ -96,7 +96,7 @@ __device__ __forceinline__ bool grid_reduce(P& acc, P* __restrict__ part, unsign
     if (!last) return false;
     __threadfence();
     P t = identity;
-    for (unsigned b = threadIdx.x; b < gridDim.x; b += kThreads) merge(t, part[b]);
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) merge(t, part[b]);
     acc = block_reduce(t, sm);
     if (threadIdx.x == 0) *counter = 0;
     return threadIdx.x == 0;
@@ -140,19 +140,23 @@ __device__ __forceinline__ SafePartial scan_safe(const double* __restrict__ Q, i
     SafePartial acc = {0, -INFINITY, -1, -INFINITY, -1};
     const bool aligned = (reinterpret_cast<uintptr_t>(S) & 15) == 0;
     const int64_t nchunks = (M + kRows - 1) / kRows;
-    for (int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x; c < nchunks; c += (int64_t)gridDim.x * kThreads) {
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < nchunks; c += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r0 = c * kRows;
         uint8_t s[kRows];
         load_mask16(S, r0, M, aligned, s);
         if (!any16(s)) continue;
+        // all loads of the chunk are issued before the first use: one memory latency per chunk instead of one per safe row
+        double2 lu[kRows];
+#pragma unroll
+        for (int k = 0; k < kRows; ++k)
+            lu[k] = s[k] ? *reinterpret_cast<const double2*>(Q + (size_t)(r0 + k) * q_stride) : make_double2(0.0, 0.0);
 #pragma unroll
         for (int k = 0; k < kRows; ++k) {
             if (!s[k]) continue;
             const int64_t r = r0 + k;
-            const double2 lu = *reinterpret_cast<const double2*>(Q + (size_t)r * q_stride);
             acc.n += 1;
-            take_max_first(acc.max_l, acc.arg_l, lu.x, row0 + r);
-            take_max_first(acc.max_u, acc.arg_u, lu.y, row0 + r);
+            take_max_first(acc.max_l, acc.arg_l, lu[k].x, row0 + r);
+            take_max_first(acc.max_u, acc.arg_u, lu[k].y, row0 + r);
         }
     }
     return acc;
@@ -165,19 +169,23 @@ __device__ __forceinline__ MaxPartial scan_maximizers(const double* __restrict__
     const int qs = 2 * G;
     const bool aligned = ((reinterpret_cast<uintptr_t>(S) | reinterpret_cast<uintptr_t>(Mmask)) & 15) == 0;
     const int64_t nchunks = (M + kRows - 1) / kRows;
-    for (int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x; c < nchunks; c += (int64_t)gridDim.x * kThreads) {
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < nchunks; c += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r0 = c * kRows;
         uint8_t s[kRows], m[kRows];
         load_mask16(S, r0, M, aligned, s);
 #pragma unroll
         for (int k = 0; k < kRows; ++k) m[k] = 0;
         if (any16(s)) {
+            double2 lus[kRows];
+#pragma unroll
+            for (int k = 0; k < kRows; ++k)
+                lus[k] = s[k] ? *reinterpret_cast<const double2*>(Q + (size_t)(r0 + k) * qs) : make_double2(0.0, 0.0);
 #pragma unroll
             for (int k = 0; k < kRows; ++k) {
                 if (!s[k]) continue;
                 const int64_t r = r0 + k;
                 const double* q = Q + (size_t)r * qs;
-                const double2 lu = *reinterpret_cast<const double2*>(q);
+                const double2 lu = lus[k];
                 if (lu.y >= max_l0) {
                     m[k] = 1;
                     acc.n += 1;
@@ -207,7 +215,7 @@ __device__ __forceinline__ void scan_candidates(const double* __restrict__ Q, in
     const int64_t nchunks = (M + kRows - 1) / kRows;
     const unsigned lane = threadIdx.x & 31;
     // whole warps iterate together (the append below uses full-mask warp collectives)
-    for (int64_t cbase = (int64_t)blockIdx.x * kThreads; cbase < nchunks; cbase += (int64_t)gridDim.x * kThreads) {
+    for (int64_t cbase = (int64_t)blockIdx.x * blockDim.x; cbase < nchunks; cbase += (int64_t)gridDim.x * blockDim.x) {
         const int64_t c = cbase + threadIdx.x;
         const int64_t r0 = c * kRows;
         uint8_t s[kRows], m[kRows], cnd[kRows];
@@ -337,26 +345,12 @@ struct FusedParams {
     long long* dbg;                      // optional: SM-clock stamps of block 0 at the phase boundaries (so_debug_fused_times)
 };
 
-#define SO_FUSED_STAMP(i) do { if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) p.dbg[i] = clock64(); } while (0)
+#define SO_FUSED_STAMP(i) do { if (p.dbg && threadIdx.x == 0) p.dbg[i] = (long long)globaltimer_dbg(); } while (0)
 
-// Self-resetting grid barrier (all blocks are co-resident: cooperative launch).  The generation is read BEFORE arriving, so it
-// cannot advance until this block has arrived too.
-__device__ __forceinline__ void grid_barrier(unsigned int* bar) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        volatile unsigned int* vgen = bar + 1;
-        const unsigned int gen = *vgen;
-        __threadfence();
-        if (atomicAdd(bar, 1u) == gridDim.x - 1) {
-            bar[0] = 0;
-            __threadfence();
-            atomicAdd(bar + 1, 1u);
-        } else {
-            while (*vgen == gen) { }
-        }
-        __threadfence();
-    }
-    __syncthreads();
+__device__ __forceinline__ unsigned long long globaltimer_dbg() {     // diagnostics only (SO_FUSED_DEBUG_TIMES): comparable across SMs
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+    return t;
 }
 
 // All `world` stamps of a phase carry `epoch`?  (block-wide; returns the same answer in every thread)
@@ -373,34 +367,55 @@ __device__ __forceinline__ void publish_flags(const XchgView& x, int par, int ph
     for (int r = 0; r < x.world; ++r) st_release_sys(&x.peer[r]->sets[par].flag[phase][x.rank], epoch);
 }
 
-__global__ void __launch_bounds__(kThreads) k_sets_fused(const __grid_constant__ FusedParams p) {
-    __shared__ SafePartial smA[kThreads / 32];
-    __shared__ MaxPartial smB[kThreads / 32];
-    const unsigned long long epoch = *p.epoch + 1;          // bumped by block 0 after the last grid barrier
+// SINGLE: one CTA of 1024 threads does everything (row blocks up to kSingleMaxRows): the grid barriers become __syncthreads and
+// no partial leaves the SM -- on small grids the multi-block kernel is nothing but ~40 serialised L2 round trips (31 us at 40 k
+// rows, measured with SO_FUSED_DEBUG_TIMES), the single-block one a handful.
+constexpr int kSingleThreads = 1024;
+constexpr int64_t kSingleMaxRows = 400000;
+
+// Publishes this block's partial and takes a ticket; returns true (in every thread) in the LAST block to arrive, which then
+// combines the partials and publishes the record -- the other blocks go straight to waiting for the stamp, so a phase costs
+// one arrival + one stamp instead of a grid barrier followed by a stamp.  The ticket counter is reset by the last block before
+// it publishes (nobody can reach the next phase's ticket before seeing that stamp).
+template <typename P>
+__device__ __forceinline__ bool arrive_last(const P& acc, P* __restrict__ part, unsigned int* __restrict__ counter) {
+    __shared__ int s_last;
+    if (threadIdx.x == 0) {
+        part[blockIdx.x] = acc;
+        __threadfence();
+        s_last = atomicAdd(counter, 1u) == gridDim.x - 1 ? 1 : 0;
+        if (s_last) { __threadfence(); *counter = 0; }
+    }
+    __syncthreads();
+    return s_last != 0;
+}
+
+template <bool SINGLE>
+__global__ void __launch_bounds__(SINGLE ? kSingleThreads : kThreads) k_sets_fused(const __grid_constant__ FusedParams p) {
+    __shared__ SafePartial smA[32];
+    __shared__ MaxPartial smB[32];
+    const unsigned long long epoch = *p.epoch + 1;          // bumped by the last block at the very end
     const int par = (int)(epoch & 1), world = p.x.world, rank = p.x.rank;
     XchgSets* mine = &p.x.local->sets[par];
     int status = SO_OK;
 
     SO_FUSED_STAMP(0);
     // ---- phase A: safe-set record
-    if (blockIdx.x == 0 && threadIdx.x == 0) *p.ncand = 0;  // first touched after the second grid barrier
     {
         SafePartial acc = block_reduce(scan_safe(p.Q, 2 * p.G, p.M, p.row0, p.S), smA);
-        if (threadIdx.x == 0) p.partA[blockIdx.x] = acc;
-    }
-    SO_FUSED_STAMP(1);
-    grid_barrier(p.bar);
-    SO_FUSED_STAMP(2);
-    if (blockIdx.x == 0) {
-        SafePartial t = {0, -INFINITY, -1, -INFINITY, -1};
-        for (unsigned b = threadIdx.x; b < gridDim.x; b += kThreads) merge(t, p.partA[b]);
-        t = block_reduce(t, smA);
-        if (threadIdx.x == 0) {
-            so_safe_record rec;
-            rec.n_safe = t.n; rec.max_l0 = t.max_l; rec.argmax_l0 = t.arg_l; rec.max_u0 = t.max_u; rec.argmax_u0 = t.arg_u;
-            rec.reserved[0] = rec.reserved[1] = rec.reserved[2] = 0;
-            for (int r = 0; r < world; ++r) p.x.peer[r]->sets[par].safe[rank] = rec;
-            publish_flags(p.x, par, 0, epoch);
+        SO_FUSED_STAMP(1);
+        if (arrive_last(acc, p.partA, p.bar)) {
+            SafePartial t = {0, -INFINITY, -1, -INFINITY, -1};
+            for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) merge(t, p.partA[b]);
+            t = block_reduce(t, smA);
+            if (threadIdx.x == 0) {
+                *p.ncand = 0;                                // first touched in phase C, two stamps from here
+                so_safe_record rec;
+                rec.n_safe = t.n; rec.max_l0 = t.max_l; rec.argmax_l0 = t.arg_l; rec.max_u0 = t.max_u; rec.argmax_u0 = t.arg_u;
+                rec.reserved[0] = rec.reserved[1] = rec.reserved[2] = 0;
+                for (int r = 0; r < world; ++r) p.x.peer[r]->sets[par].safe[rank] = rec;
+                publish_flags(p.x, par, 0, epoch);
+            }
         }
     }
     SO_FUSED_STAMP(3);
@@ -415,21 +430,18 @@ __global__ void __launch_bounds__(kThreads) k_sets_fused(const __grid_constant__
     // ---- phase B: maximisers
     {
         MaxPartial acc = block_reduce(scan_maximizers(p.Q, p.G, p.M, p.row0, p.S, max_l0, p.scaling, p.Mmask), smB);
-        if (threadIdx.x == 0) p.partB[blockIdx.x] = acc;
-    }
-    SO_FUSED_STAMP(5);
-    grid_barrier(p.bar);
-    SO_FUSED_STAMP(6);
-    if (blockIdx.x == 0) {
-        MaxPartial t = {0, -INFINITY, -INFINITY, -1};
-        for (unsigned b = threadIdx.x; b < gridDim.x; b += kThreads) merge(t, p.partB[b]);
-        t = block_reduce(t, smB);
-        if (threadIdx.x == 0) {
-            so_max_record rec;
-            rec.n_max = t.n; rec.max_width0 = t.max_w0; rec.best_value = t.best; rec.best_row = t.best_row;
-            rec.reserved[0] = rec.reserved[1] = rec.reserved[2] = rec.reserved[3] = 0;
-            for (int r = 0; r < world; ++r) p.x.peer[r]->sets[par].max[rank] = rec;
-            publish_flags(p.x, par, 1, epoch);
+        SO_FUSED_STAMP(5);
+        if (arrive_last(acc, p.partB, p.bar)) {
+            MaxPartial t = {0, -INFINITY, -INFINITY, -1};
+            for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) merge(t, p.partB[b]);
+            t = block_reduce(t, smB);
+            if (threadIdx.x == 0) {
+                so_max_record rec;
+                rec.n_max = t.n; rec.max_width0 = t.max_w0; rec.best_value = t.best; rec.best_row = t.best_row;
+                rec.reserved[0] = rec.reserved[1] = rec.reserved[2] = rec.reserved[3] = 0;
+                for (int r = 0; r < world; ++r) p.x.peer[r]->sets[par].max[rank] = rec;
+                publish_flags(p.x, par, 1, epoch);
+            }
         }
     }
     SO_FUSED_STAMP(7);
@@ -447,9 +459,11 @@ __global__ void __launch_bounds__(kThreads) k_sets_fused(const __grid_constant__
                         p.ncand);
     }
     SO_FUSED_STAMP(9);
-    grid_barrier(p.bar);
+    {
+        SafePartial none = {0, -INFINITY, -1, -INFINITY, -1};
+        if (!arrive_last(none, p.partA, p.bar)) return;     // everybody but the last block is done
+    }
     SO_FUSED_STAMP(10);
-    if (blockIdx.x != 0) return;
     if (threadIdx.x == 0) {
         const long long n = p.with_candidates ? (long long)*reinterpret_cast<volatile unsigned long long*>(p.ncand) : 0;
         for (int r = 0; r < world; ++r) p.x.peer[r]->sets[par].ncand[rank] = n;
@@ -461,16 +475,17 @@ __global__ void __launch_bounds__(kThreads) k_sets_fused(const __grid_constant__
     unsigned long long* res = reinterpret_cast<unsigned long long*>(p.result);
     const unsigned long long* src_safe = reinterpret_cast<const unsigned long long*>(mine->safe);
     const unsigned long long* src_max = reinterpret_cast<const unsigned long long*>(mine->max);
-    for (int i = threadIdx.x; i < world * 8; i += kThreads) {
+    for (int i = threadIdx.x; i < world * 8; i += blockDim.x) {
         res[i] = __ldcg(src_safe + i);
         res[world * 8 + i] = __ldcg(src_max + i);
     }
-    for (int r = threadIdx.x; r < world; r += kThreads)
+    for (int r = threadIdx.x; r < world; r += blockDim.x)
         res[world * 16 + r] = (unsigned long long)__ldcg(reinterpret_cast<const unsigned long long*>(mine->ncand) + r);
+    if (threadIdx.x == 0) res[world * 17] = (unsigned long long)(long long)status;
+    __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
-        res[world * 17] = (unsigned long long)(long long)status;
-        res[world * 17 + 1] = epoch;
+        *reinterpret_cast<volatile unsigned long long*>(res + world * 17 + 1) = epoch;     // the host polls this word (mapped pinned memory)
         *p.epoch = epoch;
     }
     SO_FUSED_STAMP(12);
@@ -567,15 +582,17 @@ static int fused_setup(so_handle* h) {
     SO_CUDA(h, cudaMalloc(&h->fused_bar, 2 * sizeof(unsigned int)));
     SO_CUDA(h, cudaMemset(h->fused_bar, 0, 2 * sizeof(unsigned int)));
     SO_CUDA(h, cudaMalloc(&h->fused_ncand, sizeof(unsigned long long)));
-    SO_CUDA(h, cudaMalloc(&h->fused_result_d, SO_SETS_RESULT_BYTES(kXchgMaxWorld)));
-    SO_CUDA(h, cudaMemset(h->fused_result_d, 0, SO_SETS_RESULT_BYTES(kXchgMaxWorld)));
-    SO_CUDA(h, cudaMallocHost(&h->fused_result_h, SO_SETS_RESULT_BYTES(kXchgMaxWorld)));
+    // the combined records land in MAPPED pinned host memory: the kernel's last store is the epoch stamp, which the host polls
+    // (no copy, no stream synchronisation on the step's critical path)
+    SO_CUDA(h, cudaHostAlloc(&h->fused_result_h, SO_SETS_RESULT_BYTES(kXchgMaxWorld), cudaHostAllocMapped));
+    memset(h->fused_result_h, 0, SO_SETS_RESULT_BYTES(kXchgMaxWorld));
+    SO_CUDA(h, cudaHostGetDevicePointer(&h->fused_result_d, h->fused_result_h, 0));
     if (std::getenv("SO_FUSED_DEBUG_TIMES")) {
         SO_CUDA(h, cudaMalloc(&h->fused_dbg, 16 * sizeof(long long)));
         SO_CUDA(h, cudaMemset(h->fused_dbg, 0, 16 * sizeof(long long)));
     }
     int per_sm = 0;
-    SO_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sets_fused, kThreads, 0));
+    SO_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sets_fused<false>, kThreads, 0));
     if (per_sm < 1) return so_fail(h, SO_ERR_CUDA, "so_sets_fused: the fused kernel does not fit on an SM");
     if (per_sm > 4) per_sm = 4;          // a few resident CTAs per SM saturate HBM; more only lengthens the grid barrier
     h->fused_grid = per_sm * h->num_sms;
@@ -583,19 +600,22 @@ static int fused_setup(so_handle* h) {
     return SO_OK;
 }
 
-extern "C" int so_sets_fused_result(so_handle* h, void* result_h, void* stream_) {
-    if (!h || !result_h) return SO_ERR_BAD_ARG;
-    if (!h->fused_part) return so_fail(h, SO_ERR_BAD_ARG, "so_sets_fused_result: so_sets_fused has not run");
-    DeviceGuard guard(h->device);
-    cudaStream_t stream = (cudaStream_t)stream_;
+static int fused_collect(so_handle* h, void* result_h) {
     const size_t bytes = SO_SETS_RESULT_BYTES(h->xchg_world);
-    SO_CUDA(h, cudaMemcpyAsync(h->fused_result_h, h->fused_result_d, bytes, cudaMemcpyDeviceToHost, stream));
-    SO_CUDA(h, cudaStreamSynchronize(stream));
     memcpy(result_h, h->fused_result_h, bytes);
     const long long status = reinterpret_cast<const long long*>(h->fused_result_h)[17 * h->xchg_world];
     if (status == SO_ERR_TIMEOUT)
         return so_fail(h, SO_ERR_TIMEOUT, "so_sets_fused: a rank never published its record (peer exchange timed out)");
     return SO_OK;
+}
+
+extern "C" int so_sets_fused_result(so_handle* h, void* result_h, void* stream_) {
+    if (!h || !result_h) return SO_ERR_BAD_ARG;
+    if (!h->fused_part) return so_fail(h, SO_ERR_BAD_ARG, "so_sets_fused_result: so_sets_fused has not run");
+    DeviceGuard guard(h->device);
+    SO_CUDA(h, cudaStreamSynchronize((cudaStream_t)stream_));
+    h->fused_inflight = 0;
+    return fused_collect(h, result_h);
 }
 
 extern "C" int so_sets_fused(so_handle* h, const double* Q_d, int n_gps, int64_t M, int64_t row0, const uint8_t* S_d,
@@ -617,12 +637,34 @@ extern "C" int so_sets_fused(so_handle* h, const double* Q_d, int n_gps, int64_t
     p.x = xchg_view(h);
     p.result = static_cast<unsigned char*>(h->fused_result_d);
     p.dbg = h->fused_dbg;
-    int grid = grid_for(h, M);
-    if (grid > h->fused_grid) grid = h->fused_grid;
-    void* args[] = {&p};
-    SO_CUDA(h, cudaLaunchCooperativeKernel((const void*)k_sets_fused, dim3(grid), dim3(kThreads), args, 0, stream));
-    if (result_h) return so_sets_fused_result(h, result_h, stream_);
-    return SO_OK;
+    volatile unsigned long long* stamp = reinterpret_cast<volatile unsigned long long*>(h->fused_result_h) + 17 * h->xchg_world + 1;
+    const unsigned long long expect = *stamp + 1;      // meaningful only when no earlier launch is still in flight (checked below)
+    const char* force = std::getenv("SO_SETS_SINGLE");  // "0": never the single-block kernel, "1": always (A/B measurements)
+    // measured (tools/time_sets.py): one CTA is latency-bound on its dependent mask -> Q loads (53 us at 40 k rows, 208 us at 250 k,
+    // against 31 us for the multi-block kernel), so it is an A/B switch only
+    const bool single = force && force[0] == '1' && M <= kSingleMaxRows;
+    if (single) {
+        k_sets_fused<true><<<1, kSingleThreads, 0, stream>>>(p);
+        SO_CHECK_LAUNCH(h, "k_sets_fused<single>");
+    } else {
+        int grid = grid_for(h, M);
+        if (grid > h->fused_grid) grid = h->fused_grid;
+        void* args[] = {&p};
+        SO_CUDA(h, cudaLaunchCooperativeKernel((const void*)k_sets_fused<false>, dim3(grid), dim3(kThreads), args, 0, stream));
+    }
+    if (!result_h) { h->fused_inflight += 1; return SO_OK; }
+    if (h->fused_inflight > 0) return so_sets_fused_result(h, result_h, stream_);
+    // poll the epoch stamp the kernel writes last into the mapped result; look at the stream now and then so that a failed
+    // launch or a faulting kernel surfaces as an error instead of a hang
+    for (unsigned long long spins = 1;; ++spins) {
+        if (*stamp == expect) break;
+        if ((spins & 0x3fffu) == 0) {
+            const cudaError_t q = cudaStreamQuery(stream);
+            if (q == cudaSuccess) { if (*stamp == expect) break; return so_sets_fused_result(h, result_h, stream_); }
+            if (q != cudaErrorNotReady) return so_fail(h, SO_ERR_CUDA, std::string("so_sets_fused: ") + cudaGetErrorString(q));
+        }
+    }
+    return fused_collect(h, result_h);
 }
 
 // Diagnostic: SM-clock stamps of block 0 at the phase boundaries of the last so_sets_fused (needs SO_FUSED_DEBUG_TIMES=1 in the

@@ -126,6 +126,12 @@ class DeviceEngine:
         panels = (8 * ((N + 7) // 8) + 31) // 32           # fit.cu: k_chol_panel per panel, k_chol_update between panels
         self.launches += 4 + 2 * panels - 1
 
+    def fit_like(self, gp: int, src_gp: int, Y):
+        """Fit of a GP that shares inputs, kernel and noise with the fitted ``src_gp``: copies its factorisation."""
+        Y = _np_f64(Y).reshape(-1)
+        self._check(self.lib.so_fit_like(self.handle, gp, src_gp, _hptr(Y), self._stream()), "so_fit_like")
+        self.launches += 1
+
     def fit_append(self, gp: int, x_new, y_new: float) -> bool:
         """One-point update of an existing fit (f4).  Returns False when the device asks for a full refit
         (buffers full, or the bordered matrix lost positive definiteness)."""

@@ -174,6 +174,7 @@ class _DeviceFits:
         self._data = [None] * len(gps)        # (X, Y, hyper key) the device fit was built from
         self.hypers = [None] * len(gps)
         self.refits = 0
+        self.copies = 0                       # refits served by copying a twin's factorisation (so_fit_like)
         self.appends = 0
         self.removals = 0
         self.incremental = os.environ.get("SAFEOPT_B200_INCREMENTAL_FIT", "1") != "0"
@@ -213,7 +214,20 @@ class _DeviceFits:
                     self.removals += 1
                     done = True
             if not done:
-                self.engine.fit(i, X, Y, hyper.kind, hyper.lengthscale, hyper.variance, hyper.noise_var)
+                # a GP fitted earlier in this pass (or still current) on the same inputs, kernel and noise shares K, L, L^-1
+                twin = None
+                if self.share and hasattr(self.engine, "fit_like"):
+                    for j in range(len(self.gps)):
+                        dj = self._data[j]
+                        if j != i and dj is not None and self._fp[j] is not None and dj[2] == key and dj[0].shape == X.shape \
+                                and np.array_equal(dj[0], X):
+                            twin = j
+                            break
+                if twin is not None:
+                    self.engine.fit_like(i, twin, Y)
+                    self.copies += 1
+                else:
+                    self.engine.fit(i, X, Y, hyper.kind, hyper.lengthscale, hyper.variance, hyper.noise_var)
                 self.refits += 1
             changed = True
             self._fp[i] = fp

@@ -45,6 +45,30 @@ def test_fit_matches_lapack(N, d, kind):
     eng.close()
 
 
+@pytest.mark.parametrize("N,d,kind", [(1, 1, 0), (31, 2, 1), (32, 2, 0), (33, 3, 0), (200, 2, 2), (256, 4, 0), (257, 4, 0), (511, 3, 0), (512, 6, 1)])
+def test_one_launch_cluster_fit_equals_kernel_per_panel_fit(N, d, kind, monkeypatch):
+    """k_fit_cluster (one launch, DMMA tiles, cluster barriers) against the kernel-per-panel factorisation and LAPACK."""
+    X, Y, ls, _ = _problem(N, d, 3 * N + d)
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("SO_FIT_CLUSTER", "16" if mode == "1" else "0")
+        eng = DeviceEngine(max_gps=1)
+        eng.fit(0, X, Y, kind, ls, 2.0, 0.05 ** 2)
+        res[mode] = eng.fit_export(0, N)
+        Xq = np.random.RandomState(5).uniform(-2, 2, (200, d))
+        mean, var = eng.empty((200,)), eng.empty((200,))
+        eng.posterior_rows(0, eng.to_device(Xq), 2.0, -np.inf, mean=mean, var=var)
+        res[mode] += (mean.cpu().numpy(), var.cpu().numpy())
+        eng.close()
+    gp = gpy_lite.GPRegression(X, Y[:, None], kernel=oracle_kernel(kind, d, 2.0, ls), noise_var=0.05 ** 2)
+    L, Linv, alpha, mean, var = res["1"]
+    assert np.abs(L - np.tril(gp.woodbury_chol)).max() < 1e-12
+    assert np.abs(Linv @ L - np.eye(N)).max() < 1e-11
+    assert np.abs(alpha - gp.woodbury_vector[:, 0]).max() < 1e-10 * max(1.0, np.abs(alpha).max())
+    assert np.abs(L - res["0"][0]).max() < 1e-12 and np.abs(Linv - res["0"][1]).max() < 1e-9 * np.abs(Linv).max()
+    assert np.abs(mean - res["0"][3]).max() < 1e-10 and np.abs(var - res["0"][4]).max() < 1e-10
+
+
 @pytest.mark.parametrize("N0,steps,d,kind", [(1, 20, 1, 0), (5, 30, 2, 0), (60, 12, 3, 1), (255, 4, 4, 0), (500, 3, 6, 2)])
 def test_fit_append_and_remove_match_refit(N0, steps, d, kind):
     """f4: one-point appends (bordered Cholesky, gp_opt.py:227) and removals (:267, :275) reproduce the
@@ -700,6 +724,7 @@ def test_config_c3_three_gps_properties():
            for i in range(3)]
     opt = sb.SafeOpt(gps, grid, w.fmin, beta=w.beta, threshold=w.threshold)
     opt.optimize()
+    assert (opt._fits.refits, opt._fits.copies) == (3, 2)      # one factorisation, two device-to-device copies (so_fit_like)
     Q, S, M = opt.Q, opt.S, opt.M
     assert Q.shape == (250000, 6)
     assert np.array_equal(S, np.all(Q[:, ::2] > 0.0, axis=1))

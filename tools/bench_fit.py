@@ -1,5 +1,6 @@
 """Times so_fit (K1: scale, Ky, blocked Cholesky + inverse, alpha, fragment packing) for a few training-set sizes."""
 import json, os, sys, time
+os.environ.setdefault("SO_FIT_VERBOSE", "1")
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
 import numpy as np
 import torch
@@ -7,7 +8,7 @@ from safeopt_b200.engine import DeviceEngine
 
 out = {}
 eng = DeviceEngine(max_gps=1)
-for N in (64, 256, 512, 1024, 2048):
+for N in (64, 128, 256, 512, 1024, 2048):
     rs = np.random.RandomState(N)
     X = rs.uniform(-2.5, 2.5, (N, 4)); Y = rs.randn(N)
     for _ in range(3):

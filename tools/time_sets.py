@@ -51,6 +51,6 @@ for M in [40_000, 250_000, 781_250, 6_250_000]:
     t2 = time.perf_counter()
     st = np.zeros(16, dtype=np.int64)
     eng.lib.so_debug_fused_times(eng.handle, st.ctypes.data)
-    d = np.diff(st[:13]) / 1.9
-    print("   launch call %.1f us, then wait %.1f us; in-kernel ns (1.9 GHz): scanA %d bar %d pubA %d waitA %d scanB %d bar %d pubB %d waitB %d scanC %d bar %d pubwaitC %d copy %d  total %d" % (
-        (t1 - t0) * 1e6, (t2 - t1) * 1e6, *d, (st[12] - st[0]) / 1.9))
+    d = np.diff(st[:13].astype(float))
+    print("   launch call %.1f us, then wait %.1f us; in-kernel ns (globaltimer; stamps of whichever block wrote last): scanA %d - %d pubA %d waitA %d scanB %d - %d pubB %d waitB %d scanC %d arrive %d pubwaitC %d copy %d  total %d" % (
+        (t1 - t0) * 1e6, (t2 - t1) * 1e6, *d, float(st[12] - st[0])))
