@@ -58,55 +58,47 @@ __device__ __forceinline__ double fc_kernel(int kind, double r2, double variance
     }
 }
 
-// Tiles are processed by single WARPS (each with its own pair of shared-memory tiles), so a CTA has eight tiles in flight and a
-// 16-CTA cluster 128 -- at N = 256 every phase is one round, and no block-level barrier sits between a tile's load and its use.
-// 32x32 tile <- global (rows r0.., cols c0.., leading dimension ld); optional transpose.  Lane l loads column l of each row.
-__device__ __forceinline__ void fc_load_tile(double (*s)[kFcLd], const double* __restrict__ G, int ld, int r0, int c0, bool transpose) {
+// Work units are 8x32 STRIPS of a 32x32 output tile, one per warp (each warp has its own shared-memory staging), so a CTA has
+// eight units in flight and a 16-CTA cluster 128: even at N = 128 (a handful of tiles per phase) most warps have work, and no
+// block-level barrier sits between a unit's loads and its use.  A unit is bounded by one L2 round trip for its operands.
+// rows x 32 block <- global (rows r0.., cols c0.., leading dimension ld); optional transpose.  Lane l loads column l of each row.
+template <int ROWS>
+__device__ __forceinline__ void fc_load(double (*s)[kFcLd], const double* __restrict__ G, int ld, int r0, int c0, bool transpose) {
     const int lane = threadIdx.x & 31;
-    double v[kFcB];
+    double v[ROWS];
 #pragma unroll
-    for (int i = 0; i < kFcB; ++i) v[i] = __ldcg(G + (size_t)(r0 + i) * ld + c0 + lane);
+    for (int i = 0; i < ROWS; ++i) v[i] = __ldcg(G + (size_t)(r0 + i) * ld + c0 + lane);
 #pragma unroll
-    for (int i = 0; i < kFcB; ++i) {
+    for (int i = 0; i < ROWS; ++i) {
         if (transpose) s[lane][i] = v[i]; else s[i][lane] = v[i];
     }
 }
 
-// C(32x32) = A(32x32, [i][k]) . B(32x32, [k][j]) on the fp64 tensor pipe, by ONE warp: sixteen 8x8 blocks, lane l ends with
-// C[8 bi + l/4][8 bj + 2 (l%4) + {0,1}] in c[bi][bj][0..1].
-__device__ __forceinline__ void fc_tile_mma(const double (*sA)[kFcLd], const double (*sB)[kFcLd], double (&c)[4][4][2]) {
+// C(8x32) = A(8x32, [i][k]) . B(32x32, [k][j]) on the fp64 tensor pipe, by one warp: four 8x8 blocks, lane l ends with
+// C[l/4][8 bj + 2 (l%4) + {0,1}] in c[bj][0..1].  `arow` = first row of the strip inside sA.
+__device__ __forceinline__ void fc_strip_mma(const double (*sA)[kFcLd], int arow, const double (*sB)[kFcLd], double (&c)[4][2]) {
     const int lane = threadIdx.x & 31;
 #pragma unroll
-    for (int bi = 0; bi < 4; ++bi)
-#pragma unroll
-        for (int bj = 0; bj < 4; ++bj) c[bi][bj][0] = c[bi][bj][1] = 0.0;
+    for (int bj = 0; bj < 4; ++bj) c[bj][0] = c[bj][1] = 0.0;
 #pragma unroll
     for (int ks = 0; ks < kFcB / 4; ++ks) {
-        double a[4], b[4];
+        const double a = sA[arow + (lane >> 2)][4 * ks + (lane & 3)];
 #pragma unroll
-        for (int bi = 0; bi < 4; ++bi) a[bi] = sA[8 * bi + (lane >> 2)][4 * ks + (lane & 3)];
-#pragma unroll
-        for (int bj = 0; bj < 4; ++bj) b[bj] = sB[4 * ks + (lane & 3)][8 * bj + (lane >> 2)];
-#pragma unroll
-        for (int bi = 0; bi < 4; ++bi)
-#pragma unroll
-            for (int bj = 0; bj < 4; ++bj) dmma884(c[bi][bj][0], c[bi][bj][1], a[bi], b[bj]);
+        for (int bj = 0; bj < 4; ++bj) dmma884(c[bj][0], c[bj][1], a, sB[4 * ks + (lane & 3)][8 * bj + (lane >> 2)]);
     }
 }
 
-// dst tile (global): mode 0 = C, 1 = -C (first touch: starts from zero), 2 = dst - C
-__device__ __forceinline__ void fc_store_tile(double* __restrict__ G, int ld, int r0, int c0, const double (&c)[4][4][2], int mode) {
+// dst strip (global rows r0 .. r0+8): mode 0 = C, 1 = -C (first touch: starts from zero), 2 = dst - C
+__device__ __forceinline__ void fc_store_strip(double* __restrict__ G, int ld, int r0, int c0, const double (&c)[4][2], int mode) {
     const int lane = threadIdx.x & 31;
 #pragma unroll
-    for (int bi = 0; bi < 4; ++bi)
-#pragma unroll
-        for (int bj = 0; bj < 4; ++bj) {
-            double2* p = reinterpret_cast<double2*>(G + (size_t)(r0 + 8 * bi + (lane >> 2)) * ld + c0 + 8 * bj + 2 * (lane & 3));
-            double2 v = make_double2(c[bi][bj][0], c[bi][bj][1]);
-            if (mode == 1) { v.x = -v.x; v.y = -v.y; }
-            else if (mode == 2) { const double2 o = __ldcg(p); v.x = o.x - v.x; v.y = o.y - v.y; }
-            *p = v;
-        }
+    for (int bj = 0; bj < 4; ++bj) {
+        double2* p = reinterpret_cast<double2*>(G + (size_t)(r0 + (lane >> 2)) * ld + c0 + 8 * bj + 2 * (lane & 3));
+        double2 v = make_double2(c[bj][0], c[bj][1]);
+        if (mode == 1) { v.x = -v.x; v.y = -v.y; }
+        else if (mode == 2) { const double2 o = __ldcg(p); v.x = o.x - v.x; v.y = o.y - v.y; }
+        *p = v;
+    }
 }
 
 __global__ void __launch_bounds__(kFcThreads, 1) k_fit_cluster(const __grid_constant__ FitClusterParams fp) {
@@ -192,20 +184,26 @@ __global__ void __launch_bounds__(kFcThreads, 1) k_fit_cluster(const __grid_cons
             // the other half of sCol is written next: its last readers passed this iteration's barrier already
         }
         __syncthreads();
-        // inv(L_PP): column c by thread c (forward substitution on e_c), two accumulators, reciprocals from the factorisation
-        if (tid < kFcB) {
-            const int c = tid;
+        // inv(L_PP): column c by the 8 threads 8c .. 8c+7 (forward substitution on e_c; thread `sub` keeps x_k for k = sub mod 8
+        // in registers and owns those terms of every dot product; three shuffles finish a row), reciprocals from the factorisation
+        {
+            const int c = tid >> 3, sub = tid & 7;
+            double x[4] = {0.0, 0.0, 0.0, 0.0};             // x[m] = x_{8 m + sub}
+#pragma unroll
             for (int i = 0; i < kFcB; ++i) {
-                double s0 = i == c ? 1.0 : 0.0, s1 = 0.0;
-                int k = c;
-                for (; k + 1 < i; k += 2) {
-                    s0 = fma(-sL[i][k], sI[k][c], s0);
-                    s1 = fma(-sL[i][k + 1], sI[k + 1][c], s1);
-                }
-                if (k < i) s0 = fma(-sL[i][k], sI[k][c], s0);
-                const double x = i >= c ? (s0 + s1) * sRinv[i] : 0.0;
-                sI[i][c] = x;
-                sIT[c][i] = x;
+                double part = 0.0;
+#pragma unroll
+                for (int m = 0; m < 4; ++m)
+                    if (8 * m < i) {                        // k = 8 m + sub < i (checked per thread below), k >= c holds because x_k = 0 for k < c
+                        const int k = 8 * m + sub;
+                        if (k < i) part = fma(-sL[i][k], x[m], part);
+                    }
+                part += __shfl_xor_sync(0xffffffffu, part, 1);
+                part += __shfl_xor_sync(0xffffffffu, part, 2);
+                part += __shfl_xor_sync(0xffffffffu, part, 4);
+                const double xi = i >= c ? ((i == c ? 1.0 : 0.0) + part) * sRinv[i] : 0.0;
+                if (sub == (i & 7)) x[i >> 3] = xi;
+                if (sub == 0) { sI[i][c] = xi; sIT[c][i] = xi; }
             }
         }
         __syncthreads();
@@ -218,25 +216,29 @@ __global__ void __launch_bounds__(kFcThreads, 1) k_fit_cluster(const __grid_cons
                 }
             }
         }
-        // ---- 2. panel solve and W[P, 0:p0]: 32x32 tiles, one per warp, round-robin over the cluster's warps
+        // ---- 2. panel solve and W[P, 0:p0]: 8x32 strips, one per warp, round-robin over the cluster's warps
         {
             const int n_rows = nblk - 1 - pi, n_cols = pi;
-            for (int t = gwarp; t < n_rows + n_cols; t += gwarps) {
-                double c[4][4][2];
-                if (t < n_rows) {
-                    // L[rb,P] = A[rb,P] inv(L_PP)^T : A tile [i][k], B[k][j] = inv[j][k]
-                    const int r0 = (pi + 1 + t) * kFcB;
-                    fc_load_tile(wA, fp.K, ld, r0, p0, false);
+            for (int u = gwarp; u < 4 * n_rows + n_cols; u += gwarps) {
+                if (u < 4 * n_rows) {
+                    // L[rb,P] = A[rb,P] inv(L_PP)^T : A strip [i][k], B[k][j] = inv[j][k]
+                    double c[4][2];
+                    const int r0 = (pi + 1 + (u >> 2)) * kFcB + 8 * (u & 3);
+                    fc_load<8>(wA, fp.K, ld, r0, p0, false);
                     __syncwarp();
-                    fc_tile_mma(wA, sIT, c);
-                    fc_store_tile(fp.K, ld, r0, p0, c, 0);
+                    fc_strip_mma(wA, 0, sIT, c);
+                    fc_store_strip(fp.K, ld, r0, p0, c, 0);
                 } else {
-                    // W[P,cb] = inv(L_PP) W[P,cb]
-                    const int c0 = (t - n_rows) * kFcB;
-                    fc_load_tile(wB, fp.W, ld, p0, c0, false);
+                    // W[P,cb] = inv(L_PP) W[P,cb], in place: the whole tile by ONE warp (every strip needs all rows of the old tile)
+                    const int c0 = (u - 4 * n_rows) * kFcB;
+                    fc_load<kFcB>(wB, fp.W, ld, p0, c0, false);
                     __syncwarp();
-                    fc_tile_mma(sI, wB, c);
-                    fc_store_tile(fp.W, ld, p0, c0, c, 0);
+#pragma unroll
+                    for (int st = 0; st < 4; ++st) {
+                        double c[4][2];
+                        fc_strip_mma(sI, 8 * st, wB, c);
+                        fc_store_strip(fp.W, ld, p0 + 8 * st, c0, c, 0);
+                    }
                 }
                 __syncwarp();
             }
@@ -247,28 +249,29 @@ __global__ void __launch_bounds__(kFcThreads, 1) k_fit_cluster(const __grid_cons
             const int m = nblk - 1 - pi;                // row blocks below the panel
             const int per_row = pi + 1;                 // W tiles per row block
             const int n_a = m * (m + 1) / 2, n_w = m * per_row;
-            for (int t = gwarp; t < n_a + n_w; t += gwarps) {
-                double c[4][4][2];
+            for (int u = gwarp; u < 4 * (n_a + n_w); u += gwarps) {
+                const int t = u >> 2, st = u & 3;
+                double c[4][2];
                 if (t < n_a) {
                     int ii = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
                     while ((ii + 1) * (ii + 2) / 2 <= t) ++ii;
                     while (ii * (ii + 1) / 2 > t) --ii;
                     const int kk = t - ii * (ii + 1) / 2;
-                    const int r0 = (pi + 1 + ii) * kFcB, c0 = (pi + 1 + kk) * kFcB;
-                    fc_load_tile(wA, fp.K, ld, r0, p0, false);
-                    fc_load_tile(wB, fp.K, ld, c0, p0, true);             // B[k][j] = L[c0 + j][p0 + k]
+                    const int r0 = (pi + 1 + ii) * kFcB + 8 * st, c0 = (pi + 1 + kk) * kFcB;
+                    fc_load<8>(wA, fp.K, ld, r0, p0, false);
+                    fc_load<kFcB>(wB, fp.K, ld, c0, p0, true);            // B[k][j] = L[c0 + j][p0 + k]
                     __syncwarp();
-                    fc_tile_mma(wA, wB, c);
-                    fc_store_tile(fp.K, ld, r0, c0, c, 2);
+                    fc_strip_mma(wA, 0, wB, c);
+                    fc_store_strip(fp.K, ld, r0, c0, c, 2);
                 } else {
-                    const int u = t - n_a;
-                    const int rb = u / per_row, cb = u - rb * per_row;
-                    const int r0 = (pi + 1 + rb) * kFcB, c0 = cb * kFcB;
-                    fc_load_tile(wA, fp.K, ld, r0, p0, false);
-                    fc_load_tile(wB, fp.W, ld, p0, c0, false);
+                    const int q = t - n_a;
+                    const int rb = q / per_row, cb = q - rb * per_row;
+                    const int r0 = (pi + 1 + rb) * kFcB + 8 * st, c0 = cb * kFcB;
+                    fc_load<8>(wA, fp.K, ld, r0, p0, false);
+                    fc_load<kFcB>(wB, fp.W, ld, p0, c0, false);
                     __syncwarp();
-                    fc_tile_mma(wA, wB, c);
-                    fc_store_tile(fp.W, ld, r0, c0, c, cb == pi ? 1 : 2);  // W[R,P] starts from zero
+                    fc_strip_mma(wA, 0, wB, c);
+                    fc_store_strip(fp.W, ld, r0, c0, c, cb == pi ? 1 : 2);  // W[R,P] starts from zero
                 }
                 __syncwarp();
             }

@@ -898,14 +898,21 @@ extern "C" int so_posterior_grid_f32(so_handle* h, int n, const int* gps_h, int6
         }
         const int Npad = 8 * g.NB;
         mq.PfastT = g.f32_PfT; mq.Pslow = g.P2 + (size_t)F * Npad; mq.n_out = n; mq.N = g.N; mq.ldp = Npad;
-        mq.TR = Npad <= 128 ? 128 : 64; mq.split = 128 / mq.TR;
+        mq.TR = g.N <= 128 ? 128 : 64; mq.SL = kMeanThreads / mq.TR;
         mq.Fpad = g.f32_Fpad; mq.fast_rows = F; mq.row0 = row0; mq.M = M;
         mq.s_lo = row0 / F; mq.s_hi = (row0 + M - 1) / F + 1;
         const int64_t gx = (F + mq.TR - 1) / mq.TR;
-        int64_t gy = ((int64_t)h->num_sms + gx - 1) / gx;                 // about one CTA per SM: each keeps its slice in L1
-        if (gy > mq.s_hi - mq.s_lo) gy = mq.s_hi - mq.s_lo;
+        int64_t gy = ((int64_t)h->num_sms + gx - 1) / gx;                 // one CTA per SM: each keeps its slice of the fast table in shared memory
+        const int64_t groups = (mq.s_hi - mq.s_lo + mq.SL - 1) / mq.SL;
+        if (gy > groups) gy = groups;
         if (gy > 65535) gy = 65535;
-        k_mean_grid<<<dim3((unsigned)gx, (unsigned)gy), 128, 0, (cudaStream_t)stream_>>>(mq);
+        const size_t msm = mean_smem_bytes(g.N, mq.TR, mq.SL, n);
+        static int mean_configured_for = -1;
+        if (mean_configured_for != h->device) {
+            SO_CUDA(h, cudaFuncSetAttribute(k_mean_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
+            mean_configured_for = h->device;
+        }
+        k_mean_grid<<<dim3((unsigned)gx, (unsigned)gy), kMeanThreads, msm, (cudaStream_t)stream_>>>(mq);
         SO_CHECK_LAUNCH(h, "k_mean_grid");
     }
     k_posterior_f32<<<fp.tpb * fp.lanes, kF32Threads, f32_smem(fp.Np, fp.stages, fp.a_resident != 0).total, (cudaStream_t)stream_>>>(fp);

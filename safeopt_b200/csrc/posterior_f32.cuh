@@ -339,53 +339,59 @@ __global__ void k_f32_pack_b(const double* __restrict__ Linv, int ld, const doub
 
 // ---------------------------------------------------------------- fp64 mean of the fp32 mode
 // mean_g(row) = sum_n Pfast[f][n] (Pslow[s][n] alpha_g[n]), f = row % F, s = row / F: N multiply-adds per row and GP on the
-// fp64 pipe.  CTA (jt, y) owns the rows [TR jt, TR jt + TR) of every slow block s = s_lo + y, s_lo + y + gridDim.y, ...: its
-// slice of the TRANSPOSED fast table (n-major, so that the TR threads of a CTA read consecutive doubles) is TR x N x 8 bytes
-// <= 128 KB and stays in L1 for the whole loop over s (the kernel uses no shared memory beyond the w_g vectors).
+// fp64 pipe.  CTA (jt, y) owns the rows [TR jt, TR jt + TR) of every slow block: its slice of the TRANSPOSED fast table
+// (n-major, so that consecutive threads read consecutive doubles) is TR x N x 8 bytes <= 128 KB and is loaded into shared
+// memory ONCE; the 512 threads are TR rows x SL "slow lanes", each lane group working on its own slow index with its own
+// w_g = Pslow[s] .* alpha_g vectors.  Shared-memory bound: one 8-byte read per multiply-add group (conflict-free rows,
+// broadcast w) -- about 1 k cycles per 128 rows x 128 training points.
+constexpr int kMeanThreads = 512;
 struct MeanParams {
     const double* PfastT;       // [n][Fpad]
     const double* Pslow;        // [s][ldp]
     const double* alpha[kMaxOut];
     double* mean[kMaxOut];
-    int n_out, N, ldp, TR, split;
+    int n_out, N, ldp, TR, SL;
     int64_t Fpad, fast_rows, s_lo, s_hi, row0, M;
 };
+__host__ __device__ inline size_t mean_smem_bytes(int N, int TR, int SL, int n_out) {
+    return ((size_t)N * TR + (size_t)SL * n_out * N) * sizeof(double);
+}
 
-__global__ void __launch_bounds__(128) k_mean_grid(const __grid_constant__ MeanParams mp) {
-    __shared__ double sW[kMaxOut][kF32MaxNp];
-    __shared__ double sPart[kMaxOut][128];
-    const int TR = mp.TR, split = mp.split, N = mp.N;
-    const int trow = threadIdx.x % TR, part = threadIdx.x / TR;
-    const int64_t frow = (int64_t)blockIdx.x * TR + trow;
-    const int nper = (N + split - 1) / split;
-    const int n0 = part * nper, n1 = n0 + nper < N ? n0 + nper : N;
-    const double* col = mp.PfastT + (frow < mp.Fpad ? frow : 0);
-    for (int64_t s = mp.s_lo + blockIdx.y; s < mp.s_hi; s += gridDim.y) {
-        __syncthreads();                                    // the previous iteration's readers of sW / sPart are done
-        for (int i = threadIdx.x; i < mp.n_out * N; i += 128) {
-            const int o = i / N, n = i - o * N;
-            sW[o][n] = mp.Pslow[(size_t)s * mp.ldp + n] * mp.alpha[o][n];
-        }
+__global__ void __launch_bounds__(kMeanThreads, 1) k_mean_grid(const __grid_constant__ MeanParams mp) {
+    extern __shared__ __align__(16) unsigned char mean_smem[];
+    const int TR = mp.TR, SL = mp.SL, N = mp.N, n_out = mp.n_out;
+    double* sT = reinterpret_cast<double*>(mean_smem);              // [n][TR]
+    double* sW = sT + (size_t)N * TR;                               // [sl][o][n]
+    const int trow = threadIdx.x % TR, sl = threadIdx.x / TR;
+    const int64_t f0 = (int64_t)blockIdx.x * TR;
+    for (int e = threadIdx.x; e < N * TR; e += kMeanThreads) {
+        const int n = e / TR, r = e - n * TR;
+        sT[e] = f0 + r < mp.Fpad ? mp.PfastT[(size_t)n * mp.Fpad + f0 + r] : 0.0;
+    }
+    const int64_t frow = f0 + trow;
+    for (int64_t sb = mp.s_lo + (int64_t)blockIdx.y * SL; sb < mp.s_hi; sb += (int64_t)gridDim.y * SL) {
+        __syncthreads();                                    // the tile is loaded / the previous iteration's readers of sW are done
+        const int64_t s = sb + sl;
+        if (s < mp.s_hi)
+            for (int i = trow; i < n_out * N; i += TR) {
+                const int o = i / N, n = i - o * N;
+                sW[((size_t)sl * n_out + o) * N + n] = mp.Pslow[(size_t)s * mp.ldp + n] * mp.alpha[o][n];
+            }
         __syncthreads();
+        if (s >= mp.s_hi) continue;
+        const double* w = sW + (size_t)sl * n_out * N;
         double acc[kMaxOut] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll 4
-        for (int n = n0; n < n1; ++n) {
-            const double k = __ldg(col + (size_t)n * mp.Fpad);
-            acc[0] = fma(k, sW[0][n], acc[0]);
-            if (mp.n_out > 1) acc[1] = fma(k, sW[1][n], acc[1]);
-            if (mp.n_out > 2) acc[2] = fma(k, sW[2][n], acc[2]);
-            if (mp.n_out > 3) acc[3] = fma(k, sW[3][n], acc[3]);
-        }
-        if (split > 1) {
-            for (int o = 0; o < mp.n_out; ++o) sPart[o][threadIdx.x] = acc[o];
-            __syncthreads();
-            if (part == 0)
-                for (int o = 0; o < mp.n_out; ++o)
-                    for (int q = 1; q < split; ++q) acc[o] += sPart[o][q * TR + trow];
+        for (int n = 0; n < N; ++n) {
+            const double k = sT[(size_t)n * TR + trow];
+            acc[0] = fma(k, w[n], acc[0]);
+            if (n_out > 1) acc[1] = fma(k, w[N + n], acc[1]);
+            if (n_out > 2) acc[2] = fma(k, w[2 * N + n], acc[2]);
+            if (n_out > 3) acc[3] = fma(k, w[3 * N + n], acc[3]);
         }
         const int64_t row = s * mp.fast_rows + frow - mp.row0;
-        if (part == 0 && frow < mp.fast_rows && row >= 0 && row < mp.M)
-            for (int o = 0; o < mp.n_out; ++o) mp.mean[o][row] = acc[o];
+        if (frow < mp.fast_rows && row >= 0 && row < mp.M)
+            for (int o = 0; o < n_out; ++o) mp.mean[o][row] = acc[o];
     }
 }
 

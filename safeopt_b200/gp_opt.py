@@ -299,12 +299,19 @@ class SafeOpt(GaussianProcessOptimization):
         parameter_set = np.asarray(parameter_set, dtype=float)
         # SAFEOPT_B200_GRID_FAST_PATH=0 forces the explicit-rows kernels (tests / A-B measurements)
         axes = None
-        if self.num_contexts == 0 and os.environ.get("SAFEOPT_B200_GRID_FAST_PATH", "1") != "0":
+        if os.environ.get("SAFEOPT_B200_GRID_FAST_PATH", "1") != "0" and parameter_set.shape[1] + self.num_contexts <= 6:
             axes = detect_grid(parameter_set)
+        self._param_axes = axes
+        self._context_on_device = None
         if self.num_contexts > 0:
             zeros = np.zeros((parameter_set.shape[0], self.num_contexts), dtype=parameter_set.dtype)
             self.inputs = np.hstack((parameter_set, zeros))
             self.parameter_set = self.inputs[:, :-self.num_contexts]
+            if axes is not None:
+                # contexts are constant over the candidates (gp_opt.py:424-451): to the device they are grid axes with ONE
+                # point each, appended after the parameter axes (the row order does not change), so a context problem keeps
+                # the separable-table kernels -- k_ctx(c, c_n) ends up folded into the per-training-point table entries
+                axes = list(axes) + [np.zeros(1) for _ in range(self.num_contexts)]
         elif axes is not None:
             # a verified product grid: bounds and num_samples (gp_opt.py:414-422) follow from the axes, without
             # the per-column np.unique sorts over all M rows
@@ -337,6 +344,7 @@ class SafeOpt(GaussianProcessOptimization):
         m_local = self._row1 - self._row0
         self._grid_axes = axes
         self._rows_d = None
+        self._grid_state = {}                 # GP index -> which grid tables are current (see _ensure_grid_tables)
         if self._grid_axes is not None:
             self._engine.define_grid(self._grid_axes)
         else:
@@ -353,7 +361,6 @@ class SafeOpt(GaussianProcessOptimization):
         self._n_cand_d = eng.zeros((1,), "i64")
         self._cand_key_d = None
         self._cand_row_d = None
-        self._grid_state = {}                 # GP index -> which grid tables are current (see _ensure_grid_tables)
         self._grid_strides = None
         self._thr_cache = None
         self._G_rows: List[int] = []          # global rows currently in the expander set
@@ -408,7 +415,14 @@ class SafeOpt(GaussianProcessOptimization):
                 raise ValueError("Need to provide value for context.")
             self.inputs[:, -self.num_contexts:] = context
             ctx = np.atleast_1d(np.asarray(context, dtype=float)).ravel()
-            self._rows_d[:, -self.num_contexts:] = self._engine.to_device(ctx)
+            if self._rows_d is not None:
+                self._rows_d[:, -self.num_contexts:] = self._engine.to_device(ctx)
+            if self._grid_axes is not None and (self._context_on_device is None or not np.array_equal(ctx, self._context_on_device)):
+                # a new context = new one-point axes: the grid description and every GP's tables are rebuilt
+                self._grid_axes = list(self._param_axes) + [np.array([c], dtype=float) for c in ctx]
+                self._engine.define_grid(self._grid_axes)
+                self._grid_state.clear()
+                self._context_on_device = ctx.copy()
 
     # ------------------------------------------------------------------ host views of device state
     def _gather_rows(self, local: np.ndarray) -> np.ndarray:

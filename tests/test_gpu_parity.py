@@ -452,6 +452,9 @@ def test_contexts_match_golden(name):
     opt = sb.SafeOpt(gp, g["pset"], float(g["fmin"]), num_contexts=1, beta=float(g["beta"]), threshold=float(g["threshold"]),
                      lipschitz=None if lip.size == 0 else float(lip[0]))
     n_rows = int(g["n_rows"])
+    # the parameter set is a product grid: contexts ride along as one-point axes and the separable-table grid kernels are
+    # used (no M x d candidate array on the device)
+    assert opt._grid_axes is not None and len(opt._grid_axes) == 2 and opt._rows_d is None
     with pytest.raises(ValueError):
         opt.optimize()                                   # a context is required (gp_opt.py:448-450)
     for k in range(2):
@@ -462,7 +465,7 @@ def test_contexts_match_golden(name):
         assert np.array_equal(opt.M, unpack_mask(g["M%d" % k], n_rows))
         assert np.array_equal(opt.G, unpack_mask(g["G%d" % k], n_rows))
         assert np.array_equal(x, g["x%d" % k]) and x.shape == (1,)
-        assert np.array_equal(opt.context, ctx)
+        assert np.array_equal(opt.context, ctx) and opt._grid_axes[1][0] == ctx[0] and opt._rows_d is None
         mx = opt.get_maximum(context=ctx)
         assert np.array_equal(mx[0], g["maxx%d" % k]) and abs(mx[1] - float(g["maxv%d" % k])) < 1e-9
     opt.add_new_data_point(x, np.array([[0.5]]), context=ctx)
