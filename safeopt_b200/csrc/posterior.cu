@@ -898,15 +898,15 @@ extern "C" int so_posterior_grid_f32(so_handle* h, int n, const int* gps_h, int6
         }
         const int Npad = 8 * g.NB;
         mq.PfastT = g.f32_PfT; mq.Pslow = g.P2 + (size_t)F * Npad; mq.n_out = n; mq.N = g.N; mq.ldp = Npad;
-        mq.TR = g.N <= 128 ? 128 : 64; mq.SL = kMeanThreads / mq.TR;
+        mq.TR = g.N <= 128 ? 128 : 64; mq.SB = kMeanCols / n; mq.N4 = (g.N + 3) / 4 * 4;
         mq.Fpad = g.f32_Fpad; mq.fast_rows = F; mq.row0 = row0; mq.M = M;
         mq.s_lo = row0 / F; mq.s_hi = (row0 + M - 1) / F + 1;
         const int64_t gx = (F + mq.TR - 1) / mq.TR;
         int64_t gy = ((int64_t)h->num_sms + gx - 1) / gx;                 // one CTA per SM: each keeps its slice of the fast table in shared memory
-        const int64_t groups = (mq.s_hi - mq.s_lo + mq.SL - 1) / mq.SL;
+        const int64_t groups = (mq.s_hi - mq.s_lo + mq.SB - 1) / mq.SB;
         if (gy > groups) gy = groups;
         if (gy > 65535) gy = 65535;
-        const size_t msm = mean_smem_bytes(g.N, mq.TR, mq.SL, n);
+        const size_t msm = mean_smem_bytes(mq.N4, mq.TR);
         static int mean_configured_for = -1;
         if (mean_configured_for != h->device) {
             SO_CUDA(h, cudaFuncSetAttribute(k_mean_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
@@ -915,7 +915,23 @@ extern "C" int so_posterior_grid_f32(so_handle* h, int n, const int* gps_h, int6
         k_mean_grid<<<dim3((unsigned)gx, (unsigned)gy), kMeanThreads, msm, (cudaStream_t)stream_>>>(mq);
         SO_CHECK_LAUNCH(h, "k_mean_grid");
     }
-    k_posterior_f32<<<fp.tpb * fp.lanes, kF32Threads, f32_smem(fp.Np, fp.stages, fp.a_resident != 0).total, (cudaStream_t)stream_>>>(fp);
+    // the tpb CTAs that share a slow index form a cluster and multicast the B slabs (1 / tpb of the L2 -> SM operand traffic,
+    // which bounds the kernel: 189 MB per launch at config 3 without it); SO_F32_MULTICAST=0 switches it off (A/B measurements)
+    const char* mc_env = std::getenv("SO_F32_MULTICAST");
+    fp.mc = (fp.a_resident && (fp.tpb == 2 || fp.tpb == 4 || fp.tpb == 8) && !(mc_env && mc_env[0] == '0')) ? fp.tpb : 1;
+    const size_t smem_bytes = f32_smem(fp.Np, fp.stages, fp.a_resident != 0).total;
+    if (fp.mc > 1) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(fp.tpb * fp.lanes); cfg.blockDim = dim3(kF32Threads); cfg.dynamicSmemBytes = smem_bytes;
+        cfg.stream = (cudaStream_t)stream_;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = fp.mc; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        SO_CUDA(h, cudaLaunchKernelEx(&cfg, k_posterior_f32, fp));
+        return SO_OK;
+    }
+    k_posterior_f32<<<fp.tpb * fp.lanes, kF32Threads, smem_bytes, (cudaStream_t)stream_>>>(fp);
     SO_CHECK_LAUNCH(h, "k_posterior_f32");
     return SO_OK;
 }

@@ -54,6 +54,8 @@ struct F32Params {
     int tpb, Np, nslab, stages;
     int lanes;                      // CTA b owns the fast tile j = b % tpb for the slow indices s_lo + b / tpb, + lanes, + 2 lanes, ...
     int a_resident;                 // the CTA's A operand (its fast tile, all slabs, hi + lo) stays in shared memory for the whole launch
+    int mc;                         // > 1: the tpb CTAs that share a slow index form a cluster of this size and MULTICAST the B slabs:
+                                    // each fetches 1 / mc of a slab from L2 and TMA delivers it to all of them
     const double* mean_in[kMaxOut]; // per output: the fp64 means of these rows (written by k_mean_grid just before)
 };
 
@@ -105,6 +107,25 @@ __device__ __forceinline__ unsigned umma_idesc_tf32(int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(n >> 3) << 17) | ((unsigned)(kF32TileRows >> 4) << 24);
 }
 
+// Multicast variants (thread-block cluster): the bulk copy lands at the same shared-memory offset of every CTA in `mask` and
+// completes bytes on the mbarrier at the same offset in each of them; the commit arrives on that barrier in every CTA of `mask`.
+__device__ __forceinline__ void tma_bulk_g2s_mc(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar,
+                                                unsigned short mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;\n" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(unsigned long long* bar, unsigned short mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void f32_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+
 __device__ __forceinline__ void mbar_arrive_plain(unsigned long long* bar) {
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -136,8 +157,11 @@ __global__ void __launch_bounds__(kF32Threads, 1) k_posterior_f32(const __grid_c
     const int j = blockIdx.x % fp.tpb;                   // this CTA's fast tile
     const int64_t s_first = fp.s_lo + blockIdx.x / fp.tpb;
 
+    const int mc = fp.mc;
+    const unsigned short mc_mask = (unsigned short)((1u << mc) - 1u);
     if (threadIdx.x == 0) {
-        for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        // with multicast a stage is refilled by every CTA of the cluster, so it is free only when all of them have released it
+        for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], mc > 1 ? mc : 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
         mbar_init(a_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -145,6 +169,7 @@ __global__ void __launch_bounds__(kF32Threads, 1) k_posterior_f32(const __grid_c
     if (warp == 1) tmem_alloc_512(tmem_slot);
     tc_fence_before();
     __syncthreads();
+    if (mc > 1) f32_cluster_sync();                      // every CTA's barriers exist before a peer's copy or commit can reach them
     tc_fence_after();
     const unsigned tmem_base = *tmem_slot;
     const unsigned char* a_src = fp.Aop + (size_t)j * nslab * kF32ASlabBytes;
@@ -170,7 +195,12 @@ __global__ void __launch_bounds__(kF32Threads, 1) k_posterior_f32(const __grid_c
                         tma_bulk_g2s(dst, a_src + (size_t)k * kF32ASlabBytes, (unsigned)kF32ASlabBytes, &full[st]);
                         dst += kF32ASlabBytes;
                     }
-                    tma_bulk_g2s(dst, b_src + f32_b_slab_offset(Np, k), bbytes, &full[st]);
+                    if (mc > 1) {
+                        const unsigned part = bbytes / (unsigned)mc;          // 256 Nk bytes, Nk a multiple of 32: divisible by 2, 4, 8
+                        tma_bulk_g2s_mc(dst + (size_t)j * part, b_src + f32_b_slab_offset(Np, k) + (size_t)j * part, part, &full[st], mc_mask);
+                    } else {
+                        tma_bulk_g2s(dst, b_src + f32_b_slab_offset(Np, k), bbytes, &full[st]);
+                    }
                     if (++st == stages) { st = 0; ph ^= 1u; }
                 }
             }
@@ -208,7 +238,8 @@ __global__ void __launch_bounds__(kF32Threads, 1) k_posterior_f32(const __grid_c
                         tc_mma_tf32(d, a_hi, b_lo, idesc, 1u);
                         tc_mma_tf32(d, a_hi, b_hi, idesc, 1u);
                     }
-                    tc_commit(&empty[st]);                   // the slab may be refilled once these MMAs have read it
+                    if (mc > 1) tc_commit_mc(&empty[st], mc_mask);       // tell every CTA of the cluster: this one has read the slab
+                    else tc_commit(&empty[st]);              // the slab may be refilled once these MMAs have read it
                     if (++st == stages) { st = 0; ph ^= 1u; }
                 }
                 tc_commit(&acc_full[acc]);
@@ -271,6 +302,7 @@ __global__ void __launch_bounds__(kF32Threads, 1) k_posterior_f32(const __grid_c
     }
     tc_fence_before();
     __syncthreads();
+    if (mc > 1) f32_cluster_sync();                      // no CTA leaves while a peer's multicast or commit may still target it
     if (warp == 1) tmem_dealloc_512(tmem_base);
 }
 
@@ -338,60 +370,76 @@ __global__ void k_f32_pack_b(const double* __restrict__ Linv, int ld, const doub
 }
 
 // ---------------------------------------------------------------- fp64 mean of the fp32 mode
-// mean_g(row) = sum_n Pfast[f][n] (Pslow[s][n] alpha_g[n]), f = row % F, s = row / F: N multiply-adds per row and GP on the
-// fp64 pipe.  CTA (jt, y) owns the rows [TR jt, TR jt + TR) of every slow block: its slice of the TRANSPOSED fast table
-// (n-major, so that consecutive threads read consecutive doubles) is TR x N x 8 bytes <= 128 KB and is loaded into shared
-// memory ONCE; the 512 threads are TR rows x SL "slow lanes", each lane group working on its own slow index with its own
-// w_g = Pslow[s] .* alpha_g vectors.  Shared-memory bound: one 8-byte read per multiply-add group (conflict-free rows,
-// broadcast w) -- about 1 k cycles per 128 rows x 128 training points.
-constexpr int kMeanThreads = 512;
+// mean_g(row) = sum_n Pfast[f][n] (Pslow[s][n] alpha_g[n]), f = row % F, s = row / F: N multiply-adds per row and GP.  For a fast
+// tile (TR rows) and a batch of SB slow indices this is a small GEMM, C[TR x (SB G)] = Pfast_tile[TR x N] . W[N x (SB G)] with
+// W[n][(s, g)] = Pslow[s][n] alpha_g[n], and runs on the fp64 tensor pipe (DMMA m8n8k4).  CTA (jt, y) owns the rows
+// [TR jt, TR jt + TR) of every slow block: its slice of the fast table (TR x N x 8 bytes <= 128 KB) is loaded ONCE into shared
+// memory, in A-fragment order ([n / 4][row][n % 4]: a warp's fragment load is 32 consecutive doubles), and stays for the whole
+// loop over the slow-index batches; W is rebuilt per batch in B-fragment order.  Each warp computes 2 row blocks x 2 column
+// blocks per k-step: four 256-byte shared-memory reads feed four DMMAs.
+constexpr int kMeanThreads = 256;
+constexpr int kMeanCols = 16;           // (slow index, GP) columns per batch: two 8-wide column blocks
 struct MeanParams {
     const double* PfastT;       // [n][Fpad]
     const double* Pslow;        // [s][ldp]
     const double* alpha[kMaxOut];
     double* mean[kMaxOut];
-    int n_out, N, ldp, TR, SL;
+    int n_out, N, N4, ldp, TR, SB;
     int64_t Fpad, fast_rows, s_lo, s_hi, row0, M;
 };
-__host__ __device__ inline size_t mean_smem_bytes(int N, int TR, int SL, int n_out) {
-    return ((size_t)N * TR + (size_t)SL * n_out * N) * sizeof(double);
+__host__ __device__ inline size_t mean_smem_bytes(int N4, int TR) {
+    return ((size_t)N4 * TR + (size_t)N4 * kMeanCols) * sizeof(double);
 }
 
 __global__ void __launch_bounds__(kMeanThreads, 1) k_mean_grid(const __grid_constant__ MeanParams mp) {
     extern __shared__ __align__(16) unsigned char mean_smem[];
-    const int TR = mp.TR, SL = mp.SL, N = mp.N, n_out = mp.n_out;
-    double* sT = reinterpret_cast<double*>(mean_smem);              // [n][TR]
-    double* sW = sT + (size_t)N * TR;                               // [sl][o][n]
-    const int trow = threadIdx.x % TR, sl = threadIdx.x / TR;
+    const int TR = mp.TR, SB = mp.SB, N = mp.N, N4 = mp.N4, n_out = mp.n_out;
+    double* sT = reinterpret_cast<double*>(mean_smem);              // [n / 4][TR][n % 4]
+    double* sW = sT + (size_t)N4 * TR;                              // [n / 4][kMeanCols][n % 4]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t f0 = (int64_t)blockIdx.x * TR;
-    for (int e = threadIdx.x; e < N * TR; e += kMeanThreads) {
-        const int n = e / TR, r = e - n * TR;
-        sT[e] = f0 + r < mp.Fpad ? mp.PfastT[(size_t)n * mp.Fpad + f0 + r] : 0.0;
+    for (int e = threadIdx.x; e < N4 * TR; e += kMeanThreads) {
+        const int n = e / TR, r = e - n * TR;                       // consecutive threads read consecutive rows of the transposed table
+        const double v = (n < N && f0 + r < mp.Fpad) ? mp.PfastT[(size_t)n * mp.Fpad + f0 + r] : 0.0;
+        sT[((size_t)(n >> 2) * TR + r) * 4 + (n & 3)] = v;
     }
-    const int64_t frow = f0 + trow;
-    for (int64_t sb = mp.s_lo + (int64_t)blockIdx.y * SL; sb < mp.s_hi; sb += (int64_t)gridDim.y * SL) {
-        __syncthreads();                                    // the tile is loaded / the previous iteration's readers of sW are done
-        const int64_t s = sb + sl;
-        if (s < mp.s_hi)
-            for (int i = trow; i < n_out * N; i += TR) {
-                const int o = i / N, n = i - o * N;
-                sW[((size_t)sl * n_out + o) * N + n] = mp.Pslow[(size_t)s * mp.ldp + n] * mp.alpha[o][n];
-            }
-        __syncthreads();
-        if (s >= mp.s_hi) continue;
-        const double* w = sW + (size_t)sl * n_out * N;
-        double acc[kMaxOut] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll 4
-        for (int n = 0; n < N; ++n) {
-            const double k = sT[(size_t)n * TR + trow];
-            acc[0] = fma(k, w[n], acc[0]);
-            if (n_out > 1) acc[1] = fma(k, w[N + n], acc[1]);
-            if (n_out > 2) acc[2] = fma(k, w[2 * N + n], acc[2]);
-            if (n_out > 3) acc[3] = fma(k, w[3 * N + n], acc[3]);
+    const int nrb = TR / 8;                                         // row blocks of the tile: 16 or 8
+    for (int64_t sb = mp.s_lo + (int64_t)blockIdx.y * SB; sb < mp.s_hi; sb += (int64_t)gridDim.y * SB) {
+        __syncthreads();                                            // the tile is loaded / the previous batch's readers of sW are done
+        for (int e = threadIdx.x; e < N4 * kMeanCols; e += kMeanThreads) {
+            const int n = e / kMeanCols, col = e - n * kMeanCols;
+            const int si = col / n_out, o = col - si * n_out;
+            double v = 0.0;
+            if (n < N && si < SB && sb + si < mp.s_hi) v = mp.Pslow[(size_t)(sb + si) * mp.ldp + n] * mp.alpha[o][n];
+            sW[((size_t)(n >> 2) * kMeanCols + col) * 4 + (n & 3)] = v;
         }
-        const int64_t row = s * mp.fast_rows + frow - mp.row0;
-        if (frow < mp.fast_rows && row >= 0 && row < mp.M)
-            for (int o = 0; o < n_out; ++o) mp.mean[o][row] = acc[o];
+        __syncthreads();
+        for (int rb0 = 2 * warp; rb0 < nrb; rb0 += 2 * (kMeanThreads / 32)) {
+            double c[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
+            const double* ap = sT + (size_t)rb0 * 32 + lane;            // fragment of row block rb at k-step ks: sT[(ks TR + 8 rb) 4 + lane]
+            const double* bp = sW + lane;
+#pragma unroll 4
+            for (int ks = 0; ks < N4 / 4; ++ks) {
+                const double a0 = ap[(size_t)ks * TR * 4], a1 = ap[(size_t)ks * TR * 4 + 32];
+                const double b0 = bp[(size_t)ks * kMeanCols * 4], b1 = bp[(size_t)ks * kMeanCols * 4 + 32];
+                dmma884(c[0][0][0], c[0][0][1], a0, b0);
+                dmma884(c[0][1][0], c[0][1][1], a0, b1);
+                dmma884(c[1][0][0], c[1][0][1], a1, b0);
+                dmma884(c[1][1][0], c[1][1][1], a1, b1);
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const int col = 8 * j + 2 * (lane & 3) + hh;
+                        const int si = col / n_out, o = col - si * n_out;
+                        const int64_t frow = f0 + 8 * (rb0 + i) + (lane >> 2);
+                        const int64_t row = (sb + si) * mp.fast_rows + frow - mp.row0;
+                        if (si < SB && sb + si < mp.s_hi && frow < mp.fast_rows && row >= 0 && row < mp.M) mp.mean[o][row] = c[i][j][hh];
+                    }
+        }
     }
 }
 
