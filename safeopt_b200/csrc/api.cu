@@ -38,13 +38,16 @@ int so_create(int device, int max_gps, so_handle** out) {
     h->num_sms = prop.multiProcessorCount;
     h->smem_optin = (int)prop.sharedMemPerBlockOptin;
     if (cudaMalloc(&h->d_status, sizeof(int)) != cudaSuccess ||
-        cudaMallocHost(&h->h_status, sizeof(int)) != cudaSuccess ||
+        cudaHostAlloc(&h->h_status, sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer(&h->status_mapped_d, h->h_status, 0) != cudaSuccess ||
+        cudaMallocHost(&h->fit_stage_h, (size_t)512 * (SO_MAX_DIM + 1) * sizeof(double)) != cudaSuccess ||
         cudaMalloc(&h->ws_partials, (size_t)SO_WS_MAX_BLOCKS * 64) != cudaSuccess ||
         cudaMalloc(&h->ws_counter, sizeof(unsigned int)) != cudaSuccess ||
         cudaMemset(h->ws_counter, 0, sizeof(unsigned int)) != cudaSuccess) {
         delete h;
         return SO_ERR_CUDA;
     }
+    h->fit_stage_bytes = (size_t)512 * (SO_MAX_DIM + 1) * sizeof(double);
     *out = h;
     return SO_OK;
 }
@@ -62,6 +65,7 @@ int so_destroy(so_handle* h) {
     cudaFree(h->grid.axis);
     cudaFree(h->d_status);
     cudaFreeHost(h->h_status);
+    cudaFreeHost(h->fit_stage_h);
     cudaFree(h->ws_partials);
     cudaFree(h->ws_counter);
     cudaFree(h->ws_z);

@@ -8,6 +8,7 @@
 #include "fit_cluster.cuh"
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 namespace {
 
@@ -335,19 +336,29 @@ extern "C" int so_fit(so_handle* h, int gp, const double* X_h, const double* Y_h
     InvLs il;
     for (int j = 0; j < SO_MAX_DIM; ++j) { il.v[j] = j < d ? 1.0 / lengthscale_h[j] : 0.0; g.inv_ls[j] = il.v[j]; }
 
-    SO_CUDA(h, cudaMemcpyAsync(g.X, X_h, sizeof(double) * N * d, cudaMemcpyHostToDevice, stream));
-    SO_CUDA(h, cudaMemcpyAsync(g.Y, Y_h, sizeof(double) * N, cudaMemcpyHostToDevice, stream));
+    const int csize_try = fit_cluster_size(h, N);
+    if (csize_try > 0 && (size_t)N * (d + 1) * sizeof(double) <= h->fit_stage_bytes) {
+        // one pinned staging buffer, one asynchronous copy: X and Y are adjacent on the device (Y follows X's capacity)
+        double* st = static_cast<double*>(h->fit_stage_h);
+        std::memcpy(st, X_h, sizeof(double) * N * d);
+        std::memcpy(st + (size_t)N * d, Y_h, sizeof(double) * N);
+        SO_CUDA(h, cudaMemcpyAsync(g.X, st, sizeof(double) * N * d, cudaMemcpyHostToDevice, stream));
+        SO_CUDA(h, cudaMemcpyAsync(g.Y, st + (size_t)N * d, sizeof(double) * N, cudaMemcpyHostToDevice, stream));
+    } else {
+        SO_CUDA(h, cudaMemcpyAsync(g.X, X_h, sizeof(double) * N * d, cudaMemcpyHostToDevice, stream));
+        SO_CUDA(h, cudaMemcpyAsync(g.Y, Y_h, sizeof(double) * N, cudaMemcpyHostToDevice, stream));
+    }
     // N <= 512: the whole fit in one launch of one thread-block cluster (fit_cluster.cuh); SO_FIT_CLUSTER=0 keeps the
     // kernel-per-panel version below (also used for larger N)
-    const int csize = fit_cluster_size(h, N);
+    const int csize = csize_try;
     if (csize > 0) {
         FitClusterParams fp;
         fp.X = g.X; fp.Y = g.Y; fp.Xs = g.Xs; fp.K = g.K; fp.W = g.Linv; fp.alpha = g.alpha; fp.zvec = g.zvec; fp.Afrag = g.Afrag;
         fp.N = N; fp.Npad = Npad; fp.NP = (Npad + kFcB - 1) / kFcB * kFcB; fp.ld = ld; fp.d = d; fp.kind = kernel_kind; fp.NB = NB;
         fp.variance = variance; fp.diag_add = noise_var + SO_JITTER;
         for (int j = 0; j < SO_MAX_DIM; ++j) fp.inv_ls[j] = il.v[j];
-        fp.status = h->d_status;
-        SO_CUDA(h, cudaMemsetAsync(h->d_status, 0, sizeof(int), stream));
+        fp.status = h->status_mapped_d;                     // mapped pinned word: no status copy after the kernel
+        *h->h_status = SO_OK;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(csize); cfg.blockDim = dim3(kFcThreads); cfg.dynamicSmemBytes = kFcDynSmem; cfg.stream = stream;
         cudaLaunchAttribute attr[1];
@@ -355,7 +366,6 @@ extern "C" int so_fit(so_handle* h, int gp, const double* X_h, const double* Y_h
         attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
         SO_CUDA(h, cudaLaunchKernelEx(&cfg, k_fit_cluster, fp));
-        SO_CUDA(h, cudaMemcpyAsync(h->h_status, h->d_status, sizeof(int), cudaMemcpyDeviceToHost, stream));
         SO_CUDA(h, cudaStreamSynchronize(stream));
         if (*h->h_status != SO_OK)
             return so_fail(h, SO_ERR_NOT_PD, "so_fit: K + (noise + 1e-8) I is not positive definite");

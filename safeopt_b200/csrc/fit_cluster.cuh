@@ -135,13 +135,16 @@ __global__ void __launch_bounds__(kFcThreads, 1) k_fit_cluster(const __grid_cons
         const int n = e / d, j = e - n * d;
         fp.Xs[e] = n < N ? fp.X[e] * fp.inv_ls[j] : 0.0;
     }
+    double* sXs = reinterpret_cast<double*>(fc_dyn);           // N x d scaled inputs (<= 64 KB of the 135 KB the tiles use later)
+    for (int e = tid; e < N * d; e += kFcThreads) sXs[e] = fp.X[e] * fp.inv_ls[e % d];
+    __syncthreads();
     for (int e = gtid; e < NP * NP; e += gthreads) {
         const int i = e / NP, j = e - i * NP;
         double v;
         if (i < N && j < N) {
             double r2 = 0.0;
             for (int c = 0; c < d; ++c) {
-                const double t = fp.X[i * d + c] * fp.inv_ls[c] - fp.X[j * d + c] * fp.inv_ls[c];
+                const double t = sXs[i * d + c] - sXs[j * d + c];
                 r2 = fma(t, t, r2);
             }
             v = fc_kernel(fp.kind, r2, fp.variance);
@@ -289,17 +292,25 @@ __global__ void __launch_bounds__(kFcThreads, 1) k_fit_cluster(const __grid_cons
         if (lane == 0) fp.zvec[i] = i < N ? part : 0.0;
     }
     fc_cluster_sync();
-    for (int c = gtid; c < fp.Npad; c += gthreads) {
+    // alpha_c = sum_{i >= c} W[i][c] z_i: eight threads per column (i = c + sub, + 8, ...), sixteen loads in flight per thread --
+    // a single thread per column walks up to N dependent-latency L2 loads and took ~30 us at N = 256
+    for (int base = 0; base < fp.Npad; base += gthreads >> 3) {      // uniform trip count: the shuffles below need whole warps
+        const int c = base + (gtid >> 3), sub = tid & 7;
         double s0 = 0.0, s1 = 0.0;
         if (c < N) {
-            int i = c;
-            for (; i + 1 < N; i += 2) {
+            int i = c + sub;
+#pragma unroll 4
+            for (; i + 8 < N; i += 16) {
                 s0 = fma(__ldcg(fp.W + (size_t)i * ld + c), __ldcg(fp.zvec + i), s0);
-                s1 = fma(__ldcg(fp.W + (size_t)(i + 1) * ld + c), __ldcg(fp.zvec + i + 1), s1);
+                s1 = fma(__ldcg(fp.W + (size_t)(i + 8) * ld + c), __ldcg(fp.zvec + i + 8), s1);
             }
             if (i < N) s0 = fma(__ldcg(fp.W + (size_t)i * ld + c), __ldcg(fp.zvec + i), s0);
         }
-        fp.alpha[c] = s0 + s1;
+        double sum = s0 + s1;
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+        if (sub == 0 && c < fp.Npad) fp.alpha[c] = sum;
     }
     {
         const size_t nfrag = tri_blocks(fp.NB) * 32;
@@ -321,7 +332,7 @@ __global__ void __launch_bounds__(kFcThreads, 1) k_fit_cluster(const __grid_cons
             fp.Afrag[e] = v;
         }
     }
-    if (rank == 0 && tid == 0 && sBad) *fp.status = SO_ERR_NOT_PD;
+    if (rank == 0 && tid == 0 && sBad) { *fp.status = SO_ERR_NOT_PD; __threadfence_system(); }
 }
 
 }  // namespace

@@ -915,10 +915,12 @@ extern "C" int so_posterior_grid_f32(so_handle* h, int n, const int* gps_h, int6
         k_mean_grid<<<dim3((unsigned)gx, (unsigned)gy), kMeanThreads, msm, (cudaStream_t)stream_>>>(mq);
         SO_CHECK_LAUNCH(h, "k_mean_grid");
     }
-    // the tpb CTAs that share a slow index form a cluster and multicast the B slabs (1 / tpb of the L2 -> SM operand traffic,
-    // which bounds the kernel: 189 MB per launch at config 3 without it); SO_F32_MULTICAST=0 switches it off (A/B measurements)
+    // SO_F32_MULTICAST=1: the tpb CTAs that share a slow index form a cluster and multicast the B slabs (1 / tpb of the L2 -> SM
+    // operand traffic, which bounds the kernel: 189 MB per launch at config 3).  Measured at config 3 (profiles/r02_f32_variants.md):
+    // 107 us with multicast against 58 us without -- a stage is free only when all four CTAs have read it, and with three stages
+    // that lock-step costs more than the saved traffic -- so it is an A/B switch, off by default.
     const char* mc_env = std::getenv("SO_F32_MULTICAST");
-    fp.mc = (fp.a_resident && (fp.tpb == 2 || fp.tpb == 4 || fp.tpb == 8) && !(mc_env && mc_env[0] == '0')) ? fp.tpb : 1;
+    fp.mc = (fp.a_resident && (fp.tpb == 2 || fp.tpb == 4 || fp.tpb == 8) && mc_env && mc_env[0] == '1') ? fp.tpb : 1;
     const size_t smem_bytes = f32_smem(fp.Np, fp.stages, fp.a_resident != 0).total;
     if (fp.mc > 1) {
         cudaLaunchConfig_t cfg = {};

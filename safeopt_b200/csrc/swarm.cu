@@ -237,7 +237,8 @@ __global__ void __launch_bounds__(kThreads) k_swarm_update_best(int64_t P, int d
             const XchgSwarm* mine = &x.local->swarm[par];
             bool ok = true;
             if (x.world > 1) {          // alone, the record just written is the whole exchange
-                for (int r = 0; r < x.world; ++r) st_release_sys(&x.peer[r]->swarm[par].flag[x.rank], epoch);
+                __threadfence_system();          // one fence, then posted stamp stores (not one acknowledged release per peer)
+                for (int r = 0; r < x.world; ++r) st_relaxed_sys(&x.peer[r]->swarm[par].flag[x.rank], epoch);
                 for (int r = 0; r < x.world; ++r) ok = xchg_wait(mine->flag, r, epoch, true) && ok;
             }
             int best = -1;

@@ -156,6 +156,21 @@ class GaussianProcessOptimization(object):
         self._y = self._y[:-1, :]
 
 
+def _raw_bytes(a):
+    return a.tobytes() if hasattr(a, "tobytes") else repr(a)
+
+
+def _quick_signature(gp):
+    """(X object, Y object, kernel object, raw parameter bytes) of a plain stationary-kernel model, or None when the model
+    does not have that shape (composite kernels take the full extract_hyper path every time)."""
+    try:
+        k = gp.kern
+        return (gp.X, gp.Y, k, (_raw_bytes(k.variance), _raw_bytes(k.lengthscale), _raw_bytes(gp.likelihood.variance),
+                                getattr(gp, "mean_function", None) is None, getattr(gp, "normalizer", None) in (None, False)))
+    except AttributeError:
+        return None
+
+
 class _DeviceFits:
     """Keeps the device-side fit of each GP in step with the user's model objects.
 
@@ -186,14 +201,17 @@ class _DeviceFits:
     def refresh(self, after_fit=None):
         changed = False
         for i, gp in enumerate(self.gps):
-            hyper = extract_hyper(gp)
-            # GPy's own posterior cache is keyed on set_XY / parameter updates, not on the array contents: the same X / Y
-            # OBJECTS under the same hyper-parameters mean nothing changed (skips hashing the data on every optimize())
-            ident = (gp.X, gp.Y, hyper.kind, hyper.variance, hyper.noise_var)
+            # Fast path (this runs before every K2 launch; on small grids the step is host-bound): the same X / Y / kernel
+            # OBJECTS with byte-identical parameter values mean nothing changed -- GPy's own posterior cache is keyed on
+            # set_XY / parameter updates too, not on array contents.  Parameter VALUES are compared (GPy's optimiser
+            # updates them in place), data by identity (set_XY replaces the arrays).
+            sig = _quick_signature(gp)
             last = self._ident[i]
-            if (last is not None and last[0] is ident[0] and last[1] is ident[1] and last[2:] == ident[2:]
-                    and self.hypers[i] is not None and np.array_equal(hyper.lengthscale, self.hypers[i].lengthscale)):
+            if sig is not None and last is not None and last[0] is sig[0] and last[1] is sig[1] and last[2] is sig[2] \
+                    and last[3] == sig[3] and self.hypers[i] is not None:
                 continue
+            hyper = extract_hyper(gp)
+            ident = sig
             fp = fingerprint(gp, hyper)
             if fp == self._fp[i]:
                 self._ident[i] = ident
