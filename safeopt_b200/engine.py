@@ -63,6 +63,7 @@ class DeviceEngine:
         self.launches = 0          # kernels launched through this engine (bench bookkeeping)
         self._raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
         self._grid_axes = None
+        self._tape = None
         self.xchg_world = 1
         self._sets_result = np.zeros(_lib.sets_result_bytes(1), dtype=np.uint8)
 
@@ -178,18 +179,44 @@ class DeviceEngine:
         return out
 
     # ------------------------------------------------------------------ K2
+    # A "tape" remembers the posterior launches of one update_confidence_intervals() with their converted arguments, so that
+    # the next call with unchanged inputs re-issues them without rebuilding anything: on small grids (and on eight GPUs, where a
+    # rank's K2 takes 1.7 ms) the host time BEFORE the K2 launch is GPU idle time, because the previous step ended with a host wait.
+    def start_tape(self):
+        self._tape = []
+
+    def stop_tape(self):
+        tape, self._tape = self._tape, None
+        return tape
+
+    def replay_tape(self, tape):
+        st = self._stream()
+        for fn, args, _keep, where, n in tape:
+            rc = fn(*args, st)
+            if rc:
+                self._check(rc, where)
+            self.launches += n
+
+    def _k2(self, fn, where, args, keep, n_launch):
+        rc = fn(*args, self._stream())
+        if rc == 0 and self._tape is not None:
+            self._tape.append((fn, args, keep, where, n_launch))
+        return rc
+
     def posterior_rows(self, gp, Xstar, beta, fmin, mean=None, var=None, Q=None, q_col=0, S=None, safe_mode=_lib.SAFE_NONE):
         M = Xstar.shape[0]
         q_stride = 0 if Q is None else Q.shape[1]
-        rc = self.lib.so_posterior_rows(self.handle, gp, _ptr(Xstar), M, float(beta), float(fmin), _ptr(mean), _ptr(var),
-                                        _ptr(Q), q_stride, q_col, _ptr(S), safe_mode, self._stream())
+        rc = self._k2(self.lib.so_posterior_rows, "so_posterior_rows",
+                      (self.handle, gp, _ptr(Xstar), M, float(beta), float(fmin), _ptr(mean), _ptr(var), _ptr(Q), q_stride, q_col,
+                       _ptr(S), safe_mode), (Xstar, mean, var, Q, S), 1 if M else 0)
         self._check(rc, "so_posterior_rows")
         self.launches += 1 if M else 0
 
     def posterior_grid(self, gp, row0, M, beta, fmin, mean=None, var=None, Q=None, q_col=0, S=None, safe_mode=_lib.SAFE_NONE):
         q_stride = 0 if Q is None else Q.shape[1]
-        rc = self.lib.so_posterior_grid(self.handle, gp, int(row0), int(M), float(beta), float(fmin), _ptr(mean), _ptr(var),
-                                        _ptr(Q), q_stride, q_col, _ptr(S), safe_mode, self._stream())
+        rc = self._k2(self.lib.so_posterior_grid, "so_posterior_grid",
+                      (self.handle, gp, int(row0), int(M), float(beta), float(fmin), _ptr(mean), _ptr(var), _ptr(Q), q_stride, q_col,
+                       _ptr(S), safe_mode), (mean, var, Q, S), 1 if M else 0)
         self._check(rc, "so_posterior_grid")
         self.launches += 1 if M else 0
 
@@ -205,12 +232,15 @@ class DeviceEngine:
         mp = (C.c_void_p * n)(*[0 if means is None or t is None else t.data_ptr() for t in (means or [None] * n)])
         vp = (C.c_void_p * n)(*[0 if variances is None or t is None else t.data_ptr() for t in (variances or [None] * n)])
         q_stride = 0 if Q is None else Q.shape[1]
+        keep = (gi, fm, qc, mp, vp, Xstar, means, variances, Q, S)
         if Xstar is None:
-            rc = self.lib.so_posterior_grid_multi(self.handle, n, gi, int(row0), int(M), float(beta), _hptr(fm), mp, vp, _ptr(Q),
-                                                  q_stride, qc, _ptr(S), safe_mode, self._stream())
+            rc = self._k2(self.lib.so_posterior_grid_multi, "so_posterior_multi",
+                          (self.handle, n, gi, int(row0), int(M), float(beta), _hptr(fm), mp, vp, _ptr(Q), q_stride, qc, _ptr(S), safe_mode),
+                          keep, 1 if M else 0)
         else:
-            rc = self.lib.so_posterior_rows_multi(self.handle, n, gi, _ptr(Xstar), int(M), float(beta), _hptr(fm), mp, vp,
-                                                  _ptr(Q), q_stride, qc, _ptr(S), safe_mode, self._stream())
+            rc = self._k2(self.lib.so_posterior_rows_multi, "so_posterior_multi",
+                          (self.handle, n, gi, _ptr(Xstar), int(M), float(beta), _hptr(fm), mp, vp, _ptr(Q), q_stride, qc, _ptr(S), safe_mode),
+                          keep, 1 if M else 0)
         if rc == _lib.SO_ERR_CAPACITY:
             return False
         self._check(rc, "so_posterior_multi")
@@ -233,8 +263,9 @@ class DeviceEngine:
         mp = (C.c_void_p * n)(*[0 if means is None or t is None else t.data_ptr() for t in (means or [None] * n)])
         vp = (C.c_void_p * n)(*[0 if variances is None or t is None else t.data_ptr() for t in (variances or [None] * n)])
         q_stride = 0 if Q is None else Q.shape[1]
-        rc = self.lib.so_posterior_grid_f32(self.handle, n, gi, int(row0), int(M), float(beta), _hptr(fm), mp, vp, _ptr(Q), q_stride,
-                                            qc, _ptr(S), safe_mode, self._stream())
+        rc = self._k2(self.lib.so_posterior_grid_f32, "so_posterior_grid_f32",
+                      (self.handle, n, gi, int(row0), int(M), float(beta), _hptr(fm), mp, vp, _ptr(Q), q_stride, qc, _ptr(S), safe_mode),
+                      (gi, fm, qc, mp, vp, means, variances, Q, S), 2 if M else 0)
         self._check(rc, "so_posterior_grid_f32")
         self.launches += 2 if M else 0            # k_mean_grid (fp64 means) + k_posterior_f32
 

@@ -188,6 +188,7 @@ class _DeviceFits:
         self._ident = [None] * len(gps)       # (X object, Y object, scalar hyper-parameters) seen at the last refresh
         self._data = [None] * len(gps)        # (X, Y, hyper key) the device fit was built from
         self.hypers = [None] * len(gps)
+        self.generation = 0                   # bumped whenever a device fit changed
         self.refits = 0
         self.copies = 0                       # refits served by copying a twin's factorisation (so_fit_like)
         self.appends = 0
@@ -255,6 +256,7 @@ class _DeviceFits:
             if after_fit is not None:
                 after_fit(i, hyper)
         if changed:
+            self.generation += 1
             self._regroup()
 
     MAX_GROUP = 4       # kMaxOut of the kernels
@@ -381,6 +383,8 @@ class SafeOpt(GaussianProcessOptimization):
         self._cand_row_d = None
         self._grid_strides = None
         self._thr_cache = None
+        self._k2_tape = None                  # (key, engine tape) of the last update_confidence_intervals
+        self._tables_version = 0
         self._G_rows: List[int] = []          # global rows currently in the expander set
         self._host_cache = {}
         self._safe_info = None                # combined record of the last compute_safe_set
@@ -434,12 +438,13 @@ class SafeOpt(GaussianProcessOptimization):
             self.inputs[:, -self.num_contexts:] = context
             ctx = np.atleast_1d(np.asarray(context, dtype=float)).ravel()
             if self._rows_d is not None:
-                self._rows_d[:, -self.num_contexts:] = self._engine.to_device(ctx)
+                self._rows_d[:, -self.num_contexts:] = self._engine.to_device(ctx)     # same buffer: a taped launch stays valid
             if self._grid_axes is not None and (self._context_on_device is None or not np.array_equal(ctx, self._context_on_device)):
                 # a new context = new one-point axes: the grid description and every GP's tables are rebuilt
                 self._grid_axes = list(self._param_axes) + [np.array([c], dtype=float) for c in ctx]
                 self._engine.define_grid(self._grid_axes)
                 self._grid_state.clear()
+                self._tables_version += 1
                 self._context_on_device = ctx.copy()
 
     # ------------------------------------------------------------------ host views of device state
@@ -557,6 +562,18 @@ class SafeOpt(GaussianProcessOptimization):
         self.context = context
         self._fits.refresh(self._after_fit)
         eng = self._engine
+        # unchanged fits, tables, thresholds and beta: re-issue the remembered launches (engine tape) -- nothing to rebuild
+        key = (self._fits.generation, self._tables_version, beta, self.fmin.tobytes(), self.precision)
+        if self._k2_tape is not None and self._k2_tape[0] == key:
+            eng.replay_tape(self._k2_tape[1])
+            self._ci_beta = beta
+            self._safe_info = None
+            if self._host_cache:
+                self._invalidate_host()
+            return
+        taping = hasattr(eng, "start_tape")
+        if taping:
+            eng.start_tape()
         m_local = self._row1 - self._row0
         first = True
         for group in self._fits.groups:
@@ -591,6 +608,7 @@ class SafeOpt(GaussianProcessOptimization):
                     else:
                         eng.posterior_rows(i, rows_arg, beta, self.fmin[i], mean=self._mean_d[i], var=self._var_d[i],
                                            Q=self._Q_d, q_col=2 * i, S=self._S_d, safe_mode=mode)
+        self._k2_tape = (key, eng.stop_tape()) if taping else None
         self._ci_beta = beta
         self._ci_fmin = self.fmin.copy()
         self._safe_info = None
@@ -889,6 +907,7 @@ class SafeOptSwarm(GaussianProcessOptimization):
         self._comm = Comm(self._engine.device, enabled=distributed)
         self._fits = _DeviceFits(self._engine, self.gps)
         self._fit_buffers = {}
+        self._fit_buffers_keep = {}
         self.optimal_velocities = self.optimize_particle_velocity()
         swarm_types = ["greedy", "maximizers", "expanders"]
         if swarm_backend == "device":
@@ -942,18 +961,25 @@ class SafeOptSwarm(GaussianProcessOptimization):
         pen[big] = -300 * pen[big] ** 2
         return pen
 
-    def _fitness_buffers(self, P):
-        """Per-swarm-size scratch (posterior planes, values, flags), reused across the ~300 fitness passes of an optimize()."""
-        buf = self._fit_buffers.get(P)
+    def _fitness_buffers(self, P, keep=False):
+        """Per-swarm-size scratch (posterior planes, values, flags), reused across the ~300 fitness passes of an optimize().
+        ``keep``: the buffers of the device swarms are never evicted -- a captured PSO iteration (CUDA graph) holds their
+        addresses, and an evicted buffer is returned to the driver by the ``empty_cache()`` of the next graph capture."""
+        buf = self._fit_buffers_keep.get(P) or self._fit_buffers.get(P)
         if buf is None:
             eng, G = self._engine, len(self.gps)
             buf = (eng.empty((G, P)), eng.empty((G, P)), eng.empty((P,)), eng.empty((P,), "u8"))
-            if len(self._fit_buffers) > 4:
-                self._fit_buffers.clear()
-            self._fit_buffers[P] = buf
+            if keep:
+                self._fit_buffers_keep[P] = buf
+            else:
+                if len(self._fit_buffers) > 4:
+                    self._fit_buffers.clear()
+                self._fit_buffers[P] = buf
+        elif keep and P not in self._fit_buffers_keep:
+            self._fit_buffers_keep[P] = buf
         return buf
 
-    def _fitness_device(self, swarm_type, particles_d, fresh=True):
+    def _fitness_device(self, swarm_type, particles_d, fresh=True, keep=False):
         """Fitness of device-resident particles; returns device tensors (values, safe).  The returned tensors are scratch
         that the next call with the same particle count overwrites (``DeviceSwarm`` consumes them at once).  Inside a swarm
         run the GP objects cannot change, so ``fresh=False`` skips the fingerprint check of the device fits."""
@@ -963,7 +989,7 @@ class SafeOptSwarm(GaussianProcessOptimization):
         beta = self.beta(self.t)
         P = particles_d.shape[0]
         G = len(self.gps)
-        mean, var, values, safe = self._fitness_buffers(P)
+        mean, var, values, safe = self._fitness_buffers(P, keep=keep)
         n_needed = 1 if swarm_type == "greedy" else G
         for group in self._fits.groups:
             group = [i for i in group if i < n_needed]
@@ -986,7 +1012,7 @@ class SafeOptSwarm(GaussianProcessOptimization):
 
     def _swarm_fitness(self, swarm_type, particles_d):
         """Fitness callback of the device swarms: the fits were refreshed by get_new_query_point before the run."""
-        return self._fitness_device(swarm_type, particles_d, fresh=False)
+        return self._fitness_device(swarm_type, particles_d, fresh=False, keep=True)
 
     def _compute_particle_fitness(self, swarm_type, particles):
         """Fitness value and safety flag of every particle (reference: gp_opt.py:901-1013).

@@ -827,6 +827,35 @@ def test_fused_set_pass_equals_chained_passes(name, monkeypatch):
     assert np.array_equal(got[("1", 2)][2], unpack_mask(g["G"], n_rows))
 
 
+def test_replayed_posterior_launches_follow_every_change():
+    """update_confidence_intervals re-issues the remembered K2 launches while fits, tables, thresholds and beta are unchanged,
+    and rebuilds them as soon as one of them changes (new observation, new fmin, new beta, new hyper-parameter, new context)."""
+    g = load_golden("expander_g2")
+    gps, grid, fmin = golden_problem(g, "gpu")
+    opt = sb.SafeOpt(gps, grid, fmin, beta=float(g["beta"]), threshold=float(g["threshold"]))
+    x0 = opt.optimize()
+    tape0 = opt._k2_tape
+    assert tape0 is not None and len(tape0[1]) >= 1
+    Q0 = opt.Q.copy()
+    launches = opt._engine.launches
+    x1 = opt.optimize()                                   # replay
+    assert opt._k2_tape is tape0 and np.array_equal(x0, x1) and np.array_equal(opt.Q, Q0) and opt._engine.launches > launches
+    opt.fmin = opt.fmin + 0.05                            # thresholds are baked into the launches
+    opt.optimize()
+    assert opt._k2_tape is not tape0 and np.array_equal(opt.S, np.all(opt.Q[:, ::2] > opt.fmin, axis=1))
+    tape1 = opt._k2_tape
+    opt.add_new_data_point(x0, np.array([[1.0, 1.0]]))    # new fit
+    opt.optimize()
+    assert opt._k2_tape is not tape1
+    ref = sb.SafeOpt(gps, grid, list(opt.fmin), beta=float(g["beta"]), threshold=float(g["threshold"]))
+    ref.optimize()
+    assert np.array_equal(ref.Q, opt.Q) and np.array_equal(ref.S, opt.S) and ref.last_query_row == opt.last_query_row
+    tape2 = opt._k2_tape
+    opt.beta = lambda t: 3.0
+    opt.optimize()
+    assert opt._k2_tape is not tape2 and np.abs((opt.Q[:, 1] - opt.Q[:, 0]) / (ref.Q[:, 1] - ref.Q[:, 0]) - 1.5).max() < 1e-9
+
+
 def test_fused_set_pass_with_no_safe_rows_and_ragged_sizes():
     """Edge cases of the fused kernel: nothing safe, a single row, sizes that are not multiples of the 16-row chunks."""
     eng = DeviceEngine(max_gps=1)
