@@ -338,6 +338,11 @@ def time_k2(eng, torch):
 
     for n in names:
         setattr(eng, n, timed(orig[n]))
+    # unchanged inputs: update_confidence_intervals re-issues its remembered launches through replay_tape (one call per step)
+    if hasattr(eng, "replay_tape"):
+        names.append("replay_tape")
+        orig["replay_tape"] = eng.replay_tape
+        eng.replay_tape = timed(orig["replay_tape"])
 
     def restore():
         for n in names:

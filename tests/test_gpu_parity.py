@@ -849,7 +849,8 @@ def test_replayed_posterior_launches_follow_every_change():
     assert opt._k2_tape is not tape1
     ref = sb.SafeOpt(gps, grid, list(opt.fmin), beta=float(g["beta"]), threshold=float(g["threshold"]))
     ref.optimize()
-    assert np.array_equal(ref.Q, opt.Q) and np.array_equal(ref.S, opt.S) and ref.last_query_row == opt.last_query_row
+    # (opt appended one row to its factorisation, ref factorises from scratch: equal to rounding, not bit for bit)
+    assert np.abs(ref.Q - opt.Q).max() < 1e-9 and np.array_equal(ref.S, opt.S) and ref.last_query_row == opt.last_query_row
     tape2 = opt._k2_tape
     opt.beta = lambda t: 3.0
     opt.optimize()
