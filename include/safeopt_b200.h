@@ -96,6 +96,14 @@ int         so_num_sms(const so_handle* h);
 int so_fit(so_handle* h, int gp, const double* X_h, const double* Y_h, int N, int d,
            int kernel_kind, const double* lengthscale_h, double variance, double noise_var,
            void* stream);
+/* Asynchronous variant for N <= 512 (the one-launch cluster fit): returns right after the launch, so the host can queue the
+ * table build and the posterior behind it while the factorisation runs.  The kernel leaves its status in mapped pinned
+ * memory; so_fit_status returns it (SO_OK / SO_ERR_NOT_PD) and must be called after the caller's next synchronisation of
+ * `stream` (safeopt_b200 does so when the records of the set pass arrive).  Larger N behaves like so_fit. */
+int so_fit_async(so_handle* h, int gp, const double* X_h, const double* Y_h, int N, int d,
+                 int kernel_kind, const double* lengthscale_h, double variance, double noise_var,
+                 void* stream);
+int so_fit_status(so_handle* h, int gp);
 /* f4 -- one-point updates of an existing fit (same hyper-parameters), O(N^2) instead of O(N^3):
  * so_fit_append stands in for the `set_XY(vstack(X, x), vstack(Y, y))` of
  * safeopt/gp_opt.py:227 (`_add_data_point`, reached from add_new_data_point :230-255):

@@ -75,6 +75,8 @@ SIGNATURES = {
     "so_last_error": (C.c_char_p, [_P]),
     "so_num_sms": (_i, [_P]),
     "so_fit": (_i, [_P, _i, _P, _P, _i, _i, _i, _P, _dbl, _dbl, _P]),
+    "so_fit_async": (_i, [_P, _i, _P, _P, _i, _i, _i, _P, _dbl, _dbl, _P]),
+    "so_fit_status": (_i, [_P, _i]),
     "so_fit_like": (_i, [_P, _i, _i, _P, _P]),
     "so_fit_append": (_i, [_P, _i, _P, _dbl, _P]),
     "so_fit_remove_last": (_i, [_P, _i, _P]),

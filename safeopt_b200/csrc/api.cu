@@ -40,7 +40,9 @@ int so_create(int device, int max_gps, so_handle** out) {
     if (cudaMalloc(&h->d_status, sizeof(int)) != cudaSuccess ||
         cudaHostAlloc(&h->h_status, sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
         cudaHostGetDevicePointer(&h->status_mapped_d, h->h_status, 0) != cudaSuccess ||
-        cudaMallocHost(&h->fit_stage_h, (size_t)512 * (SO_MAX_DIM + 1) * sizeof(double)) != cudaSuccess ||
+        cudaMallocHost(&h->fit_stage_h, (size_t)max_gps * 512 * (SO_MAX_DIM + 1) * sizeof(double)) != cudaSuccess ||
+        cudaHostAlloc(&h->fit_status_h, (size_t)max_gps * sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer(&h->fit_status_d, h->fit_status_h, 0) != cudaSuccess ||
         cudaMalloc(&h->ws_partials, (size_t)SO_WS_MAX_BLOCKS * 64) != cudaSuccess ||
         cudaMalloc(&h->ws_counter, sizeof(unsigned int)) != cudaSuccess ||
         cudaMemset(h->ws_counter, 0, sizeof(unsigned int)) != cudaSuccess) {
@@ -48,6 +50,7 @@ int so_create(int device, int max_gps, so_handle** out) {
         return SO_ERR_CUDA;
     }
     h->fit_stage_bytes = (size_t)512 * (SO_MAX_DIM + 1) * sizeof(double);
+    for (int i = 0; i < max_gps; ++i) h->fit_status_h[i] = SO_OK;
     *out = h;
     return SO_OK;
 }
@@ -66,6 +69,7 @@ int so_destroy(so_handle* h) {
     cudaFree(h->d_status);
     cudaFreeHost(h->h_status);
     cudaFreeHost(h->fit_stage_h);
+    cudaFreeHost(h->fit_status_h);
     cudaFree(h->ws_partials);
     cudaFree(h->ws_counter);
     cudaFree(h->ws_z);

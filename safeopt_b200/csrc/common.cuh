@@ -85,8 +85,10 @@ struct so_handle {
     int* d_status = nullptr;     // device int written by fit kernels
     int* h_status = nullptr;     // pinned (mapped) host mirror
     int* status_mapped_d = nullptr;  // device-side address of h_status (the one-launch fit writes its status straight to the host)
-    void* fit_stage_h = nullptr; // pinned staging buffer for X, Y of a fit (one asynchronous copy each instead of pageable copies)
+    void* fit_stage_h = nullptr; // pinned staging buffer for X, Y of a fit, one slot of fit_stage_bytes per GP
     size_t fit_stage_bytes = 0;
+    int* fit_status_h = nullptr; // mapped pinned status word per GP, written by the one-launch fit kernel
+    int* fit_status_d = nullptr; // its device-side address
     void* ws_partials = nullptr; // per-block partial records of the reduction passes (sets.cu)
     unsigned int* ws_counter = nullptr;  // last-block-done ticket, self-resetting
     double* ws_z = nullptr;      // expander batch workspace (expander.cu)

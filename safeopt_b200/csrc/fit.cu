@@ -291,8 +291,8 @@ int fit_cluster_size(so_handle* h, int N) {
 
 }  // namespace
 
-extern "C" int so_fit(so_handle* h, int gp, const double* X_h, const double* Y_h, int N, int d, int kernel_kind,
-                      const double* lengthscale_h, double variance, double noise_var, void* stream_) {
+static int fit_impl(so_handle* h, int gp, const double* X_h, const double* Y_h, int N, int d, int kernel_kind,
+                    const double* lengthscale_h, double variance, double noise_var, void* stream_, bool async) {
     if (!h) return SO_ERR_BAD_ARG;
     if (gp < 0 || gp >= h->max_gps) return so_fail(h, SO_ERR_BAD_ARG, "so_fit: gp index out of range");
     if (!X_h || !Y_h || !lengthscale_h || N < 1) return so_fail(h, SO_ERR_BAD_ARG, "so_fit: null input or N < 1");
@@ -338,8 +338,8 @@ extern "C" int so_fit(so_handle* h, int gp, const double* X_h, const double* Y_h
 
     const int csize_try = fit_cluster_size(h, N);
     if (csize_try > 0 && (size_t)N * (d + 1) * sizeof(double) <= h->fit_stage_bytes) {
-        // one pinned staging buffer, one asynchronous copy: X and Y are adjacent on the device (Y follows X's capacity)
-        double* st = static_cast<double*>(h->fit_stage_h);
+        // pinned staging (one slot per GP, so that asynchronous fits of several GPs do not overwrite each other's inputs)
+        double* st = reinterpret_cast<double*>(static_cast<unsigned char*>(h->fit_stage_h) + (size_t)gp * h->fit_stage_bytes);
         std::memcpy(st, X_h, sizeof(double) * N * d);
         std::memcpy(st + (size_t)N * d, Y_h, sizeof(double) * N);
         SO_CUDA(h, cudaMemcpyAsync(g.X, st, sizeof(double) * N * d, cudaMemcpyHostToDevice, stream));
@@ -357,8 +357,8 @@ extern "C" int so_fit(so_handle* h, int gp, const double* X_h, const double* Y_h
         fp.N = N; fp.Npad = Npad; fp.NP = (Npad + kFcB - 1) / kFcB * kFcB; fp.ld = ld; fp.d = d; fp.kind = kernel_kind; fp.NB = NB;
         fp.variance = variance; fp.diag_add = noise_var + SO_JITTER;
         for (int j = 0; j < SO_MAX_DIM; ++j) fp.inv_ls[j] = il.v[j];
-        fp.status = h->status_mapped_d;                     // mapped pinned word: no status copy after the kernel
-        *h->h_status = SO_OK;
+        fp.status = h->fit_status_d + gp;                   // mapped pinned word per GP: no status copy after the kernel
+        h->fit_status_h[gp] = SO_OK;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(csize); cfg.blockDim = dim3(kFcThreads); cfg.dynamicSmemBytes = kFcDynSmem; cfg.stream = stream;
         cudaLaunchAttribute attr[1];
@@ -366,10 +366,13 @@ extern "C" int so_fit(so_handle* h, int gp, const double* X_h, const double* Y_h
         attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
         SO_CUDA(h, cudaLaunchKernelEx(&cfg, k_fit_cluster, fp));
-        SO_CUDA(h, cudaStreamSynchronize(stream));
-        if (*h->h_status != SO_OK)
-            return so_fail(h, SO_ERR_NOT_PD, "so_fit: K + (noise + 1e-8) I is not positive definite");
         g.fitted = true;
+        if (async) return SO_OK;                            // the caller reads so_fit_status after its next synchronisation
+        SO_CUDA(h, cudaStreamSynchronize(stream));
+        if (h->fit_status_h[gp] != SO_OK) {
+            g.fitted = false;
+            return so_fail(h, SO_ERR_NOT_PD, "so_fit: K + (noise + 1e-8) I is not positive definite");
+        }
         return SO_OK;
     }
     k_scale_x<<<(Npad * d + 255) / 256, 256, 0, stream>>>(g.X, g.Xs, N, Npad, d, il);
@@ -397,6 +400,26 @@ extern "C" int so_fit(so_handle* h, int gp, const double* X_h, const double* Y_h
     if (*h->h_status != SO_OK)
         return so_fail(h, SO_ERR_NOT_PD, "so_fit: K + (noise + 1e-8) I is not positive definite");
     g.fitted = true;
+    return SO_OK;
+}
+
+extern "C" int so_fit(so_handle* h, int gp, const double* X_h, const double* Y_h, int N, int d, int kernel_kind,
+                      const double* lengthscale_h, double variance, double noise_var, void* stream) {
+    return fit_impl(h, gp, X_h, Y_h, N, d, kernel_kind, lengthscale_h, variance, noise_var, stream, false);
+}
+
+extern "C" int so_fit_async(so_handle* h, int gp, const double* X_h, const double* Y_h, int N, int d, int kernel_kind,
+                            const double* lengthscale_h, double variance, double noise_var, void* stream) {
+    return fit_impl(h, gp, X_h, Y_h, N, d, kernel_kind, lengthscale_h, variance, noise_var, stream, true);
+}
+
+extern "C" int so_fit_status(so_handle* h, int gp) {
+    if (!h || gp < 0 || gp >= h->max_gps) return SO_ERR_BAD_ARG;
+    const int st = h->fit_status_h[gp];
+    if (st != SO_OK) {
+        h->gps[gp].fitted = false;
+        return so_fail(h, st, "so_fit_async: K + (noise + 1e-8) I is not positive definite");
+    }
     return SO_OK;
 }
 

@@ -64,6 +64,7 @@ class DeviceEngine:
         self._raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
         self._grid_axes = None
         self._tape = None
+        self._pending_fits = set()
         self.xchg_world = 1
         self._sets_result = np.zeros(_lib.sets_result_bytes(1), dtype=np.uint8)
 
@@ -112,7 +113,9 @@ class DeviceEngine:
         self.torch.cuda.current_stream(self.device).synchronize()
 
     # ------------------------------------------------------------------ K1
-    def fit(self, gp: int, X, Y, kind: int, lengthscale, variance: float, noise_var: float):
+    def fit(self, gp: int, X, Y, kind: int, lengthscale, variance: float, noise_var: float, wait: bool = True):
+        """``wait=False``: do not wait for the factorisation (so_fit_async); a failed Cholesky is then reported by
+        :meth:`check_fits`, which the caller runs after its next synchronisation."""
         X = _np_f64(X)
         Y = _np_f64(Y).reshape(-1)
         N, d = X.shape
@@ -121,11 +124,19 @@ class DeviceEngine:
             ls = np.full(d, float(ls[0]))
         if ls.size != d:
             raise ValueError("lengthscale must have 1 or %d entries" % d)
-        rc = self.lib.so_fit(self.handle, gp, _hptr(X), _hptr(Y), N, d, kind, _hptr(ls), float(variance),
-                             float(noise_var), self._stream())
+        fn = self.lib.so_fit if wait else self.lib.so_fit_async
+        rc = fn(self.handle, gp, _hptr(X), _hptr(Y), N, d, kind, _hptr(ls), float(variance), float(noise_var), self._stream())
         self._check(rc, "so_fit")
+        if not wait:
+            self._pending_fits.add(gp)
         panels = (8 * ((N + 7) // 8) + 31) // 32           # fit.cu: k_chol_panel per panel, k_chol_update between panels
         self.launches += 4 + 2 * panels - 1
+
+    def check_fits(self):
+        """Status of the fits started with ``wait=False`` (call after a synchronisation of the stream)."""
+        pending, self._pending_fits = self._pending_fits, set()
+        for gp in pending:
+            self._check(self.lib.so_fit_status(self.handle, gp), "so_fit")
 
     def fit_like(self, gp: int, src_gp: int, Y):
         """Fit of a GP that shares inputs, kernel and noise with the fitted ``src_gp``: copies its factorisation."""

@@ -188,6 +188,7 @@ class _DeviceFits:
         self._ident = [None] * len(gps)       # (X object, Y object, scalar hyper-parameters) seen at the last refresh
         self._data = [None] * len(gps)        # (X, Y, hyper key) the device fit was built from
         self.hypers = [None] * len(gps)
+        self.async_fit = False                # set by an owner that checks engine.check_fits() after its next synchronisation
         self.generation = 0                   # bumped whenever a device fit changed
         self.refits = 0
         self.copies = 0                       # refits served by copying a twin's factorisation (so_fit_like)
@@ -245,6 +246,10 @@ class _DeviceFits:
                 if twin is not None:
                     self.engine.fit_like(i, twin, Y)
                     self.copies += 1
+                elif self.async_fit and hasattr(self.engine, "check_fits"):
+                    # no host wait: table build and posterior are queued behind the factorisation; a failed Cholesky is reported
+                    # when the records of the set pass arrive (the owner calls engine.check_fits() there)
+                    self.engine.fit(i, X, Y, hyper.kind, hyper.lengthscale, hyper.variance, hyper.noise_var, wait=False)
                 else:
                     self.engine.fit(i, X, Y, hyper.kind, hyper.lengthscale, hyper.variance, hyper.noise_var)
                 self.refits += 1
@@ -354,6 +359,7 @@ class SafeOpt(GaussianProcessOptimization):
         # rank-local although torch.distributed is initialised (it then evaluates ALL rows on this GPU)
         self._comm = Comm(self._engine.device, enabled=distributed)
         self._fits = _DeviceFits(self._engine, self.gps)
+        self._fits.async_fit = os.environ.get("SAFEOPT_B200_ASYNC_FIT", "1") != "0"
         # cross-rank records through peer-mapped memory written by the kernels themselves (so_xchg_*); where IPC mapping is
         # not available -- and in the CPU tests' stand-in engine -- records go through all-gathers between chained kernels
         self._peer = bool(hasattr(self._engine, "connect_exchange") and self._engine.connect_exchange(self._comm))
@@ -451,9 +457,15 @@ class SafeOpt(GaussianProcessOptimization):
     def _gather_rows(self, local: np.ndarray) -> np.ndarray:
         return gather_row_blocks(self._comm, local, self.inputs.shape[0])
 
+    def _check_fits(self):
+        """After a host wait: did a factorisation started without waiting (so_fit_async) fail?"""
+        if getattr(self._engine, "_pending_fits", None):
+            self._engine.check_fits()
+
     def _host(self, key, tensor, as_bool=False):
         if key not in self._host_cache:
             arr = tensor.cpu().numpy()
+            self._check_fits()
             arr = self._gather_rows(arr)
             self._host_cache[key] = arr.astype(bool) if as_bool else arr
         return self._host_cache[key]
@@ -627,6 +639,7 @@ class SafeOpt(GaussianProcessOptimization):
         eng = self._engine
         eng.reduce_safe(self._Q_d, len(self.gps), self._row0, self._S_d, self._rec_safe_d)
         self._safe_info = reduce_safe_records(self._comm.gather_records(self._rec_safe_d, SAFE_REC_DTYPE))
+        self._check_fits()
         self._invalidate_host("S")
 
     def _record_buffers(self):
@@ -696,6 +709,7 @@ class SafeOpt(GaussianProcessOptimization):
                                      None, self._cand_key_d, self._cand_row_d, self._n_cand_l)
                 self._share(self._ncand_all_d, self._n_cand_l)
             host = recs.cpu().numpy()                               # the one host wait of compute_sets
+        self._check_fits()
         if world == 1:
             # one rank: nothing to combine -- unpack the two records directly (this runs once per optimize(), which is
             # host-bound on small grids)

@@ -130,6 +130,7 @@ class DeviceSwarm(object):
         self._graph = None
         self._graph_key = None
         self._graph_launches = 0
+        self._side = None                   # capture stream
         self._draws = 0                     # random blocks drawn so far outside the update kernel (rng='device')
         self.swarm_size = 0                 # particles of the whole swarm
         self.p0 = self.p1 = 0               # this rank's block
@@ -243,12 +244,22 @@ class DeviceSwarm(object):
                 # capture; the fitness callback must not allocate or synchronise (SafeOptSwarm._swarm_fitness does not)
                 self._iteration_dev()
                 done = 1
+                # capture_begin / capture_end directly: the torch.cuda.graph() context also runs gc.collect() and empty_cache(),
+                # tens of milliseconds per capture, and a SafeOptSwarm.optimize() re-captures three times (new greedy bound)
                 g = t.cuda.CUDAGraph()
-                side = t.cuda.Stream(device=eng.device)
-                side.wait_stream(t.cuda.current_stream(eng.device))
+                cur = t.cuda.current_stream(eng.device)
+                if self._side is None:
+                    self._side = t.cuda.Stream(device=eng.device)
+                side = self._side
+                side.wait_stream(cur)
                 before = eng.launches
-                with t.cuda.graph(g, stream=side):
-                    self._iteration_dev()
+                with t.cuda.stream(side):
+                    g.capture_begin()
+                    try:
+                        self._iteration_dev()
+                    finally:
+                        g.capture_end()
+                cur.wait_stream(side)
                 # capturing does not execute: the captured iteration has not run yet
                 self._graph_launches = eng.launches - before
                 eng.launches = before
