@@ -624,8 +624,10 @@ extern "C" int so_sets_fused_result(so_handle* h, void* result_h, void* stream_)
 extern "C" int so_sets_fused(so_handle* h, const double* Q_d, int n_gps, int64_t M, int64_t row0, const uint8_t* S_d,
                              const double* scaling_h, const double* thr_h, int with_candidates, uint8_t* Mmask_d,
                              double* cand_key_d, int64_t* cand_row_d, int64_t cap, void* result_h, void* stream_) {
-    if (!h || !Q_d || !S_d || !scaling_h || !thr_h || !Mmask_d || n_gps < 1 || n_gps > 64 || M < 0 || cap < 0) return SO_ERR_BAD_ARG;
-    if (with_candidates && cap > 0 && (!cand_key_d || !cand_row_d)) return SO_ERR_BAD_ARG;
+    // a rank may hold no rows at all (more ranks than row blocks): it still takes part in the exchange, with empty records
+    if (!h || !scaling_h || !thr_h || n_gps < 1 || n_gps > 64 || M < 0 || cap < 0) return SO_ERR_BAD_ARG;
+    if (M > 0 && (!Q_d || !S_d || !Mmask_d)) return SO_ERR_BAD_ARG;
+    if (with_candidates && M > 0 && cap > 0 && (!cand_key_d || !cand_row_d)) return SO_ERR_BAD_ARG;
     DeviceGuard guard(h->device);
     int rc = fused_setup(h);
     if (rc) return rc;

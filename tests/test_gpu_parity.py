@@ -153,6 +153,25 @@ def test_fit_reports_not_positive_definite():
     eng.close()
 
 
+def test_failed_factorisation_surfaces_inside_optimize():
+    """SafeOpt starts its fits without waiting (so_fit_async); a Cholesky that fails is still reported by the same optimize()
+    call, when the records of the set pass arrive (and by the Q / S / M accessors)."""
+    X = np.array([[0.0], [np.nan], [1.0]])
+    gp = sb.GPRegression(X, np.zeros((3, 1)), kernel=sb.RBF(1, variance=1.0, lengthscale=1.0), noise_var=0.01)
+    grid = sb.linearly_spaced_combinations([(-1, 1)], 50)
+    opt = sb.SafeOpt(gp, grid, fmin=-1.0)
+    assert opt._fits.async_fit
+    with pytest.raises(sb.DeviceError) as err:
+        opt.optimize()
+    assert err.value.status == _lib.SO_ERR_NOT_PD
+    opt2 = sb.SafeOpt(sb.GPRegression(X, np.zeros((3, 1)), kernel=sb.RBF(1), noise_var=0.01), grid, fmin=-1.0)
+    opt2.update_confidence_intervals()
+    with pytest.raises(sb.DeviceError):
+        opt2.Q
+    gp.set_XY(np.array([[0.0], [0.5], [1.0]]), np.ones((3, 1)))          # repaired data: the next call refits and works
+    assert opt.optimize().shape == (1,)
+
+
 # ---------------------------------------------------------------- K2
 @pytest.mark.parametrize("N,d,kind,M", [(1, 1, 0, 100), (5, 1, 0, 100), (9, 2, 2, 1), (64, 2, 0, 5000), (100, 3, 1, 3000),
                                         (128, 2, 2, 4097), (256, 4, 0, 20000), (300, 2, 0, 3000), (512, 6, 0, 4000),
@@ -1113,6 +1132,11 @@ def _nccl_worker(rank, world, port_no, out):
         ok = (opt.last_query_row == int(g["row_next"]) and np.array_equal(opt.S, unpack_mask(g["S"], n_rows))
               and np.array_equal(opt.M, unpack_mask(g["M"], n_rows)) and np.array_equal(opt.G, unpack_mask(g["G"], n_rows))
               and np.abs(opt.Q - g["Q"]).max() < 1e-8)
+        # more ranks than rows: the rank without rows still takes part in the in-kernel exchange (empty records)
+        gp1 = sb.GPRegression(np.array([[0.0]]), np.array([[1.0]]), noise_var=0.01 ** 2)
+        tiny = sb.SafeOpt(gp1, np.array([[0.05]]), fmin=0.0, device=torch.device("cuda", rank))
+        x = tiny.optimize()
+        ok = ok and tiny._row1 - tiny._row0 == (1 if rank == 0 else 0) and np.array_equal(x, [0.05]) and tiny._safe_info["n_safe"] == 1
         open(os.path.join(out, "ok_%d" % rank), "w").write("1" if ok else "0")
     finally:
         dist.destroy_process_group()
