@@ -233,7 +233,7 @@ int launch_bt(so_handle* h, const PostParams& p, const LaunchPlan& lp, cudaStrea
 }
 
 // ---- TMA double-buffer kernel (grid path default) ----------------------------------------------------------------
-struct TmaPlan { int BT, RG, CG, T, TB, npass, kb_pad, warps; size_t smem; bool ring; };
+struct TmaPlan { int BT, RG, CG, T, TB, npass, kb_pad, warps; size_t smem; bool ring; bool ns2x; };
 
 // SO_K2_RING=0 keeps the resident double buffer (smaller tiles) for every N, SO_K2_RING=all streams as soon as the 48-row
 // tile does not fit twice (A/B measurements); default: stream when the 32-row tile does not fit twice either.
@@ -259,6 +259,27 @@ int plan_tma(so_handle* h, const GPState& g, TmaPlan& tp) {
     tp.kb_pad = NB;       // no padding to whole bulk-copy chunks: at NB = 33..35 that padding alone pushed the tile from 48 to 32 rows
     const int options[3] = {6, 4, 2};
     tp.ring = false;
+    tp.ns2x = false;
+    // SO_K2_SMALLN=1, N <= 128: eight warps with two block rows each, two CTAs per SM (see k_posterior_tma).  Measured on config 4's
+    // grid (profiles/r02_k2_small_n.md): N = 32 +8 %, 64 -1 %, 96 +4 %, 128 -7 % against the four-rows-per-warp kernel -- the doubled
+    // B-fragment traffic costs what the second CTA hides -- so it is an A/B switch, off by default.
+    {
+        const char* v = std::getenv("SO_K2_SMALLN");
+        if (NB <= 16 && tma_warps() == 8 && v && std::string(v) == "1") {
+            int rg = 1;
+            while (rg < 8 && 2 * rg < NB) rg *= 2;
+            const int cg = 8 / rg;
+            for (int k = 0; k < 3; ++k) {
+                const int bt = options[k];
+                const TmaSmem L = tma_smem(tp.kb_pad, bt * cg, rg, 8 * bt * cg, kMaxOut - 1);
+                if (2 * (L.total + 1024) <= (size_t)h->smem_optin) {
+                    tp.warps = 8; tp.RG = rg; tp.CG = cg; tp.npass = (NB + 2 * rg - 1) / (2 * rg);
+                    tp.BT = bt; tp.TB = bt * cg; tp.T = 8 * bt * cg; tp.smem = L.total; tp.ns2x = true;
+                    return SO_OK;
+                }
+            }
+        }
+    }
     for (int warps = tma_warps(); warps >= 8; warps -= 8) {
         const int ns = warps == 16 ? 2 : 4;
         int rg = 1;
@@ -285,25 +306,26 @@ int plan_tma(so_handle* h, const GPState& g, TmaPlan& tp) {
     return SO_ERR_CAPACITY;
 }
 
-template <int BT, int WARPS>
+template <int BT, int WARPS, bool NS2X>
 int launch_tma_one(so_handle* h, const TmaParams& tp, size_t smem, cudaStream_t stream) {
     static int configured_for = -1;
     if (configured_for != h->device) {
-        SO_CUDA(h, cudaFuncSetAttribute(k_posterior_tma<BT, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
+        SO_CUDA(h, cudaFuncSetAttribute(k_posterior_tma<BT, WARPS, NS2X>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
         configured_for = h->device;
     }
-    const int grid = (int)(tp.p.ntiles < (int64_t)h->num_sms ? tp.p.ntiles : (int64_t)h->num_sms);
-    k_posterior_tma<BT, WARPS><<<grid, WARPS * 32, smem, stream>>>(tp);
+    const int64_t slots = (int64_t)h->num_sms * (NS2X ? 2 : 1);
+    const int grid = (int)(tp.p.ntiles < slots ? tp.p.ntiles : slots);
+    k_posterior_tma<BT, WARPS, NS2X><<<grid, WARPS * 32, smem, stream>>>(tp);
     SO_CHECK_LAUNCH(h, "k_posterior_tma");
     return SO_OK;
 }
 
-template <int WARPS>
+template <int WARPS, bool NS2X = false>
 int launch_tma(so_handle* h, int bt, const TmaParams& tp, size_t smem, cudaStream_t stream) {
     switch (bt) {
-        case 6: return launch_tma_one<6, WARPS>(h, tp, smem, stream);
-        case 4: return launch_tma_one<4, WARPS>(h, tp, smem, stream);
-        default: return launch_tma_one<2, WARPS>(h, tp, smem, stream);
+        case 6: return launch_tma_one<6, WARPS, NS2X>(h, tp, smem, stream);
+        case 4: return launch_tma_one<4, WARPS, NS2X>(h, tp, smem, stream);
+        default: return launch_tma_one<2, WARPS, NS2X>(h, tp, smem, stream);
     }
 }
 
@@ -379,7 +401,7 @@ int run_posterior(so_handle* h, int gp, const double* Xstar_d, bool grid, int64_
 
     if (tma) {
         p.RG = g.tma_RG; p.CG = g.tma_CG; p.T = g.tma_T; p.TB = g.tma_BT * g.tma_CG;
-        const int ns = g.tma_warps == 16 ? 2 : 4;
+        const int ns = (g.tma_warps == 16 || g.tma_ns2x) ? 2 : 4;
         p.npass = (g.NB + ns * p.RG - 1) / (ns * p.RG);
         if (ns == 4 && p.RG == 8 && p.use_row_table) p.npass = table_npass; else p.use_row_table = 0;
         tp.PfFrag = g.PfFrag; tp.Aprime = g.Aprime; tp.a_stride = g.a_stride; tp.s0 = g.ap_s0;
@@ -407,6 +429,11 @@ int run_posterior(so_handle* h, int gp, const double* Xstar_d, bool grid, int64_
         const size_t smem = tma_smem(g.tma_kb_pad, p.TB, p.RG, p.T, n_extra).total;
         if (smem > (size_t)h->smem_optin)
             return so_fail(h, SO_ERR_CAPACITY, "posterior_multi: the tile does not fit with that many outputs; evaluate the GPs one by one");
+        if (g.tma_ns2x) {
+            if (2 * (smem + 1024) > (size_t)h->smem_optin)
+                return so_fail(h, SO_ERR_CAPACITY, "posterior_multi: the tile does not fit with that many outputs; evaluate the GPs one by one");
+            return launch_tma<8, true>(h, g.tma_BT, tp, smem, stream);
+        }
         return g.tma_warps == 16 ? launch_tma<16>(h, g.tma_BT, tp, smem, stream) : launch_tma<8>(h, g.tma_BT, tp, smem, stream);
     }
     LaunchPlan lp;
@@ -482,7 +509,7 @@ extern "C" int so_debug_tile_plans(int NB, int d, int64_t M, int n_extra, int64_
     const int rc = plan_tma(&h, g, tp);
     out_h[0] = rc;
     if (rc == SO_OK) {
-        const int ns = tp.warps == 16 ? 2 : 4;
+        const int ns = (tp.warps == 16 || tp.ns2x) ? 2 : 4;
         int npass = (NB + ns * tp.RG - 1) / (ns * tp.RG);
         if (NB >= 32 && NB % 32 != 0 && tp.RG == 8 && ns == 4) {
             short table[kMaxPass][8][4];
@@ -722,7 +749,7 @@ extern "C" int so_grid_prepare_rows(so_handle* h, int gp, int64_t row0, int64_t 
         SO_CUDA(h, cudaMemsetAsync(g.Aprime + (size_t)n_slow * a_stride, 0, sizeof(double2) * 128, stream));
         g.ap_s0 = s_lo; g.ap_s1 = s_hi;
         g.a_stride = a_stride; g.tma_T = pl.T; g.tma_tpb = tpb; g.tma_BT = pl.BT; g.tma_RG = pl.RG; g.tma_CG = pl.CG;
-        g.tma_kb_pad = pl.kb_pad; g.tma_warps = pl.warps; g.tma_ring = pl.ring; g.tma_ready = true;
+        g.tma_kb_pad = pl.kb_pad; g.tma_warps = pl.warps; g.tma_ring = pl.ring; g.tma_ns2x = pl.ns2x; g.tma_ready = true;
     }
     g.grid_ready = true;
     return SO_OK;

@@ -71,9 +71,12 @@ __host__ __device__ inline TmaSmem tma_smem(int kb_pad, int TB, int RG, int T, i
 
 // WARPS = 8: four block rows per warp and pass (default); WARPS = 16: two (contract_tile<BT, 2>), i.e. four warps per
 // scheduler instead of two -- kept for A/B measurements (see tma_warps() in posterior.cu).
-template <int BT, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 1) k_posterior_tma(const __grid_constant__ TmaParams tp) {
-    constexpr int NS = WARPS == 16 ? 2 : 4;
+// NS2X = true (8 warps, TWO block rows per warp, two CTAs per SM): for fits with at most 16 block rows (N <= 128) a tile has so
+// few k-steps that its tile-end reduction, barrier and epilogue are a sizeable share of it; with half the accumulators the kernel
+// needs ~110 registers and ~100 KB of shared memory, so two CTAs share an SM and one contracts while the other finishes a tile.
+template <int BT, int WARPS, bool NS2X = false>
+__global__ void __launch_bounds__(WARPS * 32, NS2X ? 2 : 1) k_posterior_tma(const __grid_constant__ TmaParams tp) {
+    constexpr int NS = (WARPS == 16 || NS2X) ? 2 : 4;
     constexpr int kCtaThreads = WARPS * 32;
     const PostParams& p = tp.p;
     extern __shared__ __align__(128) unsigned char smem_raw[];
