@@ -625,7 +625,8 @@ extern "C" int so_grid_define(so_handle* h, int d, const int32_t* n_h, const dou
 }
 
 // Two-level product tables of the grid path (Pfast: fast_rows x Npad, Pslow: slow_rows x Npad, back to back in g.P2).
-static int build_product_tables(so_handle* h, GPState& g, const double* inv_ls_d, cudaStream_t stream) {
+// Only the slow rows [s_lo, s_hi) are (re)computed: a rank of an R-way run needs 1/R of them.
+static int build_product_tables(so_handle* h, GPState& g, const double* inv_ls_d, cudaStream_t stream, int64_t s_lo, int64_t s_hi) {
     GridSpec& gs = h->grid;
     const int Npad = 8 * g.NB;
     const int64_t trows = gs.fast_rows + gs.slow_rows;
@@ -647,8 +648,8 @@ static int build_product_tables(so_handle* h, GPState& g, const double* inv_ls_d
         ts.in_fast[j] = j < gs.d ? gs.in_fast[j] : 0;
     }
     ts.fast_rows = gs.fast_rows; ts.slow_rows = gs.slow_rows;
-    k_grid_tables2<<<(unsigned)trows, 128, 0, stream>>>(ts, gs.axis, g.Xs, g.P2, g.P2 + (size_t)gs.fast_rows * Npad, g.N, Npad, g.d,
-                                                        g.variance, inv_ls_d);
+    k_grid_tables2<<<(unsigned)(gs.fast_rows + (s_hi - s_lo)), 128, 0, stream>>>(ts, gs.axis, g.Xs, g.P2, g.P2 + (size_t)gs.fast_rows * Npad,
+                                                                                 g.N, Npad, g.d, g.variance, inv_ls_d, s_lo);
     SO_CHECK_LAUNCH(h, "k_grid_tables2");
     return SO_OK;
 }
@@ -715,7 +716,7 @@ extern "C" int so_grid_prepare_rows(so_handle* h, int gp, int64_t row0, int64_t 
         }
     }
     if (fits) {
-        int rc2 = build_product_tables(h, g, inv_ls_d, stream);
+        int rc2 = build_product_tables(h, g, inv_ls_d, stream, s_lo, s_hi);
         if (rc2) return rc2;
         double* Pfast = g.P2;
         double* Pslow = g.P2 + (size_t)gs.fast_rows * Npad;
@@ -791,12 +792,12 @@ extern "C" int so_grid_prepare_f32(so_handle* h, int gp, int64_t row0, int64_t M
     cudaStream_t stream = (cudaStream_t)stream_;
     const int Npad = 8 * g.NB;
     const double* inv_ls_d = g.E + (size_t)gs.total * g.capN;     // left there by so_grid_prepare_rows
-    int rc = build_product_tables(h, g, inv_ls_d, stream);
-    if (rc) return rc;
     const int tpb = (int)((gs.fast_rows + kF32TileRows - 1) / kF32TileRows);
     const int64_t s_lo = M > 0 ? row0 / gs.fast_rows : 0;
     const int64_t s_hi = M > 0 ? (row0 + M - 1) / gs.fast_rows + 1 : 0;
     const int64_t n_slow = s_hi - s_lo;
+    int rc = build_product_tables(h, g, inv_ls_d, stream, s_lo, s_hi);
+    if (rc) return rc;
     if (n_slow > 65535) return so_fail(h, SO_ERR_CAPACITY, "so_grid_prepare_f32: more than 65535 slow indices in one row block");
     const size_t a_floats = (size_t)tpb * nslab * (kF32ASlabBytes / 4);
     const size_t b_stride = f32_b_bytes(Np);

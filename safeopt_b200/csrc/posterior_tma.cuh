@@ -165,10 +165,10 @@ struct TableSpec {
 
 __global__ void k_grid_tables2(TableSpec ts, const double* __restrict__ axis, const double* __restrict__ Xs,
                                double* __restrict__ Pfast, double* __restrict__ Pslow, int N, int Npad, int d,
-                               double variance, const double* __restrict__ inv_ls_d) {
-    const int64_t r = blockIdx.x;             // one table row per block
+                               double variance, const double* __restrict__ inv_ls_d, int64_t slow0) {
+    const int64_t r = blockIdx.x;             // one table row per block: the fast rows, then the slow rows slow0, slow0 + 1, ...
     const bool fast = r < ts.fast_rows;
-    const int64_t tr = fast ? r : r - ts.fast_rows;
+    const int64_t tr = fast ? r : r - ts.fast_rows + slow0;
     const int64_t grow = fast ? tr : tr * ts.fast_rows;
     for (int n = threadIdx.x; n < Npad; n += blockDim.x) {
         double v = 0.0;

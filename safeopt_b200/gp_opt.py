@@ -637,8 +637,16 @@ class SafeOpt(GaussianProcessOptimization):
             # thresholds changed since the bounds were computed: redo the (fused) pass
             self.update_confidence_intervals(context=self.context)
         eng = self._engine
-        eng.reduce_safe(self._Q_d, len(self.gps), self._row0, self._S_d, self._rec_safe_d)
-        self._safe_info = reduce_safe_records(self._comm.gather_records(self._rec_safe_d, SAFE_REC_DTYPE))
+        if self._fused:
+            # the fused set kernel without its candidate pass: the safe record of every rank arrives through the peer buffers
+            # (no collective); it also rewrites the maximiser mask, which is a function of Q and S only
+            G, world = len(self.gps), self._comm.world
+            host = eng.sets_fused(self._Q_d, G, self._row0, self._S_d, self.scaling, np.zeros(G), False, self._M_d, None, None)
+            self._safe_info = reduce_safe_records(host[:world * 64].view(SAFE_REC_DTYPE).reshape(-1))
+            self._invalidate_host("M")
+        else:
+            eng.reduce_safe(self._Q_d, len(self.gps), self._row0, self._S_d, self._rec_safe_d)
+            self._safe_info = reduce_safe_records(self._comm.gather_records(self._rec_safe_d, SAFE_REC_DTYPE))
         self._check_fits()
         self._invalidate_host("S")
 
