@@ -195,7 +195,8 @@ int so_debug_row_plan(int NB, int16_t* table_h, int* npass_h);
 /* Diagnostic, host only: the tile plans the posterior kernels would use for NB block rows on a device with
  * smem_limit bytes of opt-in shared memory and num_sms SMs (n_extra = further GPs sharing the launch).
  *   out_h[0..9]   grid kernel: status, BT, RG, CG, T, npass, ring (0/1), ring stages, shared-memory bytes, warps
- *   out_h[10..17] explicit-rows kernel for M candidates of dimension d: status, BT, RG, CG, T, npass, shared-memory bytes, 0 */
+ *   out_h[10..16] explicit-rows kernel for M candidates of dimension d: status, BT, RG, CG, T, npass, shared-memory bytes
+ *   out_h[17]     grid kernel: block rows per warp and pass (4; 2 for the 16-warp / two-CTA variants; 6 for NB = 36..48) */
 int so_debug_tile_plans(int NB, int d, int64_t M, int n_extra, int64_t smem_limit, int num_sms, int64_t* out_h);
 /* Materialise grid rows [row0, row0+M) as an (M x d) row-major array (tests, query point). */
 int so_grid_rows(so_handle* h, int64_t row0, int64_t M, double* X_d, void* stream);

@@ -45,6 +45,7 @@ struct GPState {
     int tma_T = 0, tma_tpb = 0, tma_BT = 0, tma_RG = 0, tma_CG = 0, tma_kb_pad = 0, tma_warps = 8;
     bool tma_ready = false;
     bool tma_ns2x = false;       // N <= 128: two block rows per warp, two CTAs per SM (k_posterior_tma<.., .., true>)
+    bool tma_ns6 = false;        // 33..48 block rows on a 32-row tile: six block rows per warp, one pass
     bool tma_ring = false;       // B streams through the k-chunk ring (posterior_ring.cuh) instead of a resident double buffer
     bool grid_ready = false;
     // fp32 arithmetic mode (posterior_f32.cuh): TF32 hi/lo operand planes in UMMA canonical layout

@@ -181,21 +181,24 @@ int plan_launch(so_handle* h, const GPState& g, int64_t M, bool grid, int n_extr
 
 // Block rows of the eight warps for an arbitrary NB (see PostParams::row_table): longest row first to the least loaded warp,
 // every warp at most 4 * npass rows; each warp's rows ascending, four per pass.
-int plan_rows(int NB, short (&table)[kMaxPass][8][4]) {
+int plan_rows(int NB, short (&table)[kMaxPass][8][kMaxSlots], int slots = 4) {
     const int per_warp = (NB + 7) / 8;
-    const int npass = (per_warp + 3) / 4;
+    const int npass = (per_warp + slots - 1) / slots;
     int load[8] = {0, 0, 0, 0, 0, 0, 0, 0}, count[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    int mine[8][4 * kMaxPass];
+    int mine[8][kMaxSlots * kMaxPass];
     for (int i = NB - 1; i >= 0; --i) {
         int best = -1;
         for (int w = 0; w < 8; ++w)
-            if (count[w] < 4 * npass && (best < 0 || load[w] < load[best])) best = w;
+            if (count[w] < slots * npass && (best < 0 || load[w] < load[best])) best = w;
         mine[best][count[best]++] = i;
         load[best] += i + 1;
     }
+    for (int p = 0; p < kMaxPass; ++p)
+        for (int w = 0; w < 8; ++w)
+            for (int q = 0; q < kMaxSlots; ++q) table[p][w][q] = -1;
     for (int w = 0; w < 8; ++w) {
         std::sort(mine[w], mine[w] + count[w]);
-        for (int q = 0; q < 4 * npass; ++q) table[q / 4][w][q % 4] = (short)(q < count[w] ? mine[w][q] : -1);
+        for (int q = 0; q < count[w]; ++q) table[q / slots][w][q % slots] = (short)mine[w][q];
     }
     return npass;
 }
@@ -233,7 +236,7 @@ int launch_bt(so_handle* h, const PostParams& p, const LaunchPlan& lp, cudaStrea
 }
 
 // ---- TMA double-buffer kernel (grid path default) ----------------------------------------------------------------
-struct TmaPlan { int BT, RG, CG, T, TB, npass, kb_pad, warps; size_t smem; bool ring; bool ns2x; };
+struct TmaPlan { int BT, RG, CG, T, TB, npass, kb_pad, warps; size_t smem; bool ring; bool ns2x; bool ns6; };
 
 // SO_K2_RING=0 keeps the resident double buffer (smaller tiles) for every N, SO_K2_RING=all streams as soon as the 48-row
 // tile does not fit twice (A/B measurements); default: stream when the 32-row tile does not fit twice either.
@@ -260,6 +263,7 @@ int plan_tma(so_handle* h, const GPState& g, TmaPlan& tp) {
     const int options[3] = {6, 4, 2};
     tp.ring = false;
     tp.ns2x = false;
+    tp.ns6 = false;
     // SO_K2_SMALLN=1, N <= 128: eight warps with two block rows each, two CTAs per SM (see k_posterior_tma).  Measured on config 4's
     // grid (profiles/r02_k2_small_n.md): N = 32 +8 %, 64 -1 %, 96 +4 %, 128 -7 % against the four-rows-per-warp kernel -- the doubled
     // B-fragment traffic costs what the second CTA hides -- so it is an A/B switch, off by default.
@@ -291,6 +295,12 @@ int plan_tma(so_handle* h, const GPState& g, TmaPlan& tp) {
             const TmaSmem L = tma_smem(tp.kb_pad, bt * tp.CG, tp.RG, 8 * bt * tp.CG);
             if (L.total <= (size_t)h->smem_optin) {
                 tp.BT = bt; tp.TB = bt * tp.CG; tp.T = 8 * bt * tp.CG; tp.smem = L.total;
+                // 32-row tile with 33..48 block rows: six block rows per warp, one pass (SO_K2_NS6=0: four rows, two passes)
+                const char* v6 = std::getenv("SO_K2_NS6");
+                if (bt == 4 && warps == 8 && rg == 8 && NB > 32 && NB <= 48 && !(v6 && std::string(v6) == "0")) {
+                    tp.ns6 = true;
+                    tp.npass = 1;
+                }
                 return SO_OK;
             }
             // neither a 48- nor a 32-row tile fits twice (N > 416): stream B through the k-chunk ring and keep the tile 48 rows
@@ -306,26 +316,26 @@ int plan_tma(so_handle* h, const GPState& g, TmaPlan& tp) {
     return SO_ERR_CAPACITY;
 }
 
-template <int BT, int WARPS, bool NS2X>
+template <int BT, int WARPS, int NSV>
 int launch_tma_one(so_handle* h, const TmaParams& tp, size_t smem, cudaStream_t stream) {
     static int configured_for = -1;
     if (configured_for != h->device) {
-        SO_CUDA(h, cudaFuncSetAttribute(k_posterior_tma<BT, WARPS, NS2X>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
+        SO_CUDA(h, cudaFuncSetAttribute(k_posterior_tma<BT, WARPS, NSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
         configured_for = h->device;
     }
-    const int64_t slots = (int64_t)h->num_sms * (NS2X ? 2 : 1);
+    const int64_t slots = (int64_t)h->num_sms * (NSV == 2 ? 2 : 1);
     const int grid = (int)(tp.p.ntiles < slots ? tp.p.ntiles : slots);
-    k_posterior_tma<BT, WARPS, NS2X><<<grid, WARPS * 32, smem, stream>>>(tp);
+    k_posterior_tma<BT, WARPS, NSV><<<grid, WARPS * 32, smem, stream>>>(tp);
     SO_CHECK_LAUNCH(h, "k_posterior_tma");
     return SO_OK;
 }
 
-template <int WARPS, bool NS2X = false>
+template <int WARPS, int NSV = 0>
 int launch_tma(so_handle* h, int bt, const TmaParams& tp, size_t smem, cudaStream_t stream) {
     switch (bt) {
-        case 6: return launch_tma_one<6, WARPS, NS2X>(h, tp, smem, stream);
-        case 4: return launch_tma_one<4, WARPS, NS2X>(h, tp, smem, stream);
-        default: return launch_tma_one<2, WARPS, NS2X>(h, tp, smem, stream);
+        case 6: return launch_tma_one<6, WARPS, NSV>(h, tp, smem, stream);
+        case 4: return launch_tma_one<4, WARPS, NSV>(h, tp, smem, stream);
+        default: return launch_tma_one<2, WARPS, NSV>(h, tp, smem, stream);
     }
 }
 
@@ -401,9 +411,10 @@ int run_posterior(so_handle* h, int gp, const double* Xstar_d, bool grid, int64_
 
     if (tma) {
         p.RG = g.tma_RG; p.CG = g.tma_CG; p.T = g.tma_T; p.TB = g.tma_BT * g.tma_CG;
-        const int ns = (g.tma_warps == 16 || g.tma_ns2x) ? 2 : 4;
+        const int ns = g.tma_ns6 ? 6 : ((g.tma_warps == 16 || g.tma_ns2x) ? 2 : 4);
         p.npass = (g.NB + ns * p.RG - 1) / (ns * p.RG);
-        if (ns == 4 && p.RG == 8 && p.use_row_table) p.npass = table_npass; else p.use_row_table = 0;
+        if (ns == 6) { p.npass = plan_rows(g.NB, p.row_table, 6); p.use_row_table = 1; }
+        else if (ns == 4 && p.RG == 8 && p.use_row_table) p.npass = table_npass; else p.use_row_table = 0;
         tp.PfFrag = g.PfFrag; tp.Aprime = g.Aprime; tp.a_stride = g.a_stride; tp.s0 = g.ap_s0;
         if (row0 / h->grid.fast_rows < g.ap_s0 || (row0 + M - 1) / h->grid.fast_rows >= g.ap_s1)
             return so_fail(h, SO_ERR_NOT_FITTED, "posterior_grid: rows outside the range given to so_grid_prepare_rows");
@@ -429,10 +440,11 @@ int run_posterior(so_handle* h, int gp, const double* Xstar_d, bool grid, int64_
         const size_t smem = tma_smem(g.tma_kb_pad, p.TB, p.RG, p.T, n_extra).total;
         if (smem > (size_t)h->smem_optin)
             return so_fail(h, SO_ERR_CAPACITY, "posterior_multi: the tile does not fit with that many outputs; evaluate the GPs one by one");
+        if (g.tma_ns6) return launch_tma_one<4, 8, 6>(h, tp, smem, stream);
         if (g.tma_ns2x) {
             if (2 * (smem + 1024) > (size_t)h->smem_optin)
                 return so_fail(h, SO_ERR_CAPACITY, "posterior_multi: the tile does not fit with that many outputs; evaluate the GPs one by one");
-            return launch_tma<8, true>(h, g.tma_BT, tp, smem, stream);
+            return launch_tma<8, 2>(h, g.tma_BT, tp, smem, stream);
         }
         return g.tma_warps == 16 ? launch_tma<16>(h, g.tma_BT, tp, smem, stream) : launch_tma<8>(h, g.tma_BT, tp, smem, stream);
     }
@@ -509,11 +521,11 @@ extern "C" int so_debug_tile_plans(int NB, int d, int64_t M, int n_extra, int64_
     const int rc = plan_tma(&h, g, tp);
     out_h[0] = rc;
     if (rc == SO_OK) {
-        const int ns = (tp.warps == 16 || tp.ns2x) ? 2 : 4;
+        const int ns = tp.ns6 ? 6 : ((tp.warps == 16 || tp.ns2x) ? 2 : 4);
         int npass = (NB + ns * tp.RG - 1) / (ns * tp.RG);
-        if (NB >= 32 && NB % 32 != 0 && tp.RG == 8 && ns == 4) {
-            short table[kMaxPass][8][4];
-            npass = plan_rows(NB, table);
+        if (NB >= 32 && NB % 32 != 0 && tp.RG == 8 && ns >= 4) {
+            short table[kMaxPass][8][kMaxSlots];
+            npass = plan_rows(NB, table, ns);
         }
         out_h[1] = tp.BT; out_h[2] = tp.RG; out_h[3] = tp.CG; out_h[4] = tp.T; out_h[5] = npass; out_h[6] = tp.ring ? 1 : 0;
         if (tp.ring) {
@@ -523,6 +535,7 @@ extern "C" int so_debug_tile_plans(int NB, int d, int64_t M, int n_extra, int64_
             out_h[8] = (int64_t)tma_smem(tp.kb_pad, tp.TB, tp.RG, tp.T, n_extra).total;
         }
         out_h[9] = tp.warps;
+        out_h[17] = ns;
     }
     LaunchPlan lp;
     const int rc2 = plan_launch(&h, g, M, false, n_extra, lp);
@@ -535,10 +548,7 @@ extern "C" int so_debug_tile_plans(int NB, int d, int64_t M, int n_extra, int64_
 
 extern "C" int so_debug_row_plan(int NB, int16_t* table_h, int* npass_h) {
     if (!table_h || !npass_h || NB < 1 || NB > 8 * 4 * kMaxPass) return SO_ERR_BAD_ARG;
-    short table[kMaxPass][8][4];
-    for (int p = 0; p < kMaxPass; ++p)
-        for (int w = 0; w < 8; ++w)
-            for (int s = 0; s < 4; ++s) table[p][w][s] = -1;
+    short table[kMaxPass][8][kMaxSlots];
     *npass_h = plan_rows(NB, table);
     for (int p = 0; p < kMaxPass; ++p)
         for (int w = 0; w < 8; ++w)
@@ -750,7 +760,7 @@ extern "C" int so_grid_prepare_rows(so_handle* h, int gp, int64_t row0, int64_t 
         SO_CUDA(h, cudaMemsetAsync(g.Aprime + (size_t)n_slow * a_stride, 0, sizeof(double2) * 128, stream));
         g.ap_s0 = s_lo; g.ap_s1 = s_hi;
         g.a_stride = a_stride; g.tma_T = pl.T; g.tma_tpb = tpb; g.tma_BT = pl.BT; g.tma_RG = pl.RG; g.tma_CG = pl.CG;
-        g.tma_kb_pad = pl.kb_pad; g.tma_warps = pl.warps; g.tma_ring = pl.ring; g.tma_ns2x = pl.ns2x; g.tma_ready = true;
+        g.tma_kb_pad = pl.kb_pad; g.tma_warps = pl.warps; g.tma_ring = pl.ring; g.tma_ns2x = pl.ns2x; g.tma_ns6 = pl.ns6; g.tma_ready = true;
     }
     g.grid_ready = true;
     return SO_OK;

@@ -11,6 +11,7 @@ constexpr int kWarps = 8;
 constexpr int kGridMaxDim = 6;   // grid fast path (larger d uses explicit rows)
 constexpr int kMaxOut = 4;       // GPs evaluated by one launch when they share the factorisation (so_posterior_*_multi)
 constexpr int kMaxPass = 8;      // passes of four block rows per warp: 8 warps x 8 x 4 = 256 block rows (N = 2048)
+constexpr int kMaxSlots = 6;     // block rows per warp and pass: 4 (default), 2 (16-warp / two-CTA variants) or 6 (N = 281..384)
 
 struct PostParams {
     int N, NB, d, RG, CG, T, TB, npass, kind;
@@ -47,7 +48,7 @@ struct PostParams {
     // per iteration) the host assigns the rows longest-first to the least loaded warp (plan_rows) -- with the closed form,
     // NB = 33 put the whole extra block row on one warp in a second pass and a tile took 1.7x as long.
     int use_row_table;
-    short row_table[kMaxPass][8][4];            // ascending per pass, -1 = unused slot (suffix); NB <= 256
+    short row_table[kMaxPass][8][kMaxSlots];    // ascending per pass, -1 = unused slot (suffix); NB <= 256
 };
 
 struct SmemLayout {
@@ -306,7 +307,7 @@ __device__ __forceinline__ void contract_tile(const PostParams& p, const double2
                                               double* __restrict__ sSST, double* __restrict__ sMeanT,
                                               double* __restrict__ sMeanXT, int g, int cg, int lane) {
     static_assert(BT % 2 == 0, "BT must be even");
-    static_assert(NS == 2 || NS == 4, "two or four block rows per warp and pass");
+    static_assert(NS == 2 || NS == 4 || NS == 6, "two, four or six block rows per warp and pass");
     const int RG = p.RG, NB = p.NB, T = p.T;
     for (int pass = 0; pass < p.npass; ++pass) {
         const int base = NS * RG * pass;
@@ -315,7 +316,9 @@ __device__ __forceinline__ void contract_tile(const PostParams& p, const double2
         int rows[NS];
 #pragma unroll
         for (int i = 0; i < NS; ++i) {
-            int r = (NS == 4 && p.use_row_table) ? (int)p.row_table[pass][g][i & 3] : warp_row<NS>(base, RG, g, i);
+            int r;
+            if constexpr (NS == 6) r = (int)p.row_table[pass][g][i];           // six rows per warp: always planned by the host
+            else r = (NS == 4 && p.use_row_table) ? (int)p.row_table[pass][g][i & 3] : warp_row<NS>(base, RG, g, i);
             rows[i] = r < NB ? r : -1;
         }
         int na = 0;

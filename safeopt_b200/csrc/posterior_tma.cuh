@@ -74,9 +74,14 @@ __host__ __device__ inline TmaSmem tma_smem(int kb_pad, int TB, int RG, int T, i
 // NS2X = true (8 warps, TWO block rows per warp, two CTAs per SM): for fits with at most 16 block rows (N <= 128) a tile has so
 // few k-steps that its tile-end reduction, barrier and epilogue are a sizeable share of it; with half the accumulators the kernel
 // needs ~110 registers and ~100 KB of shared memory, so two CTAs share an SM and one contracts while the other finishes a tile.
-template <int BT, int WARPS, bool NS2X = false>
-__global__ void __launch_bounds__(WARPS * 32, NS2X ? 2 : 1) k_posterior_tma(const __grid_constant__ TmaParams tp) {
-    constexpr int NS = (WARPS == 16 || NS2X) ? 2 : 4;
+// NSV = 6 (8 warps, SIX block rows per warp, 32-row tiles): for 281 <= N <= 384 the 48-row tile no longer fits twice; with four rows
+// per warp the 32-row tile needs two passes over its B tile (the second with one or two rows per warp); six rows per warp keep
+// the 24 accumulator pairs of the N = 256 configuration and cover up to 48 block rows in ONE pass.
+template <int BT, int WARPS, int NSV = 0>
+__global__ void __launch_bounds__(WARPS * 32, NSV == 2 ? 2 : 1) k_posterior_tma(const __grid_constant__ TmaParams tp) {
+    constexpr bool NS2X = NSV == 2;
+    constexpr int NS = NSV != 0 ? NSV : (WARPS == 16 ? 2 : 4);
+    (void)NS2X;
     constexpr int kCtaThreads = WARPS * 32;
     const PostParams& p = tp.p;
     extern __shared__ __align__(128) unsigned char smem_raw[];

@@ -284,7 +284,7 @@ def test_posterior_safe_modes_and_columns():
 
 
 @pytest.mark.parametrize("d,n,N", [(1, 100, 5), (2, 60, 64), (3, [7, 9, 11], 30), (4, 12, 256), (5, 4, 20), (6, 3, 40), (4, 12, 257), (2, 70, 300),
-                                   (3, 20, 390), (2, 64, 520)])
+                                   (3, 20, 390), (2, 64, 520), (4, 12, 281), (4, 12, 330), (3, 40, 384)])
 def test_grid_path_equals_rows_path(d, n, N):
     from safeopt_b200.utilities import detect_grid
     w = workloads.grid_workload("t", d, 10, N)

@@ -80,7 +80,7 @@ def test_tile_plans_fit_the_device_for_every_size():
                 # the tile is planned for one output; with further outputs a launch that no longer fits is refused with
                 # SO_ERR_CAPACITY and the host evaluates the GPs one by one (the ring re-sizes itself and always fits)
                 assert (smem <= limit or (n_extra > 0 and not ring)) and bt in (2, 4, 6) and rg * cg == warps == 8 and T == 8 * bt * cg
-                assert 4 * rg * npass >= nb
+                assert out[17] in (2, 4, 6) and out[17] * rg * npass >= nb
                 if ring:
                     assert stages >= 4 and T == 48 and rg == 8
                     seen_ring += 1
@@ -94,10 +94,12 @@ def test_tile_plans_fit_the_device_for_every_size():
             else:
                 assert st2 == _lib.SO_ERR_CAPACITY and nb > 150           # the resident K tile caps the explicit-rows kernel
     assert seen_ring > 0 and seen_db48 > 0
-    # config 4: N = 256 -> 48-row double buffer; N = 257..280 keep it; N = 512 streams
-    for nb, want_T, want_ring in [(32, 48, 0), (33, 48, 0), (35, 48, 0), (36, 32, 0), (52, 32, 0), (64, 48, 1)]:
+    # config 4: N = 256 -> 48-row double buffer; N = 257..280 keep it; N = 281..384: 32-row tile, six block rows per warp in
+    # one pass; N = 512 streams
+    for nb, want_T, want_ring, want_ns, want_pass in [(32, 48, 0, 4, 1), (33, 48, 0, 4, 2), (35, 48, 0, 4, 2), (36, 32, 0, 6, 1),
+                                                      (48, 32, 0, 6, 1), (49, 32, 0, 4, 2), (52, 32, 0, 4, 2), (64, 48, 1, 4, 2)]:
         lib.so_debug_tile_plans(nb, 4, 6_250_000, 0, limit, sms, out.ctypes.data)
-        assert (out[4], out[6]) == (want_T, want_ring), nb
+        assert (out[4], out[6], out[17], out[5]) == (want_T, want_ring, want_ns, want_pass), nb
 
 
 def test_record_layouts_match_header():
