@@ -365,7 +365,28 @@ static int fit_impl(so_handle* h, int gp, const double* X_h, const double* Y_h, 
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
+#ifdef SO_FIT_STAMPS
+        static long long* stamps_d = nullptr;
+        if (!stamps_d) { cudaMalloc(&stamps_d, 256 * sizeof(long long)); }
+        cudaMemsetAsync(stamps_d, 0, 256 * sizeof(long long), stream);
+        fp.stamps = stamps_d;
+#endif
         SO_CUDA(h, cudaLaunchKernelEx(&cfg, k_fit_cluster, fp));
+#ifdef SO_FIT_STAMPS
+        if (std::getenv("SO_FIT_VERBOSE")) {
+            long long st_h[256];
+            cudaStreamSynchronize(stream);
+            cudaMemcpy(st_h, stamps_d, sizeof(st_h), cudaMemcpyDeviceToHost);
+            const int nblk = fp.NP / kFcB;
+            std::fprintf(stderr, "[fit stamps N=%d] phase0 %lld sync %lld |", N, st_h[1] - st_h[0], st_h[2] - st_h[1]);
+            for (int pi = 0; pi < nblk; ++pi) {
+                const long long* q = st_h + 2 + 6 * pi;
+                std::fprintf(stderr, " p%d: factor+inv %lld solve %lld sync %lld trail %lld sync %lld |", pi, q[2] - q[0],
+                             q[3] - q[2], q[4] - q[3], q[5] - q[4], q[6] - q[5]);
+            }
+            std::fprintf(stderr, " tail %lld total %lld cycles\n", st_h[3 + 6 * nblk] - st_h[2 + 6 * nblk], st_h[3 + 6 * nblk] - st_h[0]);
+        }
+#endif
         g.fitted = true;
         if (async) return SO_OK;                            // the caller reads so_fit_status after its next synchronisation
         SO_CUDA(h, cudaStreamSynchronize(stream));

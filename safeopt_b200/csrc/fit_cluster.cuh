@@ -40,12 +40,23 @@ struct FitClusterParams {
     double variance, diag_add;
     double inv_ls[SO_MAX_DIM];
     int* status;
+#ifdef SO_FIT_STAMPS
+    long long* stamps;       // timing experiments only (tools/build_variant.sh): clock64 of CTA 0 at the phase boundaries
+#endif
 };
+
+#ifdef SO_FIT_STAMPS
+#define FC_STAMP(i) do { if (rank == 0 && tid == 0) fp.stamps[i] = clock64(); } while (0)
+#else
+#define FC_STAMP(i) do {} while (0)
+#endif
 
 __device__ __forceinline__ unsigned fc_cluster_rank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r)); return r; }
 __device__ __forceinline__ unsigned fc_cluster_size() { unsigned r; asm volatile("mov.u32 %0, %%cluster_nctarank;\n" : "=r"(r)); return r; }
 __device__ __forceinline__ void fc_cluster_sync() {
+#ifndef SO_FIT_NO_FENCE
     __threadfence();
+#endif
     asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
 }
@@ -106,8 +117,9 @@ __global__ void __launch_bounds__(kFcThreads, 1) k_fit_cluster(const __grid_cons
     __shared__ double sL[kFcB][kFcLd];      // L_PP
     __shared__ double sI[kFcB][kFcLd];      // inv(L_PP), lower
     __shared__ double sIT[kFcB][kFcLd];     // its transpose
-    __shared__ double sCol[2][kFcB];        // unscaled column j of the block being factored (double buffered over j)
-    __shared__ double sRinv[kFcB];          // 1 / L_jj
+    __shared__ double sU[kFcB][kFcLd];      // sU[j][t] = unscaled column j of the block being factored (d_jj on the diagonal)
+    __shared__ double sRcp[kFcB];           // 1 / d_jj
+    __shared__ double sD[kFcB];             // d_jj (1 where the factorisation failed)
     __shared__ int sBad;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned rank = fc_cluster_rank(), csize = fc_cluster_size();
@@ -118,18 +130,24 @@ __global__ void __launch_bounds__(kFcThreads, 1) k_fit_cluster(const __grid_cons
     double (*wA)[kFcLd] = reinterpret_cast<double (*)[kFcLd]>(fc_dyn + (size_t)warp * 2 * kFcB * kFcLd * sizeof(double));
     double (*wB)[kFcLd] = wA + kFcB;
 
-    // the (up to three) elements of the 32x32 lower triangle this thread keeps in registers while a diagonal block is factored
-    int ei[3], ek[3];
+    // Diagonal block, two roles that meet at one barrier per column (see the panel loop): warps 0..5 factor it (a thread keeps up
+    // to three elements of the 32x32 lower triangle in registers), warps 6..7 invert it one column step behind.
+    constexpr int kFcFactorThreads = kFcThreads - 2 * kFcB, kFcElems = 3;
+    static_assert(kFcFactorThreads * kFcElems >= kFcB * (kFcB + 1) / 2, "the factoring warps cover the lower triangle");
+    const bool factoring = tid < kFcFactorThreads;
+    int ei[kFcElems], ek[kFcElems];
 #pragma unroll
-    for (int q = 0; q < 3; ++q) {
-        const int e = tid + q * kFcThreads;
+    for (int q = 0; q < kFcElems; ++q) {
+        const int e = tid + q * kFcFactorThreads;
         int ii = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
         while ((ii + 1) * (ii + 2) / 2 <= e) ++ii;
         while (ii * (ii + 1) / 2 > e) --ii;
-        ei[q] = e < kFcB * (kFcB + 1) / 2 ? ii : -1;
-        ek[q] = e - ii * (ii + 1) / 2;
+        const bool mine = factoring && e < kFcB * (kFcB + 1) / 2;
+        ei[q] = mine ? ii : -1;
+        ek[q] = mine ? e - ii * (ii + 1) / 2 : 0;
     }
 
+    FC_STAMP(0);
     // ---- phase 0: scaled inputs, Ky (identity in the padding), W = 0
     for (int e = gtid; e < fp.Npad * d; e += gthreads) {
         const int n = e / d, j = e - n * d;
@@ -156,60 +174,105 @@ __global__ void __launch_bounds__(kFcThreads, 1) k_fit_cluster(const __grid_cons
         fp.W[(size_t)i * ld + j] = 0.0;
     }
     if (tid == 0) sBad = 0;
+    FC_STAMP(1);
     fc_cluster_sync();
 
     for (int pi = 0; pi < nblk; ++pi) {
         const int p0 = pi * kFcB;
+        FC_STAMP(2 + 6 * pi);
         // ---- 1. diagonal block: factor and invert (every CTA, redundantly).  The trailing elements live in registers; per
         //         column j the owners of a_ij (k == j) put the unscaled column into shared memory, one barrier, and every
         //         remaining element takes a_ik -= a_ij a_kj / d_jj.  1 / L_jj = rsqrt(d_jj), no division, no sqrt.
-        double a[3];
+        double a[kFcElems];
 #pragma unroll
-        for (int q = 0; q < 3; ++q) a[q] = ei[q] >= 0 ? __ldcg(fp.K + (size_t)(p0 + ei[q]) * ld + p0 + ek[q]) : 0.0;
+        for (int q = 0; q < kFcElems; ++q) a[q] = ei[q] >= 0 ? __ldcg(fp.K + (size_t)(p0 + ei[q]) * ld + p0 + ek[q]) : 0.0;
+        // A dependent fp64 operation takes ~40 cycles here and every column step is a chain of them (measured: ~340 cycles per column
+        // of the factorisation and ~310 per row of the inverse when all eight warps did one after the other), so
+        //  * the factorisation works on the UNSCALED columns u_j (L = U diag(d)^-1/2): per column only d_jj -> 1 / d_jj ->
+        //    a_ik -= u_ij u_kj / d_jj is sequential.  1 / d = r0 (1 + e + e^2 + ...) with the MUFU seed r0 and e = 1 - d r0
+        //    (|e| < 2^-20); with t = u_ij u_kj r0 formed while e is in flight, a - t - t (e + e^2) leaves three dependent
+        //    operations behind the seed.  No square root in the loop at all;
+        //  * the inverse rides along one column step behind in warps 6..7, also unscaled and RIGHT-looking: Y = inv(U), column c by
+        //    two threads that keep the running right-hand sides P_i = delta_ic - sum_{k' < k} u_ik' y_k' of the rows i = sub mod 2
+        //    in registers.  When column k of U and 1 / d_kk are published: y_k = P_k / d_kk (one multiply), one shuffle to the
+        //    partner, P_i -= u_ik y_k for i > k (independent FMAs) -- two dependent operations per step instead of a 31-term sum;
+        //  * after the last column one pass scales both: L_ik = u_ik rsqrt(d_kk), inv(L)_ic = sqrt(d_ii) Y_ic.
+        const int c = (tid - kFcFactorThreads) >> 1, sub = tid & 1;
+        double P[16];                                       // P[m] = running right-hand side of row 2 m + sub
+#pragma unroll
+        for (int m = 0; m < 16; ++m) P[m] = (2 * m + sub == c) ? 1.0 : 0.0;
+        auto inverse_col = [&](const int k) {
+            double yk = P[k >> 1] * sRcp[k];                // right in the thread that owns row k
+            yk = __shfl_sync(0xffffffffu, yk, (lane & ~1) | (k & 1));
+            if (sub == 0) sI[k][c] = yk;
+#pragma unroll
+            for (int m = 0; m < 16; ++m)
+                if (2 * m + 1 > k) {                        // rows i = 2 m + sub > k (checked per thread below)
+                    const int i = 2 * m + sub;
+                    if (i > k) P[m] = fma(-sU[k][i], yk, P[m]);
+                }
+        };
+#pragma unroll
         for (int j = 0; j < kFcB; ++j) {
-            double* col = sCol[j & 1];
+            double* col = sU[j];
 #pragma unroll
-            for (int q = 0; q < 3; ++q)
+            for (int q = 0; q < kFcElems; ++q)
                 if (ei[q] >= 0 && ek[q] == j) col[ei[q]] = a[q];
             __syncthreads();
-            const double djj = col[j];
-            const bool ok = djj > 0.0 && !isinf(djj);
-            const double dd = ok ? djj : 1.0;
-            if (!ok && tid == 0) sBad = 1;
-            const double inv_s = rsqrt(dd), inv_d = inv_s * inv_s;
-            if (tid < kFcB) {
-                sL[tid][j] = tid > j ? col[tid] * inv_s : (tid == j ? dd * inv_s : 0.0);
-                if (tid == j) sRinv[j] = inv_s;
-            }
+            if (factoring) {
+#ifdef SO_FC_SKIP_FACTOR      // SO_FC_SKIP_*: timing experiments only (tools/build_variant.sh), results are garbage
+                if (tid > 1000)
+#endif
+                {
+                    double prod[kFcElems];
 #pragma unroll
-            for (int q = 0; q < 3; ++q)
-                if (ei[q] >= 0 && ek[q] > j) a[q] = fma(-col[ei[q]] * inv_d, col[ek[q]], a[q]);
-            // the other half of sCol is written next: its last readers passed this iteration's barrier already
-        }
-        __syncthreads();
-        // inv(L_PP): column c by the 8 threads 8c .. 8c+7 (forward substitution on e_c; thread `sub` keeps x_k for k = sub mod 8
-        // in registers and owns those terms of every dot product; three shuffles finish a row), reciprocals from the factorisation
-        {
-            const int c = tid >> 3, sub = tid & 7;
-            double x[4] = {0.0, 0.0, 0.0, 0.0};             // x[m] = x_{8 m + sub}
+                    for (int q = 0; q < kFcElems; ++q) prod[q] = col[ei[q] >= 0 ? ei[q] : 0] * col[ek[q]];
+                    const double djj = col[j];
+                    const bool ok = djj > 0.0 && !isinf(djj);
+                    const double dd = ok ? djj : 1.0;       // a failed factorisation is flagged; the arithmetic stays finite
+                    double r0;
+                    asm("rcp.approx.ftz.f64 %0, %1;\n" : "=d"(r0) : "d"(dd));
+                    const double e = fma(-dd, r0, 1.0);
+                    const double pe = fma(e, e, e);
 #pragma unroll
-            for (int i = 0; i < kFcB; ++i) {
-                double part = 0.0;
-#pragma unroll
-                for (int m = 0; m < 4; ++m)
-                    if (8 * m < i) {                        // k = 8 m + sub < i (checked per thread below), k >= c holds because x_k = 0 for k < c
-                        const int k = 8 * m + sub;
-                        if (k < i) part = fma(-sL[i][k], x[m], part);
+                    for (int q = 0; q < kFcElems; ++q) {
+                        const double t = prod[q] * r0;
+                        const double u = a[q] - t;
+                        if (ei[q] >= 0 && ek[q] > j) a[q] = fma(-t, pe, u);
                     }
-                part += __shfl_xor_sync(0xffffffffu, part, 1);
-                part += __shfl_xor_sync(0xffffffffu, part, 2);
-                part += __shfl_xor_sync(0xffffffffu, part, 4);
-                const double xi = i >= c ? ((i == c ? 1.0 : 0.0) + part) * sRinv[i] : 0.0;
-                if (sub == (i & 7)) x[i >> 3] = xi;
-                if (sub == 0) { sI[i][c] = xi; sIT[c][i] = xi; }
+                    if (tid == 0) {
+                        sRcp[j] = fma(r0, pe, r0);
+                        sD[j] = dd;
+                        if (!ok) sBad = 1;
+                    }
+                }
+            } else if (j > 0) {
+#ifdef SO_FC_SKIP_INV
+                if (tid > 1000)
+#endif
+                inverse_col(j - 1);                         // column j-1 of U and 1 / d_{j-1,j-1} were published before this step's barrier
             }
         }
         __syncthreads();
+        if (!factoring) inverse_col(kFcB - 1);
+        __syncthreads();
+        // scaling pass: rsqrt(d_kk) once per column, then L, inv(L) and its transpose
+        if (tid < kFcB) sRcp[tid] = rsqrt(sD[tid]);         // the reciprocals are not needed any more
+        __syncthreads();
+        {
+            const int i = tid >> 3, k0 = (tid & 7) * 4;
+            const double sq = sD[i] * sRcp[i];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int k = k0 + q;
+                const double y = k <= i ? sI[i][k] * sq : 0.0;
+                sI[i][k] = y;
+                sIT[k][i] = y;
+                sL[i][k] = k <= i ? sU[k][i] * sRcp[k] : 0.0;
+            }
+        }
+        __syncthreads();
+        FC_STAMP(4 + 6 * pi);
         if (rank == 0) {                                // L_PP into K, inv(L_PP) into W[P,P]
             for (int e = tid; e < kFcB * kFcB; e += kFcThreads) {
                 const int i = e >> 5, j = e & 31;
@@ -246,7 +309,9 @@ __global__ void __launch_bounds__(kFcThreads, 1) k_fit_cluster(const __grid_cons
                 __syncwarp();
             }
         }
+        FC_STAMP(5 + 6 * pi);
         fc_cluster_sync();
+        FC_STAMP(6 + 6 * pi);
         // ---- 3. trailing update: A[rb,cb] -= L[rb,P] L[cb,P]^T (pi < cb <= rb) and W[rb,cb] -= L[rb,P] W[P,cb] (cb <= pi)
         {
             const int m = nblk - 1 - pi;                // row blocks below the panel
@@ -279,8 +344,10 @@ __global__ void __launch_bounds__(kFcThreads, 1) k_fit_cluster(const __grid_cons
                 __syncwarp();
             }
         }
+        FC_STAMP(7 + 6 * pi);
         fc_cluster_sync();
     }
+    FC_STAMP(2 + 6 * nblk);
 
     // ---- z = W y (one warp per row), alpha = W^T z (one thread per column), fragment packing
     for (int i = rank * (kFcThreads / 32) + warp; i < fp.Npad; i += csize * (kFcThreads / 32)) {
@@ -332,6 +399,7 @@ __global__ void __launch_bounds__(kFcThreads, 1) k_fit_cluster(const __grid_cons
             fp.Afrag[e] = v;
         }
     }
+    FC_STAMP(3 + 6 * nblk);
     if (rank == 0 && tid == 0 && sBad) { *fp.status = SO_ERR_NOT_PD; __threadfence_system(); }
 }
 

@@ -50,8 +50,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_posterior(const __grid_constant
         double* sSST = sSS + (size_t)par * RG * T;
         double* sMeanT = sMean + (size_t)par * RG * T;
         double* sMeanXT = sMeanX + (size_t)par * n_extra * RG * T;
+#ifndef SO_K2_SKIP_GEN     // defined for timing experiments only (tools/build_variant.sh): contracts whatever shared memory holds
         if (GRID) gen_grid(p, sK, p.row0 + tile_local0, warp, lane);
         else gen_rows<KIND>(p, sK, sXs, sXt + (size_t)par * T * p.d, sExpT, warp, lane);
+#endif
         __syncthreads();
         if (!GRID) {
             // the next tile's candidate rows are fetched under the contraction

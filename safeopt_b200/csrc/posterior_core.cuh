@@ -77,18 +77,31 @@ __host__ __device__ inline SmemLayout smem_layout(int NB, int T, int d, int RG, 
 // The generator is bound by the fp64 dependency chain (distance -> exp -> scale), not by the pipe: with 8 warps per SM
 // only ILP hides the latency, so the body is branch-free and works on two k-blocks = four kernel values at a time, with
 // the candidate row held in registers (D = compile-time dimension; D = 0 keeps the runtime loop for d > 6).
+#ifndef SO_K2_GEN_SPLIT
+#define SO_K2_GEN_SPLIT 1
+#endif
 template <int KIND, int D>
 __device__ __forceinline__ void gen_rows_d(const PostParams& p, double2* __restrict__ sK, const double* __restrict__ sXs,
                                            const double* __restrict__ sXt, const double* __restrict__ sExpT, int warp, int lane) {
     const int d = D ? D : p.d, N = p.N, NB = p.NB, TB = p.TB;
     const int q = lane & 3, tl = lane >> 2;
     const double variance = p.variance;
-    for (int ct = warp; ct < TB; ct += kWarps) {
+    // work items = (column tile, part of the k range): with fewer column tiles than warps (TB = 2, 4, 6) the k-blocks of a
+    // column tile are split over 4, 2, 4 warps so that all eight warps generate
+#if SO_K2_GEN_SPLIT
+    const int S = TB == 4 ? 2 : ((TB == 2 || TB == 6) ? 4 : 1);
+#else
+    const int S = 1;
+#endif
+    const int kb_part = (((NB + S - 1) / S) + 1) & ~1;          // even, so that the pairs (kb, kb + 1) never straddle parts
+    for (int item = warp; item < TB * S; item += kWarps) {
+        const int ct = item % TB, part = item / TB;
+        const int kb_lo = part * kb_part, kb_hi = min(NB, kb_lo + kb_part);
         const double* xt = sXt + (ct * 8 + tl) * d;
         double xr[D ? D : 1];
 #pragma unroll
         for (int j = 0; j < D; ++j) xr[j] = xt[j];
-        for (int kb = 0; kb < NB; kb += 2) {
+        for (int kb = kb_lo; kb < kb_hi; kb += 2) {
             const int kb1 = kb + 1 < NB ? kb + 1 : kb;        // odd NB: the last pass recomputes block kb (same store)
             const int n0 = 8 * kb + 2 * q, n1 = 8 * kb1 + 2 * q;
             const double* x0 = sXs + n0 * d;

@@ -175,7 +175,8 @@ def test_failed_factorisation_surfaces_inside_optimize():
 # ---------------------------------------------------------------- K2
 @pytest.mark.parametrize("N,d,kind,M", [(1, 1, 0, 100), (5, 1, 0, 100), (9, 2, 2, 1), (64, 2, 0, 5000), (100, 3, 1, 3000),
                                         (128, 2, 2, 4097), (256, 4, 0, 20000), (300, 2, 0, 3000), (512, 6, 0, 4000),
-                                        (40, 2, 0, 70000), (700, 3, 1, 900), (1100, 3, 0, 600)])
+                                        (40, 2, 0, 70000), (700, 3, 1, 900), (1100, 3, 0, 600),
+                                        (512, 6, 0, 20000), (300, 2, 1, 25000), (400, 3, 2, 30000)])      # generation split over all eight warps
 def test_posterior_matches_oracle(N, d, kind, M):
     X, Y, ls, rs = _problem(N, d, N + 1)
     Xs = rs.uniform(-5, 5, (M, d))

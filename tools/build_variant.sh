@@ -5,7 +5,7 @@ set -e
 name=$1; shift
 root=$(cd "$(dirname "$0")/.." && pwd)
 out=$root/tools/ab; mkdir -p $out/obj_$name
-for f in api fit posterior sets expander lipschitz swarm safeset; do
+for f in $(ls $root/safeopt_b200/csrc/*.cu | xargs -n1 basename | sed 's/\.cu$//'); do
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr "$@" \
        -c $root/safeopt_b200/csrc/$f.cu -o $out/obj_$name/$f.o &
 done
