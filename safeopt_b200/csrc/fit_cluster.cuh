@@ -156,22 +156,43 @@ __global__ void __launch_bounds__(kFcThreads, 1) k_fit_cluster(const __grid_cons
     double* sXs = reinterpret_cast<double*>(fc_dyn);           // N x d scaled inputs (<= 64 KB of the 135 KB the tiles use later)
     for (int e = tid; e < N * d; e += kFcThreads) sXs[e] = fp.X[e] * fp.inv_ls[e % d];
     __syncthreads();
-    for (int e = gtid; e < NP * NP; e += gthreads) {
-        const int i = e / NP, j = e - i * NP;
-        double v;
-        if (i < N && j < N) {
-            double r2 = 0.0;
+    // Ky: only the lower triangle is ever read (diagonal blocks, panels and trailing tiles below the diagonal), so only it is
+    // evaluated -- two elements per thread and trip, so that two distance -> exp chains are in flight
+    {
+        const int ntri = NP * (NP + 1) / 2;
+        auto tri_row = [](int t) {
+            int i = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+            while ((i + 1) * (i + 2) / 2 <= t) ++i;
+            while (i * (i + 1) / 2 > t) --i;
+            return i;
+        };
+        for (int t0 = gtid; t0 < ntri; t0 += 2 * gthreads) {
+            const int t1 = t0 + gthreads < ntri ? t0 + gthreads : t0;       // the last odd trip repeats t0 (same store)
+            const int i0 = tri_row(t0), j0 = t0 - i0 * (i0 + 1) / 2, i1 = tri_row(t1), j1 = t1 - i1 * (i1 + 1) / 2;
+            const bool in0 = i0 < N, in1 = i1 < N;                          // j <= i: inside as soon as the row is
+            const double* xa0 = sXs + (in0 ? i0 : 0) * d;
+            const double* xb0 = sXs + (in0 ? j0 : 0) * d;
+            const double* xa1 = sXs + (in1 ? i1 : 0) * d;
+            const double* xb1 = sXs + (in1 ? j1 : 0) * d;
+            double r0 = 0.0, r1 = 0.0;
             for (int c = 0; c < d; ++c) {
-                const double t = sXs[i * d + c] - sXs[j * d + c];
-                r2 = fma(t, t, r2);
+                const double u0 = xa0[c] - xb0[c], u1 = xa1[c] - xb1[c];
+                r0 = fma(u0, u0, r0);
+                r1 = fma(u1, u1, r1);
             }
-            v = fc_kernel(fp.kind, r2, fp.variance);
-            if (i == j) v += fp.diag_add;
-        } else {
-            v = i == j ? 1.0 : 0.0;
+            double v0 = fc_kernel(fp.kind, r0, fp.variance), v1 = fc_kernel(fp.kind, r1, fp.variance);
+            if (i0 == j0) v0 += fp.diag_add;
+            if (i1 == j1) v1 += fp.diag_add;
+            if (!in0) v0 = i0 == j0 ? 1.0 : 0.0;                            // identity in the padding
+            if (!in1) v1 = i1 == j1 ? 1.0 : 0.0;
+            fp.K[(size_t)i0 * ld + j0] = v0;
+            fp.K[(size_t)i1 * ld + j1] = v1;
         }
-        fp.K[(size_t)i * ld + j] = v;
-        fp.W[(size_t)i * ld + j] = 0.0;
+        for (int e = gtid; e < NP * NP; e += gthreads) {
+            const int i = e / NP, j = e - i * NP;
+            fp.W[(size_t)i * ld + j] = 0.0;
+            if (j > i) fp.K[(size_t)i * ld + j] = 0.0;
+        }
     }
     if (tid == 0) sBad = 0;
     FC_STAMP(1);
