@@ -53,10 +53,9 @@ struct FitClusterParams {
 
 __device__ __forceinline__ unsigned fc_cluster_rank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r)); return r; }
 __device__ __forceinline__ unsigned fc_cluster_size() { unsigned r; asm volatile("mov.u32 %0, %%cluster_nctarank;\n" : "=r"(r)); return r; }
+// The release / acquire pair of the hardware cluster barrier orders the CTAs' global-memory traffic at cluster scope (every
+// consumer reads with ld.global.cg); a __threadfence() in front of it cost 6 % of the warp samples and is not needed.
 __device__ __forceinline__ void fc_cluster_sync() {
-#ifndef SO_FIT_NO_FENCE
-    __threadfence();
-#endif
     asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
 }
