@@ -308,6 +308,50 @@ def test_grid_path_equals_rows_path(d, n, N):
     eng.close()
 
 
+@pytest.mark.parametrize("N,d,n", [(80, 2, 120), (257, 2, 90), (300, 2, 100), (330, 3, 30), (384, 2, 80), (512, 2, 70)])
+def test_multi_output_launch_equals_single_launches(N, d, n):
+    """Three GPs on one factorisation (so_fit_like) evaluated by ONE launch -- one contraction, one V.z per GP -- against three
+    single launches, on the grid path (every tile plan: 48-row double buffer, six block rows per warp, ring) and on explicit
+    rows: means, variances, bounds and the AND-ed safe bit are bit-identical."""
+    rs = np.random.RandomState(N)
+    X = rs.uniform(-2, 2, (N, d))
+    Ys = [np.sin(X.sum(1) + o) + 0.05 * rs.randn(N) for o in (0.0, 0.7, 1.9)]
+    ls = rs.uniform(0.7, 1.3, d)
+    grid = sb.linearly_spaced_combinations([(-2.0, 2.0)] * d, n)
+    M = grid.shape[0]
+    from safeopt_b200.utilities import detect_grid
+    eng = DeviceEngine(max_gps=3)
+    eng.fit(0, X, Ys[0], 0, ls, 2.0, 0.05 ** 2)
+    eng.fit_like(1, 0, Ys[1])
+    eng.fit_like(2, 0, Ys[2])
+    eng.define_grid(detect_grid(grid))
+    eng.prepare_grid(0, 0, M)
+    fmins = [-0.2, 0.0, 0.1]
+    for rows in (None, eng.to_device(grid)):
+        out = {}
+        for multi in (True, False):
+            means = [eng.empty((M,)) for _ in range(3)]
+            variances = [eng.empty((M,)) for _ in range(3)]
+            Q, S = eng.empty((M, 6)), eng.zeros((M,), "u8")
+            if multi:
+                assert eng.posterior_multi([0, 1, 2], rows, 0, M, 2.0, fmins, means=means, variances=variances, Q=Q, q_cols=[0, 2, 4], S=S,
+                                           safe_mode=_lib.SAFE_WRITE)
+            else:
+                for i in range(3):
+                    mode = _lib.SAFE_WRITE if i == 0 else _lib.SAFE_AND
+                    if rows is None:
+                        if i:
+                            eng.prepare_grid(i, 0, M)
+                        eng.posterior_grid(i, 0, M, 2.0, fmins[i], mean=means[i], var=variances[i], Q=Q, q_col=2 * i, S=S, safe_mode=mode)
+                    else:
+                        eng.posterior_rows(i, rows, 2.0, fmins[i], mean=means[i], var=variances[i], Q=Q, q_col=2 * i, S=S, safe_mode=mode)
+            out[multi] = [t.cpu().numpy() for t in means + variances + [Q, S]]
+        for a, b in zip(out[True], out[False]):
+            assert np.array_equal(a, b)
+        assert 0 < out[True][-1].sum() < M                     # the safe bit discriminates on this problem
+    eng.close()
+
+
 @pytest.mark.parametrize("explicit", [False, True])
 def test_shared_factorisation_equals_separate_launches(explicit, monkeypatch):
     """GPs with identical inputs, kernel and noise are evaluated by one launch (one contraction, one V.z per GP):
