@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SO_ABI_VERSION 3
+#define SO_ABI_VERSION 4
 
 /* status codes */
 #define SO_OK                  0
@@ -192,6 +192,9 @@ int so_posterior_grid_f32(so_handle* h, int n, const int* gps_h, int64_t row0, i
  * the contraction for a fit with NB = ceil(N/8) block rows, as the posterior kernels use it when NB is not a
  * multiple of 32.  table_h: 8 passes x 8 warps x 4 slots (int16, ascending per pass, -1 = unused). */
 int so_debug_row_plan(int NB, int16_t* table_h, int* npass_h);
+/* The same plan with `slots` (4 or 6) block rows per warp and pass -- 6 is what the grid kernel uses for
+ * NB = 36..48 (one pass over a 32-row tile).  table_h: 8 passes x 8 warps x 6 slots (int16, -1 = unused). */
+int so_debug_row_plan_slots(int NB, int slots, int16_t* table_h, int* npass_h);
 /* Diagnostic, host only: the tile plans the posterior kernels would use for NB block rows on a device with
  * smem_limit bytes of opt-in shared memory and num_sms SMs (n_extra = further GPs sharing the launch).
  *   out_h[0..9]   grid kernel: status, BT, RG, CG, T, npass, ring (0/1), ring stages, shared-memory bytes, warps

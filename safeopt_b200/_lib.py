@@ -29,7 +29,7 @@ SWARM_GREEDY, SWARM_MAXIMIZERS, SWARM_EXPANDERS, SWARM_SAFE_SET = 0, 1, 2, 3
 SWARM_KINDS = {"greedy": SWARM_GREEDY, "maximizers": SWARM_MAXIMIZERS, "expanders": SWARM_EXPANDERS,
                "safe_set": SWARM_SAFE_SET}
 EXPANDER_MAX_BATCH = 32
-ABI_VERSION = 3
+ABI_VERSION = 4
 SWARM_REC_DOUBLES = 18
 XCHG_HANDLE_BYTES = 64
 XCHG_MAX_WORLD = 16
@@ -91,6 +91,7 @@ SIGNATURES = {
     "so_grid_prepare_f32": (_i, [_P, _i, _i64, _i64, _P]),
     "so_posterior_grid_f32": (_i, [_P, _i, _P, _i64, _i64, _dbl, _P, _P, _P, _P, _i, _P, _P, _i, _P]),
     "so_debug_row_plan": (_i, [_i, _P, _P]),
+    "so_debug_row_plan_slots": (_i, [_i, _i, _P, _P]),
     "so_debug_tile_plans": (_i, [_i, _i, _i64, _i, _i64, _i, _P]),
     "so_posterior_rows_simple": (_i, [_P, _i, _P, _i64, _P, _P, _P]),
     "so_grid_rows": (_i, [_P, _i64, _i64, _P, _P]),

@@ -558,6 +558,16 @@ extern "C" int so_debug_row_plan(int NB, int16_t* table_h, int* npass_h) {
     return SO_OK;
 }
 
+extern "C" int so_debug_row_plan_slots(int NB, int slots, int16_t* table_h, int* npass_h) {
+    if (!table_h || !npass_h || NB < 1 || (slots != 4 && slots != 6) || (NB + 7) / 8 > slots * kMaxPass) return SO_ERR_BAD_ARG;
+    short table[kMaxPass][8][kMaxSlots];
+    *npass_h = plan_rows(NB, table, slots);
+    for (int p = 0; p < kMaxPass; ++p)
+        for (int w = 0; w < 8; ++w)
+            for (int s = 0; s < kMaxSlots; ++s) table_h[(p * 8 + w) * kMaxSlots + s] = (int16_t)table[p][w][s];
+    return SO_OK;
+}
+
 extern "C" int so_posterior_rows_simple(so_handle* h, int gp, const double* Xstar_d, int64_t M, double* mean_d,
                                         double* var_d, void* stream_) {
     if (!h || gp < 0 || gp >= h->max_gps || !Xstar_d || !mean_d || !var_d || M < 0) return SO_ERR_BAD_ARG;

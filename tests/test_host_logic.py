@@ -64,6 +64,35 @@ def test_block_row_plan_is_a_balanced_partition(NB):
     assert lib.so_debug_row_plan(0, table.ctypes.data, ctypes.byref(npass)) == _lib.SO_ERR_BAD_ARG
 
 
+@pytest.mark.parametrize("NB", [33, 36, 37, 40, 44, 47, 48, 49, 96])
+def test_six_row_plan_is_a_balanced_partition(NB):
+    """The same plan with six block rows per warp and pass (grid kernel, NB = 36..48: the whole triangle in ONE pass)."""
+    import ctypes
+    lib = _lib.load()
+    table = np.full(8 * 8 * 6, -2, dtype=np.int16)
+    npass = ctypes.c_int(0)
+    assert lib.so_debug_row_plan_slots(NB, 6, table.ctypes.data, ctypes.byref(npass)) == 0
+    t = table.reshape(8, 8, 6)
+    n = npass.value
+    assert n == -(-(-(-NB // 8)) // 6) and np.all(t[n:] == -1) and (n == 1) == (NB <= 48)
+    rows = t[:n][t[:n] >= 0]
+    assert sorted(rows.tolist()) == list(range(NB))
+    for p in range(n):
+        for w in range(8):
+            slot = t[p, w]
+            used = slot[slot >= 0]
+            assert np.all(np.diff(used) > 0) and np.all(slot[len(used):] == -1)
+    load = np.array([sum(int(r) + 1 for r in t[:n, w].ravel() if r >= 0) for w in range(8)])
+    assert load.max() <= NB * (NB + 1) / 2 / 8 + NB
+    # four slots through the same entry point give the plan of so_debug_row_plan
+    t4 = np.full(8 * 8 * 4, -2, dtype=np.int16)
+    n4 = ctypes.c_int(0)
+    assert lib.so_debug_row_plan(NB, t4.ctypes.data, ctypes.byref(n4)) == 0
+    assert lib.so_debug_row_plan_slots(NB, 4, table.ctypes.data, ctypes.byref(npass)) == 0 and npass.value == n4.value
+    assert np.array_equal(table.reshape(8, 8, 6)[:, :, :4], t4.reshape(8, 8, 4)) and np.all(table.reshape(8, 8, 6)[:, :, 4:] == -1)
+    assert lib.so_debug_row_plan_slots(NB, 5, table.ctypes.data, ctypes.byref(npass)) == _lib.SO_ERR_BAD_ARG
+
+
 def test_tile_plans_fit_the_device_for_every_size():
     """Host-side planning of the posterior kernels for every NB (N = 8 .. 2048) and 0..3 further outputs, on a B200's
     227 KB of opt-in shared memory: whatever is planned fits, tiles are whole 8-row blocks, the eight warps are split
