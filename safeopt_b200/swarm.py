@@ -14,6 +14,9 @@ new value is better AND safe):
 """
 from __future__ import annotations
 
+import gc
+import os
+
 import numpy as np
 
 __all__ = ["SwarmOptimization", "DeviceSwarm"]
@@ -253,12 +256,24 @@ class DeviceSwarm(object):
                 side = self._side
                 side.wait_stream(cur)
                 before = eng.launches
-                with t.cuda.stream(side):
-                    g.capture_begin()
-                    try:
-                        self._iteration_dev()
-                    finally:
-                        g.capture_end()
+                # No cyclic garbage collection while the stream is capturing: a collection may finalise an engine of an earlier
+                # optimiser (SafeOptSwarm <-> DeviceSwarm is a reference cycle, so such objects die only in the collector), its
+                # so_destroy() calls cudaFree / cudaFreeHost, and those are forbidden during a capture -- the capture is
+                # invalidated and capture_end raises (seen as an intermittent torch.AcceleratorError that depended on what ran
+                # before).  torch.cuda.graph() avoids the same thing by collecting up front, at tens of milliseconds per capture.
+                gc_was_enabled = gc.isenabled() and os.environ.get("SAFEOPT_B200_GC_IN_CAPTURE", "0") != "1"
+                if gc_was_enabled:
+                    gc.disable()
+                try:
+                    with t.cuda.stream(side):
+                        g.capture_begin()
+                        try:
+                            self._iteration_dev()
+                        finally:
+                            g.capture_end()
+                finally:
+                    if gc_was_enabled:
+                        gc.enable()
                 cur.wait_stream(side)
                 # capturing does not execute: the captured iteration has not run yet
                 self._graph_launches = eng.launches - before

@@ -1240,6 +1240,44 @@ def _nccl_device_rng_worker(rank, world, port_no, out):
         dist.destroy_process_group()
 
 
+def test_graph_capture_survives_garbage_of_earlier_optimisers(monkeypatch):
+    """SafeOptSwarm <-> DeviceSwarm is a reference cycle, so an abandoned optimiser (and its engine: cudaFree / cudaFreeHost in
+    so_destroy) dies only in Python's cyclic collector.  If that collection ran while a PSO iteration is being captured into a
+    CUDA graph, the capture would be invalidated ('operation not permitted when stream is capturing' -> torch.AcceleratorError):
+    the capture therefore runs with the collector switched off.  Here two optimisers become garbage INSIDE the capture and an
+    automatic collection is simulated at that point (collect iff the collector is enabled)."""
+    import gc
+    from safeopt_b200.swarm import DeviceSwarm
+    g = load_golden("swarm_query_2d")
+    victims = []
+    for _ in range(2):
+        o = _swarm_query_problem(g, swarm_backend="device", rng="device", seed=3)
+        o.optimize()
+        victims.append(o)
+    torch.cuda.synchronize()
+    orig = DeviceSwarm._iteration_dev
+    seen = {"captures": 0, "collections": 0}
+
+    def patched(self):
+        if torch.cuda.is_current_stream_capturing():
+            seen["captures"] += 1
+            if victims:
+                victims.pop()
+            if gc.isenabled():
+                seen["collections"] += 1
+                gc.collect()
+        orig(self)
+
+    monkeypatch.setattr(DeviceSwarm, "_iteration_dev", patched)
+    assert gc.isenabled()
+    test_device_swarm_device_rng_runs()
+    torch.cuda.synchronize()
+    assert gc.isenabled()                                   # switched back on after every capture
+    assert seen["captures"] >= 3 and seen["collections"] == 0 and not victims
+    gc.collect()                                            # the abandoned engines are finalised here, outside any capture
+    torch.cuda.synchronize()
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 def test_two_gpu_device_rng_swarm_equals_single_gpu(tmp_path):
     import os
