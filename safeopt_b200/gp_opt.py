@@ -986,7 +986,7 @@ class SafeOptSwarm(GaussianProcessOptimization):
     def _fitness_buffers(self, P, keep=False):
         """Per-swarm-size scratch (posterior planes, values, flags), reused across the ~300 fitness passes of an optimize().
         ``keep``: the buffers of the device swarms are never evicted -- a captured PSO iteration (CUDA graph) holds their
-        addresses, and an evicted buffer is returned to the driver by the ``empty_cache()`` of the next graph capture."""
+        addresses, and an evicted buffer would be handed to the next tensor of that size while the graph still writes to it."""
         buf = self._fit_buffers_keep.get(P) or self._fit_buffers.get(P)
         if buf is None:
             eng, G = self._engine, len(self.gps)
