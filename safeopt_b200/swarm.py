@@ -109,7 +109,6 @@ class DeviceSwarm(object):
     """
 
     def __init__(self, engine, velocity, fitness_device, bounds=None, rng="host", seed=0, comm=None, peer=None):
-        import os
         from . import _lib
         from .distributed import Comm
         self.engine = engine
